@@ -2,17 +2,21 @@
  * wrsn_b200.h — C ABI of the B200-native batched WRSN simulator (libwrsn_b200.so).
  *
  * The reference has no FFI layer: its boundary for this hot path is the Python class
- * rl_env.WRSN.WRSN (reset :41, step :289, get_state :130, get_network_fitness :188,
- * get_reward :222, update_reward :100) over physical_env/{network,mc}.  The entry points
- * below are what a ctypes binding of that class binds instead of running SimPy:
- * plain pointers and sizes, device pointers owned by the caller (PyTorch tensors are only
- * the allocator), a CUDA stream handle, int return codes (0 = ok) and wrsn_last_error().
- * INTEGRATION.md shows the reference-side stub.
+ * rl_env.WRSN.WRSN (reset rl_env/WRSN.py:41, step :289, get_state :130,
+ * get_network_fitness :188, get_reward :222, update_reward :100) over
+ * physical_env/{network,mc}.  The entry points below are what a ctypes binding of that
+ * class binds instead of running SimPy: plain pointers and sizes, device memory owned by
+ * the caller (PyTorch is only the allocator), a CUDA stream handle, int return codes
+ * (0 = ok) and wrsn_last_error().  INTEGRATION.md shows the reference-side stub.
  *
- * All state is struct-of-arrays in HBM:  per-environment node rows [B][Npad], per-scenario
- * static graph rows [n_scen][...].  Records that only the per-environment leader thread
- * touches (event clock, charger records, charger process slots) are rows of doubles whose
- * field indices are the enums below, so a host can read them without knowing a C layout.
+ * Memory model.  Two caller-allocated device buffers:
+ *   scen  [n_scen][scen_bytes]   static graph + constants of every distinct scenario
+ *   state [B][state_bytes]       one contiguous record per environment; inside the record the
+ *                                node quantities are struct-of-arrays rows of pitch Npad
+ * The byte offsets of every field inside a record come from wrsn_state_layout() /
+ * wrsn_scen_layout(), so a host can build typed views without knowing a C struct.
+ * Records that only the per-environment leader thread touches (event clock, charger
+ * records, charger process slots) are rows of doubles indexed by the enums below.
  */
 #ifndef WRSN_B200_H
 #define WRSN_B200_H
@@ -22,10 +26,11 @@
 extern "C" {
 #endif
 
+#define WRSN_ABI_VERSION 2
 #define WRSN_MAX_MC 16          /* chargers per environment */
 #define WRSN_RING 10            /* Node.operate keeps the last 10 per-second consumptions (Node.py:70-77) */
 
-/* ---- per-scenario scalar row  par[n_scen][WRSN_P_LEN]  (filled by the host loader with the
+/* ---- per-scenario scalar row  par[WRSN_P_LEN]  (filled by the host loader with the
  *      reference's own Python arithmetic so thresholds / constants are bit-identical) ---- */
 enum {
     WRSN_P_CAP = 0, WRSN_P_THR, WRSN_P_ERECV,          /* node capacity, threshold, er*package_size */
@@ -36,139 +41,149 @@ enum {
     WRSN_P_MC_CAP, WRSN_P_MC_THR, WRSN_P_MC_V, WRSN_P_MC_PM, WRSN_P_MC_R, WRSN_P_MC_ALPHA, WRSN_P_MC_BETA,
     WRSN_P_MC_EPS, WRSN_P_MC_AB2,                      /* alpha / beta**2 */
     WRSN_P_MC_CAP200, WRSN_P_MC_PMV,                   /* capacity / 200.0 ; pm * velocity */
-    WRSN_P_DENX1, WRSN_P_DENY1, WRSN_P_DENX2, WRSN_P_DENY2,  /* -2*hX**2 terms of get_state (WRSN.py:16-18,144-155) */
     WRSN_P_EPSENV,                                     /* WRSN.epsilon = 1e-9 */
     WRSN_P_CAPMTHR,                                    /* capacity - threshold */
-    WRSN_P_LEN = 40
+    WRSN_P_ESMAX,                                      /* largest per-hop cost in the scenario (slack of the no-death test) */
+    WRSN_P_LEN = 32
 };
 
-/* ---- per-environment event clock  hdr[B][WRSN_H_LEN] ---- */
+/* ---- per-environment event clock  hdr[WRSN_H_LEN] ---- */
 enum {
     WRSN_H_NOW = 0, WRSN_H_SEQ,
-    WRSN_H_NET_T, WRSN_H_NET_SEQ, WRSN_H_NET_STATE,    /* Network.operate: 1 next=setLevels, 2 next=exit check, 3 finished */
-    WRSN_H_UR_T, WRSN_H_UR_SEQ, WRSN_H_UR_ON,          /* WRSN.update_reward */
-    WRSN_H_NODES_T, WRSN_H_NODES_SEQ, WRSN_H_NODES_PHASE, /* Node.operate block: 1 next=k+0.5 drain, 2 next=k+1.0 bookkeeping */
-    WRSN_H_ALIVE, WRSN_H_BFS_DIRTY, WRSN_H_TREE_DIRTY, WRSN_H_LOG_LEN, WRSN_H_LOG_HEAD,
-    WRSN_H_UNTIL_T, WRSN_H_UNTIL_SEQ, WRSN_H_UNTIL_ON,
-    WRSN_H_CHAIN_N, WRSN_H_ERR, WRSN_H_HANG,
-    WRSN_H_NTICKS, WRSN_H_NEVENTS, WRSN_H_NDEATH_TICKS, WRSN_H_NBFS,
-    WRSN_H_CHAIN_AGENT = 32,                           /* [WRSN_MAX_MC] agent id of chain member j */
-    WRSN_H_CHAIN_TRIG = WRSN_H_CHAIN_AGENT + WRSN_MAX_MC,
-    WRSN_H_COND_ON = WRSN_H_CHAIN_TRIG + WRSN_MAX_MC,
-    WRSN_H_COND_T = WRSN_H_COND_ON + WRSN_MAX_MC,
+    WRSN_H_NET_ON, WRSN_H_NET_T, WRSN_H_NET_SEQ, WRSN_H_NET_STATE,  /* Network.operate: 1 next=setLevels, 2 next=exit check */
+    WRSN_H_UR_ON, WRSN_H_UR_T, WRSN_H_UR_SEQ,                       /* WRSN.update_reward */
+    WRSN_H_NODES_T, WRSN_H_NODES_SEQ, WRSN_H_NODES_PHASE,           /* Node.operate block: 1 next=k+0.5 drain, 2 next=k+1.0 bookkeeping */
+    WRSN_H_UNTIL_ON, WRSN_H_UNTIL_T, WRSN_H_UNTIL_SEQ,              /* env.run(until=number) */
+    WRSN_H_ALIVE, WRSN_H_BFS_DIRTY, WRSN_H_LOG_LEN, WRSN_H_LOG_HEAD, WRSN_H_LOG_UNIFORM, WRSN_H_LOG_LITERAL,
+    WRSN_H_FIT_MIN,                                                 /* min(get_network_fitness()) at the last request */
+    WRSN_H_ERR, WRSN_H_HANG,
+    WRSN_H_NTICKS, WRSN_H_NEVENTS, WRSN_H_NSLOW, WRSN_H_NBFS, WRSN_H_NDECISIONS,
+    WRSN_H_CHAIN_N, WRSN_H_CHAIN_DETACH,                            /* AnyOf chain of WRSN.step (:307-311) */
+    WRSN_H_CHAIN_SLOT = 32,                                         /* [WRSN_MAX_MC] process slot watched by member j */
+    WRSN_H_COND_TRIG = WRSN_H_CHAIN_SLOT + WRSN_MAX_MC,
+    WRSN_H_COND_PEND = WRSN_H_COND_TRIG + WRSN_MAX_MC,
+    WRSN_H_COND_T = WRSN_H_COND_PEND + WRSN_MAX_MC,
     WRSN_H_COND_SEQ = WRSN_H_COND_T + WRSN_MAX_MC,
-    WRSN_H_LEN = WRSN_H_COND_SEQ + WRSN_MAX_MC         /* 112 */
+    WRSN_H_LEN = WRSN_H_COND_SEQ + WRSN_MAX_MC                      /* 112 */
 };
 
-/* ---- charger record  mc[B][M][WRSN_MC_LEN]  (MobileCharger.py:6-32 + WRSN per-agent lists) ---- */
+/* ---- charger record  mc[M][WRSN_MC_LEN]  (MobileCharger.py:6-32 + WRSN per-agent lists) ---- */
 enum {
     WRSN_MC_X = 0, WRSN_MC_Y, WRSN_MC_ENERGY, WRSN_MC_STATUS,
     WRSN_MC_CPA0, WRSN_MC_CPA1, WRSN_MC_CPA2,          /* cur_phy_action */
     WRSN_MC_TYPE,                                      /* 0 "moving", 1 "charging" */
-    WRSN_MC_RATE, WRSN_MC_CHTIME,
+    WRSN_MC_RATE, WRSN_MC_CHTIME, WRSN_MC_NCONN,
     WRSN_MC_EXCL, WRSN_MC_PREVFIT,                     /* agents_exclusive_reward, min(agents_prev_fitness) */
     WRSN_MC_ACT0, WRSN_MC_ACT1, WRSN_MC_ACT2,          /* agents_action (clipped) */
-    WRSN_MC_LEN = 16
+    WRSN_MC_SLOT,                                      /* process slot holding agents_process[id] */
+    WRSN_MC_LEN = 20
 };
 
-/* ---- charger process slot  proc[B][M][2][WRSN_PR_LEN]  (slot 0 = agents_process[id], slot 1 = a
- *      still-running predecessor, e.g. the reset-time process of agent 0) ---- */
+/* ---- charger process slot  proc[n_slot][WRSN_PR_LEN]  (one running MobileCharger.operate_step
+ *      generator tree: operate_step -> move -> move_step / recharge / charge -> charge_step) ---- */
 enum {
-    WRSN_PR_ACTIVE = 0, WRSN_PR_DONE, WRSN_PR_STATE, WRSN_PR_T, WRSN_PR_PRIO, WRSN_PR_SEQ,
+    WRSN_PR_USED = 0, WRSN_PR_PENDING, WRSN_PR_PROCESSED, WRSN_PR_CURRENT, WRSN_PR_AGENT,
+    WRSN_PR_PC, WRSN_PR_T, WRSN_PR_PRIO, WRSN_PR_SEQ,
     WRSN_PR_PHY0, WRSN_PR_PHY1, WRSN_PR_PHY2, WRSN_PR_STAGE,
     WRSN_PR_DESTX, WRSN_PR_DESTY, WRSN_PR_MT, WRSN_PR_VX, WRSN_PR_VY, WRSN_PR_TOTAL, WRSN_PR_SPAN,
     WRSN_PR_SVX, WRSN_PR_SVY, WRSN_PR_CHTMP, WRSN_PR_CHSPAN,
     WRSN_PR_LEN = 24
 };
 
+/* ---- fields of one environment record (wrsn_state_layout) ---- */
+enum {
+    WRSN_F_HDR = 0, WRSN_F_MC, WRSN_F_PROC,            /* double rows, leader-only */
+    WRSN_F_ENERGY, WRSN_F_RR, WRSN_F_CS,               /* double[Npad]  Node.energy / energyRR / energyCS */
+    WRSN_F_ESEND, WRSN_F_LOGC,                         /* double[Npad]  e_send to the current receiver; log_energy of a no-death tick */
+    WRSN_F_NBEF, WRSN_F_NAFT,                          /* uint16[Npad]  packets relayed per tick for lower / higher source ids */
+    WRSN_F_LEVEL, WRSN_F_PARENT,                       /* int16[Npad]   Node.level; receiver (-2 base station, -1 none) */
+    WRSN_F_STATUS,                                     /* uint8[Npad] */
+    WRSN_F_TACT,                                       /* uint32[Tw]    Network.targets_active as a bitmask */
+    WRSN_F_CONN,                                       /* uint32[M][W]  MobileCharger.connected_nodes as bitmasks */
+    WRSN_F_LOGTICK,                                    /* double[Npad]  literal log_energy of a death tick */
+    WRSN_F_RING,                                       /* double[WRSN_RING][Npad]  Node.log */
+    WRSN_F_COUNT
+};
+
+/* ---- fields of one scenario record (wrsn_scen_layout) ---- */
+enum {
+    WRSN_S_PAR = 0,                                    /* double[WRSN_P_LEN] */
+    WRSN_S_NX, WRSN_S_NY, WRSN_S_BS_ESEND,             /* double[Npad] */
+    WRSN_S_NBR_DIST, WRSN_S_NBR_ESEND,                 /* double[Emax]  per CSR entry (Node.probe_neighbors :80, send_package :107-115) */
+    WRSN_S_NBR_PTR, WRSN_S_TGT_PTR,                    /* int32[Npad+1] */
+    WRSN_S_NBR_IDX,                                    /* int32[Emax]   neighbour ids in id order */
+    WRSN_S_TGT_IDX,                                    /* int32[TEmax]  covered target ids in id order (Node.probe_targets :86) */
+    WRSN_S_DIRECT,                                     /* uint8[Npad]   d(node, BS) <= com_range (BaseStation.probe_neighbors :20) */
+    WRSN_S_COUNT
+};
+
 typedef struct wrsn_dims {
     int32_t B;        /* environments in this shard */
     int32_t N, T, M;  /* nodes, targets, chargers (same for every scenario of the batch) */
     int32_t S;        /* map_size */
-    int32_t Npad;     /* row pitch of node arrays (multiple of 4) */
-    int32_t Tpad;     /* row pitch of target arrays */
-    int32_t Emax;     /* row pitch of neighbour CSR payloads */
-    int32_t TEmax;    /* row pitch of node->target CSR payload */
-    int32_t W;        /* 32-bit words per node bitmask = ceil(N/32) */
-    int32_t n_scen;   /* number of distinct scenarios */
-    int32_t threads;  /* CTA size for per-environment kernels (one CTA per environment) */
+    int32_t Emax;     /* neighbour CSR capacity per scenario */
+    int32_t TEmax;    /* node->target CSR capacity per scenario */
+    int32_t n_scen;   /* distinct scenarios */
+    int32_t threads;  /* threads per environment (one CTA per environment), multiple of 32; 0 = choose */
+    /* filled by wrsn_dims_finalize */
+    int32_t Npad;     /* row pitch of node arrays (multiple of 16) */
+    int32_t W;        /* 32-bit words per node bitmask */
+    int32_t Tw;       /* 32-bit words per target bitmask */
+    int32_t n_slot;   /* charger process slots per environment */
+    int32_t state_bytes, state_resident_bytes, scen_bytes, smem_bytes;
 } wrsn_dims;
 
-/* static graph, device pointers, one row per scenario (Node.probe_neighbors :80, probe_targets :86,
- * BaseStation.probe_neighbors :20, send_package's e_send :107-115 precomputed per edge) */
-typedef struct wrsn_static {
-    const double *node_x, *node_y;      /* [n_scen][Npad] */
-    const int32_t *nbr_ptr;             /* [n_scen][Npad+1] */
-    const int32_t *nbr_idx;             /* [n_scen][Emax]  neighbour ids in id order */
-    const double *nbr_dist;             /* [n_scen][Emax]  euclidean(node, neighbour) */
-    const double *nbr_esend;            /* [n_scen][Emax]  e_send for that hop */
-    const int32_t *tgt_ptr;             /* [n_scen][Npad+1] */
-    const int32_t *tgt_idx;             /* [n_scen][TEmax] covered target ids in id order */
-    const uint8_t *direct;              /* [n_scen][Npad]  d(node, BS) <= com_range */
-    const double *bs_esend;             /* [n_scen][Npad]  e_send straight to the base station */
-    const double *par;                  /* [n_scen][WRSN_P_LEN] */
-} wrsn_static;
-
-/* dynamic state, device pointers, one row per environment */
-typedef struct wrsn_state {
-    const int32_t *scen_id;             /* [B] */
-    double *energy, *cs, *rr, *log_energy;   /* [B][Npad]  Node.energy / energyCS / energyRR / log_energy */
-    double *ring;                       /* [B][WRSN_RING][Npad]  Node.log */
-    uint8_t *status;                    /* [B][Npad] */
-    int32_t *level, *parent;            /* [B][Npad]  Node.level; receiver (-2 base station, -1 none) */
-    int32_t *nbef, *naft;               /* [B][Npad]  relayed packets per tick from lower / higher source ids */
-    double *esend, *logc;               /* [B][Npad]  e_send to the current receiver; cached per-tick log_energy */
-    uint8_t *targets_active;            /* [B][Tpad] */
-    double *scratch;                    /* [B][2*max(Npad,Tpad)] */
-    uint32_t *nearmask;                 /* [B][W] */
-    double *hdr;                        /* [B][WRSN_H_LEN] */
-    double *mc;                         /* [B][M][WRSN_MC_LEN] */
-    double *proc;                       /* [B][M][2][WRSN_PR_LEN] */
-    uint32_t *conn;                     /* [B][M][W]  MobileCharger.connected_nodes as a bitmask */
-} wrsn_state;
-
-/* request record written by reset / step, one row per environment */
+/* request record written by reset / step, device pointers, one row per environment */
 typedef struct wrsn_request {
-    int32_t *agent_id;                  /* [B]  -1 = None (terminal), -2 = implicit None (Q7) */
+    int32_t *agent_id;                  /* [B]  -1 = None (terminal), -2 = implicit None, -3 = untouched (masked out) */
     uint8_t *terminal;                  /* [B] */
     double *reward;                     /* [B] */
     double *now;                        /* [B]  env.now */
     double *action;                     /* [B][3] agents_action[agent_id] */
     double *detail;                     /* [B][2] term_all, term_exclusive of get_reward (WRSN.py:225-226) */
+    int32_t *flags;                     /* [B]  bit0 = every charger dead (the reference would never return, Q1), bit1 = engine error */
 } wrsn_request;
 
 const char *wrsn_last_error(void);
 int wrsn_abi_version(void);
-int wrsn_sizeof_dims(void);
-int wrsn_field_count(int which);        /* 0 par, 1 hdr, 2 mc, 3 proc */
+int wrsn_field_count(int which);        /* 0 par, 1 hdr, 2 mc, 3 proc, 4 state fields, 5 scenario fields */
+int wrsn_dims_finalize(wrsn_dims *d);
+int wrsn_state_layout(const wrsn_dims *d, int64_t *offsets /* [WRSN_F_COUNT] */);
+int wrsn_scen_layout(const wrsn_dims *d, int64_t *offsets /* [WRSN_S_COUNT] */);
+int wrsn_device_ok(void);               /* 1 when a CUDA device of compute capability 10.x is usable */
 
-/* NetworkIO.makeNetwork + Network.operate start: initialise node / clock state at t = 0.
- * with_reward_process != 0 also starts WRSN.update_reward (WRSN.py:43). `env_mask` (may be NULL) selects rows. */
-int wrsn_init_network(const wrsn_dims *d, const wrsn_static *st, wrsn_state *s, const uint8_t *env_mask,
-                      int with_reward_process, void *stream);
+/* NetworkIO.makeNetwork + Network.operate start (NetworkIO.py:19-34, Network.py:69-73): node / clock state at
+ * t = 0.  with_reward_process != 0 also starts WRSN.update_reward (WRSN.py:43).  env_mask (may be NULL) selects rows. */
+int wrsn_init_network(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state,
+                      const uint8_t *env_mask, int with_reward_process, void *stream);
 /* env.run(until=t) (WRSN.py:53): advance every selected environment to simulated time t_until[b]. */
-int wrsn_run_until(const wrsn_dims *d, const wrsn_static *st, wrsn_state *s, const uint8_t *env_mask,
-                   const double *t_until, void *stream);
+int wrsn_run_until(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state,
+                   const uint8_t *env_mask, const double *t_until, void *stream);
 /* remainder of WRSN.reset after the warm-up (:44-83): chargers at the base station, fitness, reset-time
  * charger processes, first request. */
-int wrsn_reset_finish(const wrsn_dims *d, const wrsn_static *st, wrsn_state *s, const uint8_t *env_mask,
-                      wrsn_request *req, void *stream);
-/* WRSN.step (:289-330): agent_id_in[b] < 0 = "no new action" (agent_id None). */
-int wrsn_step(const wrsn_dims *d, const wrsn_static *st, wrsn_state *s, const int32_t *agent_id_in,
-              const double *action_in, wrsn_request *req, void *stream);
+int wrsn_reset_finish(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state,
+                      const uint8_t *env_mask, wrsn_request *req, void *stream);
+/* reset from a snapshot: state[b] = snap[scen_id[b]] for selected rows (the t = warm_up state is a pure function
+ * of the scenario), then wrsn_reset_finish. */
+int wrsn_reset_from_snapshot(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state,
+                             const void *snap, const uint8_t *env_mask, wrsn_request *req, void *stream);
+/* WRSN.step (:289-330): agent_id_in[b] = -1 means "no new action" (agent_id None); env_mask as above. */
+int wrsn_step(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state,
+              const uint8_t *env_mask, const int32_t *agent_id_in, const double *action_in,
+              wrsn_request *req, void *stream);
 /* WRSN.get_state (:130-186) for agent agent_id[b] of every environment with agent_id[b] >= 0, written to
- * obs[b][4][S][S] as float (obs_f64 == 0) or double. */
-int wrsn_observe(const wrsn_dims *d, const wrsn_static *st, const wrsn_state *s, const int32_t *agent_id,
-                 void *obs, int obs_f64, void *stream);
-/* WRSN.get_network_fitness (:188-220): per-target values fitness[B][Tpad] and their minimum. */
-int wrsn_fitness(const wrsn_dims *d, const wrsn_static *st, wrsn_state *s, double *fitness, double *fit_min,
-                 void *stream);
+ * obs[b][4][S][S] as float (obs_f64 == 0) or double.  Rows with agent_id[b] < 0 are left untouched. */
+int wrsn_observe(const wrsn_dims *d, const void *scen, const int32_t *scen_id, const void *state,
+                 const int32_t *agent_id, void *obs, int obs_f64, void *stream);
+/* WRSN.get_network_fitness (:188-220): per-target values fitness[B][T] (may be NULL) and their minimum fit_min[B]. */
+int wrsn_fitness(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state,
+                 double *fitness, double *fit_min, void *stream);
 
-/* standalone per-tick kernels (same device functions the fused step uses; unit parity + ncu evidence) */
-int wrsn_k_bfs(const wrsn_dims *d, const wrsn_static *st, wrsn_state *s, void *stream);       /* Network.setLevels + receivers + relay counts */
-int wrsn_k_drain(const wrsn_dims *d, const wrsn_static *st, wrsn_state *s, void *stream);     /* Node.operate k+0.5 tick */
-int wrsn_k_bookkeep(const wrsn_dims *d, const wrsn_static *st, wrsn_state *s, void *stream);  /* Node.operate k+1.0 tick */
-int wrsn_k_charge(const wrsn_dims *d, const wrsn_static *st, wrsn_state *s, int connect, void *stream); /* charger_(dis)connection for every charging charger */
+/* standalone per-tick kernels (the same device functions the fused step uses; unit parity + ncu evidence) */
+int wrsn_k_bfs(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state, void *stream);      /* Network.setLevels + receivers + relay counts */
+int wrsn_k_drain(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state, void *stream);    /* Node.operate k+0.5 tick */
+int wrsn_k_bookkeep(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state, void *stream); /* Node.operate k+1.0 tick */
+int wrsn_k_reward(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state, void *stream);   /* WRSN.update_reward tick */
 
 #ifdef __cplusplus
 }

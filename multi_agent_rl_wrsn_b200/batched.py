@@ -1,0 +1,279 @@
+"""``BatchedWRSN`` — B independent WRSN environments advanced in lockstep on one B200.
+
+Host-side mirror of ``rl_env.WRSN.WRSN`` (``rl_env/WRSN.py:21``): the same ``reset`` / ``step`` /
+``get_state`` / ``get_network_fitness`` contract, but every argument and result carries a leading
+environment axis and lives in HBM as a torch tensor.  All simulation work happens in the sm_100a kernels
+behind the C ABI of ``include/wrsn_b200.h``; torch is the allocator and the stream provider only.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .scenario import Scenario, build_static, load_mc_type
+
+_NP = {"f64": np.float64, "i32": np.int32, "u8": np.uint8}
+_S_FIELDS = (  # (enum, dtype, which size)
+    ("WRSN_S_PAR", "f64", "P"), ("WRSN_S_NX", "f64", "Npad"), ("WRSN_S_NY", "f64", "Npad"),
+    ("WRSN_S_BS_ESEND", "f64", "Npad"), ("WRSN_S_NBR_DIST", "f64", "Emax"), ("WRSN_S_NBR_ESEND", "f64", "Emax"),
+    ("WRSN_S_NBR_PTR", "i32", "Npad1"), ("WRSN_S_TGT_PTR", "i32", "Npad1"), ("WRSN_S_NBR_IDX", "i32", "Emax"),
+    ("WRSN_S_TGT_IDX", "i32", "TEmax"), ("WRSN_S_DIRECT", "u8", "Npad"))
+
+
+class Requests:
+    """The request record of ``WRSN.reset`` / ``WRSN.step`` (``WRSN.py:68-83,313-330``) for every environment.
+
+    ``agent_id``: >= 0 deciding charger, -1 ``None`` (terminal), -2 implicit ``None``, -3 row not
+    touched by the call (masked out).  ``flags`` bit0: every charger is dead (the reference would never
+    return, Q1); bit1: engine error.
+    """
+
+    def __init__(self, B, device):
+        self.agent_id = torch.full((B,), -3, dtype=torch.int32, device=device)
+        self.terminal = torch.zeros((B,), dtype=torch.uint8, device=device)
+        self.reward = torch.zeros((B,), dtype=torch.float64, device=device)
+        self.now = torch.zeros((B,), dtype=torch.float64, device=device)
+        self.action = torch.zeros((B, 3), dtype=torch.float64, device=device)
+        self.detail = torch.zeros((B, 2), dtype=torch.float64, device=device)
+        self.flags = torch.zeros((B,), dtype=torch.int32, device=device)
+        self.c = _lib.Request(self.agent_id.data_ptr(), self.terminal.data_ptr(), self.reward.data_ptr(),
+                              self.now.data_ptr(), self.action.data_ptr(), self.detail.data_ptr(), self.flags.data_ptr())
+
+
+class BatchedWRSN:
+    def __init__(self, scenarios, num_agent=3, mc_type=None, num_envs=None, scenario_index=None, map_size=100,
+                 warm_up_time=100, device=None, threads=0):
+        """``scenarios``: one or several ``Scenario`` / YAML paths (all with the same N and T);
+        ``scenario_index[b]`` picks the scenario of environment b (default: round robin)."""
+        self.L = _lib.lib()
+        emu = _lib.is_emulation(self.L)
+        if device is None:
+            device = "cpu" if emu else "cuda"
+        self.device = torch.device(device)
+        if emu:
+            if self.device.type != "cpu":
+                raise RuntimeError("the host emulation only works on CPU tensors")
+        else:
+            if self.device.type != "cuda" or not torch.cuda.is_available():
+                raise RuntimeError("BatchedWRSN needs a CUDA device (sm_100a); there is no CPU path")
+            with torch.cuda.device(self.device):
+                if not self.L.wrsn_device_ok():
+                    raise RuntimeError("wrsn_b200: " + self.L.wrsn_last_error().decode())
+        if isinstance(scenarios, (str, Scenario)):
+            scenarios = [scenarios]
+        self.scenarios = [s if isinstance(s, Scenario) else Scenario.load_yaml(s) for s in scenarios]
+        self.mc_type = load_mc_type(mc_type)
+        self.num_agent = int(num_agent)
+        self.map_size = int(map_size)
+        self.warm_up_time = float(warm_up_time)
+        statics = [build_static(s, self.mc_type, self.warm_up_time) for s in self.scenarios]
+        self.statics = statics
+        N, T = statics[0]["N"], statics[0]["T"]
+        if any(st["N"] != N or st["T"] != T for st in statics):
+            raise ValueError("all scenarios of a batch must have the same number of nodes and targets")
+        n_scen = len(statics)
+        B = int(num_envs) if num_envs is not None else (len(scenario_index) if scenario_index is not None else n_scen)
+        self.B, self.N, self.T, self.M, self.S = B, N, T, self.num_agent, self.map_size
+        self.E = _lib.enums()
+        d = _lib.Dims()
+        d.B, d.N, d.T, d.M, d.S = B, N, T, self.M, self.S
+        d.Emax = max(len(st["nbr_idx"]) for st in statics)
+        d.TEmax = max(len(st["tgt_idx"]) for st in statics)
+        d.n_scen, d.threads = n_scen, int(threads)
+        _lib.check(self.L.wrsn_dims_finalize(C.byref(d)), self.L)
+        self.dims = d
+        self._foff = (C.c_int64 * self.E["WRSN_F_COUNT"])()
+        self._soff = (C.c_int64 * self.E["WRSN_S_COUNT"])()
+        _lib.check(self.L.wrsn_state_layout(C.byref(d), self._foff), self.L)
+        _lib.check(self.L.wrsn_scen_layout(C.byref(d), self._soff), self.L)
+
+        self.scen = torch.from_numpy(self._pack_scenarios(statics)).to(self.device)
+        if scenario_index is None:
+            scenario_index = np.arange(B) % n_scen
+        self.scen_id = torch.as_tensor(np.asarray(scenario_index, np.int32), device=self.device)
+        self.state = torch.zeros((B, d.state_bytes), dtype=torch.uint8, device=self.device)
+        self.req = Requests(B, self.device)
+        self._all = None
+        self._snap = None
+        self._agent_obs = None
+        self._make_snapshot()
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream) if self.device.type == "cuda" else None
+
+    def _pack_scenarios(self, statics):
+        d, E = self.dims, self.E
+        buf = np.zeros((d.n_scen, d.scen_bytes), np.uint8)
+        sizes = dict(P=E["WRSN_P_LEN"], Npad=d.Npad, Npad1=d.Npad + 1, Emax=d.Emax, TEmax=d.TEmax)
+        for s, st in enumerate(statics):
+            par = np.zeros(E["WRSN_P_LEN"], np.float64)
+            for k, v in st["par"].items():
+                par[E["WRSN_P_" + k]] = v
+            n = st["N"]
+            ptr_n = np.full(d.Npad + 1, st["nbr_ptr"][-1], np.int32); ptr_n[:n + 1] = st["nbr_ptr"]
+            ptr_t = np.full(d.Npad + 1, st["tgt_ptr"][-1], np.int32); ptr_t[:n + 1] = st["tgt_ptr"]
+            vals = dict(WRSN_S_PAR=par, WRSN_S_NX=st["x"], WRSN_S_NY=st["y"], WRSN_S_BS_ESEND=st["bs_esend"],
+                        WRSN_S_NBR_DIST=st["nbr_dist"], WRSN_S_NBR_ESEND=st["nbr_esend"], WRSN_S_NBR_PTR=ptr_n,
+                        WRSN_S_TGT_PTR=ptr_t, WRSN_S_NBR_IDX=st["nbr_idx"], WRSN_S_TGT_IDX=st["tgt_idx"],
+                        WRSN_S_DIRECT=st["direct"])
+            for name, dt, size in _S_FIELDS:
+                off = int(self._soff[E[name]])
+                a = np.zeros(sizes[size], _NP[dt])
+                v = np.asarray(vals[name], _NP[dt])
+                a[:len(v)] = v
+                buf[s, off:off + a.nbytes] = a.view(np.uint8)
+        return buf
+
+    def _view(self, state, field, dtype, count):
+        off = int(self._foff[self.E[field]])
+        nbytes = count * torch.empty((), dtype=dtype).element_size()
+        return state[:, off:off + nbytes].view(dtype)
+
+    def _mask_ptr(self, mask):
+        if mask is None:
+            return None, None
+        m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+        return m, C.c_void_p(m.data_ptr())
+
+    def _make_snapshot(self):
+        """The state at t = warm_up is a pure function of the scenario: simulate the warm-up once per
+        scenario on the device and let ``reset`` restore it (``wrsn_reset_from_snapshot``)."""
+        d = self.dims
+        ds = _lib.Dims.from_buffer_copy(d)
+        ds.B = d.n_scen
+        snap = torch.zeros((d.n_scen, d.state_bytes), dtype=torch.uint8, device=self.device)
+        ids = torch.arange(d.n_scen, dtype=torch.int32, device=self.device)
+        until = torch.full((d.n_scen,), self.warm_up_time, dtype=torch.float64, device=self.device)
+        L, st = self.L, self._stream()
+        _lib.check(L.wrsn_init_network(C.byref(ds), self.scen.data_ptr(), ids.data_ptr(), snap.data_ptr(), None, 1, st), L)
+        _lib.check(L.wrsn_run_until(C.byref(ds), self.scen.data_ptr(), ids.data_ptr(), snap.data_ptr(), None,
+                                    until.data_ptr(), st), L)
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+        self._snap = snap
+
+    # ------------------------------------------------------------------ the WRSN interface, batched
+    def reset(self, mask=None):
+        """``WRSN.reset`` (:41-83) for the selected environments (all when ``mask`` is None)."""
+        m, mp = self._mask_ptr(mask)
+        L = self.L
+        _lib.check(L.wrsn_reset_from_snapshot(C.byref(self.dims), self.scen.data_ptr(), self.scen_id.data_ptr(),
+                                              self.state.data_ptr(), self._snap.data_ptr(), mp, C.byref(self.req.c),
+                                              self._stream()), L)
+        return self.req
+
+    def step(self, agent_id, action, mask=None):
+        """``WRSN.step`` (:289-330).  ``agent_id``: int32[B] (-1 = None), ``action``: float64[B, 3]."""
+        L = self.L
+        a = torch.as_tensor(agent_id, device=self.device).to(torch.int32).contiguous()
+        x = torch.as_tensor(action, device=self.device).to(torch.float64).contiguous()
+        if a.shape != (self.B,) or x.shape != (self.B, 3):
+            raise ValueError("agent_id must be [B], action [B, 3]")
+        m, mp = self._mask_ptr(mask)
+        _lib.check(L.wrsn_step(C.byref(self.dims), self.scen.data_ptr(), self.scen_id.data_ptr(), self.state.data_ptr(),
+                               mp, a.data_ptr(), x.data_ptr(), C.byref(self.req.c), self._stream()), L)
+        return self.req
+
+    def get_state(self, agent_id=None, out=None, dtype=torch.float32):
+        """``WRSN.get_state`` (:130-186) of charger ``agent_id[b]`` in every environment with ``agent_id[b] >= 0``
+        (default: the deciding charger of the last request), written to ``out`` [B, 4, S, S]."""
+        if agent_id is None:
+            agent_id = self.req.agent_id
+        a = torch.as_tensor(agent_id, device=self.device).to(torch.int32).contiguous()
+        if out is None:
+            out = torch.zeros((self.B, 4, self.S, self.S), dtype=dtype, device=self.device)
+        if out.dtype not in (torch.float32, torch.float64) or not out.is_contiguous() or out.shape != (self.B, 4, self.S, self.S):
+            raise ValueError("out must be a contiguous float32/float64 tensor [B, 4, S, S]")
+        _lib.check(self.L.wrsn_observe(C.byref(self.dims), self.scen.data_ptr(), self.scen_id.data_ptr(),
+                                       self.state.data_ptr(), a.data_ptr(), out.data_ptr(),
+                                       1 if out.dtype == torch.float64 else 0, self._stream()), self.L)
+        return out
+
+    def get_network_fitness(self):
+        """``WRSN.get_network_fitness`` (:188-220): per-target values [B, T] and their minimum [B]."""
+        fit = torch.zeros((self.B, max(self.T, 1)), dtype=torch.float64, device=self.device)
+        mn = torch.zeros((self.B,), dtype=torch.float64, device=self.device)
+        _lib.check(self.L.wrsn_fitness(C.byref(self.dims), self.scen.data_ptr(), self.scen_id.data_ptr(),
+                                       self.state.data_ptr(), fit.data_ptr(), mn.data_ptr(), self._stream()), self.L)
+        return fit[:, :self.T], mn
+
+    # ------------------------------------------------------------------ lower-level entry points (tests / profiling)
+    def init_network(self, with_reward_process=True, mask=None):
+        m, mp = self._mask_ptr(mask)
+        _lib.check(self.L.wrsn_init_network(C.byref(self.dims), self.scen.data_ptr(), self.scen_id.data_ptr(),
+                                            self.state.data_ptr(), mp, 1 if with_reward_process else 0, self._stream()), self.L)
+
+    def run_until(self, t, mask=None):
+        m, mp = self._mask_ptr(mask)
+        tt = torch.as_tensor(t, dtype=torch.float64, device=self.device)
+        if tt.ndim == 0:
+            tt = tt.expand(self.B)
+        tt = tt.contiguous()
+        _lib.check(self.L.wrsn_run_until(C.byref(self.dims), self.scen.data_ptr(), self.scen_id.data_ptr(),
+                                         self.state.data_ptr(), mp, tt.data_ptr(), self._stream()), self.L)
+
+    def reset_finish(self, mask=None):
+        m, mp = self._mask_ptr(mask)
+        _lib.check(self.L.wrsn_reset_finish(C.byref(self.dims), self.scen.data_ptr(), self.scen_id.data_ptr(),
+                                            self.state.data_ptr(), mp, C.byref(self.req.c), self._stream()), self.L)
+        return self.req
+
+    def kernel(self, name):
+        """Standalone per-tick kernels: 'bfs', 'drain', 'bookkeep', 'reward'."""
+        fn = getattr(self.L, "wrsn_k_" + name)
+        _lib.check(fn(C.byref(self.dims), self.scen.data_ptr(), self.scen_id.data_ptr(), self.state.data_ptr(),
+                      self._stream()), self.L)
+
+    # ------------------------------------------------------------------ typed views of the state records (no copies)
+    def view(self, name, state=None):
+        st = self.state if state is None else state
+        d, E = self.dims, self.E
+        f64, i16, u8, i32 = torch.float64, torch.int16, torch.uint8, torch.int32
+        if name in ("energy", "rr", "cs", "esend", "logc", "logtick"):
+            return self._view(st, "WRSN_F_" + name.upper(), f64, d.Npad)[:, :self.N]
+        if name in ("nbef", "naft", "level", "parent"):
+            return self._view(st, "WRSN_F_" + name.upper(), i16, d.Npad)[:, :self.N]
+        if name == "status":
+            return self._view(st, "WRSN_F_STATUS", u8, d.Npad)[:, :self.N]
+        if name == "hdr":
+            return self._view(st, "WRSN_F_HDR", f64, E["WRSN_H_LEN"])
+        if name == "mc":
+            return self._view(st, "WRSN_F_MC", f64, max(self.M, 1) * E["WRSN_MC_LEN"]).view(st.shape[0], max(self.M, 1), E["WRSN_MC_LEN"])
+        if name == "proc":
+            return self._view(st, "WRSN_F_PROC", f64, d.n_slot * E["WRSN_PR_LEN"]).view(st.shape[0], d.n_slot, E["WRSN_PR_LEN"])
+        if name == "ring":
+            return self._view(st, "WRSN_F_RING", f64, E["WRSN_RING"] * d.Npad).view(st.shape[0], E["WRSN_RING"], d.Npad)[:, :, :self.N]
+        if name == "tact_words":
+            return self._view(st, "WRSN_F_TACT", i32, d.Tw)
+        if name == "conn_words":
+            return self._view(st, "WRSN_F_CONN", i32, max(self.M, 1) * d.W).view(st.shape[0], max(self.M, 1), d.W)
+        raise KeyError(name)
+
+    def hdr(self, field):
+        return self.view("hdr")[:, self.E["WRSN_H_" + field]]
+
+    def mc(self, field):
+        return self.view("mc")[:, :self.M, self.E["WRSN_MC_" + field]]
+
+    @property
+    def now(self):
+        return self.hdr("NOW")
+
+    @property
+    def alive(self):
+        return self.hdr("ALIVE").to(torch.uint8)
+
+    def targets_active(self):
+        """``Network.targets_active`` as uint8 [B, T]."""
+        w = self.view("tact_words").to(torch.int64) & 0xFFFFFFFF
+        bits = (w.unsqueeze(-1) >> torch.arange(32, device=self.device)) & 1
+        return bits.reshape(w.shape[0], -1)[:, :self.T].to(torch.uint8)
+
+    def counters(self):
+        """Device counters summed over environments: simulated seconds, events, serial (death) ticks, BFS runs, decisions."""
+        h = self.view("hdr")
+        E = self.E
+        return {k: float(h[:, E["WRSN_H_" + n]].sum().item()) for k, n in
+                (("ticks", "NTICKS"), ("events", "NEVENTS"), ("serial_ticks", "NSLOW"), ("bfs", "NBFS"), ("decisions", "NDECISIONS"))}

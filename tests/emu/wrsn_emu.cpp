@@ -1,0 +1,129 @@
+/*
+ * wrsn_emu.cpp — TEST INFRASTRUCTURE.  Single-lane host build of the kernel source
+ * (multi_agent_rl_wrsn_b200/csrc/wrsn_engine.cuh with WRSN_HOST_EMU): the same event logic the
+ * sm_100a kernels run, with one "thread" per environment, on host memory.  It exists so the
+ * `-m "not gpu"` tests can check the engine's event ordering and arithmetic against the oracle on a box
+ * without a GPU.  It is built only by tests/ (tests/emu/Makefile), exports the C ABI of
+ * include/wrsn_b200.h, and is never loaded by the product package, which has no CPU path.
+ * wrsn_observe is not emulated (the raster kernel is checked on the GPU).
+ */
+#define WRSN_HOST_EMU 1
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
+
+#include "wrsn_engine.cuh"
+
+static thread_local char g_err[512] = "";
+#define WRSN_FAIL(...) do { snprintf(g_err, sizeof(g_err), __VA_ARGS__); return -1; } while (0)
+
+enum { MODE_INIT = 0, MODE_RUN_UNTIL, MODE_RESET_FINISH, MODE_RESTORE_RESET, MODE_STEP, MODE_FITNESS, MODE_K_BFS,
+       MODE_K_DRAIN, MODE_K_BOOK, MODE_K_REWARD };
+
+struct Args {
+    const wrsn_dims *d; const char *scen; const int32_t *scen_id; char *state; const char *snap; const uint8_t *mask;
+    const double *t_until; const int32_t *agent_in; const double *action_in; wrsn_request *req;
+    double *fitness, *fit_min; int with_reward;
+};
+
+static int run_mode(int mode, const Args &A) {
+    const wrsn_dims &d = *A.d;
+    if (d.Npad < d.N || (d.Npad & 15) || d.state_bytes <= 0) WRSN_FAIL("dims not finalized");
+    WrsnLayout L; wrsn_make_layout(&d, &L);
+    std::vector<char> smem((size_t)L.smem_total + 64);
+    for (int b = 0; b < d.B; b++) {
+        if (A.mask && !A.mask[b]) continue;
+        char *row = A.state + (size_t)b * L.total;
+        const char *scen_row = A.scen + (size_t)A.scen_id[b] * L.scen_total;
+        Ctx c;
+        ctx_bind(c, d, L, scen_row, row, smem.data(), 0, 1);
+        if (mode == MODE_RESTORE_RESET) {
+            const char *src = A.snap + (size_t)A.scen_id[b] * L.total;
+            memcpy(row + L.resident, src + L.resident, (size_t)(L.total - L.resident));
+            memcpy(smem.data(), src, (size_t)L.resident);
+        } else if (mode != MODE_INIT) memcpy(smem.data(), row, (size_t)L.resident);
+        for (int i = 0; i < c.Npad; i++) c.own[i] = i < c.N ? (uint16_t)(c.tgt_ptr[i + 1] - c.tgt_ptr[i]) : 0;
+        ReqOut r; memset(&r, 0, sizeof(r)); r.agent = -3;
+        switch (mode) {
+        case MODE_INIT: entry_init_network(c, A.with_reward); break;
+        case MODE_RUN_UNTIL: entry_run_until(c, A.t_until[b]); break;
+        case MODE_RESET_FINISH: case MODE_RESTORE_RESET: entry_reset_finish(c, &r); break;
+        case MODE_STEP: entry_step(c, A.agent_in ? A.agent_in[b] : -1, A.action_in ? A.action_in + 3 * (size_t)b : nullptr, &r); break;
+        case MODE_FITNESS: { double mn = do_fitness(c, A.fitness ? A.fitness + (size_t)b * d.T : nullptr); if (A.fit_min) A.fit_min[b] = mn; break; }
+        case MODE_K_BFS: do_bfs(c); break;
+        case MODE_K_DRAIN: ev_nodes_drain(c); break;
+        case MODE_K_BOOK: ev_nodes_book(c); break;
+        case MODE_K_REWARD: ev_update_reward(c); break;
+        }
+        if (mode != MODE_FITNESS) memcpy(row, smem.data(), (size_t)L.resident);
+        if (mode == MODE_RESET_FINISH || mode == MODE_RESTORE_RESET || mode == MODE_STEP) {
+            wrsn_request &q = *A.req;
+            if (q.agent_id) q.agent_id[b] = r.agent;
+            if (q.terminal) q.terminal[b] = (uint8_t)r.terminal;
+            if (q.reward) q.reward[b] = r.reward;
+            if (q.now) q.now[b] = r.now;
+            if (q.action) for (int k = 0; k < 3; k++) q.action[3 * b + k] = r.act[k];
+            if (q.detail) { q.detail[2 * b] = r.detail[0]; q.detail[2 * b + 1] = r.detail[1]; }
+            if (q.flags) q.flags[b] = r.flags;
+        }
+    }
+    return 0;
+}
+
+extern "C" {
+const char *wrsn_last_error(void) { return g_err; }
+int wrsn_abi_version(void) { return WRSN_ABI_VERSION; }
+int wrsn_is_emulation(void) { return 1; }
+int wrsn_field_count(int which) {
+    switch (which) {
+    case 0: return WRSN_P_LEN; case 1: return WRSN_H_LEN; case 2: return WRSN_MC_LEN; case 3: return WRSN_PR_LEN;
+    case 4: return WRSN_F_COUNT; case 5: return WRSN_S_COUNT; default: return -1;
+    }
+}
+int wrsn_dims_finalize(wrsn_dims *d) {
+    d->Npad = (d->N + 15) & ~15; d->W = (d->N + 31) / 32; d->Tw = (d->T + 31) / 32; if (d->Tw < 1) d->Tw = 1;
+    d->n_slot = 2 * d->M + 2; if (d->Emax < 1) d->Emax = 1; if (d->TEmax < 1) d->TEmax = 1;
+    d->threads = 32;
+    WrsnLayout L; wrsn_make_layout(d, &L);
+    d->state_bytes = (int32_t)L.total; d->state_resident_bytes = (int32_t)L.resident;
+    d->scen_bytes = (int32_t)L.scen_total; d->smem_bytes = (int32_t)L.smem_total;
+    return 0;
+}
+int wrsn_state_layout(const wrsn_dims *d, int64_t *o) { WrsnLayout L; wrsn_make_layout(d, &L); for (int k = 0; k < WRSN_F_COUNT; k++) o[k] = L.off[k]; return 0; }
+int wrsn_scen_layout(const wrsn_dims *d, int64_t *o) { WrsnLayout L; wrsn_make_layout(d, &L); for (int k = 0; k < WRSN_S_COUNT; k++) o[k] = L.soff[k]; return 0; }
+int wrsn_device_ok(void) { return 0; }
+
+int wrsn_init_network(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state, const uint8_t *m, int wr, void *) {
+    Args A = {d, (const char *)scen, scen_id, (char *)state, nullptr, m, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, wr};
+    return run_mode(MODE_INIT, A);
+}
+int wrsn_run_until(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state, const uint8_t *m, const double *t, void *) {
+    Args A = {d, (const char *)scen, scen_id, (char *)state, nullptr, m, t, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+    return run_mode(MODE_RUN_UNTIL, A);
+}
+int wrsn_reset_finish(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state, const uint8_t *m, wrsn_request *req, void *) {
+    Args A = {d, (const char *)scen, scen_id, (char *)state, nullptr, m, nullptr, nullptr, nullptr, req, nullptr, nullptr, 0};
+    return run_mode(MODE_RESET_FINISH, A);
+}
+int wrsn_reset_from_snapshot(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state, const void *snap, const uint8_t *m, wrsn_request *req, void *) {
+    Args A = {d, (const char *)scen, scen_id, (char *)state, (const char *)snap, m, nullptr, nullptr, nullptr, req, nullptr, nullptr, 0};
+    return run_mode(MODE_RESTORE_RESET, A);
+}
+int wrsn_step(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state, const uint8_t *m, const int32_t *ag, const double *act, wrsn_request *req, void *) {
+    Args A = {d, (const char *)scen, scen_id, (char *)state, nullptr, m, nullptr, ag, act, req, nullptr, nullptr, 0};
+    return run_mode(MODE_STEP, A);
+}
+int wrsn_fitness(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state, double *fit, double *fmin_, void *) {
+    Args A = {d, (const char *)scen, scen_id, (char *)state, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, fit, fmin_, 0};
+    return run_mode(MODE_FITNESS, A);
+}
+int wrsn_observe(const wrsn_dims *, const void *, const int32_t *, const void *, const int32_t *, void *, int, void *) {
+    WRSN_FAIL("wrsn_observe is not available in the host emulation");
+}
+#define EMU_K(NAME, MODE) int NAME(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state, void *) { \
+    Args A = {d, (const char *)scen, scen_id, (char *)state, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0}; return run_mode(MODE, A); }
+EMU_K(wrsn_k_bfs, MODE_K_BFS)
+EMU_K(wrsn_k_drain, MODE_K_DRAIN)
+EMU_K(wrsn_k_bookkeep, MODE_K_BOOK)
+EMU_K(wrsn_k_reward, MODE_K_REWARD)
+}
