@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py — agent-decisions/s of the batched WRSN hot path (reset / step / observation / reward).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--envs B] [--nodes 100] [--chargers 3]
+    python bench.py --impl reference ...        # the CPU restatement of the reference on the host cores
+
+One *step* = one pass of the hot path over the batch: ``step`` for every environment (advance to the
+next charger decision), the observation raster of every deciding charger, and the reset of every
+environment that terminated.  Workload at N = 1: BASELINE.json configs[1] — 100 nodes / 3 chargers / 4096
+environments; controller = counter-based uniform 3-vector actions (a ~ U[0,1]^3, a[2] *= 0.05).
+Environments shard across ranks by index with no data-path collective (weak scaling: B per GPU is fixed).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+METRIC = "agent-decisions/sec"
+UNIT = "decisions/s"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=60)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--envs", type=int, default=4096, help="environments per GPU")
+    p.add_argument("--nodes", type=int, default=100)
+    p.add_argument("--targets", type=int, default=None)
+    p.add_argument("--chargers", type=int, default=3)
+    p.add_argument("--topologies", type=int, default=64, help="distinct synthetic scenarios per GPU")
+    p.add_argument("--threads", type=int, default=0)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+def workload_name(a):
+    return "%d-node/%d-charger synthetic WRSN, %d envs per GPU, uniform 3-vector actions" % (a.nodes, a.chargers, a.envs)
+
+
+def scenarios_for(a, rank):
+    from multi_agent_rl_wrsn_b200 import synthetic
+    T = a.nodes if a.targets is None else a.targets
+    return [synthetic(num_nodes=a.nodes, num_targets=T, seed=1000 + rank * a.topologies + k) for k in range(a.topologies)]
+
+
+# ----------------------------------------------------------------------------------------------- CPU side
+def _cpu_worker(args):
+    """One host core: oracle environments (C restatement of the reference) stepped with the same action law."""
+    sc_dict, M, seed, budget_s, want_state = args
+    from oracle.wrsn_oracle import OracleWRSN, scenario_from_dict
+    rng = np.random.default_rng(seed)
+    o = OracleWRSN(scenario_from_dict(sc_dict), num_agent=M)
+    t0 = time.perf_counter()
+    r = o.reset(want_state=want_state)
+    n = 1
+    ticks = 0.0
+    while time.perf_counter() - t0 < budget_s:
+        if r["raw_agent_id"] < 0:
+            ticks += o.now
+            r = o.reset(want_state=want_state)
+            n += 1
+            continue
+        act = rng.uniform(0, 1, 3)
+        act[2] *= 0.05
+        r = o.step(r["raw_agent_id"], act, want_state=want_state)
+        if r["raw_agent_id"] >= 0:
+            n += 1
+    ticks += o.now
+    return n, time.perf_counter() - t0, ticks
+
+
+def cpu_baseline(a, cores, budget_s):
+    import multiprocessing as mp
+    scs = scenarios_for(a, 0)
+    jobs = [(scs[k % len(scs)].to_dict(), a.chargers, k, budget_s, True) for k in range(cores)]
+    t0 = time.perf_counter()
+    if cores == 1:
+        res = [_cpu_worker(jobs[0])]
+    else:
+        with mp.get_context("spawn").Pool(cores) as pool:
+            res = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    n = sum(r[0] for r in res)
+    per = sum(r[0] / r[1] for r in res)
+    return dict(value=per, unit=UNIT, cores=cores, kind="port",
+                sample="%d oracle envs (C restatement of rl_env/WRSN.py, one per core), %.0f s each, reset+step+get_state, "
+                       "%d decisions, %.0f simulated s" % (cores, budget_s, n, sum(r[2] for r in res)),
+                wall_s=wall)
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step = max(2.0, min(20.0, 120.0 / max(1, a.steps + a.warmup)))
+    vals = []
+    for k in range(a.warmup + a.steps):
+        cb = cpu_baseline(a, cores, per_step)
+        if k >= a.warmup:
+            vals.append(cb)
+    v = float(np.mean([c["value"] for c in vals]))
+    ms = 1e3 * float(np.mean([c["wall_s"] for c in vals]))
+    line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=a.gpus, steps=a.steps, warmup=a.warmup, ms_per_step=ms,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                config=dict(workload=workload_name(a), note="each step = a %.0f s sample on every host core" % per_step),
+                impl="reference",
+                cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind="port", sample=vals[-1]["sample"]),
+                e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- GPU side
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append((time.perf_counter(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    from multi_agent_rl_wrsn_b200 import BatchedWRSN
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, M, S = a.envs, a.chargers, 100
+    env = BatchedWRSN(scenarios_for(a, rank), num_agent=M, num_envs=B, device=dev, threads=a.threads, map_size=S)
+    N, T = env.N, env.T
+    obs = torch.zeros((B, 4, S, S), dtype=torch.float32, device=dev)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    scale = torch.tensor([1.0, 1.0, 0.05], dtype=torch.float64, device=dev)
+    total = a.warmup + a.steps
+    launches = [0]
+
+    def one_step(action, events=None, acc=None):
+        """the public API a user calls: step -> observation of the deciding chargers -> reset of finished episodes
+        (+ their first observation).  No host synchronisation inside."""
+        req = env.req
+        aid = req.agent_id
+        m = aid >= 0
+        if acc is not None:
+            now_before = req.now.clone()
+        if events is not None:
+            events[0].record()
+        env.step(aid, action, mask=m)
+        if events is not None:
+            events[1].record()
+        env.get_state(out=obs)
+        if events is not None:
+            events[2].record()
+        done = req.agent_id < 0
+        if acc is not None:
+            acc[0] += (req.agent_id >= 0).sum()
+            acc[1] += torch.where(m, req.now - now_before, torch.zeros_like(req.now)).sum()
+        env.reset(mask=done)
+        env.get_state(out=obs, agent_id=torch.where(done, req.agent_id, torch.full_like(aid, -1)))
+        if acc is not None:
+            acc[0] += (done & (req.agent_id >= 0)).sum()
+        launches[0] += 4
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def counters():
+        h = env.view("hdr")
+        E = env.E
+        return (float(h[:, E["WRSN_H_NDECISIONS"]].sum().item()), float(h[:, E["WRSN_H_NTICKS"]].sum().item()))
+
+    # ---- device-resident run (value): actions already in HBM
+    env.reset()
+    env.get_state(out=obs)
+    actions = torch.rand((total, B, 3), generator=gen, dtype=torch.float64, device=dev) * scale
+    for k in range(a.warmup):
+        one_step(actions[k])
+    sync_all()
+    # NDECISIONS / NTICKS restart at every reset, so count decisions from the request records instead
+    dec_count = torch.zeros((), dtype=torch.int64, device=dev)
+    tick_acc = torch.zeros((), dtype=torch.float64, device=dev)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(a.steps)]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches[0] = 0
+    sync_all()
+    t_wall0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    acc = [dec_count, tick_acc]
+    for k in range(a.steps):
+        one_step(actions[a.warmup + k], events=ev[k], acc=acc)
+    e1.record()
+    sync_all()
+    t_wall1 = time.perf_counter()
+    elapsed_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    decisions = float(dec_count.item())
+    ticks = float(tick_acc.item())
+    step_ms = sum(x[0].elapsed_time(x[1]) for x in ev)
+    obs_ms = sum(x[1].elapsed_time(x[2]) for x in ev)
+    n_launch = launches[0]
+
+    # ---- end-to-end run (e2e): per step, actions come from pinned host memory and the request record goes back
+    host_actions = (torch.rand((a.steps, B, 3), dtype=torch.float64) * scale.cpu()).pin_memory()
+    host_req = dict(agent_id=torch.zeros(B, dtype=torch.int32).pin_memory(), reward=torch.zeros(B, dtype=torch.float64).pin_memory(),
+                    terminal=torch.zeros(B, dtype=torch.uint8).pin_memory(), now=torch.zeros(B, dtype=torch.float64).pin_memory())
+    dev_action = torch.zeros((B, 3), dtype=torch.float64, device=dev)
+    h2d = host_actions[0].numel() * 8
+    d2h = sum(v.numel() * v.element_size() for v in host_req.values())
+    sync_all()
+    e2e_dec = 0
+    t0 = time.perf_counter()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for k in range(a.steps):
+        dev_action.copy_(host_actions[k], non_blocking=True)
+        one_step(dev_action)
+        for name, v in host_req.items():
+            v.copy_(getattr(env.req, name), non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()          # the caller reads the request on the host
+        e2e_dec += int((host_req["agent_id"] >= 0).sum())
+    f1.record()
+    sync_all()
+    e2e_ms = f0.elapsed_time(f1)
+
+    # ---- reduce over ranks: max time, summed work
+    t = torch.tensor([elapsed_ms, e2e_ms, step_ms, obs_ms], dtype=torch.float64, device=dev)
+    w = torch.tensor([decisions, ticks, float(e2e_dec)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+    elapsed_ms, e2e_ms, step_ms_max, obs_ms_max = [float(x) for x in t.tolist()]
+    decisions_all, ticks_all, e2e_dec_all = [float(x) for x in w.tolist()]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = decisions_all / (elapsed_ms * 1e-3)
+    peaks = {}
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    # rank-0 kernels (per-launch averages), algorithmic bytes per SURVEY §8(d)
+    b_tick = 82 * N + T
+    b_dec_step = 16 * T + 88
+    b_dec_obs = 4 * S * S * 4
+    step_bytes = (ticks * b_tick + decisions * b_dec_step) / a.steps
+    obs_bytes = decisions * b_dec_obs / a.steps
+    step_gbs = step_bytes / (step_ms / a.steps * 1e-3) / 1e9
+    obs_gbs = obs_bytes / (obs_ms / a.steps * 1e-3) / 1e9
+    dominant = "k_env<MODE_STEP>" if step_ms >= obs_ms else "k_observe<float>"
+    ach = step_gbs if step_ms >= obs_ms else obs_gbs
+    line = dict(
+        metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=a.warmup,
+        ms_per_step=elapsed_ms / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+        data="synthetic",
+        config=dict(workload=workload_name(a), nodes=N, targets=T, chargers=M, envs_per_gpu=B, map_size=S,
+                    topologies_per_gpu=a.topologies, threads_per_env=int(env.dims.threads), observation="float32 [B,4,100,100] kept in HBM",
+                    l2="working set (state %.0f MB + observations %.0f MB per GPU) exceeds the 126 MB L2; no explicit flush"
+                       % (B * env.dims.state_bytes / 1e6, obs.numel() * 4 / 1e6),
+                    sim_seconds_per_decision=ticks_all / max(decisions_all, 1.0),
+                    env_ticks_per_s=ticks_all / (elapsed_ms * 1e-3)),
+        clocks=clocks,
+        e2e=dict(value=e2e_dec_all / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                 note="actions from pinned host memory; request record (agent_id, reward, terminal, now) read back every step; "
+                      "observations stay in HBM for the policy networks"),
+        gpu_launches=n_launch,
+        roofline=dict(bound="hbm", kernel=dominant, achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=None,
+                      peak_source=peak_src,
+                      kernels={"k_env<MODE_STEP>": dict(ms_per_launch=step_ms / a.steps, algorithmic_bytes=step_bytes, gbs=step_gbs,
+                                                        share_of_step=step_ms / elapsed_ms),
+                               "k_observe<float>": dict(ms_per_launch=obs_ms / a.steps, algorithmic_bytes=obs_bytes, gbs=obs_gbs,
+                                                        share_of_step=obs_ms / elapsed_ms)}),
+    )
+    if world == 1 and not a.no_cpu_baseline:
+        line["cpu_baseline"] = {k: v for k, v in cpu_baseline(a, 1, a.cpu_seconds).items() if k != "wall_s"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)

@@ -282,10 +282,10 @@ static int launch_env(KParams &P, void *stream) {
     if (check_dims(&P.d)) return -1;
     wrsn_make_layout(&P.d, &P.L);
     if (!P.scen || !P.scen_id || !P.state) WRSN_FAIL("scen / scen_id / state must not be NULL");
-    static bool attr_done = false;                   /* per template instance */
-    if (!attr_done || P.L.smem_total > 48 * 1024) {
+    static int64_t attr_bytes = 48 * 1024;           /* per template instance; the opt-in limit only ever grows */
+    if (P.L.smem_total > attr_bytes) {
         WRSN_CUDA(cudaFuncSetAttribute(k_env<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.L.smem_total));
-        attr_done = true;
+        attr_bytes = P.L.smem_total;
     }
     k_env<MODE><<<P.d.B, P.d.threads, (size_t)P.L.smem_total, (cudaStream_t)stream>>>(P);
     WRSN_CUDA(cudaGetLastError());

@@ -1,0 +1,169 @@
+"""Parity checks shared by the CPU (host emulation) and GPU test files (TEST INFRASTRUCTURE).
+
+Every check drives ``BatchedWRSN`` through the C ABI and compares with either the committed golden
+fixtures (outputs of the unmodified reference, see oracle/gen_golden.py) or the C oracle run on the same
+inputs.  Discrete quantities (agent ids, termination, status / level / coverage sets, event times) must be
+identical; energies are compared at 1e-9 relative (spec: 1e-5; observed: bit-exact); rewards and
+observations, which go through exp(), at 1e-9 relative / 1e-9 absolute.
+"""
+import numpy as np
+import torch
+
+from multi_agent_rl_wrsn_b200 import BatchedWRSN, Scenario
+from oracle.wrsn_oracle import OracleWRSN, scenario_from_dict
+from tests.helpers import golden, mc_dict_of
+
+E_RTOL = 1e-9
+
+
+def sc_from_golden(g):
+    p = g["sc_par"]
+    spe = dict(capacity=p[0], threshold=p[1], com_range=p[2], sen_range=p[3], prob_gp=p[4], package_size=p[5],
+               er=p[6], et=p[7], efs=p[8], emp=p[9])
+    return Scenario(nodes=g["sc_nodes"].reshape(-1, 2), targets=g["sc_targets"].reshape(-1, 2),
+                    base_station=g["sc_bs"], node_phy_spe=spe, max_time=float(p[10]))
+
+
+def _np(t):
+    return t.detach().cpu().numpy().copy()
+
+
+def check_pure_network(name, device, replicas=1):
+    """runner/test_network.py logic (no chargers) against net_<scenario>.npz, every snapshot."""
+    g = golden(name)
+    env = BatchedWRSN(sc_from_golden(g), num_agent=0, num_envs=replicas, device=device)
+    env.init_network(with_reward_process=False)
+    bit_exact = 0
+    for key in g["snap_keys"]:
+        key = str(key)
+        env.run_until(float(key[1:]))
+        for b in range(replicas):
+            assert np.array_equal(_np(env.view("status"))[b], g[key + "_status"]), (name, key)
+            assert np.array_equal(_np(env.view("level"))[b].astype(np.int32), g[key + "_level"]), (name, key)
+            assert np.array_equal(_np(env.targets_active())[b], g[key + "_targets_active"]), (name, key)
+            assert int(_np(env.alive)[b]) == int(g[key + "_alive"]), (name, key)
+            np.testing.assert_allclose(_np(env.view("energy"))[b], g[key + "_energy"], rtol=E_RTOL)
+            np.testing.assert_allclose(_np(env.view("cs"))[b], g[key + "_cs"], rtol=E_RTOL)
+            bit_exact += int(np.array_equal(_np(env.view("energy"))[b], g[key + "_energy"]))
+    env.run_until(float(g["end_time"]) + 0.75)
+    e = _np(env.view("energy"))[0]
+    np.testing.assert_allclose(e, g["final_energy"], rtol=E_RTOL)
+    assert abs(float(e.sum()) - float(g["sum_energy_end"])) < 1e-6
+    assert int((_np(env.targets_active())[0] == 0).sum()) == int(g["inactive_targets"])
+    assert float(_np(env.hdr("NET_ON"))[0]) == 0.0          # Network.operate has finished
+    assert float(_np(env.hdr("ERR")).max()) == 0.0
+    return bit_exact, len(g["snap_keys"]) * replicas
+
+
+def check_episode(name, device, check_obs=False, replicas=1):
+    """WRSN.reset/step with the fixture's injected actions against ep_<case>.npz, every decision."""
+    g = golden(name)
+    M, S = int(g["num_agent"]), int(g["map_size"])
+    env = BatchedWRSN(sc_from_golden(g), num_agent=M, mc_type=mc_dict_of(g), num_envs=replicas, map_size=S, device=device)
+    full = {int(i): k for k, i in enumerate(g["full_state_idx"])}
+    n = int(g["n"])
+    for i in range(n):
+        if i == 0:
+            req = env.reset()
+        else:
+            req = env.step(np.full(replicas, int(g["fed_agent"][i]), np.int32), np.tile(g["fed_action"][i], (replicas, 1)))
+        for b in range(replicas):
+            tag = (name, i, b)
+            aid = int(_np(req.agent_id)[b])
+            assert aid == int(g["agent_id"][i]), tag
+            assert int(_np(req.terminal)[b]) == int(g["terminal"][i]), tag
+            assert float(_np(req.now)[b]) == float(g["now"][i]), tag
+            assert int(_np(req.flags)[b]) == 0, tag
+            assert np.array_equal(_np(env.view("status"))[b], g["status"][i]), tag
+            assert np.array_equal(_np(env.view("level"))[b].astype(np.int32), g["level"][i]), tag
+            assert np.array_equal(_np(env.targets_active())[b], g["targets_active"][i]), tag
+            assert int(_np(env.alive)[b]) == int(g["alive"][i]), tag
+            np.testing.assert_allclose(_np(env.view("energy"))[b], g["energy"][i], rtol=E_RTOL)
+            np.testing.assert_allclose(_np(env.view("cs"))[b], g["cs"][i], rtol=E_RTOL)
+            np.testing.assert_allclose(_np(env.view("rr"))[b], g["rr"][i], rtol=E_RTOL, atol=1e-12)
+            np.testing.assert_allclose(_np(env.mc("X"))[b], g["mc_loc"][i][:, 0], rtol=1e-12)
+            np.testing.assert_allclose(_np(env.mc("Y"))[b], g["mc_loc"][i][:, 1], rtol=1e-12)
+            np.testing.assert_allclose(_np(env.mc("ENERGY"))[b], g["mc_energy"][i], rtol=E_RTOL)
+            assert np.array_equal(_np(env.mc("STATUS"))[b].astype(np.uint8), g["mc_status"][i]), tag
+            assert np.array_equal(_np(env.mc("TYPE"))[b].astype(np.uint8), g["mc_type"][i]), tag
+            assert np.array_equal(_np(env.mc("NCONN"))[b].astype(np.int32), g["mc_nconn"][i]), tag
+            np.testing.assert_allclose(_np(env.mc("CPA2"))[b], g["mc_cpa"][i][:, 2], rtol=1e-12)
+            np.testing.assert_allclose(_np(env.mc("EXCL"))[b], g["excl"][i], rtol=1e-9, atol=1e-15)
+            if aid >= 0:
+                assert np.array_equal(_np(req.action)[b], g["action"][i]), tag
+                if i > 0:
+                    np.testing.assert_allclose(float(_np(req.reward)[b]), float(g["reward"][i]), rtol=1e-9, atol=1e-18)
+        if check_obs and int(g["agent_id"][i]) >= 0:
+            obs = _np(env.get_state(dtype=torch.float64))
+            for b in range(replicas):
+                np.testing.assert_allclose(obs[b].reshape(4, -1).sum(1), g["chan_sum"][i], rtol=1e-9, atol=1e-9)
+                if i in full:
+                    np.testing.assert_allclose(obs[b], g["full_state"][full[i]], rtol=1e-9, atol=1e-12)
+            if i in full:
+                obs32 = _np(env.get_state(dtype=torch.float32))
+                np.testing.assert_allclose(obs32[0], g["full_state"][full[i]], rtol=2e-6, atol=1e-6)
+    fm = _np(env.get_network_fitness()[1])
+    if np.isfinite(g["fitness_min"][n - 1]):
+        np.testing.assert_allclose(fm[0], g["fitness_min"][n - 1], rtol=1e-12)
+    return env.counters()
+
+
+def check_vs_oracle(scenarios, device, num_envs, steps, seed, num_agent=3, mc=None, check_obs=False, scale2=0.05,
+                    map_size=100, scenario_index=None):
+    """B environments with DIFFERENT action streams (and possibly different scenarios) vs B oracle runs (ladder L6)."""
+    if isinstance(scenarios, Scenario):
+        scenarios = [scenarios]
+    env = BatchedWRSN(scenarios, num_agent=num_agent, mc_type=mc, num_envs=num_envs, device=device, map_size=map_size,
+                      scenario_index=scenario_index)
+    sid = _np(env.scen_id)
+    B = num_envs
+    rng = np.random.default_rng(seed)
+    acts = rng.uniform(0.0, 1.0, size=(steps, B, 3))
+    acts[..., 2] *= scale2
+    oracles = [OracleWRSN(scenario_from_dict(scenarios[sid[b]].to_dict()), num_agent=num_agent, mc=mc, map_size=map_size)
+               for b in range(B)]
+    for o in oracles:
+        o.set_event_budget(3_000_000)
+    req = env.reset()
+    oreq = [o.reset(want_state=check_obs) for o in oracles]
+    live = np.ones(B, bool)
+    n_dec = 0
+    for k in range(steps + 1):
+        aid = _np(req.agent_id)
+        for b in range(B):
+            if not live[b]:
+                continue
+            r = oreq[b]
+            tag = (b, k)
+            assert int(aid[b]) == r["raw_agent_id"], tag
+            assert int(_np(req.terminal)[b]) == int(r["terminal"]), tag
+            assert float(_np(req.now)[b]) == r["now"], tag
+            nd = oracles[b].nodes()
+            assert np.array_equal(_np(env.view("status"))[b], nd["status"]), tag
+            assert np.array_equal(_np(env.view("level"))[b].astype(np.int32), nd["level"]), tag
+            assert np.array_equal(_np(env.targets_active())[b], oracles[b].targets_active()), tag
+            np.testing.assert_allclose(_np(env.view("energy"))[b], nd["energy"], rtol=E_RTOL)
+            mcs = oracles[b].mcs()
+            np.testing.assert_allclose(_np(env.mc("ENERGY"))[b], mcs["energy"], rtol=E_RTOL)
+            assert np.array_equal(_np(env.mc("STATUS"))[b].astype(np.uint8), mcs["status"]), tag
+            if r["raw_agent_id"] >= 0:
+                n_dec += 1
+                if k > 0:
+                    np.testing.assert_allclose(float(_np(req.reward)[b]), r["reward"], rtol=1e-9, atol=1e-18)
+        if check_obs:
+            obs = _np(env.get_state(dtype=torch.float64))
+            for b in range(B):
+                if live[b] and oreq[b]["raw_agent_id"] >= 0:
+                    np.testing.assert_allclose(obs[b], oreq[b]["state"], rtol=1e-9, atol=1e-12)
+        if k == steps:
+            break
+        live &= aid >= 0
+        if not live.any():
+            break
+        mask = torch.as_tensor(live.astype(np.uint8))
+        req = env.step(np.where(live, aid, -1).astype(np.int32), acts[k], mask=mask)
+        for b in range(B):
+            if live[b]:
+                oreq[b] = oracles[b].step(int(aid[b]), acts[k, b], want_state=check_obs)
+    assert float(_np(env.hdr("ERR")).max()) == 0.0
+    return n_dec, env.counters()

@@ -1,0 +1,63 @@
+"""CPU-side tests of the engine logic: the kernel source compiled single-lane for the host (tests/emu) is driven
+through the same C ABI and host layer as the CUDA library and checked against the reference's golden fixtures and
+the C oracle.  The parity tests proper (CUDA path) are tests/test_gpu_parity.py (-m gpu)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from multi_agent_rl_wrsn_b200 import _lib, synthetic
+from tests import parity_cases as pc
+from tests.helpers import REPO, golden_names
+
+EMU_DIR = os.path.join(REPO, "tests", "emu")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def emu_library():
+    subprocess.check_call(["make", "-C", EMU_DIR, "libwrsn_emu.so"], stdout=subprocess.DEVNULL)
+    prev = _lib._lib
+    _lib.use_library(os.path.join(EMU_DIR, "libwrsn_emu.so"))
+    yield
+    _lib._lib = prev
+
+
+@pytest.mark.parametrize("name", golden_names("net_"))
+def test_pure_network_golden(name):
+    exact, total = pc.check_pure_network(name, "cpu")
+    assert exact == total          # energies bit-identical to the reference at every snapshot
+
+
+@pytest.mark.parametrize("name", golden_names("ep_"))
+def test_episode_golden(name):
+    pc.check_episode(name, "cpu")
+
+
+def test_batched_replicas_identical():
+    pc.check_episode("ep_edge_n50", "cpu", replicas=3)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_random_episodes_vs_oracle(seed):
+    sc = synthetic(num_nodes=60, num_targets=70, seed=10 + seed)
+    n_dec, cnt = pc.check_vs_oracle(sc, "cpu", num_envs=6, steps=40, seed=seed)
+    assert n_dec > 100
+
+
+def test_heterogeneous_scenarios_vs_oracle():
+    scs = [synthetic(num_nodes=48, num_targets=48, seed=s) for s in (21, 22, 23)]
+    pc.check_vs_oracle(scs, "cpu", num_envs=6, steps=25, seed=5)
+
+
+def test_long_charging_and_deaths_vs_oracle():
+    # long charge phases (capacity clamp, Q19) and episodes that run into node deaths
+    sc = synthetic(num_nodes=40, num_targets=120, seed=3, num_gateways=2)
+    n_dec, cnt = pc.check_vs_oracle(sc, "cpu", num_envs=4, steps=60, seed=9, scale2=0.5)
+    assert cnt["serial_ticks"] >= 1
+
+
+def test_small_charger_exhaustion_vs_oracle():
+    mc = dict(capacity=2500, threshold=0, velocity=5, pm=1, charging_range=27, alpha=4500, beta=30, epsilon=1e-10)
+    sc = synthetic(num_nodes=50, num_targets=50, seed=4)
+    pc.check_vs_oracle(sc, "cpu", num_envs=4, steps=50, seed=2, mc=mc, scale2=0.01)

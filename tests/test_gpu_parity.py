@@ -1,0 +1,114 @@
+"""Parity tests proper: the sm_100a kernels, called through the C ABI (libwrsn_b200.so), against the reference's
+golden fixtures and the C oracle.  Run on the B200 box:  python -m pytest tests -m gpu"""
+import numpy as np
+import pytest
+import torch
+
+from multi_agent_rl_wrsn_b200 import BatchedWRSN, _lib, synthetic
+from tests import parity_cases as pc
+from tests.helpers import golden_names
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def cuda_library():
+    prev = _lib._lib
+    _lib._lib = None
+    L = _lib.lib()                      # raises if the extension is missing: no fallback
+    assert not _lib.is_emulation(L)
+    assert torch.cuda.is_available()
+    yield
+    _lib._lib = prev
+
+
+@pytest.mark.parametrize("name", golden_names("net_"))
+def test_pure_network_golden(name):
+    exact, total = pc.check_pure_network(name, DEV, replicas=2)
+    assert exact == total
+
+
+@pytest.mark.parametrize("name", golden_names("ep_"))
+def test_episode_golden(name):
+    pc.check_episode(name, DEV, check_obs=True)
+
+
+def test_batched_replicas_identical():
+    pc.check_episode("ep_edge_n50", DEV, replicas=5)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_random_episodes_vs_oracle(seed):
+    sc = synthetic(num_nodes=60, num_targets=70, seed=10 + seed)
+    n_dec, cnt = pc.check_vs_oracle(sc, DEV, num_envs=8, steps=40, seed=seed, check_obs=(seed == 0))
+    assert n_dec > 100
+
+
+def test_heterogeneous_scenarios_vs_oracle():
+    scs = [synthetic(num_nodes=48, num_targets=48, seed=s) for s in (21, 22, 23)]
+    pc.check_vs_oracle(scs, DEV, num_envs=9, steps=25, seed=5)
+
+
+def test_long_charging_and_deaths_vs_oracle():
+    sc = synthetic(num_nodes=40, num_targets=120, seed=3, num_gateways=2)
+    n_dec, cnt = pc.check_vs_oracle(sc, DEV, num_envs=6, steps=60, seed=9, scale2=0.5)
+    assert cnt["serial_ticks"] >= 1
+
+
+def test_small_charger_exhaustion_vs_oracle():
+    mc = dict(capacity=2500, threshold=0, velocity=5, pm=1, charging_range=27, alpha=4500, beta=30, epsilon=1e-10)
+    sc = synthetic(num_nodes=50, num_targets=50, seed=4)
+    pc.check_vs_oracle(sc, DEV, num_envs=6, steps=50, seed=2, mc=mc, scale2=0.01)
+
+
+@pytest.mark.parametrize("threads", [32, 64, 128])
+def test_group_size_independent(threads):
+    """The result must not depend on how many threads share an environment."""
+    sc = synthetic(num_nodes=100, num_targets=100, seed=7)
+    rng = np.random.default_rng(3)
+    acts = rng.uniform(0, 1, size=(30, 4, 3)); acts[..., 2] *= 0.05
+    outs = []
+    for th in (32, threads):
+        env = BatchedWRSN(sc, num_agent=3, num_envs=4, device=DEV, threads=th)
+        req = env.reset()
+        rec = []
+        for k in range(30):
+            a = req.agent_id.clone()
+            req = env.step(torch.where(a >= 0, a, torch.full_like(a, -1)), torch.as_tensor(acts[k], device=DEV), mask=(a >= 0))
+            rec.append((req.agent_id.cpu().numpy().copy(), req.now.cpu().numpy().copy(), env.view("energy").cpu().numpy().copy()))
+        outs.append(rec)
+    for (a0, n0, e0), (a1, n1, e1) in zip(*outs):
+        assert np.array_equal(a0, a1) and np.array_equal(n0, n1) and np.array_equal(e0, e1)
+
+
+def test_full_size_properties():
+    """BASELINE config 2 size (100 nodes / 3 chargers / 4096 environments): size-independent properties.
+    Replicated environments fed identical actions must stay bit-identical; energies stay inside
+    [threshold, capacity]; dead nodes never come back; time never runs backwards."""
+    sc = synthetic(num_nodes=100, num_targets=100, seed=1)
+    B = 4096
+    env = BatchedWRSN(sc, num_agent=3, num_envs=B, device=DEV)
+    rng = np.random.default_rng(0)
+    req = env.reset()
+    prev_now = req.now.clone()
+    prev_status = env.view("status").clone()
+    for k in range(12):
+        a = rng.uniform(0, 1, size=(2, 3)); a[:, 2] *= 0.05
+        act = torch.as_tensor(np.concatenate([np.tile(a[0], (B // 2, 1)), np.tile(a[1], (B // 2, 1))]), device=DEV)
+        aid = req.agent_id.clone()
+        req = env.step(aid, act, mask=(aid >= 0))
+        e = env.view("energy")
+        assert float(e.min()) >= 540.0 and float(e.max()) <= 10800.0
+        assert bool((req.now >= prev_now).all())
+        st = env.view("status")
+        assert bool((st <= prev_status).all())
+        prev_now, prev_status = req.now.clone(), st.clone()
+        for half in (slice(0, B // 2), slice(B // 2, B)):
+            assert bool((e[half] == e[half][0:1]).all())
+            assert bool((req.agent_id[half] == req.agent_id[half][0]).all())
+            assert bool((req.now[half] == req.now[half][0]).all())
+    assert float(env.hdr("ERR").max()) == 0.0
+    obs = env.get_state()
+    assert obs.shape == (B, 4, 100, 100) and bool(torch.isfinite(obs).all())
+    assert bool((obs[0] == obs[1]).all())
