@@ -32,80 +32,28 @@
  * The same source compiles for the device (nvcc, sm_100a) and, with WRSN_HOST_EMU, as plain
  * single-lane C++ used ONLY by tests/ to check the event logic on a box without a GPU.
  */
-#pragma once
-#include <math.h>
-#include <stdint.h>
-#include <string.h>
-
-#include "wrsn_b200.h"
-
-#if defined(WRSN_HOST_EMU)
-#define WRSN_HD static inline
-#define WRSN_D static inline
-#else
-#define WRSN_HD __host__ __device__ static inline
-#define WRSN_D __device__ static
+/* NOTE: no include guard — this file is included once per group-size specialisation, inside a namespace, after
+ * wrsn_layout.h, with WRSN_GFIX defined: 32 = one warp per environment (every barrier is a __syncwarp, every
+ * reduction a shuffle tree), 0 = any multiple of 32 threads (__syncthreads), 1 = the tests' single-lane host build. */
+#ifndef WRSN_GFIX
+#error "define WRSN_GFIX before including wrsn_engine.cuh"
 #endif
 
-/* ------------------------------------------------------------------ layouts */
-struct WrsnLayout {
-    int64_t off[WRSN_F_COUNT];
-    int64_t resident, total;                        /* bytes mirrored in shared memory / bytes per record */
-    int64_t s_own, s_scr0, s_scr1, s_bcast, s_red, smem_total;
-    int64_t soff[WRSN_S_COUNT];
-    int64_t scen_total;
-    int32_t scr_len;                                /* doubles per scratch row */
-};
-
-WRSN_HD int64_t wrsn_a16(int64_t x) { return (x + 15) & ~(int64_t)15; }
-
-WRSN_HD void wrsn_make_layout(const wrsn_dims *d, WrsnLayout *L) {
-    const int64_t Np = d->Npad;
-    int64_t o = 0;
-    L->off[WRSN_F_HDR] = o; o += wrsn_a16(8 * WRSN_H_LEN);
-    L->off[WRSN_F_MC] = o; o += wrsn_a16(8 * (int64_t)(d->M > 0 ? d->M : 1) * WRSN_MC_LEN);
-    L->off[WRSN_F_PROC] = o; o += wrsn_a16(8 * (int64_t)d->n_slot * WRSN_PR_LEN);
-    L->off[WRSN_F_ENERGY] = o; o += 8 * Np;
-    L->off[WRSN_F_RR] = o; o += 8 * Np;
-    L->off[WRSN_F_CS] = o; o += 8 * Np;
-    L->off[WRSN_F_ESEND] = o; o += 8 * Np;
-    L->off[WRSN_F_LOGC] = o; o += 8 * Np;
-    L->off[WRSN_F_NBEF] = o; o += 2 * Np;
-    L->off[WRSN_F_NAFT] = o; o += 2 * Np;
-    L->off[WRSN_F_LEVEL] = o; o += 2 * Np;
-    L->off[WRSN_F_PARENT] = o; o += 2 * Np;
-    L->off[WRSN_F_STATUS] = o; o += Np;
-    L->off[WRSN_F_TACT] = o; o += wrsn_a16(4 * (int64_t)d->Tw);
-    L->off[WRSN_F_CONN] = o; o += wrsn_a16(4 * (int64_t)(d->M > 0 ? d->M : 1) * d->W);
-    L->resident = o;
-    L->off[WRSN_F_LOGTICK] = o; o += 8 * Np;
-    L->off[WRSN_F_RING] = o; o += 8 * Np * WRSN_RING;
-    L->total = o;
-    /* shared-memory extras behind the resident image */
-    int64_t Tp = ((int64_t)d->T + 15) & ~(int64_t)15;
-    L->scr_len = (int32_t)(Np > Tp ? Np : Tp);
-    int64_t s = L->resident;
-    L->s_own = s; s += 2 * Np;
-    L->s_scr0 = s; s += 8 * (int64_t)L->scr_len;
-    L->s_scr1 = s; s += 8 * (int64_t)L->scr_len;
-    L->s_bcast = s; s += 64;
-    L->s_red = s; s += 8 * 32;
-    L->smem_total = s;
-    /* scenario record */
-    o = 0;
-    L->soff[WRSN_S_PAR] = o; o += wrsn_a16(8 * WRSN_P_LEN);
-    L->soff[WRSN_S_NX] = o; o += 8 * Np;
-    L->soff[WRSN_S_NY] = o; o += 8 * Np;
-    L->soff[WRSN_S_BS_ESEND] = o; o += 8 * Np;
-    L->soff[WRSN_S_NBR_DIST] = o; o += wrsn_a16(8 * (int64_t)d->Emax);
-    L->soff[WRSN_S_NBR_ESEND] = o; o += wrsn_a16(8 * (int64_t)d->Emax);
-    L->soff[WRSN_S_NBR_PTR] = o; o += wrsn_a16(4 * (Np + 1));
-    L->soff[WRSN_S_TGT_PTR] = o; o += wrsn_a16(4 * (Np + 1));
-    L->soff[WRSN_S_NBR_IDX] = o; o += wrsn_a16(4 * (int64_t)d->Emax);
-    L->soff[WRSN_S_TGT_IDX] = o; o += wrsn_a16(4 * (int64_t)d->TEmax);
-    L->soff[WRSN_S_DIRECT] = o; o += Np;
-    L->scen_total = wrsn_a16(o);
-}
+#undef WRSN_D
+#undef WRSN_NOINLINE
+#undef WRSN_GSZ
+#if defined(WRSN_HOST_EMU)
+#define WRSN_D static inline
+#define WRSN_NOINLINE static
+#else
+#define WRSN_D __device__ static
+#define WRSN_NOINLINE __device__ __noinline__ static   /* cold or shared code kept out of the hot loop's I-cache footprint */
+#endif
+#if WRSN_GFIX
+#define WRSN_GSZ(c) WRSN_GFIX
+#else
+#define WRSN_GSZ(c) ((c).G)
+#endif
 
 /* ------------------------------------------------------------------ context */
 struct Ctx {
@@ -164,7 +112,12 @@ WRSN_D void ctx_bind(Ctx &c, const wrsn_dims &d, const WrsnLayout &L, const char
     c.red = (double *)(smem + L.s_red);
     c.logtick = (double *)(state_row + L.off[WRSN_F_LOGTICK]);
     c.ring = (double *)(state_row + L.off[WRSN_F_RING]);
-    c.par = (const double *)(scen_row + L.soff[WRSN_S_PAR]);
+    {
+        const double *gpar = (const double *)(scen_row + L.soff[WRSN_S_PAR]);
+        double *spar = (double *)(smem + L.s_par);
+        for (int k = tid; k < WRSN_P_LEN; k += G) spar[k] = gpar[k];   /* visible after the caller's first barrier */
+        c.par = spar;
+    }
     c.nx = (const double *)(scen_row + L.soff[WRSN_S_NX]);
     c.ny = (const double *)(scen_row + L.soff[WRSN_S_NY]);
     c.bs_esend = (const double *)(scen_row + L.soff[WRSN_S_BS_ESEND]);
@@ -179,54 +132,65 @@ WRSN_D void ctx_bind(Ctx &c, const wrsn_dims &d, const WrsnLayout &L, const char
 
 /* ------------------------------------------------------------------ group primitives */
 WRSN_D void gsync(const Ctx &c) {
-#if !defined(WRSN_HOST_EMU)
-    if (c.G == 32) __syncwarp(); else __syncthreads();
-#else
+#if defined(WRSN_HOST_EMU)
     (void)c;
+#elif WRSN_GFIX == 32
+    (void)c; __syncwarp();
+#else
+    (void)c; __syncthreads();
 #endif
 }
 
 #if !defined(WRSN_HOST_EMU)
-#define WRSN_WARP_RED(v, OP)                                                  \
-    for (int o_ = 16; o_ > 0; o_ >>= 1) { auto w_ = __shfl_xor_sync(0xffffffffu, v, o_); v = OP(v, w_); }
-#define WRSN_OP_ADD(a, b) ((a) + (b))
-#define WRSN_OP_OR(a, b) ((a) | (b))
+WRSN_NOINLINE double warp_sum(double v) {
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+WRSN_NOINLINE double warp_min(double v) {
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
 #endif
 
 WRSN_D double red_sum(const Ctx &c, double v) {
-#if !defined(WRSN_HOST_EMU)
-    WRSN_WARP_RED(v, WRSN_OP_ADD)
-    if (c.G == 32) return v;
+#if defined(WRSN_HOST_EMU)
+    (void)c; return v;
+#elif WRSN_GFIX == 32
+    (void)c; return warp_sum(v);
+#else
+    v = warp_sum(v);
     __syncthreads();
     if ((c.tid & 31) == 0) c.red[c.tid >> 5] = v;
     __syncthreads();
     double s = 0.0;
     for (int k = 0; k < (c.G >> 5); k++) s += c.red[k];
     return s;
-#else
-    (void)c; return v;
 #endif
 }
 WRSN_D double red_min(const Ctx &c, double v) {
-#if !defined(WRSN_HOST_EMU)
-    WRSN_WARP_RED(v, fmin)
-    if (c.G == 32) return v;
+#if defined(WRSN_HOST_EMU)
+    (void)c; return v;
+#elif WRSN_GFIX == 32
+    (void)c; return warp_min(v);
+#else
+    v = warp_min(v);
     __syncthreads();
     if ((c.tid & 31) == 0) c.red[c.tid >> 5] = v;
     __syncthreads();
     double s = c.red[0];
     for (int k = 1; k < (c.G >> 5); k++) s = fmin(s, c.red[k]);
     return s;
-#else
-    (void)c; return v;
 #endif
 }
 WRSN_D int red_or(const Ctx &c, int v) {
-#if !defined(WRSN_HOST_EMU)
-    if (c.G == 32) return __any_sync(0xffffffffu, v) ? 1 : 0;
-    return __syncthreads_or(v) ? 1 : 0;
-#else
+#if defined(WRSN_HOST_EMU)
     (void)c; return v ? 1 : 0;
+#elif WRSN_GFIX == 32
+    (void)c; return __any_sync(0xffffffffu, v) ? 1 : 0;
+#else
+    (void)c; return __syncthreads_or(v) ? 1 : 0;
 #endif
 }
 WRSN_D void atomic_or_u32(uint32_t *p, uint32_t v) {
@@ -251,7 +215,22 @@ WRSN_D void atomic_max_nonneg(double *p, double v) {      /* v >= 0: order of th
 #endif
 }
 
-WRSN_D double euclid2(double ax, double ay, double bx, double by) {
+WRSN_D int wrsn_ctz(uint32_t v) {
+#if !defined(WRSN_HOST_EMU)
+    return __ffs((int)v) - 1;
+#else
+    return __builtin_ctz(v);
+#endif
+}
+WRSN_D int wrsn_popc(uint32_t v) {
+#if !defined(WRSN_HOST_EMU)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+
+WRSN_NOINLINE double euclid2(double ax, double ay, double bx, double by) {
     /* scipy.spatial.distance.euclidean == sqrt(dot(u - v, u - v)) for 2-vectors */
     double dx = ax - bx, dy = ay - by;
     return sqrt(dx * dx + dy * dy);
@@ -278,6 +257,11 @@ WRSN_D int wrsn_biased_exp(double e) {
     uint64_t b; memcpy(&b, &e, 8); return (int)((b >> 52) & 0x7ffull);
 #endif
 }
+WRSN_NOINLINE double sub_chain_literal(double e, double a, int n_single, double b, int n_pair) {
+    for (int k = 0; k < n_single; k++) e -= a;
+    for (int k = 0; k < n_pair; k++) { e -= b; e -= a; }
+    return e;
+}
 WRSN_D double sub_chain(double e, double a, int n_single, double b, int n_pair) {
     int n_a = n_single + n_pair;
     if (n_a == 0) return e;
@@ -294,57 +278,94 @@ WRSN_D double sub_chain(double e, double a, int n_single, double b, int n_pair) 
             if (r >= lo) return r;
         }
     }
-    for (int k = 0; k < n_single; k++) e -= a;
-    for (int k = 0; k < n_pair; k++) { e -= b; e -= a; }
-    return e;
+    return sub_chain_literal(e, a, n_single, b, n_pair);
 }
 
-/* ------------------------------------------------------------------ event clock helpers (leader only) */
-WRSN_D double take_seq(Ctx &c) { double s = c.hdr[WRSN_H_SEQ]; c.hdr[WRSN_H_SEQ] = s + 1.0; return s; }
-WRSN_D double *slot_of(Ctx &c, int s) { return c.proc + (size_t)s * WRSN_PR_LEN; }
-WRSN_D double *mc_of(Ctx &c, int a) { return c.mc + (size_t)a * WRSN_MC_LEN; }
+/* ------------------------------------------------------------------ event clock
+ * While run_loop() is active the clock lives in REGISTERS, identical in every thread of the environment: all
+ * threads execute the (scalar) clock and charger logic redundantly from broadcast shared-memory loads, thread 0
+ * alone stores.  Nothing is broadcast through shared memory and no thread waits for a leader.  Outside
+ * run_loop() the clock is the hdr row (the *_h helpers, leader only).
+ * An event's position in SimPy's queue is (time, priority, insertion counter); priority and counter are folded
+ * into one double key = priority * 2^40 + counter, a pending time of +inf means "nothing pending". */
+#define WRSN_KEY_NORMAL 1099511627776.0            /* 2^40 */
 
-WRSN_D void slot_sched(Ctx &c, double *p, int pc, int prio, double delay) {
-    p[WRSN_PR_PC] = pc; p[WRSN_PR_PRIO] = prio; p[WRSN_PR_T] = c.hdr[WRSN_H_NOW] + delay;
-    p[WRSN_PR_SEQ] = take_seq(c); p[WRSN_PR_PENDING] = 1.0;
+struct Clk {
+    double now, seq, nev;
+    double net_t, net_key, ur_t, ur_key, nodes_t, nodes_key, until_t, until_key;
+    int net_state, nodes_phase, stop;
+    int mc_idx;                                      /* earliest pending charger-slot (< n_slot) / condition (>= n_slot) event */
+    double mc_t, mc_key, mc_other_t;                 /* its position; earliest time among the OTHER slot / condition events */
+};
+
+WRSN_D double *slot_of(Ctx &c, int s) { return c.proc + s * WRSN_PR_LEN; }
+WRSN_D int *slot_i(double *p) { return (int *)p; }
+WRSN_D double *mc_of(Ctx &c, int a) { return c.mc + a * WRSN_MC_LEN; }
+WRSN_D double take_seq(Clk &k) { double s = k.seq; k.seq = s + 1.0; return s; }
+WRSN_D double take_seq_h(Ctx &c) { double s = c.hdr[WRSN_H_SEQ]; c.hdr[WRSN_H_SEQ] = s + 1.0; return s; }
+WRSN_D bool ev_before(double t, double key, double bt, double bkey) { return t < bt || (t == bt && key < bkey); }
+
+WRSN_D void clk_load(Ctx &c, Clk &k) {
+    const double *h = c.hdr;
+    k.now = h[WRSN_H_NOW]; k.seq = h[WRSN_H_SEQ]; k.nev = 0.0;
+    k.net_t = h[WRSN_H_NET_ON] != 0.0 ? h[WRSN_H_NET_T] : INFINITY; k.net_key = WRSN_KEY_NORMAL + h[WRSN_H_NET_SEQ];
+    k.net_state = (int)h[WRSN_H_NET_STATE];
+    k.ur_t = h[WRSN_H_UR_ON] != 0.0 ? h[WRSN_H_UR_T] : INFINITY; k.ur_key = WRSN_KEY_NORMAL + h[WRSN_H_UR_SEQ];
+    k.nodes_t = h[WRSN_H_NODES_T]; k.nodes_key = WRSN_KEY_NORMAL + h[WRSN_H_NODES_SEQ]; k.nodes_phase = (int)h[WRSN_H_NODES_PHASE];
+    k.until_t = h[WRSN_H_UNTIL_ON] != 0.0 ? h[WRSN_H_UNTIL_T] : INFINITY; k.until_key = h[WRSN_H_UNTIL_SEQ];   /* URGENT */
+    k.stop = 0; k.mc_idx = -1; k.mc_t = INFINITY; k.mc_key = 0.0; k.mc_other_t = INFINITY;
 }
-
-WRSN_D bool ev_before(double t, double p, double s, double bt, double bp, double bs) {
-    if (t != bt) return t < bt;
-    if (p != bp) return p < bp;
-    return s < bs;
-}
-
-/* pick the next event: smallest (time, priority, insertion counter) */
-WRSN_D void pick_next(Ctx &c, int *kind, int *idx) {
-    double *h = c.hdr;
-    int bk = K_NONE, bi = 0;
-    double bt = 0, bp = 0, bs = 0;
-#define WRSN_CAND(K, I, T, P, S)                                                   \
-    { double t_ = (T), p_ = (P), s_ = (S);                                         \
-      if (bk == K_NONE || ev_before(t_, p_, s_, bt, bp, bs)) { bk = (K); bi = (I); bt = t_; bp = p_; bs = s_; } }
-    if (h[WRSN_H_NET_ON] != 0.0) WRSN_CAND(K_NET, 0, h[WRSN_H_NET_T], WRSN_NORMAL, h[WRSN_H_NET_SEQ])
-    if (h[WRSN_H_UR_ON] != 0.0) WRSN_CAND(K_UR, 0, h[WRSN_H_UR_T], WRSN_NORMAL, h[WRSN_H_UR_SEQ])
-    WRSN_CAND(K_NODES, 0, h[WRSN_H_NODES_T], WRSN_NORMAL, h[WRSN_H_NODES_SEQ])
-    if (h[WRSN_H_UNTIL_ON] != 0.0) WRSN_CAND(K_UNTIL, 0, h[WRSN_H_UNTIL_T], WRSN_URGENT, h[WRSN_H_UNTIL_SEQ])
-    for (int s = 0; s < c.n_slot; s++) {
-        double *p = slot_of(c, s);
-        if (p[WRSN_PR_PENDING] != 0.0) WRSN_CAND(K_SLOT, s, p[WRSN_PR_T], p[WRSN_PR_PRIO], p[WRSN_PR_SEQ])
+WRSN_D void clk_store(Ctx &c, const Clk &k) {
+    gsync(c);
+    if (c.tid == 0) {
+        double *h = c.hdr;
+        h[WRSN_H_NOW] = k.now; h[WRSN_H_SEQ] = k.seq; h[WRSN_H_NEVENTS] += k.nev;
+        h[WRSN_H_NET_ON] = k.net_t < INFINITY ? 1.0 : 0.0; if (k.net_t < INFINITY) h[WRSN_H_NET_T] = k.net_t;
+        h[WRSN_H_NET_SEQ] = k.net_key - WRSN_KEY_NORMAL; h[WRSN_H_NET_STATE] = k.net_state;
+        h[WRSN_H_UR_ON] = k.ur_t < INFINITY ? 1.0 : 0.0; if (k.ur_t < INFINITY) h[WRSN_H_UR_T] = k.ur_t;
+        h[WRSN_H_UR_SEQ] = k.ur_key - WRSN_KEY_NORMAL;
+        h[WRSN_H_NODES_T] = k.nodes_t; h[WRSN_H_NODES_SEQ] = k.nodes_key - WRSN_KEY_NORMAL; h[WRSN_H_NODES_PHASE] = k.nodes_phase;
+        h[WRSN_H_UNTIL_ON] = k.until_t < INFINITY ? 1.0 : 0.0; if (k.until_t < INFINITY) h[WRSN_H_UNTIL_T] = k.until_t;
+        h[WRSN_H_UNTIL_SEQ] = k.until_key;
     }
-    int nch = (int)h[WRSN_H_CHAIN_N];
-    for (int j = 0; j < nch; j++)
-        if (h[WRSN_H_COND_PEND + j] != 0.0) WRSN_CAND(K_COND, j, h[WRSN_H_COND_T + j], WRSN_NORMAL, h[WRSN_H_COND_SEQ + j])
-#undef WRSN_CAND
-    *kind = bk; *idx = bi;
-    if (bk != K_NONE) h[WRSN_H_NOW] = bt;
+    gsync(c);
+}
+
+/* earliest pending slot / condition event and the earliest time among the others (all threads, broadcast loads) */
+WRSN_D void mc_scan(Ctx &c, Clk &k) {
+    int bi = -1;
+    double bt = INFINITY, bkey = 0.0, ot = INFINITY;
+    const int ns = c.n_slot;
+#pragma unroll 1
+    for (int s = 0; s < ns; s++) {
+        const double *p = c.proc + s * WRSN_PR_LEN;
+        const double t = p[WRSN_PR_T];
+        if (t < INFINITY) {
+            const double key = p[WRSN_PR_KEY];
+            if (ev_before(t, key, bt, bkey)) { ot = bt; bi = s; bt = t; bkey = key; }
+            else ot = fmin(ot, t);
+        }
+    }
+    const double *h = c.hdr;
+    const int nch = (int)h[WRSN_H_CHAIN_N];
+#pragma unroll 1
+    for (int j = 0; j < nch; j++) {
+        const double t = h[WRSN_H_COND_T + j];
+        if (t < INFINITY) {
+            const double key = h[WRSN_H_COND_KEY + j];
+            if (ev_before(t, key, bt, bkey)) { ot = bt; bi = ns + j; bt = t; bkey = key; }
+            else ot = fmin(ot, t);
+        }
+    }
+    k.mc_idx = bi; k.mc_t = bt; k.mc_key = bkey; k.mc_other_t = ot;
 }
 
 /* ------------------------------------------------------------------ Node.log ring: leave the "all ten entries equal
  * logc" shortcut (entries were not written while it held) */
-WRSN_D void leave_uniform(Ctx &c) {
+WRSN_NOINLINE void leave_uniform(Ctx &c) {
     bool uni = c.hdr[WRSN_H_LOG_UNIFORM] >= 10.0 && c.hdr[WRSN_H_LOG_LEN] >= 10.0;
     if (uni)
-        for (int i = c.tid; i < c.N; i += c.G) {
+        for (int i = c.tid; i < c.N; i += WRSN_GSZ(c)) {
             double v = c.logc[i];
             for (int k = 0; k < WRSN_RING; k++) c.ring[(size_t)k * c.Npad + i] = v;
         }
@@ -356,19 +377,19 @@ WRSN_D void leave_uniform(Ctx &c) {
 /* ------------------------------------------------------------------ Network.setLevels + check_targets (Network.py:37-66,84)
  * plus the routing tree the drain tick replays: receiver (Node.find_receiver :92-100), e_send, relay counts,
  * and the per-tick log_energy of every node. */
-WRSN_D void do_bfs(Ctx &c) {
+WRSN_NOINLINE void do_bfs(Ctx &c) {
     leave_uniform(c);
     const int N = c.N;
     int *cnt = (int *)c.scr0;                       /* 2 ints per node: relayed packets from lower / higher ids */
-    for (int i = c.tid; i < N; i += c.G) {
+    for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
         c.level[i] = (c.status[i] == 1 && c.direct[i]) ? 1 : -1;
         cnt[2 * i] = 0; cnt[2 * i + 1] = 0;
     }
-    for (int w = c.tid; w < c.Tw; w += c.G) c.tact[w] = 0u;
+    for (int w = c.tid; w < c.Tw; w += WRSN_GSZ(c)) c.tact[w] = 0u;
     gsync(c);
     for (int cur = 1;; cur++) {
         int any = 0;
-        for (int i = c.tid; i < N; i += c.G) {
+        for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
             if (c.level[i] != cur) continue;
             for (int e = c.tgt_ptr[i]; e < c.tgt_ptr[i + 1]; e++) {
                 int t = c.tgt_idx[e];
@@ -384,14 +405,14 @@ WRSN_D void do_bfs(Ctx &c) {
     }
     /* alive = min(targets_active) */
     int dead_t = 0;
-    for (int w = c.tid; w < c.Tw; w += c.G) {
+    for (int w = c.tid; w < c.Tw; w += WRSN_GSZ(c)) {
         int bits = c.T - 32 * w; if (bits > 32) bits = 32;
         uint32_t full = bits == 32 ? 0xffffffffu : ((1u << bits) - 1u);
         if ((c.tact[w] & full) != full) dead_t = 1;
     }
     dead_t = red_or(c, dead_t);
     /* receivers */
-    for (int i = c.tid; i < N; i += c.G) {
+    for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
         int par = -1; double es = 0.0;
         if (c.status[i] == 1 && c.level[i] >= 1) {
             if (c.direct[i]) { par = -2; es = c.bs_esend[i]; }
@@ -410,14 +431,14 @@ WRSN_D void do_bfs(Ctx &c) {
     }
     gsync(c);
     /* relay counts: every packet of source s crosses all its ancestors */
-    for (int s = c.tid; s < N; s += c.G) {
+    for (int s = c.tid; s < N; s += WRSN_GSZ(c)) {
         int ow = c.own[s];
         if (c.status[s] != 1 || ow == 0 || c.parent[s] == -1) continue;
         for (int h = c.parent[s]; h >= 0; h = c.parent[h]) atomic_add_i32(&cnt[2 * h + (s < h ? 0 : 1)], ow);
     }
     gsync(c);
     const double er = c.par[WRSN_P_ERECV];
-    for (int i = c.tid; i < N; i += c.G) {
+    for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
         int nb = cnt[2 * i], na = cnt[2 * i + 1];
         c.nbef[i] = (uint16_t)nb; c.naft[i] = (uint16_t)na;
         double lg = 0.0, es = c.esend[i];
@@ -444,7 +465,7 @@ WRSN_D void check_status_node(Ctx &c, int i) {     /* Node.py:148-151 */
 }
 
 /* exact serial tick: packet by packet, hop by hop, as the reference does it (leader only) */
-WRSN_D int drain_serial(Ctx &c) {
+WRSN_NOINLINE int drain_serial(Ctx &c) {
     const int N = c.N;
     const double thr = c.par[WRSN_P_THR], cap = c.par[WRSN_P_CAP], er = c.par[WRSN_P_ERECV];
     int deaths = 0;
@@ -499,7 +520,8 @@ WRSN_D void ev_nodes_drain(Ctx &c) {
     const double thr = c.par[WRSN_P_THR], cap = c.par[WRSN_P_CAP], er = c.par[WRSN_P_ERECV];
     const double slack = 1e-6;
     int slow = c.hdr[WRSN_H_BFS_DIRTY] != 0.0 ? 1 : 0;   /* routing tree is stale (Network.operate has stopped): serial path */
-    for (int i = c.tid; i < N; i += c.G) {
+    _Pragma("unroll 1")
+    for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
         if (c.status[i] != 1) continue;
         double e = c.energy[i], es = c.esend[i];
         int nb = c.nbef[i], na = c.naft[i];
@@ -514,7 +536,8 @@ WRSN_D void ev_nodes_drain(Ctx &c) {
     gsync(c);
     slow = red_or(c, slow);
     if (!slow) {
-        for (int i = c.tid; i < N; i += c.G)
+        _Pragma("unroll 1")
+        for (int i = c.tid; i < N; i += WRSN_GSZ(c))
             if (c.status[i] == 1) c.energy[i] = c.scr0[i];
         gsync(c);
         return;
@@ -536,7 +559,8 @@ WRSN_D void ev_nodes_book(Ctx &c) {
     const int L = (int)c.hdr[WRSN_H_LOG_LEN], head = (int)c.hdr[WRSN_H_LOG_HEAD];
     const bool literal = c.hdr[WRSN_H_LOG_LITERAL] != 0.0;
     const bool uni = !literal && L >= WRSN_RING && c.hdr[WRSN_H_LOG_UNIFORM] >= 10.0;
-    for (int i = c.tid; i < N; i += c.G) {
+    _Pragma("unroll 1")
+    for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
         if (c.status[i] != 1) continue;
         c.energy[i] = fmin(c.energy[i] + c.rr[i] * 0.5, cap);
         double lg = literal ? c.logtick[i] : c.logc[i];
@@ -566,42 +590,52 @@ WRSN_D double charge_rate_to(Ctx &c, const double *m, int node) {   /* alpha / (
     return c.par[WRSN_P_MC_ALPHA] / (t * t);
 }
 
+/* the softmax priority + incentive sums; only reached when some incentive sum is non-empty */
+WRSN_NOINLINE void update_reward_body(Ctx &c);
+
 WRSN_D void ev_update_reward(Ctx &c) {
-    bool any = false;
+    bool any = false;                                /* is there any (charging charger, connected alive node) pair? */
     for (int a = 0; a < c.M; a++) {
-        const double *m = mc_of(c, a);
-        if (m[WRSN_MC_STATUS] != 0.0 && m[WRSN_MC_TYPE] != 0.0) any = true;
+        const double *m = c.mc + a * WRSN_MC_LEN;
+        if (m[WRSN_MC_STATUS] == 0.0 || m[WRSN_MC_TYPE] == 0.0 || m[WRSN_MC_NCONN] == 0.0) continue;
+        const uint32_t *cm = c.conn + a * c.W;
+        for (int w = 0; w < c.W; w++)
+            for (uint32_t bits = cm[w]; bits; bits &= bits - 1u)
+                if (c.status[32 * w + wrsn_ctz(bits)] == 1) any = true;
     }
-    if (!any) return;                                /* the priority vector has no other reader */
+    if (any) update_reward_body(c);                  /* otherwise every incentive sum is empty: excl += 0 */
+}
+
+WRSN_NOINLINE void update_reward_body(Ctx &c) {
     const int N = c.N;
     const double thr = c.par[WRSN_P_THR], cap = c.par[WRSN_P_CAP], eps = c.par[WRSN_P_EPSENV];
     double s = 0.0;
-    for (int i = c.tid; i < N; i += c.G) {
+    _Pragma("unroll 1")
+    for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
         double p = c.status[i] != 0 ? c.cs[i] / (c.energy[i] - thr + eps) : 0.0;
         c.scr0[i] = p; s += p;
     }
     double mean = red_sum(c, s) / (double)N;
     s = 0.0;
-    for (int i = c.tid; i < N; i += c.G) { double x = c.scr0[i] - mean; s += x * x; }
+    _Pragma("unroll 1")
+    for (int i = c.tid; i < N; i += WRSN_GSZ(c)) { double x = c.scr0[i] - mean; s += x * x; }
     double sd = sqrt(red_sum(c, s) / (double)N);
     if (sd == 0.0) sd = eps;
     s = 0.0;
-    for (int i = c.tid; i < N; i += c.G) { double q = exp((c.scr0[i] - mean) / sd); c.scr0[i] = q; s += q; }
+    _Pragma("unroll 1")
+    for (int i = c.tid; i < N; i += WRSN_GSZ(c)) { double q = exp((c.scr0[i] - mean) / sd); c.scr0[i] = q; s += q; }
     double tot = red_sum(c, s);
     if (tot == 0.0) tot = eps;
     gsync(c);
     if (c.tid == 0) {
         for (int a = 0; a < c.M; a++) {
-            double *m = mc_of(c, a);
+            double *m = c.mc + (size_t)a * WRSN_MC_LEN;
             if (m[WRSN_MC_STATUS] == 0.0 || m[WRSN_MC_TYPE] == 0.0) continue;
             double incentive = 0.0;
             const uint32_t *cm = c.conn + (size_t)a * c.W;
             for (int w = 0; w < c.W; w++) {
-                uint32_t bits = cm[w];
-                while (bits) {
-                    int b = 0; while (!((bits >> b) & 1u)) b++;
-                    bits &= bits - 1u;
-                    int i = 32 * w + b;
+                for (uint32_t bits = cm[w]; bits; bits &= bits - 1u) {
+                    int i = 32 * w + wrsn_ctz(bits);
                     if (c.status[i] != 1) continue;
                     double rate = charge_rate_to(c, m, i);
                     double e_no = fmin(c.energy[i] - c.cs[i], thr);
@@ -616,11 +650,11 @@ WRSN_D void ev_update_reward(Ctx &c) {
 }
 
 /* ------------------------------------------------------------------ WRSN.get_network_fitness (WRSN.py:188-220) -> min */
-WRSN_D double do_fitness(Ctx &c, double *per_target /* global, may be NULL */) {
+WRSN_NOINLINE double do_fitness(Ctx &c, double *per_target /* global, may be NULL */) {
     const int N = c.N;
     const double thr = c.par[WRSN_P_THR];
     double *node_t = c.scr0, *lt = c.scr1;
-    for (int i = c.tid; i < N; i += c.G) {
+    for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
         double v = -1.0, l = 0.0;
         if (c.status[i] == 1) {
             l = (c.cs[i] == 0.0) ? INFINITY : (c.energy[i] - thr) / c.cs[i];
@@ -631,7 +665,7 @@ WRSN_D double do_fitness(Ctx &c, double *per_target /* global, may be NULL */) {
     gsync(c);
     for (;;) {                                       /* widest path to the base station; only min / max, so any order is exact */
         int changed = 0;
-        for (int i = c.tid; i < N; i += c.G) {
+        for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
             if (c.status[i] != 1 || c.direct[i]) continue;
             double best = -1.0;
             for (int e = c.nbr_ptr[i]; e < c.nbr_ptr[i + 1]; e++) {
@@ -648,16 +682,16 @@ WRSN_D double do_fitness(Ctx &c, double *per_target /* global, may be NULL */) {
     }
     double *tt = c.scr1;                             /* lt no longer needed */
     gsync(c);
-    for (int t = c.tid; t < c.T; t += c.G) tt[t] = 0.0;
+    for (int t = c.tid; t < c.T; t += WRSN_GSZ(c)) tt[t] = 0.0;
     gsync(c);
-    for (int i = c.tid; i < N; i += c.G) {
+    for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
         double v = node_t[i];
         if (v <= 0.0) continue;
         for (int e = c.tgt_ptr[i]; e < c.tgt_ptr[i + 1]; e++) atomic_max_nonneg(&tt[c.tgt_idx[e]], v);
     }
     gsync(c);
     double mn = INFINITY;
-    for (int t = c.tid; t < c.T; t += c.G) {
+    for (int t = c.tid; t < c.T; t += WRSN_GSZ(c)) {
         double v = tt[t];
         if (per_target) per_target[t] = v;
         mn = fmin(mn, v);
@@ -668,16 +702,12 @@ WRSN_D double do_fitness(Ctx &c, double *per_target /* global, may be NULL */) {
 }
 
 /* ------------------------------------------------------------------ chargers (MobileCharger.py) */
-WRSN_D void mc_check_status(Ctx &c, double *m) {   /* :134-140 */
-    if (m[WRSN_MC_ENERGY] <= c.par[WRSN_P_MC_THR]) { m[WRSN_MC_STATUS] = 0.0; m[WRSN_MC_ENERGY] = c.par[WRSN_P_MC_THR]; }
-}
-
 /* all threads: bitmask of nodes with d(node, (x, y)) <= charging_range */
-WRSN_D void near_mask(Ctx &c, double x, double y, uint32_t *mask) {
-    for (int w = c.tid; w < c.W; w += c.G) mask[w] = 0u;
+WRSN_NOINLINE void near_mask(Ctx &c, double x, double y, uint32_t *mask) {
+    for (int w = c.tid; w < c.W; w += WRSN_GSZ(c)) mask[w] = 0u;
     gsync(c);
     const double R = c.par[WRSN_P_MC_R];
-    for (int i = c.tid; i < c.N; i += c.G)
+    for (int i = c.tid; i < c.N; i += WRSN_GSZ(c))
         if (euclid2(c.nx[i], c.ny[i], x, y) <= R) atomic_or_u32(&mask[i >> 5], 1u << (i & 31));
     gsync(c);
 }
@@ -687,66 +717,55 @@ WRSN_D void near_mask(Ctx &c, double x, double y, uint32_t *mask) {
         for (uint32_t bits_ = (mask)[w_]; bits_; bits_ &= bits_ - 1u)          \
             for (int i = 32 * w_ + wrsn_ctz(bits_), once_ = 1; once_; once_ = 0)
 
-WRSN_D int wrsn_ctz(uint32_t v) {
-#if !defined(WRSN_HOST_EMU)
-    return __ffs((int)v) - 1;
-#else
-    return __builtin_ctz(v);
-#endif
+WRSN_D double charge_rate_xy(Ctx &c, double mx, double my, int node) {   /* alpha / (d + beta) ** 2 */
+    double t = euclid2(c.nx[node], c.ny[node], mx, my) + c.par[WRSN_P_MC_BETA];
+    return c.par[WRSN_P_MC_ALPHA] / (t * t);
 }
 
-/* leader: the move loop head (MobileCharger.move :85-96) */
-WRSN_D void mc_move_loop(Ctx &c, double *p, double *m) {
-    if (p[WRSN_PR_MT] <= 0.0) { slot_sched(c, p, PC_MOVE_DONE, WRSN_NORMAL, 0.0); return; }
-    if (m[WRSN_MC_STATUS] == 0.0) { slot_sched(c, p, PC_MOVE_DEADWAIT, WRSN_NORMAL, p[WRSN_PR_MT]); return; }
-    const double v = c.par[WRSN_P_MC_V];
-    p[WRSN_PR_MT] = euclid2(p[WRSN_PR_DESTX], p[WRSN_PR_DESTY], m[WRSN_MC_X], m[WRSN_MC_Y]) / v;
-    double span = fmin(fmin(p[WRSN_PR_MT], 1.0), (m[WRSN_MC_ENERGY] - c.par[WRSN_P_MC_THR]) / c.par[WRSN_P_MC_PMV]);
-    p[WRSN_PR_SPAN] = span;
-    p[WRSN_PR_SVX] = p[WRSN_PR_VX] / p[WRSN_PR_TOTAL] * span;
-    p[WRSN_PR_SVY] = p[WRSN_PR_VY] / p[WRSN_PR_TOTAL] * span;
-    slot_sched(c, p, PC_MS_INIT, WRSN_URGENT, 0.0);
+/* schedule the slot's next event (all threads keep the clock, thread 0 stores) */
+WRSN_D void slot_sched(Ctx &c, Clk &k, double *p, int pc, int prio, double delay) {
+    double t = k.now + delay, key = take_seq(k) + (prio ? WRSN_KEY_NORMAL : 0.0);
+    if (c.tid == 0) { slot_i(p)[WRSN_PRI_PC] = pc; p[WRSN_PR_T] = t; p[WRSN_PR_KEY] = key; }
 }
 
-/* leader: the charge loop head (MobileCharger.charge :59-72) */
-WRSN_D void mc_charge_loop(Ctx &c, double *p, double *m) {
-    if (p[WRSN_PR_CHTMP] == 0.0) { slot_sched(c, p, PC_CH_DONE, WRSN_NORMAL, 0.0); return; }
-    if (m[WRSN_MC_STATUS] == 0.0) {
-        m[WRSN_MC_CPA2] = 0.0;
-        slot_sched(c, p, PC_CH_DEADWAIT, WRSN_NORMAL, p[WRSN_PR_CHTMP]);
-        return;
-    }
-    double span = fmin(p[WRSN_PR_CHTMP], 1.0);
-    if (m[WRSN_MC_RATE] != 0.0) span = fmin(span, (m[WRSN_MC_ENERGY] - c.par[WRSN_P_MC_THR]) / m[WRSN_MC_RATE]);
-    p[WRSN_PR_CHSPAN] = span;
-    slot_sched(c, p, PC_CS_INIT, WRSN_URGENT, 0.0);
+WRSN_D void cond_check(Ctx &c, Clk &k, int j) {   /* simpy Condition._check for AnyOf (all threads; state read before) */
+    double *h = c.hdr;
+    if (h[WRSN_H_COND_TRIG + j] != 0.0) return;
+    double s = take_seq(k);
+    gsync(c);
+    if (c.tid == 0) { h[WRSN_H_COND_TRIG + j] = 1.0; h[WRSN_H_COND_T + j] = k.now; h[WRSN_H_COND_KEY + j] = WRSN_KEY_NORMAL + s; }
+    gsync(c);
 }
-
-WRSN_D void cond_check(Ctx &c, int j) {            /* simpy Condition._check for AnyOf */
+WRSN_D void cond_check_h(Ctx &c, int j) {          /* leader-only variant used while building the chain */
     double *h = c.hdr;
     if (h[WRSN_H_COND_TRIG + j] != 0.0) return;
     h[WRSN_H_COND_TRIG + j] = 1.0;
-    h[WRSN_H_COND_PEND + j] = 1.0;
-    h[WRSN_H_COND_T + j] = h[WRSN_H_NOW];
-    h[WRSN_H_COND_SEQ + j] = take_seq(c);
+    h[WRSN_H_COND_T + j] = h[WRSN_H_NOW]; h[WRSN_H_COND_KEY + j] = WRSN_KEY_NORMAL + take_seq_h(c);
 }
 
-/* one event of a charger process slot.  Called by ALL threads (node-parallel pieces inside). */
-WRSN_D void ev_slot(Ctx &c, int s) {
+/* Events of one charger process slot, starting with the pending one.  Zero-delay follow-up events of the same slot
+ * (process start / completion hops of the generator tree) are executed back to back as long as NO other event of the
+ * environment is due at the current instant (`other_t` > now): then the (time, priority, counter) order would pick
+ * them next anyway; every hop still draws its insertion counter, so later ties resolve as in the reference. */
+WRSN_D void ev_slot(Ctx &c, Clk &k, int s, double other_t) {
     double *p = slot_of(c, s);
-    const int a = (int)p[WRSN_PR_AGENT];
+    const int a = slot_i(p)[WRSN_PRI_AGENT];
     double *m = mc_of(c, a);
-    const int pc = (int)p[WRSN_PR_PC];
     uint32_t *cm = c.conn + (size_t)a * c.W;
-    gsync(c);
-    if (c.tid == 0) p[WRSN_PR_PENDING] = 0.0;
-    switch (pc) {
-    case PC_OP_INIT: {                               /* MobileCharger.operate_step :105-132, up to the first yield */
-        uint32_t *near = (uint32_t *)c.scr1;
-        near_mask(c, p[WRSN_PR_PHY0], p[WRSN_PR_PHY1], near);
-        if (c.tid == 0) {
+    const double *par = c.par;
+    const bool lead = c.tid == 0;
+    for (;;) {
+        const int pc = slot_i(p)[WRSN_PRI_PC];
+        k.nev += 1.0;
+        bool again = false;                          /* the slot's next event is due now */
+        int nx_pc = 0, nx_prio = 0;                  /* the slot's next event: scheduled at ONE site below */
+        double nx_delay = 0.0;
+        switch (pc) {
+        case PC_OP_INIT: {                           /* MobileCharger.operate_step :105-132, up to the first yield */
             const double dx = p[WRSN_PR_PHY0], dy = p[WRSN_PR_PHY1], ct = p[WRSN_PR_PHY2];
-            const double pm = c.par[WRSN_P_MC_PM], beta = c.par[WRSN_P_MC_BETA], alpha = c.par[WRSN_P_MC_ALPHA];
+            uint32_t *near = (uint32_t *)c.scr1;
+            near_mask(c, dx, dy, near);
+            const double pm = par[WRSN_P_MC_PM], beta = par[WRSN_P_MC_BETA], alpha = par[WRSN_P_MC_ALPHA];
             double used = euclid2(dx, dy, m[WRSN_MC_X], m[WRSN_MC_Y]) * pm;
             double tmp = 0.0;
             WRSN_FOR_BITS(near, c.W, i) {
@@ -756,225 +775,240 @@ WRSN_D void ev_slot(Ctx &c, int s) {
                 }
             }
             used += tmp * ct;
-            used += euclid2(dx, dy, c.par[WRSN_P_BSX], c.par[WRSN_P_BSY]) * pm;
-            m[WRSN_MC_CPA0] = dx; m[WRSN_MC_CPA1] = dy; m[WRSN_MC_CPA2] = ct;
-            m[WRSN_MC_TYPE] = 0.0;
-            if (used > m[WRSN_MC_ENERGY] - c.par[WRSN_P_MC_THR] - c.par[WRSN_P_MC_CAP200]) {
-                p[WRSN_PR_STAGE] = 1.0; p[WRSN_PR_DESTX] = c.par[WRSN_P_BSX]; p[WRSN_PR_DESTY] = c.par[WRSN_P_BSY];
+            used += euclid2(dx, dy, par[WRSN_P_BSX], par[WRSN_P_BSY]) * pm;
+            const bool detour = used > m[WRSN_MC_ENERGY] - par[WRSN_P_MC_THR] - par[WRSN_P_MC_CAP200];
+            gsync(c);
+            if (lead) {
+                m[WRSN_MC_CPA0] = dx; m[WRSN_MC_CPA1] = dy; m[WRSN_MC_CPA2] = ct; m[WRSN_MC_TYPE] = 0.0;
+                slot_i(p)[WRSN_PRI_STAGE] = detour ? 1 : 3;
+                p[WRSN_PR_DESTX] = detour ? par[WRSN_P_BSX] : dx; p[WRSN_PR_DESTY] = detour ? par[WRSN_P_BSY] : dy;
+            }
+            { nx_pc = PC_MOVE_INIT; nx_prio = WRSN_URGENT; nx_delay = 0.0; } again = true;
+            break;
+        }
+        case PC_MOVE_INIT:                           /* MobileCharger.move :82-84, then the loop head :85-94 */
+        case PC_MS_DONE: {                           /* back from move_step :95-96, then the loop head */
+            const double destx = p[WRSN_PR_DESTX], desty = p[WRSN_PR_DESTY], v = par[WRSN_P_MC_V];
+            const double mx = m[WRSN_MC_X], my = m[WRSN_MC_Y];
+            double mt, vx, vy, total, en = m[WRSN_MC_ENERGY], st = m[WRSN_MC_STATUS];
+            if (pc == PC_MOVE_INIT) {
+                mt = euclid2(destx, desty, mx, my) / v; vx = destx - mx; vy = desty - my; total = mt;
             } else {
-                p[WRSN_PR_STAGE] = 3.0; p[WRSN_PR_DESTX] = dx; p[WRSN_PR_DESTY] = dy;
+                mt = p[WRSN_PR_MT] - p[WRSN_PR_SPAN]; vx = p[WRSN_PR_VX]; vy = p[WRSN_PR_VY]; total = p[WRSN_PR_TOTAL];
+                if (en <= par[WRSN_P_MC_THR]) { st = 0.0; en = par[WRSN_P_MC_THR]; }      /* checkStatus */
             }
-            slot_sched(c, p, PC_MOVE_INIT, WRSN_URGENT, 0.0);
+            gsync(c);
+            if (lead) {
+                m[WRSN_MC_ENERGY] = en; m[WRSN_MC_STATUS] = st;
+                if (pc == PC_MOVE_INIT) { p[WRSN_PR_VX] = vx; p[WRSN_PR_VY] = vy; p[WRSN_PR_TOTAL] = total; }
+            }
+            if (mt <= 0.0) {
+                if (lead) p[WRSN_PR_MT] = mt;
+                { nx_pc = PC_MOVE_DONE; nx_prio = WRSN_NORMAL; nx_delay = 0.0; } again = true;
+            } else if (st == 0.0) {
+                if (lead) p[WRSN_PR_MT] = mt;
+                { nx_pc = PC_MOVE_DEADWAIT; nx_prio = WRSN_NORMAL; nx_delay = mt; }
+            } else {
+                mt = euclid2(destx, desty, mx, my) / v;
+                double span = fmin(fmin(mt, 1.0), (en - par[WRSN_P_MC_THR]) / par[WRSN_P_MC_PMV]);
+                if (lead) {
+                    p[WRSN_PR_MT] = mt; p[WRSN_PR_SPAN] = span;
+                    p[WRSN_PR_SVX] = vx / total * span; p[WRSN_PR_SVY] = vy / total * span;
+                }
+                { nx_pc = PC_MS_INIT; nx_prio = WRSN_URGENT; nx_delay = 0.0; } again = true;
+            }
+            break;
         }
-        break;
-    }
-    case PC_MOVE_INIT:                               /* MobileCharger.move :82-84 */
-        if (c.tid == 0) {
-            p[WRSN_PR_MT] = euclid2(p[WRSN_PR_DESTX], p[WRSN_PR_DESTY], m[WRSN_MC_X], m[WRSN_MC_Y]) / c.par[WRSN_P_MC_V];
-            p[WRSN_PR_VX] = p[WRSN_PR_DESTX] - m[WRSN_MC_X];
-            p[WRSN_PR_VY] = p[WRSN_PR_DESTY] - m[WRSN_MC_Y];
-            p[WRSN_PR_TOTAL] = p[WRSN_PR_MT];
-            mc_move_loop(c, p, m);
+        case PC_MS_INIT: {                           /* move_step :76 */
+            const double span = p[WRSN_PR_SPAN];
+            gsync(c);
+            { nx_pc = PC_MS_FIRE; nx_prio = WRSN_NORMAL; nx_delay = span; } again = span == 0.0;
+            break;
         }
-        break;
-    case PC_MS_INIT:                                 /* move_step :76 */
-        if (c.tid == 0) slot_sched(c, p, PC_MS_FIRE, WRSN_NORMAL, p[WRSN_PR_SPAN]);
-        break;
-    case PC_MS_FIRE:                                 /* move_step :77-78 */
-        if (c.tid == 0) {
-            m[WRSN_MC_X] = m[WRSN_MC_X] + p[WRSN_PR_SVX];
-            m[WRSN_MC_Y] = m[WRSN_MC_Y] + p[WRSN_PR_SVY];
-            m[WRSN_MC_ENERGY] -= c.par[WRSN_P_MC_PM] * p[WRSN_PR_SPAN] * c.par[WRSN_P_MC_V];
-            slot_sched(c, p, PC_MS_DONE, WRSN_NORMAL, 0.0);
+        case PC_MS_FIRE: {                           /* move_step :77-78 */
+            const double x = m[WRSN_MC_X] + p[WRSN_PR_SVX], y = m[WRSN_MC_Y] + p[WRSN_PR_SVY];
+            const double en = m[WRSN_MC_ENERGY] - par[WRSN_P_MC_PM] * p[WRSN_PR_SPAN] * par[WRSN_P_MC_V];
+            gsync(c);
+            if (lead) { m[WRSN_MC_X] = x; m[WRSN_MC_Y] = y; m[WRSN_MC_ENERGY] = en; }
+            { nx_pc = PC_MS_DONE; nx_prio = WRSN_NORMAL; nx_delay = 0.0; } again = true;
+            break;
         }
-        break;
-    case PC_MS_DONE:                                 /* move :95-96 */
-        if (c.tid == 0) {
-            p[WRSN_PR_MT] -= p[WRSN_PR_SPAN];
-            mc_check_status(c, m);
-            mc_move_loop(c, p, m);
-        }
-        break;
-    case PC_MOVE_DEADWAIT:
-        if (c.tid == 0) slot_sched(c, p, PC_MOVE_DONE, WRSN_NORMAL, 0.0);
-        break;
-    case PC_MOVE_DONE:                               /* back in operate_step */
-        if (c.tid == 0) {
-            if (p[WRSN_PR_STAGE] == 1.0) slot_sched(c, p, PC_RC_INIT, WRSN_URGENT, 0.0);
+        case PC_MOVE_DEADWAIT:
+            gsync(c);
+            { nx_pc = PC_MOVE_DONE; nx_prio = WRSN_NORMAL; nx_delay = 0.0; } again = true;
+            break;
+        case PC_MOVE_DONE: {                         /* back in operate_step */
+            const bool detour = slot_i(p)[WRSN_PRI_STAGE] == 1;
+            const double ct = p[WRSN_PR_PHY2];
+            gsync(c);
+            if (detour) { nx_pc = PC_RC_INIT; nx_prio = WRSN_URGENT; nx_delay = 0.0; }
             else {
-                m[WRSN_MC_TYPE] = 1.0;
-                p[WRSN_PR_CHTMP] = p[WRSN_PR_PHY2];
-                slot_sched(c, p, PC_CH_INIT, WRSN_URGENT, 0.0);
+                if (lead) { m[WRSN_MC_TYPE] = 1.0; p[WRSN_PR_CHTMP] = ct; }
+                { nx_pc = PC_CH_INIT; nx_prio = WRSN_URGENT; nx_delay = 0.0; }
             }
+            again = true;
+            break;
         }
-        break;
-    case PC_RC_INIT:                                 /* recharge :99-103 */
-        if (c.tid == 0) {
-            if (euclid2(m[WRSN_MC_X], m[WRSN_MC_Y], c.par[WRSN_P_BSX], c.par[WRSN_P_BSY]) <= c.par[WRSN_P_MC_EPS]) {
-                m[WRSN_MC_X] = c.par[WRSN_P_BSX]; m[WRSN_MC_Y] = c.par[WRSN_P_BSY];
-                m[WRSN_MC_ENERGY] = c.par[WRSN_P_MC_CAP];
+        case PC_RC_INIT: {                           /* recharge :99-103 */
+            const bool at_bs = euclid2(m[WRSN_MC_X], m[WRSN_MC_Y], par[WRSN_P_BSX], par[WRSN_P_BSY]) <= par[WRSN_P_MC_EPS];
+            gsync(c);
+            if (lead && at_bs) { m[WRSN_MC_X] = par[WRSN_P_BSX]; m[WRSN_MC_Y] = par[WRSN_P_BSY]; m[WRSN_MC_ENERGY] = par[WRSN_P_MC_CAP]; }
+            { nx_pc = PC_RC_FIRE; nx_prio = WRSN_NORMAL; nx_delay = 0.0; } again = true;
+            break;
+        }
+        case PC_RC_FIRE:
+            gsync(c);
+            { nx_pc = PC_RC_DONE; nx_prio = WRSN_NORMAL; nx_delay = 0.0; } again = true;
+            break;
+        case PC_RC_DONE: {
+            const double dx = p[WRSN_PR_PHY0], dy = p[WRSN_PR_PHY1];
+            gsync(c);
+            if (lead) { slot_i(p)[WRSN_PRI_STAGE] = 3; p[WRSN_PR_DESTX] = dx; p[WRSN_PR_DESTY] = dy; }
+            { nx_pc = PC_MOVE_INIT; nx_prio = WRSN_URGENT; nx_delay = 0.0; } again = true;
+            break;
+        }
+        case PC_CH_INIT:                             /* charge :53-58, then the loop head :59-68 */
+        case PC_CS_DONE: {                           /* back from charge_step :69-71, then the loop head */
+            double tmp, en = m[WRSN_MC_ENERGY], st = m[WRSN_MC_STATUS];
+            const double rate = m[WRSN_MC_RATE];
+            if (pc == PC_CH_INIT) {
+                tmp = p[WRSN_PR_CHTMP];
+                near_mask(c, m[WRSN_MC_X], m[WRSN_MC_Y], cm);
+                int n = 0;
+                for (int w = 0; w < c.W; w++) n += wrsn_popc(cm[w]);
+                gsync(c);
+                if (lead) m[WRSN_MC_NCONN] = n;
+            } else {
+                tmp = p[WRSN_PR_CHTMP] - p[WRSN_PR_CHSPAN];
+                if (en <= par[WRSN_P_MC_THR]) { st = 0.0; en = par[WRSN_P_MC_THR]; }      /* checkStatus */
+                gsync(c);
+                if (lead) { m[WRSN_MC_ENERGY] = en; m[WRSN_MC_STATUS] = st; }
             }
-            slot_sched(c, p, PC_RC_FIRE, WRSN_NORMAL, 0.0);
-        }
-        break;
-    case PC_RC_FIRE:
-        if (c.tid == 0) slot_sched(c, p, PC_RC_DONE, WRSN_NORMAL, 0.0);
-        break;
-    case PC_RC_DONE:
-        if (c.tid == 0) {
-            p[WRSN_PR_STAGE] = 3.0; p[WRSN_PR_DESTX] = p[WRSN_PR_PHY0]; p[WRSN_PR_DESTY] = p[WRSN_PR_PHY1];
-            slot_sched(c, p, PC_MOVE_INIT, WRSN_URGENT, 0.0);
-        }
-        break;
-    case PC_CH_INIT: {                               /* charge :53-58 */
-        near_mask(c, m[WRSN_MC_X], m[WRSN_MC_Y], cm);
-        if (c.tid == 0) {
-            m[WRSN_MC_CHTIME] = p[WRSN_PR_CHTMP];
-            int n = 0;
-            for (int w = 0; w < c.W; w++) {
-#if !defined(WRSN_HOST_EMU)
-                n += __popc(cm[w]);
-#else
-                n += __builtin_popcount(cm[w]);
-#endif
+            if (lead) { p[WRSN_PR_CHTMP] = tmp; m[WRSN_MC_CHTIME] = tmp; }
+            if (tmp == 0.0) { { nx_pc = PC_CH_DONE; nx_prio = WRSN_NORMAL; nx_delay = 0.0; } again = true; }
+            else if (st == 0.0) {
+                if (lead) m[WRSN_MC_CPA2] = 0.0;
+                { nx_pc = PC_CH_DEADWAIT; nx_prio = WRSN_NORMAL; nx_delay = tmp; }
+            } else {
+                double span = fmin(tmp, 1.0);
+                if (rate != 0.0) span = fmin(span, (en - par[WRSN_P_MC_THR]) / rate);
+                if (lead) p[WRSN_PR_CHSPAN] = span;
+                { nx_pc = PC_CS_INIT; nx_prio = WRSN_URGENT; nx_delay = 0.0; } again = true;
             }
-            m[WRSN_MC_NCONN] = n;
-            mc_charge_loop(c, p, m);
+            break;
         }
-        break;
-    }
-    case PC_CS_INIT:                                 /* charge_step :40-44 + Node.charger_connection :134-139 */
-        if (c.tid == 0) {
+        case PC_CS_INIT:                             /* charge_step :40-44 + Node.charger_connection :134-139 */
+        case PC_CS_FIRE: {                           /* charge_step :45-50 + Node.charger_disconnection :141-146 */
+            const double mx = m[WRSN_MC_X], my = m[WRSN_MC_Y], span = p[WRSN_PR_CHSPAN];
+            double rate = m[WRSN_MC_RATE], en = m[WRSN_MC_ENERGY], cpa2 = m[WRSN_MC_CPA2];
+            const bool connect = pc == PC_CS_INIT;
+            if (!connect) { en = en - rate * span; cpa2 = fmax(0.0, cpa2 - span); }
+            gsync(c);
             WRSN_FOR_BITS(cm, c.W, i) {
                 if (c.status[i] == 0) continue;
-                double r = charge_rate_to(c, m, i);
-                c.rr[i] += r; m[WRSN_MC_RATE] += r;
+                double r = charge_rate_xy(c, mx, my, i);
+                if (lead) c.rr[i] = connect ? c.rr[i] + r : c.rr[i] - r;
+                rate = connect ? rate + r : rate - r;
             }
-            slot_sched(c, p, PC_CS_FIRE, WRSN_NORMAL, p[WRSN_PR_CHSPAN]);
+            if (!connect) rate = 0.0;
+            if (lead) { m[WRSN_MC_RATE] = rate; m[WRSN_MC_ENERGY] = en; m[WRSN_MC_CPA2] = cpa2; }
+            if (connect) { { nx_pc = PC_CS_FIRE; nx_prio = WRSN_NORMAL; nx_delay = span; } again = span == 0.0; }
+            else { { nx_pc = PC_CS_DONE; nx_prio = WRSN_NORMAL; nx_delay = 0.0; } again = true; }
+            break;
         }
-        break;
-    case PC_CS_FIRE:                                 /* charge_step :45-50 + Node.charger_disconnection :141-146 */
-        if (c.tid == 0) {
-            const double t = p[WRSN_PR_CHSPAN];
-            m[WRSN_MC_ENERGY] = m[WRSN_MC_ENERGY] - m[WRSN_MC_RATE] * t;
-            m[WRSN_MC_CPA2] = fmax(0.0, m[WRSN_MC_CPA2] - t);
-            WRSN_FOR_BITS(cm, c.W, i) {
-                if (c.status[i] == 0) continue;
-                double r = charge_rate_to(c, m, i);
-                c.rr[i] -= r; m[WRSN_MC_RATE] -= r;
-            }
-            m[WRSN_MC_RATE] = 0.0;
-            slot_sched(c, p, PC_CS_DONE, WRSN_NORMAL, 0.0);
-        }
-        break;
-    case PC_CS_DONE:                                 /* charge :69-71 */
-        if (c.tid == 0) {
-            p[WRSN_PR_CHTMP] -= p[WRSN_PR_CHSPAN];
-            m[WRSN_MC_CHTIME] = p[WRSN_PR_CHTMP];
-            mc_check_status(c, m);
-            mc_charge_loop(c, p, m);
-        }
-        break;
-    case PC_CH_DEADWAIT:
-        if (c.tid == 0) slot_sched(c, p, PC_CH_DONE, WRSN_NORMAL, 0.0);
-        break;
-    case PC_CH_DONE:                                 /* operate_step returns */
-        if (c.tid == 0) slot_sched(c, p, PC_OP_DONE, WRSN_NORMAL, 0.0);
-        break;
-    case PC_OP_DONE:                                 /* the process event itself: callbacks = condition checks */
-        if (c.tid == 0) {
-            p[WRSN_PR_PROCESSED] = 1.0;
-            if (p[WRSN_PR_CURRENT] == 0.0) p[WRSN_PR_USED] = 0.0;     /* superseded process: nobody holds it any more */
+        case PC_CH_DEADWAIT:
+            gsync(c);
+            { nx_pc = PC_CH_DONE; nx_prio = WRSN_NORMAL; nx_delay = 0.0; } again = true;
+            break;
+        case PC_CH_DONE:                             /* operate_step returns */
+            gsync(c);
+            { nx_pc = PC_OP_DONE; nx_prio = WRSN_NORMAL; nx_delay = 0.0; } again = true;
+            break;
+        case PC_OP_DONE: {                           /* the process event itself: callbacks = condition checks */
+            const bool current = slot_i(p)[WRSN_PRI_CURRENT] != 0;
             const int nch = (int)c.hdr[WRSN_H_CHAIN_N], det = (int)c.hdr[WRSN_H_CHAIN_DETACH];
+            gsync(c);
+            if (lead) { p[WRSN_PR_T] = INFINITY; slot_i(p)[WRSN_PRI_PROCESSED] = 1; if (!current) slot_i(p)[WRSN_PRI_USED] = 0; }
             for (int j = 0; j < nch; j++)
-                if ((int)c.hdr[WRSN_H_CHAIN_SLOT + j] == s && j > det) cond_check(c, j);
+                if ((int)c.hdr[WRSN_H_CHAIN_SLOT + j] == s && j > det) cond_check(c, k, j);
+            break;
         }
-        break;
-    default:
-        if (c.tid == 0) c.hdr[WRSN_H_ERR] = 2.0;
-        break;
+        default:
+            if (lead) { c.hdr[WRSN_H_ERR] = 2.0; p[WRSN_PR_T] = INFINITY; }
+            k.stop = 1;
+            break;
+        }
+        if (nx_pc) slot_sched(c, k, p, nx_pc, nx_prio, nx_delay);
+        gsync(c);
+        if (!again || !(other_t > k.now)) break;
     }
-    gsync(c);
 }
 
-/* a condition event of the AnyOf chain; returns via bcast[2] whether run() stops */
-WRSN_D void ev_cond(Ctx &c, int j) {
-    if (c.tid == 0) {
-        double *h = c.hdr;
-        h[WRSN_H_COND_PEND + j] = 0.0;
-        const int nch = (int)h[WRSN_H_CHAIN_N];
-        /* _build_value: remove the check callbacks of this condition and, recursively, of the nested ones */
-        if ((double)j > h[WRSN_H_CHAIN_DETACH]) h[WRSN_H_CHAIN_DETACH] = (double)j;
-        if (j + 1 < nch) { if ((double)(j + 1) > h[WRSN_H_CHAIN_DETACH]) cond_check(c, j + 1); }
-        else c.bcast[2] = 1;                         /* StopSimulation */
-    }
+/* a condition event of the AnyOf chain */
+WRSN_D void ev_cond(Ctx &c, Clk &k, int j) {
+    double *h = c.hdr;
+    const int nch = (int)h[WRSN_H_CHAIN_N];
+    double det = h[WRSN_H_CHAIN_DETACH];
+    k.nev += 1.0;
+    /* _build_value: remove the check callbacks of this condition and, recursively, of the nested ones */
+    if ((double)j > det) det = (double)j;
     gsync(c);
+    if (c.tid == 0) { h[WRSN_H_COND_T + j] = INFINITY; h[WRSN_H_CHAIN_DETACH] = det; }
+    gsync(c);
+    if (j + 1 < nch) { if ((double)(j + 1) > det) cond_check(c, k, j + 1); }
+    else k.stop = 1;                                 /* StopSimulation */
 }
 
 /* ------------------------------------------------------------------ the event loop: env.run(...) */
 WRSN_D void run_loop(Ctx &c) {
-    if (c.tid == 0) c.bcast[2] = 0;
-    gsync(c);
-    for (long guard = 0;; guard++) {
-        if (c.tid == 0) {
-            int kind, idx;
-            pick_next(c, &kind, &idx);
-            if (guard > 200000000L) { kind = K_NONE; }
-            c.bcast[0] = kind; c.bcast[1] = idx;
-            c.hdr[WRSN_H_NEVENTS] += 1.0;
-        }
-        gsync(c);
-        const int kind = c.bcast[0], idx = c.bcast[1];
-        const bool net_levels = c.hdr[WRSN_H_NET_STATE] == 1.0, dirty = c.hdr[WRSN_H_BFS_DIRTY] != 0.0;
-        const bool drain_phase = c.hdr[WRSN_H_NODES_PHASE] == 1.0;
-        gsync(c);
-        switch (kind) {
-        case K_NET:                                  /* Network.operate :74-80 */
-            if (net_levels) {
-                if (dirty) do_bfs(c);
-                if (c.tid == 0) {
-                    c.hdr[WRSN_H_NET_T] = c.hdr[WRSN_H_NOW] + 0.9; c.hdr[WRSN_H_NET_SEQ] = take_seq(c);
-                    c.hdr[WRSN_H_NET_STATE] = 2.0;
-                }
-            } else if (c.tid == 0) {
-                if (c.hdr[WRSN_H_ALIVE] == 0.0 || c.hdr[WRSN_H_NOW] >= c.par[WRSN_P_MAXTIME]) c.hdr[WRSN_H_NET_ON] = 0.0;
-                else {
-                    c.hdr[WRSN_H_NET_T] = c.hdr[WRSN_H_NOW] + 0.1; c.hdr[WRSN_H_NET_SEQ] = take_seq(c);
-                    c.hdr[WRSN_H_NET_STATE] = 1.0;
-                }
+    Clk k;
+    clk_load(c, k);
+    mc_scan(c, k);
+    const double maxtime = c.par[WRSN_P_MAXTIME];
+    for (long guard = 0; guard < 400000000L; guard++) {
+        /* earliest of the grid items (Network.operate, update_reward, the node block, run(until=t)) */
+        int gk = K_NODES;
+        double gt = k.nodes_t, gkey = k.nodes_key;
+        if (ev_before(k.net_t, k.net_key, gt, gkey)) { gk = K_NET; gt = k.net_t; gkey = k.net_key; }
+        if (ev_before(k.ur_t, k.ur_key, gt, gkey)) { gk = K_UR; gt = k.ur_t; gkey = k.ur_key; }
+        if (ev_before(k.until_t, k.until_key, gt, gkey)) { gk = K_UNTIL; gt = k.until_t; gkey = k.until_key; }
+        if (ev_before(k.mc_t, k.mc_key, gt, gkey)) {
+            k.now = k.mc_t;
+            if (k.mc_idx < c.n_slot) {
+                double other = fmin(fmin(k.mc_other_t, k.nodes_t), fmin(fmin(k.net_t, k.ur_t), k.until_t));
+                ev_slot(c, k, k.mc_idx, other);
+            } else ev_cond(c, k, k.mc_idx - c.n_slot);
+            mc_scan(c, k);
+        } else {
+            k.now = gt;
+            k.nev += 1.0;
+            if (gk == K_NODES) {
+                if (k.nodes_phase == 1) { ev_nodes_drain(c); k.nodes_phase = 2; }
+                else { ev_nodes_book(c); k.nodes_phase = 1; }
+                k.nodes_t = gt + 0.5; k.nodes_key = WRSN_KEY_NORMAL + take_seq(k);
+            } else if (gk == K_NET) {                /* Network.operate :74-80 */
+                if (k.net_state == 1) {
+                    if (c.hdr[WRSN_H_BFS_DIRTY] != 0.0) do_bfs(c);
+                    k.net_t = gt + 0.9; k.net_key = WRSN_KEY_NORMAL + take_seq(k); k.net_state = 2;
+                } else if (c.hdr[WRSN_H_ALIVE] == 0.0 || gt >= maxtime) k.net_t = INFINITY;
+                else { k.net_t = gt + 0.1; k.net_key = WRSN_KEY_NORMAL + take_seq(k); k.net_state = 1; }
+            } else if (gk == K_UR) {
+                ev_update_reward(c);
+                k.ur_t = gt + 1.0; k.ur_key = WRSN_KEY_NORMAL + take_seq(k);
+            } else {                                 /* K_UNTIL */
+                k.until_t = INFINITY; k.stop = 1;
             }
-            break;
-        case K_UR:
-            ev_update_reward(c);
-            if (c.tid == 0) { c.hdr[WRSN_H_UR_T] = c.hdr[WRSN_H_NOW] + 1.0; c.hdr[WRSN_H_UR_SEQ] = take_seq(c); }
-            break;
-        case K_NODES:
-            if (drain_phase) ev_nodes_drain(c); else ev_nodes_book(c);
-            if (c.tid == 0) {
-                c.hdr[WRSN_H_NODES_PHASE] = drain_phase ? 2.0 : 1.0;
-                c.hdr[WRSN_H_NODES_T] = c.hdr[WRSN_H_NOW] + 0.5; c.hdr[WRSN_H_NODES_SEQ] = take_seq(c);
-            }
-            break;
-        case K_UNTIL:
-            if (c.tid == 0) { c.hdr[WRSN_H_UNTIL_ON] = 0.0; c.bcast[2] = 1; }
-            break;
-        case K_SLOT: ev_slot(c, idx); break;
-        case K_COND: ev_cond(c, idx); break;
-        default:
-            if (c.tid == 0) { c.hdr[WRSN_H_ERR] = 1.0; c.bcast[2] = 1; }
-            break;
         }
-        gsync(c);
-        if (c.bcast[2]) break;
+        if (k.stop) break;
     }
-    gsync(c);
+    clk_store(c, k);
 }
 
 /* ------------------------------------------------------------------ entry points (one environment) */
 
 /* NetworkIO.makeNetwork + the t = 0 starts of Network.operate / update_reward / Node.operate */
 WRSN_D void entry_init_network(Ctx &c, int with_reward) {
-    for (int i = c.tid; i < c.Npad; i += c.G) {
+    for (int i = c.tid; i < c.Npad; i += WRSN_GSZ(c)) {
         bool real = i < c.N;
         c.energy[i] = real ? c.par[WRSN_P_CAP] : 0.0;
         c.rr[i] = 0.0; c.cs[i] = 0.0; c.esend[i] = 0.0; c.logc[i] = 0.0;
@@ -983,24 +1017,25 @@ WRSN_D void entry_init_network(Ctx &c, int with_reward) {
         c.logtick[i] = 0.0;
         for (int k = 0; k < WRSN_RING; k++) c.ring[(size_t)k * c.Npad + i] = 0.0;
     }
-    for (int w = c.tid; w < c.Tw; w += c.G) {
+    for (int w = c.tid; w < c.Tw; w += WRSN_GSZ(c)) {
         int bits = c.T - 32 * w; if (bits > 32) bits = 32;
         c.tact[w] = bits == 32 ? 0xffffffffu : ((1u << bits) - 1u);
     }
-    for (int w = c.tid; w < (c.M > 0 ? c.M : 1) * c.W; w += c.G) c.conn[w] = 0u;
-    for (int k = c.tid; k < WRSN_H_LEN; k += c.G) c.hdr[k] = 0.0;
-    for (int k = c.tid; k < (c.M > 0 ? c.M : 1) * WRSN_MC_LEN; k += c.G) c.mc[k] = 0.0;
-    for (int k = c.tid; k < c.n_slot * WRSN_PR_LEN; k += c.G) c.proc[k] = 0.0;
+    for (int w = c.tid; w < (c.M > 0 ? c.M : 1) * c.W; w += WRSN_GSZ(c)) c.conn[w] = 0u;
+    for (int k = c.tid; k < WRSN_H_LEN; k += WRSN_GSZ(c)) c.hdr[k] = 0.0;
+    for (int k = c.tid; k < (c.M > 0 ? c.M : 1) * WRSN_MC_LEN; k += WRSN_GSZ(c)) c.mc[k] = 0.0;
+    for (int k = c.tid; k < c.n_slot * WRSN_PR_LEN; k += WRSN_GSZ(c)) c.proc[k] = (k % WRSN_PR_LEN) == WRSN_PR_T ? INFINITY : 0.0;
+    for (int j = c.tid; j < WRSN_MAX_MC; j += WRSN_GSZ(c)) c.hdr[WRSN_H_COND_T + j] = INFINITY;
     gsync(c);
-    for (int i = c.tid; i < c.N; i += c.G) check_status_node(c, i);   /* Node.__init__ :43 */
+    for (int i = c.tid; i < c.N; i += WRSN_GSZ(c)) check_status_node(c, i);   /* Node.__init__ :43 */
     if (c.tid == 0) {
         double *h = c.hdr;
         h[WRSN_H_ALIVE] = 1.0; h[WRSN_H_BFS_DIRTY] = 1.0; h[WRSN_H_CHAIN_DETACH] = -1.0;
         /* scheduling order at t = 0: Network.operate's timeout(0.1), update_reward's timeout(1.0), the nodes'
            timeout(0.5) (the process starts themselves are URGENT events at t = 0 and have all run) */
-        h[WRSN_H_NET_ON] = 1.0; h[WRSN_H_NET_T] = 1.0 / 10.0; h[WRSN_H_NET_SEQ] = take_seq(c); h[WRSN_H_NET_STATE] = 1.0;
-        if (with_reward) { h[WRSN_H_UR_ON] = 1.0; h[WRSN_H_UR_T] = 1.0; h[WRSN_H_UR_SEQ] = take_seq(c); }
-        h[WRSN_H_NODES_T] = 0.5; h[WRSN_H_NODES_SEQ] = take_seq(c); h[WRSN_H_NODES_PHASE] = 1.0;
+        h[WRSN_H_NET_ON] = 1.0; h[WRSN_H_NET_T] = 1.0 / 10.0; h[WRSN_H_NET_SEQ] = take_seq_h(c); h[WRSN_H_NET_STATE] = 1.0;
+        if (with_reward) { h[WRSN_H_UR_ON] = 1.0; h[WRSN_H_UR_T] = 1.0; h[WRSN_H_UR_SEQ] = take_seq_h(c); }
+        h[WRSN_H_NODES_T] = 0.5; h[WRSN_H_NODES_SEQ] = take_seq_h(c); h[WRSN_H_NODES_PHASE] = 1.0;
     }
     gsync(c);
 }
@@ -1008,8 +1043,9 @@ WRSN_D void entry_init_network(Ctx &c, int with_reward) {
 /* env.run(until=t) */
 WRSN_D void entry_run_until(Ctx &c, double at) {
     if (!(at > c.hdr[WRSN_H_NOW])) return;
+    gsync(c);
     if (c.tid == 0) {
-        c.hdr[WRSN_H_UNTIL_ON] = 1.0; c.hdr[WRSN_H_UNTIL_T] = at; c.hdr[WRSN_H_UNTIL_SEQ] = take_seq(c);
+        c.hdr[WRSN_H_UNTIL_ON] = 1.0; c.hdr[WRSN_H_UNTIL_T] = at; c.hdr[WRSN_H_UNTIL_SEQ] = take_seq_h(c);
     }
     gsync(c);
     run_loop(c);
@@ -1024,19 +1060,20 @@ WRSN_D int scan_decider(Ctx &c) {                  /* WRSN.py:321-322 */
     return -1;
 }
 
-WRSN_D int new_slot(Ctx &c, int agent, double phy0, double phy1, double phy2) {   /* env.process(agent.operate_step(phy)) */
+/* leader: env.process(agent.operate_step(phy)) */
+WRSN_D int new_slot_h(Ctx &c, int agent, double phy0, double phy1, double phy2) {
     int s = -1;
-    for (int k = 0; k < c.n_slot; k++) if (slot_of(c, k)[WRSN_PR_USED] == 0.0) { s = k; break; }
+    for (int k = 0; k < c.n_slot; k++) if (slot_i(slot_of(c, k))[WRSN_PRI_USED] == 0) { s = k; break; }
     if (s < 0) { c.hdr[WRSN_H_ERR] = 3.0; return -1; }
     double *p = slot_of(c, s);
     for (int k = 0; k < WRSN_PR_LEN; k++) p[k] = 0.0;
-    p[WRSN_PR_USED] = 1.0; p[WRSN_PR_CURRENT] = 1.0; p[WRSN_PR_AGENT] = agent;
+    int *pi = slot_i(p);
+    pi[WRSN_PRI_USED] = 1; pi[WRSN_PRI_CURRENT] = 1; pi[WRSN_PRI_AGENT] = agent; pi[WRSN_PRI_PC] = PC_OP_INIT;
     p[WRSN_PR_PHY0] = phy0; p[WRSN_PR_PHY1] = phy1; p[WRSN_PR_PHY2] = phy2;
-    slot_sched(c, p, PC_OP_INIT, WRSN_URGENT, 0.0);
+    p[WRSN_PR_T] = c.hdr[WRSN_H_NOW]; p[WRSN_PR_KEY] = take_seq_h(c);       /* URGENT */
     return s;
 }
 
-struct ReqOut { int agent; int terminal; double reward, now, act[3], detail[2]; int flags; };
 
 /* the rest of WRSN.reset after env.run(until=warm_up) (WRSN.py:44-83) */
 WRSN_D void entry_reset_finish(Ctx &c, ReqOut *r) {
@@ -1046,11 +1083,12 @@ WRSN_D void entry_reset_finish(Ctx &c, ReqOut *r) {
             for (int k = 0; k < WRSN_MC_LEN; k++) m[k] = 0.0;
             m[WRSN_MC_X] = c.par[WRSN_P_BSX]; m[WRSN_MC_Y] = c.par[WRSN_P_BSY];
             m[WRSN_MC_ENERGY] = c.par[WRSN_P_MC_CAP]; m[WRSN_MC_STATUS] = 1.0;
-            mc_check_status(c, m);
+            if (m[WRSN_MC_ENERGY] <= c.par[WRSN_P_MC_THR]) { m[WRSN_MC_STATUS] = 0.0; m[WRSN_MC_ENERGY] = c.par[WRSN_P_MC_THR]; }
             m[WRSN_MC_CPA0] = c.par[WRSN_P_BSX]; m[WRSN_MC_CPA1] = c.par[WRSN_P_BSY]; m[WRSN_MC_CPA2] = 0.0;
             m[WRSN_MC_SLOT] = -1.0;
         }
-        for (int k = 0; k < c.n_slot * WRSN_PR_LEN; k++) c.proc[k] = 0.0;
+        for (int k = 0; k < c.n_slot * WRSN_PR_LEN; k++) c.proc[k] = (k % WRSN_PR_LEN) == WRSN_PR_T ? INFINITY : 0.0;
+        for (int j = 0; j < WRSN_MAX_MC; j++) c.hdr[WRSN_H_COND_T + j] = INFINITY;
         for (int w = 0; w < c.M * c.W; w++) c.conn[w] = 0u;
         c.hdr[WRSN_H_CHAIN_N] = 0.0; c.hdr[WRSN_H_CHAIN_DETACH] = -1.0; c.hdr[WRSN_H_HANG] = 0.0;
     }
@@ -1064,7 +1102,7 @@ WRSN_D void entry_reset_finish(Ctx &c, ReqOut *r) {
             m[WRSN_MC_ACT0] = (c.par[WRSN_P_BSX] - f0) / (f1 - f0);          /* down_mapping :86-88 */
             m[WRSN_MC_ACT1] = (c.par[WRSN_P_BSY] - f2) / (f3 - f2);
             m[WRSN_MC_ACT2] = 0.0;
-            m[WRSN_MC_SLOT] = new_slot(c, a, m[WRSN_MC_CPA0], m[WRSN_MC_CPA1], m[WRSN_MC_CPA2]);
+            m[WRSN_MC_SLOT] = new_slot_h(c, a, m[WRSN_MC_CPA0], m[WRSN_MC_CPA1], m[WRSN_MC_CPA2]);
             m[WRSN_MC_PREVFIT] = fit; m[WRSN_MC_EXCL] = 0.0;
         }
         int id = scan_decider(c);
@@ -1092,14 +1130,14 @@ WRSN_D void entry_step(Ctx &c, int agent_id, const double *input_action, ReqOut 
             double phy2 = c.par[WRSN_P_CTM] * act[2];
             int old = (int)m[WRSN_MC_SLOT];
             if (old >= 0) {
-                double *po = slot_of(c, old);
-                po[WRSN_PR_CURRENT] = 0.0;
-                if (po[WRSN_PR_PROCESSED] != 0.0) po[WRSN_PR_USED] = 0.0;
+                int *po = slot_i(slot_of(c, old));
+                po[WRSN_PRI_CURRENT] = 0;
+                if (po[WRSN_PRI_PROCESSED] != 0) po[WRSN_PRI_USED] = 0;
             }
-            m[WRSN_MC_SLOT] = new_slot(c, agent_id, phy0, phy1, phy2);
+            m[WRSN_MC_SLOT] = new_slot_h(c, agent_id, phy0, phy1, phy2);
             m[WRSN_MC_PREVFIT] = h[WRSN_H_FIT_MIN];   /* the network has not moved since the last request */
             m[WRSN_MC_EXCL] = 0.0;
-        }
+        } else if (agent_id >= c.M) h[WRSN_H_ERR] = 4.0;
         /* general_process = net_process | p_0 | p_1 ... over chargers with status != 0 (:307-310) */
         int n = 0;
         h[WRSN_H_CHAIN_DETACH] = -1.0;
@@ -1107,28 +1145,19 @@ WRSN_D void entry_step(Ctx &c, int agent_id, const double *input_action, ReqOut 
             const double *m = mc_of(c, a);
             if (m[WRSN_MC_STATUS] == 0.0) continue;
             int s = (int)m[WRSN_MC_SLOT];
-            h[WRSN_H_CHAIN_SLOT + n] = s; h[WRSN_H_COND_TRIG + n] = 0.0; h[WRSN_H_COND_PEND + n] = 0.0;
-            h[WRSN_H_CHAIN_N] = n + 1;
-            if (s >= 0 && slot_of(c, s)[WRSN_PR_PROCESSED] != 0.0) cond_check(c, n);   /* operand already processed */
+            h[WRSN_H_CHAIN_SLOT + n] = s; h[WRSN_H_COND_TRIG + n] = 0.0; h[WRSN_H_COND_T + n] = INFINITY;
+            if (s >= 0 && slot_i(slot_of(c, s))[WRSN_PRI_PROCESSED] != 0) cond_check_h(c, n);   /* operand already processed */
             n++;
         }
         h[WRSN_H_CHAIN_N] = n;
         h[WRSN_H_HANG] = n == 0 ? 1.0 : 0.0;
-        c.bcast[3] = n;
     }
     gsync(c);
-    const int watched = c.bcast[3];
-    gsync(c);
+    const int watched = (int)c.hdr[WRSN_H_CHAIN_N];
     if (watched > 0) run_loop(c);
+    gsync(c);
     int id = -1;
-    if (c.tid == 0) {
-        if (watched == 0 || c.hdr[WRSN_H_ALIVE] == 0.0) id = -1;
-        else { id = scan_decider(c); if (id < 0) id = -2; }
-        c.bcast[4] = id;
-    }
-    gsync(c);
-    id = c.bcast[4];
-    gsync(c);
+    if (!(watched == 0 || c.hdr[WRSN_H_ALIVE] == 0.0)) { id = scan_decider(c); if (id < 0) id = -2; }   /* all threads */
     double fit = 0.0;
     if (id >= 0) fit = do_fitness(c, (double *)0);   /* get_reward :222-227 */
     if (c.tid == 0) {

@@ -8,7 +8,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 
-#include "wrsn_engine.cuh"
+#include "wrsn_layout.h"
 
 static thread_local char g_err[512] = "";
 #define WRSN_FAIL(...) do { snprintf(g_err, sizeof(g_err), __VA_ARGS__); return -1; } while (0)
@@ -50,68 +50,43 @@ __device__ __forceinline__ void write_request(const wrsn_request &q, int b, cons
     if (q.flags) q.flags[b] = r.flags;
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(256) k_env(const KParams P) {
-    extern __shared__ uint4 smem_u4[];
-    char *smem = reinterpret_cast<char *>(smem_u4);
-    const int b = blockIdx.x, tid = threadIdx.x, G = blockDim.x;
-    if (P.mask && !P.mask[b]) return;
-    char *row = P.state + (size_t)b * P.L.total;
-    const char *scen_row = P.scen + (size_t)P.scen_id[b] * P.L.scen_total;
-    Ctx c;
-    ctx_bind(c, P.d, P.L, scen_row, row, smem, tid, G);
-    if (MODE == MODE_RESTORE_RESET) {
-        const char *src = P.snap + (size_t)P.scen_id[b] * P.L.total;
-        copy16(row + P.L.resident, src + P.L.resident, P.L.total - P.L.resident, tid, G);
-        copy16(smem, src, P.L.resident, tid, G);
-    } else if (MODE != MODE_INIT) {
-        copy16(smem, row, P.L.resident, tid, G);
-    }
-    for (int i = tid; i < c.Npad; i += G) c.own[i] = i < c.N ? (uint16_t)(c.tgt_ptr[i + 1] - c.tgt_ptr[i]) : (uint16_t)0;
-    if (G == 32) __syncwarp(); else __syncthreads();
-
-    ReqOut r;
-    r.agent = -3; r.terminal = 0; r.reward = 0; r.now = 0; r.flags = 0;
-    r.act[0] = r.act[1] = r.act[2] = 0; r.detail[0] = r.detail[1] = 0;
-    switch (MODE) {
-    case MODE_INIT: entry_init_network(c, P.with_reward); break;
-    case MODE_RUN_UNTIL: entry_run_until(c, P.t_until[b]); break;
-    case MODE_RESET_FINISH:
-    case MODE_RESTORE_RESET: entry_reset_finish(c, &r); break;
-    case MODE_STEP: entry_step(c, P.agent_in ? P.agent_in[b] : -1, P.action_in ? P.action_in + 3 * (size_t)b : nullptr, &r); break;
-    case MODE_FITNESS: {
-        double mn = do_fitness(c, P.fitness ? P.fitness + (size_t)b * P.d.T : nullptr);
-        if (tid == 0 && P.fit_min) P.fit_min[b] = mn;
-        break;
-    }
-    case MODE_K_BFS: do_bfs(c); break;
-    case MODE_K_DRAIN: ev_nodes_drain(c); break;
-    case MODE_K_BOOK: ev_nodes_book(c); break;
-    case MODE_K_REWARD: ev_update_reward(c); break;
-    }
-    if (G == 32) __syncwarp(); else __syncthreads();
-    if (MODE != MODE_FITNESS) copy16(row, smem, P.L.resident, tid, G);
-    if ((MODE == MODE_RESET_FINISH || MODE == MODE_RESTORE_RESET || MODE == MODE_STEP) && tid == 0) write_request(P.req, b, r);
+namespace g32 {                                      /* one warp per environment (N <= 128) */
+#define WRSN_GFIX 32
+#include "wrsn_engine.cuh"
+#include "wrsn_env_kernel.cuh"
+#undef WRSN_GFIX
+}
+namespace gany {                                     /* 64 ... 256 threads per environment */
+#define WRSN_GFIX 0
+#include "wrsn_engine.cuh"
+#include "wrsn_env_kernel.cuh"
+#undef WRSN_GFIX
 }
 
 /* ------------------------------------------------------------------ WRSN.get_state (rl_env/WRSN.py:130-186)
  * 4 x S x S map per environment.  Every source (alive node, charger) contributes w * G(x - x0; hX) * G(y - y0; hY)
- * with G(u; h) = exp(u^2 / (-2 h^2)) — separable, so a chunk of sources is expanded into two S-vectors each in
- * shared memory (2 S exponentials per source instead of S^2) and every thread accumulates its own output cells
- * over the sources IN SOURCE ORDER, in fp64, exactly as the reference's `map += pdf` does. */
+ * with G(u; h) = exp(u^2 / (-2 h^2)) — separable, so the raster is a rank-(number of sources) outer-product sum.
+ * A chunk of sources is expanded into two S-vectors each in shared memory (2 S exponentials per source instead of
+ * S^2, always evaluated in fp64) and every thread accumulates a 4 x 10 register tile of output cells over the sources
+ * IN SOURCE ORDER.  AccT = double: multiply and add rounded separately, exactly the reference's `map += w*gx*gy`
+ * (parity path, float64 out).  AccT = float: the vectors are rounded to fp32 once and accumulated with FFMA (the
+ * observation the policy networks consume is float32; error ~1e-6 of the channel maximum). */
 #define OBS_THREADS 256
-#define OBS_CHUNK 16
-#define OBS_EPT 40            /* output cells per thread per pass: 256 * 40 >= 100 * 100 */
+#define OBS_TI 4
+#define OBS_TJ 10
 
-struct ObsSrc { double x0, y0, hx, hy, w; int mode; };     /* mode 0: (w*gx)*gy ; 1: gx*gy*w/mtm */
+struct ObsSrc { double x0, y0, hx, hy, w; int mode; };     /* mode 0: (w*gx)*gy ; 1: ((gx*gy)*w)/mtm */
 
-template <typename OutT>
-__global__ void __launch_bounds__(OBS_THREADS) k_observe(const KParams P, const int32_t *agent_id, OutT *obs) {
+template <typename AccT>
+__global__ void __launch_bounds__(OBS_THREADS) k_observe(const KParams P, const int32_t *agent_id, AccT *obs) {
+    constexpr int CH = sizeof(AccT) == 4 ? 32 : 16;
     extern __shared__ uint4 smem_u4[];
-    double *gx = reinterpret_cast<double *>(smem_u4);                 /* [OBS_CHUNK][S] */
     const int S = P.d.S, N = P.d.N, M = P.d.M;
-    double *gy = gx + OBS_CHUNK * S;                                  /* [OBS_CHUNK][S] */
-    __shared__ ObsSrc src[OBS_CHUNK];
+    const int tiles_i = (S + OBS_TI - 1) / OBS_TI, tiles_j = (S + OBS_TJ - 1) / OBS_TJ;
+    const int PI = tiles_i * OBS_TI, PJ = (tiles_j * OBS_TJ + 3) & ~3;        /* padded vector lengths */
+    AccT *gx = reinterpret_cast<AccT *>(smem_u4);                             /* [CH][PI] */
+    AccT *gy = gx + CH * PI;                                                  /* [CH][PJ] */
+    __shared__ ObsSrc src[CH];
     __shared__ int nsrc_s;
     const int b = blockIdx.x, tid = threadIdx.x;
     const int ag = agent_id[b];
@@ -128,83 +103,106 @@ __global__ void __launch_bounds__(OBS_THREADS) k_observe(const KParams P, const 
     const double f0 = par[WRSN_P_F0], f1 = par[WRSN_P_F1], f2 = par[WRSN_P_F2], f3 = par[WRSN_P_F3];
     const double Wd = f1 - f0, Hd = f3 - f2;
     const double unit = 1.0 / (double)S, start = unit / 2.0, delta = (start + unit) - start;   /* np.arange(unit/2, 1.0, unit) */
-    const double R = par[WRSN_P_MC_R];
+    const double R = par[WRSN_P_MC_R], mtm = par[WRSN_P_MTM];
     const double *me = mc + (size_t)ag * WRSN_MC_LEN;
     const int SS = S * S;
-    OutT *out = obs + (size_t)b * 4 * SS;
+    AccT *out = obs + (size_t)b * 4 * SS;
+    const int n_tiles = tiles_i * tiles_j;
 
-    for (int base = 0; base < SS; base += OBS_THREADS * OBS_EPT) {
+    for (int tbase = 0; tbase < n_tiles; tbase += OBS_THREADS) {
+        const int tile = tbase + tid;
+        const bool has_tile = tile < n_tiles;
+        const int ti = has_tile ? tile / tiles_j : 0, tj = has_tile ? tile - ti * tiles_j : 0;
+        const int i0 = ti * OBS_TI, j0 = tj * OBS_TJ;
         for (int ch = 0; ch < 4; ch++) {
-            double acc[OBS_EPT];
+            AccT acc[OBS_TI][OBS_TJ];
 #pragma unroll
-            for (int k = 0; k < OBS_EPT; k++) acc[k] = 0.0;
+            for (int r = 0; r < OBS_TI; r++)
+#pragma unroll
+                for (int q = 0; q < OBS_TJ; q++) acc[r][q] = (AccT)0;
             const int total = ch == 0 ? N : (ch == 1 ? 1 : M);
-            for (int s0 = 0; s0 < total; s0 += OBS_CHUNK) {
+            for (int s0 = 0; s0 < total; s0 += CH) {
                 __syncthreads();
-                if (tid == 0) {                      /* gather this chunk's sources, in id order */
-                    int n = 0;
-                    for (int s = s0; s < total && s < s0 + OBS_CHUNK; s++) {
-                        ObsSrc q; q.mode = 0;
+                if (tid < 32) {                      /* gather this chunk's sources, compacted in id order (CH <= 32) */
+                    const int s = s0 + tid;
+                    bool use = tid < CH && s < total;
+                    ObsSrc q; q.mode = 0; q.x0 = q.y0 = q.w = 0.0; q.hx = q.hy = 1.0;
+                    if (use) {
                         if (ch == 0) {
-                            if (status[s] == 0) continue;
-                            q.x0 = (nx[s] - f0) / Wd; q.y0 = (ny[s] - f2) / Hd; q.hx = R / Wd; q.hy = R / Hd;
-                            q.w = (cs[s] / par[WRSN_P_MC_AB2]) / ((energy[s] - par[WRSN_P_THR]) / par[WRSN_P_CAPMTHR]);
+                            use = status[s] != 0;
+                            if (use) {
+                                q.x0 = (nx[s] - f0) / Wd; q.y0 = (ny[s] - f2) / Hd; q.hx = R / Wd; q.hy = R / Hd;
+                                q.w = (cs[s] / par[WRSN_P_MC_AB2]) / ((energy[s] - par[WRSN_P_THR]) / par[WRSN_P_CAPMTHR]);
+                            }
                         } else if (ch == 1) {
                             double tmp = fmin(Hd, Wd);
                             q.x0 = (me[WRSN_MC_X] - f0) / Wd; q.y0 = (me[WRSN_MC_Y] - f2) / Hd;
                             q.hx = 0.5 * tmp / Wd; q.hy = 0.5 * tmp / Hd;
                             q.w = me[WRSN_MC_ENERGY] / par[WRSN_P_MC_CAP];
                         } else {
-                            if (s == ag) continue;
                             const double *an = mc + (size_t)s * WRSN_MC_LEN;
-                            bool charging = an[WRSN_MC_TYPE] != 0.0;
-                            if (ch == 2 ? !charging : charging) continue;
-                            q.x0 = (an[WRSN_MC_CPA0] - f0) / Wd; q.y0 = (an[WRSN_MC_CPA1] - f2) / Hd; q.hx = R / Wd; q.hy = R / Hd;
-                            if (ch == 2) q.w = an[WRSN_MC_CPA2] / par[WRSN_P_CTM];
-                            else {                   /* the observer's destination y */
-                                double dx = an[WRSN_MC_X] - an[WRSN_MC_CPA0], dy = an[WRSN_MC_Y] - me[WRSN_MC_CPA1];
-                                q.w = sqrt(dx * dx + dy * dy) / par[WRSN_P_MC_V];
-                                q.mode = 1;
+                            const bool charging = an[WRSN_MC_TYPE] != 0.0;
+                            use = s != ag && (ch == 2 ? charging : !charging);
+                            if (use) {
+                                q.x0 = (an[WRSN_MC_CPA0] - f0) / Wd; q.y0 = (an[WRSN_MC_CPA1] - f2) / Hd; q.hx = R / Wd; q.hy = R / Hd;
+                                if (ch == 2) q.w = an[WRSN_MC_CPA2] / par[WRSN_P_CTM];
+                                else {               /* the observer's destination y */
+                                    double dx = an[WRSN_MC_X] - an[WRSN_MC_CPA0], dy = an[WRSN_MC_Y] - me[WRSN_MC_CPA1];
+                                    q.w = sqrt(dx * dx + dy * dy) / par[WRSN_P_MC_V];
+                                    q.mode = 1;
+                                }
                             }
                         }
-                        src[n++] = q;
                     }
-                    nsrc_s = n;
+                    const unsigned bal = __ballot_sync(0xffffffffu, use);
+                    if (use) src[__popc(bal & ((1u << tid) - 1u))] = q;
+                    if (tid == 0) nsrc_s = __popc(bal);
                 }
                 __syncthreads();
                 const int n = nsrc_s;
-                for (int k = tid; k < n * S; k += OBS_THREADS) {
-                    int q = k / S, i = k - q * S;
-                    double cc = start + (double)i * delta;
-                    double ux = cc - src[q].x0, uy = cc - src[q].y0;
-                    double ex = exp(ux * ux / (-2.0 * (src[q].hx * src[q].hx)));
-                    double ey = exp(uy * uy / (-2.0 * (src[q].hy * src[q].hy)));
-                    gx[k] = src[q].mode == 0 ? src[q].w * ex : ex;
-                    gy[k] = ey;
+                if (n == 0) continue;
+                for (int k = tid; k < n * PI; k += OBS_THREADS) {
+                    const int q = k / PI, i = k - q * PI;
+                    const double u = (start + (double)i * delta) - src[q].x0;
+                    const double e = i < S ? exp(u * u / (-2.0 * (src[q].hx * src[q].hx))) : 0.0;
+                    gx[k] = (AccT)(src[q].mode == 0 ? src[q].w * e : e);
+                }
+                for (int k = tid; k < n * PJ; k += OBS_THREADS) {
+                    const int q = k / PJ, j = k - q * PJ;
+                    const double u = (start + (double)j * delta) - src[q].y0;
+                    gy[k] = (AccT)(j < S ? exp(u * u / (-2.0 * (src[q].hy * src[q].hy))) : 0.0);
                 }
                 __syncthreads();
+                if (!has_tile) continue;
                 for (int q = 0; q < n; q++) {
-                    const double *gxq = gx + q * S, *gyq = gy + q * S;
+                    AccT a[OBS_TI], v[OBS_TJ];
+#pragma unroll
+                    for (int r = 0; r < OBS_TI; r++) a[r] = gx[q * PI + i0 + r];
+#pragma unroll
+                    for (int x = 0; x < OBS_TJ; x++) v[x] = gy[q * PJ + j0 + x];
                     if (src[q].mode == 0) {
 #pragma unroll
-                        for (int k = 0; k < OBS_EPT; k++) {
-                            int o = base + tid + k * OBS_THREADS;
-                            if (o < SS) { int i = o / S, j = o - i * S; acc[k] += gxq[i] * gyq[j]; }
-                        }
-                    } else {
-                        const double w = src[q].w, mtm = par[WRSN_P_MTM];
+                        for (int r = 0; r < OBS_TI; r++)
 #pragma unroll
-                        for (int k = 0; k < OBS_EPT; k++) {
-                            int o = base + tid + k * OBS_THREADS;
-                            if (o < SS) { int i = o / S, j = o - i * S; acc[k] += gxq[i] * gyq[j] * w / mtm; }
-                        }
+                            for (int x = 0; x < OBS_TJ; x++) {
+                                if (sizeof(AccT) == 4) acc[r][x] = fmaf((float)a[r], (float)v[x], (float)acc[r][x]);
+                                else acc[r][x] = acc[r][x] + a[r] * v[x];       /* -fmad=false: two roundings, as numpy */
+                            }
+                    } else {
+                        const AccT w = (AccT)src[q].w, d = (AccT)mtm;
+#pragma unroll
+                        for (int r = 0; r < OBS_TI; r++)
+#pragma unroll
+                            for (int x = 0; x < OBS_TJ; x++) acc[r][x] = acc[r][x] + a[r] * v[x] * w / d;
                     }
                 }
             }
+            if (has_tile) {
 #pragma unroll
-            for (int k = 0; k < OBS_EPT; k++) {
-                int o = base + tid + k * OBS_THREADS;
-                if (o < SS) out[(size_t)ch * SS + o] = (OutT)acc[k];
+                for (int r = 0; r < OBS_TI; r++)
+#pragma unroll
+                    for (int x = 0; x < OBS_TJ; x++)
+                        if (i0 + r < S && j0 + x < S) out[(size_t)ch * SS + (size_t)(i0 + r) * S + j0 + x] = acc[r][x];
             }
         }
     }
@@ -235,7 +233,7 @@ int wrsn_dims_finalize(wrsn_dims *d) {
     d->Npad = (d->N + 15) & ~15;
     d->W = (d->N + 31) / 32;
     d->Tw = (d->T + 31) / 32; if (d->Tw < 1) d->Tw = 1;
-    d->n_slot = 2 * d->M + 2;
+    d->n_slot = d->M + 3;
     if (d->Emax < 1) d->Emax = 1;
     if (d->TEmax < 1) d->TEmax = 1;
     if (d->threads <= 0) {
@@ -282,12 +280,15 @@ static int launch_env(KParams &P, void *stream) {
     if (check_dims(&P.d)) return -1;
     wrsn_make_layout(&P.d, &P.L);
     if (!P.scen || !P.scen_id || !P.state) WRSN_FAIL("scen / scen_id / state must not be NULL");
-    static int64_t attr_bytes = 48 * 1024;           /* per template instance; the opt-in limit only ever grows */
-    if (P.L.smem_total > attr_bytes) {
-        WRSN_CUDA(cudaFuncSetAttribute(k_env<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.L.smem_total));
-        attr_bytes = P.L.smem_total;
+    static int64_t attr_bytes[2] = {48 * 1024, 48 * 1024};   /* per template instance; the opt-in limit only ever grows */
+    const int w = P.d.threads == 32 ? 0 : 1;
+    if (P.L.smem_total > attr_bytes[w]) {
+        if (w == 0) WRSN_CUDA(cudaFuncSetAttribute(g32::k_env<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.L.smem_total));
+        else WRSN_CUDA(cudaFuncSetAttribute(gany::k_env<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.L.smem_total));
+        attr_bytes[w] = P.L.smem_total;
     }
-    k_env<MODE><<<P.d.B, P.d.threads, (size_t)P.L.smem_total, (cudaStream_t)stream>>>(P);
+    if (w == 0) g32::k_env<MODE><<<P.d.B, 32, (size_t)P.L.smem_total, (cudaStream_t)stream>>>(P);
+    else gany::k_env<MODE><<<P.d.B, P.d.threads, (size_t)P.L.smem_total, (cudaStream_t)stream>>>(P);
     WRSN_CUDA(cudaGetLastError());
     return 0;
 }
@@ -356,13 +357,17 @@ int wrsn_observe(const wrsn_dims *d, const void *scen, const int32_t *scen_id, c
     if (!agent_id || !obs || !scen || !scen_id || !state) WRSN_FAIL("NULL argument");
     KParams P = base_params(d, scen, scen_id, const_cast<void *>(state), nullptr);
     wrsn_make_layout(&P.d, &P.L);
-    size_t smem = sizeof(double) * 2 * OBS_CHUNK * (size_t)d->S;
-    if (smem > 200 * 1024) WRSN_FAIL("map_size too large");
+    const int tiles_i = (d->S + OBS_TI - 1) / OBS_TI, tiles_j = (d->S + OBS_TJ - 1) / OBS_TJ;
+    const size_t vec = (size_t)tiles_i * OBS_TI + (size_t)((tiles_j * OBS_TJ + 3) & ~3);
     if (obs_f64) {
-        if (smem > 48 * 1024) WRSN_CUDA(cudaFuncSetAttribute(k_observe<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        size_t smem = sizeof(double) * 16 * vec;
+        if (smem > 200 * 1024) WRSN_FAIL("map_size too large");
+        if (smem > 48 * 1024) WRSN_CUDA(cudaFuncSetAttribute(k_observe<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         k_observe<double><<<d->B, OBS_THREADS, smem, (cudaStream_t)stream>>>(P, agent_id, (double *)obs);
     } else {
-        if (smem > 48 * 1024) WRSN_CUDA(cudaFuncSetAttribute(k_observe<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        size_t smem = sizeof(float) * 32 * vec;
+        if (smem > 200 * 1024) WRSN_FAIL("map_size too large");
+        if (smem > 48 * 1024) WRSN_CUDA(cudaFuncSetAttribute(k_observe<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         k_observe<float><<<d->B, OBS_THREADS, smem, (cudaStream_t)stream>>>(P, agent_id, (float *)obs);
     }
     WRSN_CUDA(cudaGetLastError());

@@ -12,6 +12,8 @@
 #include <stdlib.h>
 #include <vector>
 
+#include "wrsn_layout.h"
+#define WRSN_GFIX 1
 #include "wrsn_engine.cuh"
 
 static thread_local char g_err[512] = "";
@@ -82,7 +84,7 @@ int wrsn_field_count(int which) {
 }
 int wrsn_dims_finalize(wrsn_dims *d) {
     d->Npad = (d->N + 15) & ~15; d->W = (d->N + 31) / 32; d->Tw = (d->T + 31) / 32; if (d->Tw < 1) d->Tw = 1;
-    d->n_slot = 2 * d->M + 2; if (d->Emax < 1) d->Emax = 1; if (d->TEmax < 1) d->TEmax = 1;
+    d->n_slot = d->M + 3; if (d->Emax < 1) d->Emax = 1; if (d->TEmax < 1) d->TEmax = 1;
     d->threads = 32;
     WrsnLayout L; wrsn_make_layout(d, &L);
     d->state_bytes = (int32_t)L.total; d->state_resident_bytes = (int32_t)L.resident;

@@ -100,8 +100,13 @@ def check_episode(name, device, check_obs=False, replicas=1):
                 if i in full:
                     np.testing.assert_allclose(obs[b], g["full_state"][full[i]], rtol=1e-9, atol=1e-12)
             if i in full:
-                obs32 = _np(env.get_state(dtype=torch.float32))
-                np.testing.assert_allclose(obs32[0], g["full_state"][full[i]], rtol=2e-6, atol=1e-6)
+                # float32 observation (what the policy networks consume; fp32 FFMA accumulation of fp64 exponentials):
+                # within 1e-5 of the channel maximum, the tolerance the north star sets for floating-point state
+                obs32 = _np(env.get_state(dtype=torch.float32)).astype(np.float64)
+                ref = g["full_state"][full[i]]
+                for ch in range(4):
+                    tol = 1e-5 * max(float(np.abs(ref[ch]).max()), 1e-3)
+                    assert float(np.abs(obs32[0][ch] - ref[ch]).max()) <= tol, (name, i, ch)
     fm = _np(env.get_network_fitness()[1])
     if np.isfinite(g["fitness_min"][n - 1]):
         np.testing.assert_allclose(fm[0], g["fitness_min"][n - 1], rtol=1e-12)
