@@ -276,4 +276,5 @@ class BatchedWRSN:
         h = self.view("hdr")
         E = self.E
         return {k: float(h[:, E["WRSN_H_" + n]].sum().item()) for k, n in
-                (("ticks", "NTICKS"), ("events", "NEVENTS"), ("serial_ticks", "NSLOW"), ("bfs", "NBFS"), ("decisions", "NDECISIONS"))}
+                (("ticks", "NTICKS"), ("events", "NEVENTS"), ("serial_ticks", "NSLOW"), ("bfs", "NBFS"),
+                 ("stale_rebuilds", "NSTALE"), ("decisions", "NDECISIONS"))}

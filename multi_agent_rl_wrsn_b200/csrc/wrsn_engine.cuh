@@ -40,13 +40,16 @@
 #endif
 
 #undef WRSN_D
+#undef WRSN_DI
 #undef WRSN_NOINLINE
 #undef WRSN_GSZ
 #if defined(WRSN_HOST_EMU)
 #define WRSN_D static inline
+#define WRSN_DI static inline
 #define WRSN_NOINLINE static
 #else
 #define WRSN_D __device__ static
+#define WRSN_DI __device__ __forceinline__ static      /* takes the register-resident clock by reference: must inline */
 #define WRSN_NOINLINE __device__ __noinline__ static   /* cold or shared code kept out of the hot loop's I-cache footprint */
 #endif
 #if WRSN_GFIX
@@ -301,11 +304,11 @@ struct Clk {
 WRSN_D double *slot_of(Ctx &c, int s) { return c.proc + s * WRSN_PR_LEN; }
 WRSN_D int *slot_i(double *p) { return (int *)p; }
 WRSN_D double *mc_of(Ctx &c, int a) { return c.mc + a * WRSN_MC_LEN; }
-WRSN_D double take_seq(Clk &k) { double s = k.seq; k.seq = s + 1.0; return s; }
+WRSN_DI double take_seq(Clk &k) { double s = k.seq; k.seq = s + 1.0; return s; }
 WRSN_D double take_seq_h(Ctx &c) { double s = c.hdr[WRSN_H_SEQ]; c.hdr[WRSN_H_SEQ] = s + 1.0; return s; }
-WRSN_D bool ev_before(double t, double key, double bt, double bkey) { return t < bt || (t == bt && key < bkey); }
+WRSN_DI bool ev_before(double t, double key, double bt, double bkey) { return t < bt || (t == bt && key < bkey); }
 
-WRSN_D void clk_load(Ctx &c, Clk &k) {
+WRSN_DI void clk_load(Ctx &c, Clk &k) {
     const double *h = c.hdr;
     k.now = h[WRSN_H_NOW]; k.seq = h[WRSN_H_SEQ]; k.nev = 0.0;
     k.net_t = h[WRSN_H_NET_ON] != 0.0 ? h[WRSN_H_NET_T] : INFINITY; k.net_key = WRSN_KEY_NORMAL + h[WRSN_H_NET_SEQ];
@@ -315,7 +318,7 @@ WRSN_D void clk_load(Ctx &c, Clk &k) {
     k.until_t = h[WRSN_H_UNTIL_ON] != 0.0 ? h[WRSN_H_UNTIL_T] : INFINITY; k.until_key = h[WRSN_H_UNTIL_SEQ];   /* URGENT */
     k.stop = 0; k.mc_idx = -1; k.mc_t = INFINITY; k.mc_key = 0.0; k.mc_other_t = INFINITY;
 }
-WRSN_D void clk_store(Ctx &c, const Clk &k) {
+WRSN_DI void clk_store(Ctx &c, const Clk &k) {
     gsync(c);
     if (c.tid == 0) {
         double *h = c.hdr;
@@ -332,7 +335,7 @@ WRSN_D void clk_store(Ctx &c, const Clk &k) {
 }
 
 /* earliest pending slot / condition event and the earliest time among the others (all threads, broadcast loads) */
-WRSN_D void mc_scan(Ctx &c, Clk &k) {
+WRSN_DI void mc_scan(Ctx &c, Clk &k) {
     int bi = -1;
     double bt = INFINITY, bkey = 0.0, ot = INFINITY;
     const int ns = c.n_slot;
@@ -374,17 +377,62 @@ WRSN_NOINLINE void leave_uniform(Ctx &c) {
     gsync(c);
 }
 
-/* ------------------------------------------------------------------ Network.setLevels + check_targets (Network.py:37-66,84)
- * plus the routing tree the drain tick replays: receiver (Node.find_receiver :92-100), e_send, relay counts,
- * and the per-tick log_energy of every node. */
-WRSN_NOINLINE void do_bfs(Ctx &c) {
-    leave_uniform(c);
+/* Routing tree for the current `level` / `status` rows: receiver of every node (Node.find_receiver :92-100, first
+ * nearest alive neighbour of lower level; the base station for direct nodes), its transmit cost, the relay counts and
+ * the per-tick log_energy.  With fresh levels every reached node has a receiver; with STALE levels (Network.operate
+ * has stopped, later deaths) a chain can end at a node without receiver: that node still pays the receive cost of what
+ * its children send, forwards nothing (e_send = 0) and sends nothing itself — as the reference does. */
+WRSN_NOINLINE void build_tree(Ctx &c) {
     const int N = c.N;
     int *cnt = (int *)c.scr0;                       /* 2 ints per node: relayed packets from lower / higher ids */
     for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
-        c.level[i] = (c.status[i] == 1 && c.direct[i]) ? 1 : -1;
         cnt[2 * i] = 0; cnt[2 * i + 1] = 0;
+        int par = -1; double es = 0.0;
+        if (c.status[i] == 1 && c.level[i] >= 1) {
+            if (c.direct[i]) { par = -2; es = c.bs_esend[i]; }
+            else {
+                double bd = 0.0; int lv = c.level[i];
+                for (int e = c.nbr_ptr[i]; e < c.nbr_ptr[i + 1]; e++) {
+                    int j = c.nbr_idx[e];
+                    if (c.level[j] < lv && c.status[j] == 1) {
+                        double dd = c.nbr_dist[e];
+                        if (par < 0 || dd < bd) { par = j; bd = dd; es = c.nbr_esend[e]; }   /* np.argmin: first minimum */
+                    }
+                }
+            }
+        }
+        c.parent[i] = (int16_t)par; c.esend[i] = es;
     }
+    gsync(c);
+    /* relay counts: every packet of source s crosses its ancestors up to the base station (or the chain's end) */
+    for (int s = c.tid; s < N; s += WRSN_GSZ(c)) {
+        int ow = c.own[s];
+        if (c.status[s] != 1 || ow == 0 || c.parent[s] == -1) continue;
+        for (int h = c.parent[s]; h >= 0; h = c.parent[h]) atomic_add_i32(&cnt[2 * h + (s < h ? 0 : 1)], ow);
+    }
+    gsync(c);
+    const double er = c.par[WRSN_P_ERECV];
+    for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
+        int nb = cnt[2 * i], na = cnt[2 * i + 1];
+        c.nbef[i] = (uint16_t)nb; c.naft[i] = (uint16_t)na;
+        double lg = 0.0, es = c.esend[i];
+        if (c.status[i] == 1) {
+            for (int k = 0; k < nb; k++) { lg += es; lg += er; }
+            int ow = c.parent[i] != -1 ? (int)c.own[i] : 0;
+            for (int k = 0; k < ow; k++) lg += es;
+            for (int k = 0; k < na; k++) { lg += es; lg += er; }
+        }
+        c.logc[i] = lg;
+    }
+    gsync(c);
+}
+
+/* ------------------------------------------------------------------ Network.setLevels + check_targets (Network.py:37-66,84),
+ * then the routing tree the drain tick replays. */
+WRSN_NOINLINE void do_bfs(Ctx &c) {
+    leave_uniform(c);
+    const int N = c.N;
+    for (int i = c.tid; i < N; i += WRSN_GSZ(c)) c.level[i] = (c.status[i] == 1 && c.direct[i]) ? 1 : -1;
     for (int w = c.tid; w < c.Tw; w += WRSN_GSZ(c)) c.tact[w] = 0u;
     gsync(c);
     for (int cur = 1;; cur++) {
@@ -411,46 +459,7 @@ WRSN_NOINLINE void do_bfs(Ctx &c) {
         if ((c.tact[w] & full) != full) dead_t = 1;
     }
     dead_t = red_or(c, dead_t);
-    /* receivers */
-    for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
-        int par = -1; double es = 0.0;
-        if (c.status[i] == 1 && c.level[i] >= 1) {
-            if (c.direct[i]) { par = -2; es = c.bs_esend[i]; }
-            else {
-                double bd = 0.0; int lv = c.level[i];
-                for (int e = c.nbr_ptr[i]; e < c.nbr_ptr[i + 1]; e++) {
-                    int j = c.nbr_idx[e];
-                    if (c.level[j] < lv && c.status[j] == 1) {
-                        double dd = c.nbr_dist[e];
-                        if (par < 0 || dd < bd) { par = j; bd = dd; es = c.nbr_esend[e]; }   /* np.argmin: first minimum */
-                    }
-                }
-            }
-        }
-        c.parent[i] = (int16_t)par; c.esend[i] = es;
-    }
-    gsync(c);
-    /* relay counts: every packet of source s crosses all its ancestors */
-    for (int s = c.tid; s < N; s += WRSN_GSZ(c)) {
-        int ow = c.own[s];
-        if (c.status[s] != 1 || ow == 0 || c.parent[s] == -1) continue;
-        for (int h = c.parent[s]; h >= 0; h = c.parent[h]) atomic_add_i32(&cnt[2 * h + (s < h ? 0 : 1)], ow);
-    }
-    gsync(c);
-    const double er = c.par[WRSN_P_ERECV];
-    for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
-        int nb = cnt[2 * i], na = cnt[2 * i + 1];
-        c.nbef[i] = (uint16_t)nb; c.naft[i] = (uint16_t)na;
-        double lg = 0.0, es = c.esend[i];
-        if (c.status[i] == 1 && c.parent[i] != -1) {
-            for (int k = 0; k < nb; k++) { lg += es; lg += er; }
-            int ow = c.own[i];
-            for (int k = 0; k < ow; k++) lg += es;
-            for (int k = 0; k < na; k++) { lg += es; lg += er; }
-        }
-        c.logc[i] = lg;
-    }
-    gsync(c);
+    build_tree(c);
     if (c.tid == 0) {
         c.hdr[WRSN_H_ALIVE] = dead_t ? 0.0 : 1.0;
         c.hdr[WRSN_H_BFS_DIRTY] = 0.0;
@@ -486,9 +495,11 @@ WRSN_NOINLINE int drain_serial(Ctx &c) {
                     }
                     c.energy[h] -= er;
                 }
-                int recv = -1; double es = 0.0;      /* send_package */
-                if (c.direct[h]) { recv = -2; es = c.bs_esend[h]; }
-                else {
+                /* send_package: find_receiver() = the tree's receiver unless that node died earlier in this very tick
+                   (a death can only remove candidates, never bring a nearer one), then the literal neighbour scan */
+                int recv = c.parent[h]; double es = c.esend[h];
+                if (recv >= 0 && c.status[recv] != 1) {
+                    recv = -1; es = 0.0;
                     double bd = 0.0; int lv = c.level[h];
                     for (int e = c.nbr_ptr[h]; e < c.nbr_ptr[h + 1]; e++) {
                         int j = c.nbr_idx[e];
@@ -519,7 +530,14 @@ WRSN_D void ev_nodes_drain(Ctx &c) {
     const int N = c.N;
     const double thr = c.par[WRSN_P_THR], cap = c.par[WRSN_P_CAP], er = c.par[WRSN_P_ERECV];
     const double slack = 1e-6;
-    int slow = c.hdr[WRSN_H_BFS_DIRTY] != 0.0 ? 1 : 0;   /* routing tree is stale (Network.operate has stopped): serial path */
+    if (c.hdr[WRSN_H_BFS_DIRTY] != 0.0) {            /* a death after Network.operate stopped: levels stay stale (as in the
+                                                        reference), only the receivers / relay counts are rebuilt */
+        leave_uniform(c);
+        build_tree(c);
+        if (c.tid == 0) { c.hdr[WRSN_H_BFS_DIRTY] = 0.0; c.hdr[WRSN_H_NSTALE] += 1.0; }
+        gsync(c);
+    }
+    int slow = 0;
     _Pragma("unroll 1")
     for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
         if (c.status[i] != 1) continue;
@@ -723,12 +741,12 @@ WRSN_D double charge_rate_xy(Ctx &c, double mx, double my, int node) {   /* alph
 }
 
 /* schedule the slot's next event (all threads keep the clock, thread 0 stores) */
-WRSN_D void slot_sched(Ctx &c, Clk &k, double *p, int pc, int prio, double delay) {
+WRSN_DI void slot_sched(Ctx &c, Clk &k, double *p, int pc, int prio, double delay) {
     double t = k.now + delay, key = take_seq(k) + (prio ? WRSN_KEY_NORMAL : 0.0);
     if (c.tid == 0) { slot_i(p)[WRSN_PRI_PC] = pc; p[WRSN_PR_T] = t; p[WRSN_PR_KEY] = key; }
 }
 
-WRSN_D void cond_check(Ctx &c, Clk &k, int j) {   /* simpy Condition._check for AnyOf (all threads; state read before) */
+WRSN_DI void cond_check(Ctx &c, Clk &k, int j) {   /* simpy Condition._check for AnyOf (all threads; state read before) */
     double *h = c.hdr;
     if (h[WRSN_H_COND_TRIG + j] != 0.0) return;
     double s = take_seq(k);
@@ -747,7 +765,7 @@ WRSN_D void cond_check_h(Ctx &c, int j) {          /* leader-only variant used w
  * (process start / completion hops of the generator tree) are executed back to back as long as NO other event of the
  * environment is due at the current instant (`other_t` > now): then the (time, priority, counter) order would pick
  * them next anyway; every hop still draws its insertion counter, so later ties resolve as in the reference. */
-WRSN_D void ev_slot(Ctx &c, Clk &k, int s, double other_t) {
+WRSN_DI void ev_slot(Ctx &c, Clk &k, int s, double other_t) {
     double *p = slot_of(c, s);
     const int a = slot_i(p)[WRSN_PRI_AGENT];
     double *m = mc_of(c, a);
@@ -945,7 +963,7 @@ WRSN_D void ev_slot(Ctx &c, Clk &k, int s, double other_t) {
 }
 
 /* a condition event of the AnyOf chain */
-WRSN_D void ev_cond(Ctx &c, Clk &k, int j) {
+WRSN_DI void ev_cond(Ctx &c, Clk &k, int j) {
     double *h = c.hdr;
     const int nch = (int)h[WRSN_H_CHAIN_N];
     double det = h[WRSN_H_CHAIN_DETACH];
@@ -960,12 +978,13 @@ WRSN_D void ev_cond(Ctx &c, Clk &k, int j) {
 }
 
 /* ------------------------------------------------------------------ the event loop: env.run(...) */
-WRSN_D void run_loop(Ctx &c) {
+WRSN_DI void run_loop(Ctx &c) {
     Clk k;
     clk_load(c, k);
-    mc_scan(c, k);
     const double maxtime = c.par[WRSN_P_MAXTIME];
+    bool rescan = true;
     for (long guard = 0; guard < 400000000L; guard++) {
+        if (rescan) { mc_scan(c, k); rescan = false; }
         /* earliest of the grid items (Network.operate, update_reward, the node block, run(until=t)) */
         int gk = K_NODES;
         double gt = k.nodes_t, gkey = k.nodes_key;
@@ -978,7 +997,7 @@ WRSN_D void run_loop(Ctx &c) {
                 double other = fmin(fmin(k.mc_other_t, k.nodes_t), fmin(fmin(k.net_t, k.ur_t), k.until_t));
                 ev_slot(c, k, k.mc_idx, other);
             } else ev_cond(c, k, k.mc_idx - c.n_slot);
-            mc_scan(c, k);
+            rescan = true;
         } else {
             k.now = gt;
             k.nev += 1.0;

@@ -161,26 +161,27 @@ __global__ void __launch_bounds__(OBS_THREADS) k_observe(const KParams P, const 
                 __syncthreads();
                 const int n = nsrc_s;
                 if (n == 0) continue;
-                for (int k = tid; k < n * PI; k += OBS_THREADS) {
-                    const int q = k / PI, i = k - q * PI;
-                    const double u = (start + (double)i * delta) - src[q].x0;
-                    const double e = i < S ? exp(u * u / (-2.0 * (src[q].hx * src[q].hx))) : 0.0;
-                    gx[k] = (AccT)(src[q].mode == 0 ? src[q].w * e : e);
-                }
-                for (int k = tid; k < n * PJ; k += OBS_THREADS) {
-                    const int q = k / PJ, j = k - q * PJ;
-                    const double u = (start + (double)j * delta) - src[q].y0;
-                    gy[k] = (AccT)(j < S ? exp(u * u / (-2.0 * (src[q].hy * src[q].hy))) : 0.0);
+                /* one exponential per (source, coordinate): threads [0, PI) fill gx, threads [PI, PI + PJ) fill gy */
+                for (int t = tid; t < PI + PJ; t += OBS_THREADS) {
+                    const bool isx = t < PI;
+                    const int i = isx ? t : t - PI;
+                    const double cc = start + (double)i * delta;
+                    for (int q = 0; q < n; q++) {
+                        const double u = cc - (isx ? src[q].x0 : src[q].y0), h = isx ? src[q].hx : src[q].hy;
+                        double e = i < S ? exp(u * u / (-2.0 * (h * h))) : 0.0;
+                        if (isx) gx[q * PI + i] = (AccT)(src[q].mode == 0 ? src[q].w * e : e);
+                        else gy[q * PJ + i] = (AccT)e;
+                    }
                 }
                 __syncthreads();
                 if (!has_tile) continue;
-                for (int q = 0; q < n; q++) {
-                    AccT a[OBS_TI], v[OBS_TJ];
+                if (ch != 3) {
+                    for (int q = 0; q < n; q++) {
+                        AccT a[OBS_TI], v[OBS_TJ];
 #pragma unroll
-                    for (int r = 0; r < OBS_TI; r++) a[r] = gx[q * PI + i0 + r];
+                        for (int r = 0; r < OBS_TI; r++) a[r] = gx[q * PI + i0 + r];
 #pragma unroll
-                    for (int x = 0; x < OBS_TJ; x++) v[x] = gy[q * PJ + j0 + x];
-                    if (src[q].mode == 0) {
+                        for (int x = 0; x < OBS_TJ; x++) v[x] = gy[q * PJ + j0 + x];
 #pragma unroll
                         for (int r = 0; r < OBS_TI; r++)
 #pragma unroll
@@ -188,12 +189,15 @@ __global__ void __launch_bounds__(OBS_THREADS) k_observe(const KParams P, const 
                                 if (sizeof(AccT) == 4) acc[r][x] = fmaf((float)a[r], (float)v[x], (float)acc[r][x]);
                                 else acc[r][x] = acc[r][x] + a[r] * v[x];       /* -fmad=false: two roundings, as numpy */
                             }
-                    } else {
+                    }
+                } else {
+                    for (int q = 0; q < n; q++) {
                         const AccT w = (AccT)src[q].w, d = (AccT)mtm;
 #pragma unroll
                         for (int r = 0; r < OBS_TI; r++)
 #pragma unroll
-                            for (int x = 0; x < OBS_TJ; x++) acc[r][x] = acc[r][x] + a[r] * v[x] * w / d;
+                            for (int x = 0; x < OBS_TJ; x++)
+                                acc[r][x] = acc[r][x] + gx[q * PI + i0 + r] * gy[q * PJ + j0 + x] * w / d;
                     }
                 }
             }

@@ -172,3 +172,23 @@ def check_vs_oracle(scenarios, device, num_envs, steps, seed, num_agent=3, mc=No
                 oreq[b] = oracles[b].step(int(aid[b]), acts[k, b], want_state=check_obs)
     assert float(_np(env.hdr("ERR")).max()) == 0.0
     return n_dec, env.counters()
+
+
+def check_network_after_operate_stopped(scenario, device, horizon, every=50.0):
+    """Nodes keep running after Network.operate has finished (alive == 0): levels stay stale, later deaths re-route
+    through the stale levels (Node.find_receiver) — engine vs oracle far past the end of Network.operate."""
+    env = BatchedWRSN(scenario, num_agent=0, num_envs=1, device=device)
+    env.init_network(with_reward_process=False)
+    o = OracleWRSN(scenario_from_dict(scenario.to_dict()), num_agent=0)
+    o.start_network_only()
+    t = 0.25
+    while t < horizon:
+        env.run_until(t)
+        o.run_until(t)
+        nd = o.nodes()
+        assert np.array_equal(_np(env.view("status"))[0], nd["status"]), t
+        assert np.array_equal(_np(env.view("level"))[0].astype(np.int32), nd["level"]), t
+        np.testing.assert_allclose(_np(env.view("energy"))[0], nd["energy"], rtol=E_RTOL)
+        np.testing.assert_allclose(_np(env.view("cs"))[0], nd["cs"], rtol=E_RTOL)
+        t += every
+    return env.counters(), int((nd["status"] == 0).sum())

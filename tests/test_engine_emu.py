@@ -61,3 +61,11 @@ def test_small_charger_exhaustion_vs_oracle():
     mc = dict(capacity=2500, threshold=0, velocity=5, pm=1, charging_range=27, alpha=4500, beta=30, epsilon=1e-10)
     sc = synthetic(num_nodes=50, num_targets=50, seed=4)
     pc.check_vs_oracle(sc, "cpu", num_envs=4, steps=50, seed=2, mc=mc, scale2=0.01)
+
+
+def test_deaths_after_network_operate_stopped():
+    """hanoi1000n50 far past the end of Network.operate: four more nodes die while the levels are stale."""
+    from tests.helpers import golden
+    sc = pc.sc_from_golden(golden("net_hanoi1000n50"))
+    cnt, dead = pc.check_network_after_operate_stopped(sc, "cpu", horizon=12000.0, every=100.0)
+    assert dead >= 5 and cnt["stale_rebuilds"] >= 4

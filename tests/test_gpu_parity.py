@@ -62,6 +62,14 @@ def test_small_charger_exhaustion_vs_oracle():
     pc.check_vs_oracle(sc, DEV, num_envs=6, steps=50, seed=2, mc=mc, scale2=0.01)
 
 
+def test_deaths_after_network_operate_stopped():
+    """hanoi1000n50 far past the end of Network.operate: four more nodes die while the levels are stale."""
+    from tests.helpers import golden
+    sc = pc.sc_from_golden(golden("net_hanoi1000n50"))
+    cnt, dead = pc.check_network_after_operate_stopped(sc, DEV, horizon=12000.0, every=100.0)
+    assert dead >= 5 and cnt["stale_rebuilds"] >= 4
+
+
 @pytest.mark.parametrize("threads", [32, 64, 128])
 def test_group_size_independent(threads):
     """The result must not depend on how many threads share an environment."""
