@@ -38,6 +38,8 @@ def parse():
     p.add_argument("--chargers", type=int, default=3)
     p.add_argument("--topologies", type=int, default=64, help="distinct synthetic scenarios per GPU")
     p.add_argument("--threads", type=int, default=0)
+    p.add_argument("--preroll", type=int, default=160, help="untimed steps before warm-up that desynchronise the episodes")
+    p.add_argument("--groups", type=int, default=4, help="asynchronous environment groups (CUDA streams) per GPU")
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -173,41 +175,22 @@ def run_b200(a):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B, M, S = a.envs, a.chargers, 100
-    env = BatchedWRSN(scenarios_for(a, rank), num_agent=M, num_envs=B, device=dev, threads=a.threads, map_size=S)
-    N, T = env.N, env.T
-    obs = torch.zeros((B, 4, S, S), dtype=torch.float32, device=dev)
+    B, M, S, G = a.envs, a.chargers, 100, max(1, a.groups)
+    if B % G:
+        raise SystemExit("--envs must be a multiple of --groups")
+    Bg = B // G
+    scs = scenarios_for(a, rank)
+    # G asynchronous groups of environments, one CUDA stream each: a group's launch waits only for ITS slowest
+    # environment, the other groups keep the SMs busy meanwhile (environments are independent; no collective).
+    groups = [BatchedWRSN(scs, num_agent=M, num_envs=Bg, device=dev, threads=a.threads, map_size=S,
+                          scenario_index=(np.arange(Bg) + g * Bg) % len(scs)) for g in range(G)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(G)]
+    N, T = groups[0].N, groups[0].T
+    obs = [torch.zeros((Bg, 4, S, S), dtype=torch.float32, device=dev) for _ in range(G)]
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
     scale = torch.tensor([1.0, 1.0, 0.05], dtype=torch.float64, device=dev)
     total = a.warmup + a.steps
-    launches = [0]
-
-    def one_step(action, events=None, acc=None):
-        """the public API a user calls: step -> observation of the deciding chargers -> reset of finished episodes
-        (+ their first observation).  No host synchronisation inside."""
-        req = env.req
-        aid = req.agent_id
-        m = aid >= 0
-        if acc is not None:
-            now_before = req.now.clone()
-        if events is not None:
-            events[0].record()
-        env.step(aid, action, mask=m)
-        if events is not None:
-            events[1].record()
-        env.get_state(out=obs)
-        if events is not None:
-            events[2].record()
-        done = req.agent_id < 0
-        if acc is not None:
-            acc[0] += (req.agent_id >= 0).sum()
-            acc[1] += torch.where(m, req.now - now_before, torch.zeros_like(req.now)).sum()
-        env.reset(mask=done)
-        env.get_state(out=obs, agent_id=torch.where(done, req.agent_id, torch.full_like(aid, -1)))
-        if acc is not None:
-            acc[0] += (done & (req.agent_id >= 0)).sum()
-        launches[0] += 4
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -215,76 +198,124 @@ def run_b200(a):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    def counters():
-        h = env.view("hdr")
-        E = env.E
-        return (float(h[:, E["WRSN_H_NDECISIONS"]].sum().item()), float(h[:, E["WRSN_H_NTICKS"]].sum().item()))
-
-    # ---- device-resident run (value): actions already in HBM
-    env.reset()
-    env.get_state(out=obs)
-    actions = torch.rand((total, B, 3), generator=gen, dtype=torch.float64, device=dev) * scale
-    for k in range(a.warmup):
-        one_step(actions[k])
+    # ---- device-resident run (value): the actions of every step are already in HBM
+    actions = [torch.rand((total, Bg, 3), generator=gen, dtype=torch.float64, device=dev) * scale for _ in range(G)]
+    for g in range(G):
+        groups[g].reset()
+        groups[g].get_state(out=obs[g])
     sync_all()
-    # NDECISIONS / NTICKS restart at every reset, so count decisions from the request records instead
-    dec_count = torch.zeros((), dtype=torch.int64, device=dev)
-    tick_acc = torch.zeros((), dtype=torch.float64, device=dev)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(a.steps)]
+
+    def group_step(g, k):
+        with torch.cuda.stream(streams[g]):
+            groups[g].rollout_step(actions[g][k % total], obs[g])   # 3 launches: step | reset finished episodes | observe
+
+    def totals():
+        """(decisions, simulated seconds) so far, from the kernels' own running totals"""
+        st = torch.stack([env.req.stats.sum(0) for env in groups]).sum(0)
+        return float(st[0].item()), float(st[1].item())
+
+    # untimed pre-roll: all episodes start at the same instant; run long enough for their phases to spread out, so the
+    # timed window sees the steady state of a rollout (resets, death ticks and charging phases mixed) whatever K is
+    for k in range(a.preroll):
+        for g in range(G):
+            group_step(g, k)
+    for k in range(a.warmup):
+        for g in range(G):
+            group_step(g, k)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    launches[0] = 0
     sync_all()
+    dec0, sim0 = totals()
     t_wall0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    acc = [dec_count, tick_acc]
+    e0.record(torch.cuda.current_stream(dev))
+    for st in streams:
+        st.wait_stream(torch.cuda.current_stream(dev))
     for k in range(a.steps):
-        one_step(actions[a.warmup + k], events=ev[k], acc=acc)
-    e1.record()
+        for g in range(G):
+            group_step(g, a.warmup + k)
+    for st in streams:
+        torch.cuda.current_stream(dev).wait_stream(st)
+    e1.record(torch.cuda.current_stream(dev))
     sync_all()
     t_wall1 = time.perf_counter()
     elapsed_ms = e0.elapsed_time(e1)
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
-    decisions = float(dec_count.item())
-    ticks = float(tick_acc.item())
-    step_ms = sum(x[0].elapsed_time(x[1]) for x in ev)
-    obs_ms = sum(x[1].elapsed_time(x[2]) for x in ev)
-    n_launch = launches[0]
+    dec1, sim1 = totals()
+    decisions, ticks = dec1 - dec0, sim1 - sim0
+    n_launch = 3 * G * a.steps
 
-    # ---- end-to-end run (e2e): per step, actions come from pinned host memory and the request record goes back
-    host_actions = (torch.rand((a.steps, B, 3), dtype=torch.float64) * scale.cpu()).pin_memory()
-    host_req = dict(agent_id=torch.zeros(B, dtype=torch.int32).pin_memory(), reward=torch.zeros(B, dtype=torch.float64).pin_memory(),
-                    terminal=torch.zeros(B, dtype=torch.uint8).pin_memory(), now=torch.zeros(B, dtype=torch.float64).pin_memory())
-    dev_action = torch.zeros((B, 3), dtype=torch.float64, device=dev)
-    h2d = host_actions[0].numel() * 8
-    d2h = sum(v.numel() * v.element_size() for v in host_req.values())
+    # ---- end-to-end run (e2e): per step and group, actions come from pinned host memory and the request record is
+    # read back on the host before that group's next step is issued
+    host_actions = [(torch.rand((a.steps, Bg, 3), dtype=torch.float64) * scale.cpu()).pin_memory() for _ in range(G)]
+    host_req = [dict(agent_id=torch.zeros(Bg, dtype=torch.int32).pin_memory(), reward=torch.zeros(Bg, dtype=torch.float64).pin_memory(),
+                     terminal=torch.zeros(Bg, dtype=torch.uint8).pin_memory(), now=torch.zeros(Bg, dtype=torch.float64).pin_memory())
+                for _ in range(G)]
+    dev_action = [torch.zeros((Bg, 3), dtype=torch.float64, device=dev) for _ in range(G)]
+    done_ev = [torch.cuda.Event() for _ in range(G)]
+    h2d = G * host_actions[0][0].numel() * 8
+    d2h = G * sum(v.numel() * v.element_size() for v in host_req[0].values())
     sync_all()
     e2e_dec = 0
-    t0 = time.perf_counter()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for k in range(a.steps):
-        dev_action.copy_(host_actions[k], non_blocking=True)
-        one_step(dev_action)
-        for name, v in host_req.items():
-            v.copy_(getattr(env.req, name), non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()          # the caller reads the request on the host
-        e2e_dec += int((host_req["agent_id"] >= 0).sum())
-    f1.record()
+    f0.record(torch.cuda.current_stream(dev))
+    for st in streams:
+        st.wait_stream(torch.cuda.current_stream(dev))
+    for k in range(a.steps + 1):
+        for g in range(G):
+            if k > 0:
+                done_ev[g].synchronize()                   # the caller reads step k-1's request of this group
+                e2e_dec += int((host_req[g]["agent_id"] >= 0).sum())
+            if k == a.steps:
+                continue
+            with torch.cuda.stream(streams[g]):
+                dev_action[g].copy_(host_actions[g][k], non_blocking=True)
+                groups[g].rollout_step(dev_action[g], obs[g])
+                for name, v in host_req[g].items():
+                    v.copy_(getattr(groups[g].req, name), non_blocking=True)
+                done_ev[g].record(streams[g])
+    for st in streams:
+        torch.cuda.current_stream(dev).wait_stream(st)
+    f1.record(torch.cuda.current_stream(dev))
     sync_all()
     e2e_ms = f0.elapsed_time(f1)
 
+    # ---- roofline pass: the same hot path issued serially on ONE stream through the separate entry points, CUDA events
+    # around every launch (concurrent groups would time-share the SMs and blur per-launch durations)
+    R = min(a.steps, 12)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(R * G)]
+    sync_all()
+    rd0, rs0 = totals()
+    for k in range(R):
+        for g in range(G):
+            env = groups[g]
+            act = actions[g][a.warmup + (k % a.steps)]
+            aid = env.req.agent_id
+            m = aid >= 0
+            e = ev[k * G + g]
+            e[0].record()
+            env.step(aid, act, mask=m)
+            e[1].record()
+            env.get_state(out=obs[g])
+            e[2].record()
+            done = env.req.agent_id < 0
+            env.reset(mask=done)
+            env.get_state(out=obs[g], agent_id=torch.where(done, env.req.agent_id, torch.full_like(aid, -1)))
+    sync_all()
+    step_ms = sum(x[0].elapsed_time(x[1]) for x in ev)
+    obs_ms = sum(x[1].elapsed_time(x[2]) for x in ev)
+    rd1, rs1 = totals()
+    r_decisions, r_ticks = rd1 - rd0, rs1 - rs0
+
     # ---- reduce over ranks: max time, summed work
-    t = torch.tensor([elapsed_ms, e2e_ms, step_ms, obs_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([elapsed_ms, e2e_ms], dtype=torch.float64, device=dev)
     w = torch.tensor([decisions, ticks, float(e2e_dec)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(w, op=dist.ReduceOp.SUM)
-    elapsed_ms, e2e_ms, step_ms_max, obs_ms_max = [float(x) for x in t.tolist()]
+    elapsed_ms, e2e_ms = [float(x) for x in t.tolist()]
     decisions_all, ticks_all, e2e_dec_all = [float(x) for x in w.tolist()]
     if rank != 0:
         if world > 1:
@@ -300,14 +331,13 @@ def run_b200(a):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    # rank-0 kernels (per-launch averages), algorithmic bytes per SURVEY §8(d)
-    b_tick = 82 * N + T
-    b_dec_step = 16 * T + 88
-    b_dec_obs = 4 * S * S * 4
-    step_bytes = (ticks * b_tick + decisions * b_dec_step) / a.steps
-    obs_bytes = decisions * b_dec_obs / a.steps
-    step_gbs = step_bytes / (step_ms / a.steps * 1e-3) / 1e9
-    obs_gbs = obs_bytes / (obs_ms / a.steps * 1e-3) / 1e9
+    # algorithmic bytes per SURVEY §8(d): 82 N + T per environment and simulated second, 16 T + 88 per decision in the
+    # step kernel, 4 S^2 float32 per decision in the observation kernel
+    n_l = R * G
+    step_bytes = (r_ticks * (82 * N + T) + r_decisions * (16 * T + 88)) / n_l
+    obs_bytes = r_decisions * (4 * S * S * 4) / n_l
+    step_gbs = step_bytes / (step_ms / n_l * 1e-3) / 1e9
+    obs_gbs = obs_bytes / (obs_ms / n_l * 1e-3) / 1e9
     dominant = "k_env<MODE_STEP>" if step_ms >= obs_ms else "k_observe<float>"
     ach = step_gbs if step_ms >= obs_ms else obs_gbs
     line = dict(
@@ -315,22 +345,25 @@ def run_b200(a):
         ms_per_step=elapsed_ms / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
         data="synthetic",
         config=dict(workload=workload_name(a), nodes=N, targets=T, chargers=M, envs_per_gpu=B, map_size=S,
-                    topologies_per_gpu=a.topologies, threads_per_env=int(env.dims.threads), observation="float32 [B,4,100,100] kept in HBM",
+                    groups="%d asynchronous groups of %d environments, one CUDA stream each" % (G, Bg),
+                    topologies_per_gpu=a.topologies, threads_per_env=int(groups[0].dims.threads),
+                    observation="float32 [B,4,100,100] kept in HBM",
                     l2="working set (state %.0f MB + observations %.0f MB per GPU) exceeds the 126 MB L2; no explicit flush"
-                       % (B * env.dims.state_bytes / 1e6, obs.numel() * 4 / 1e6),
+                       % (B * groups[0].dims.state_bytes / 1e6, B * 4 * S * S * 4 / 1e6),
                     sim_seconds_per_decision=ticks_all / max(decisions_all, 1.0),
                     env_ticks_per_s=ticks_all / (elapsed_ms * 1e-3)),
         clocks=clocks,
         e2e=dict(value=e2e_dec_all / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                 note="actions from pinned host memory; request record (agent_id, reward, terminal, now) read back every step; "
-                      "observations stay in HBM for the policy networks"),
+                 note="per step: actions from pinned host memory, rollout_step (step | reset | observe), request record "
+                      "(agent_id, reward, terminal, now) read back on the host; observations stay in HBM for the policy networks"),
         gpu_launches=n_launch,
         roofline=dict(bound="hbm", kernel=dominant, achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=None,
                       peak_source=peak_src,
-                      kernels={"k_env<MODE_STEP>": dict(ms_per_launch=step_ms / a.steps, algorithmic_bytes=step_bytes, gbs=step_gbs,
-                                                        share_of_step=step_ms / elapsed_ms),
-                               "k_observe<float>": dict(ms_per_launch=obs_ms / a.steps, algorithmic_bytes=obs_bytes, gbs=obs_gbs,
-                                                        share_of_step=obs_ms / elapsed_ms)}),
+                      how="serialized pass of %d launches per kernel on one stream right after the timed region" % n_l,
+                      kernels={"k_env<MODE_STEP>": dict(ms_per_launch=step_ms / n_l, algorithmic_bytes=step_bytes, gbs=step_gbs,
+                                                        share=step_ms / (step_ms + obs_ms)),
+                               "k_observe<float>": dict(ms_per_launch=obs_ms / n_l, algorithmic_bytes=obs_bytes, gbs=obs_gbs,
+                                                        share=obs_ms / (step_ms + obs_ms))}),
     )
     if world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = {k: v for k, v in cpu_baseline(a, 1, a.cpu_seconds).items() if k != "wall_s"}

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define WRSN_ABI_VERSION 3
+#define WRSN_ABI_VERSION 5
 #define WRSN_MAX_MC 16          /* chargers per environment */
 #define WRSN_RING 10            /* Node.operate keeps the last 10 per-second consumptions (Node.py:70-77) */
 
@@ -144,6 +144,8 @@ typedef struct wrsn_request {
     double *action;                     /* [B][3] agents_action[agent_id] */
     double *detail;                     /* [B][2] term_all, term_exclusive of get_reward (WRSN.py:225-226) */
     int32_t *flags;                     /* [B]  bit0 = every charger dead (the reference would never return, Q1), bit1 = engine error */
+    double *stats;                      /* [B][2] running totals, never cleared by the library (may be NULL): requests handed out
+                                           with a deciding charger; simulated seconds advanced by step */
 } wrsn_request;
 
 const char *wrsn_last_error(void);
@@ -173,6 +175,15 @@ int wrsn_reset_from_snapshot(const wrsn_dims *d, const void *scen, const int32_t
 int wrsn_step(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state,
               const uint8_t *env_mask, const int32_t *agent_id_in, const double *action_in,
               wrsn_request *req, void *stream);
+/* One rollout step of every environment, three launches on `stream`, no host round trip:
+ *   1. WRSN.step for the rows whose last request names a deciding charger (req->agent_id[b] >= 0), with that charger
+ *      and action_in[b];
+ *   2. WRSN.reset (from `snap`) for the rows whose episode has just ended (req->agent_id[b] < 0 after 1.);
+ *   3. WRSN.get_state of the deciding charger of every row into obs (skipped when obs == NULL).
+ * This is the reference's rollout loop body (controller/ippo/IPPO.py:137-143: reset on terminal, else step) for B
+ * environments at once. */
+int wrsn_rollout_step(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state, const void *snap,
+                      const double *action_in, wrsn_request *req, void *obs, int obs_f64, void *stream);
 /* WRSN.get_state (:130-186) for agent agent_id[b] of every environment with agent_id[b] >= 0, written to
  * obs[b][4][S][S] as float (obs_f64 == 0) or double.  Rows with agent_id[b] < 0 are left untouched. */
 int wrsn_observe(const wrsn_dims *d, const void *scen, const int32_t *scen_id, const void *state,

@@ -26,7 +26,7 @@ class Dims(C.Structure):
 
 class Request(C.Structure):
     _fields_ = [("agent_id", C.c_void_p), ("terminal", C.c_void_p), ("reward", C.c_void_p), ("now", C.c_void_p),
-                ("action", C.c_void_p), ("detail", C.c_void_p), ("flags", C.c_void_p)]
+                ("action", C.c_void_p), ("detail", C.c_void_p), ("flags", C.c_void_p), ("stats", C.c_void_p)]
 
 
 def enums():
@@ -71,6 +71,7 @@ def _bind(L):
     L.wrsn_reset_finish.argtypes = [dp, vp, vp, vp, vp, C.POINTER(Request), vp]
     L.wrsn_reset_from_snapshot.argtypes = [dp, vp, vp, vp, vp, vp, C.POINTER(Request), vp]
     L.wrsn_step.argtypes = [dp, vp, vp, vp, vp, vp, vp, C.POINTER(Request), vp]
+    L.wrsn_rollout_step.argtypes = [dp, vp, vp, vp, vp, vp, C.POINTER(Request), vp, ip, vp]
     L.wrsn_observe.argtypes = [dp, vp, vp, vp, vp, vp, ip, vp]
     L.wrsn_fitness.argtypes = [dp, vp, vp, vp, vp, vp, vp]
     for k in ("wrsn_k_bfs", "wrsn_k_drain", "wrsn_k_bookkeep", "wrsn_k_reward"):

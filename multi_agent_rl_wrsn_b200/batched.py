@@ -37,8 +37,10 @@ class Requests:
         self.action = torch.zeros((B, 3), dtype=torch.float64, device=device)
         self.detail = torch.zeros((B, 2), dtype=torch.float64, device=device)
         self.flags = torch.zeros((B,), dtype=torch.int32, device=device)
+        self.stats = torch.zeros((B, 2), dtype=torch.float64, device=device)   # running totals: decisions, simulated seconds
         self.c = _lib.Request(self.agent_id.data_ptr(), self.terminal.data_ptr(), self.reward.data_ptr(),
-                              self.now.data_ptr(), self.action.data_ptr(), self.detail.data_ptr(), self.flags.data_ptr())
+                              self.now.data_ptr(), self.action.data_ptr(), self.detail.data_ptr(), self.flags.data_ptr(),
+                              self.stats.data_ptr())
 
 
 class BatchedWRSN:
@@ -174,6 +176,23 @@ class BatchedWRSN:
         m, mp = self._mask_ptr(mask)
         _lib.check(L.wrsn_step(C.byref(self.dims), self.scen.data_ptr(), self.scen_id.data_ptr(), self.state.data_ptr(),
                                mp, a.data_ptr(), x.data_ptr(), C.byref(self.req.c), self._stream()), L)
+        return self.req
+
+    def rollout_step(self, action, obs=None):
+        """The rollout loop body of the reference's trainers (``controller/ippo/IPPO.py:137-143``) for every environment
+        in one call and three kernel launches: ``step`` where the last request named a deciding charger (with
+        ``action[b]``), ``reset`` where the episode has just ended, then ``get_state`` of every deciding charger into
+        ``obs`` ([B, 4, S, S] float32 / float64; skipped when None).  No host synchronisation, no temporaries."""
+        if action.dtype != torch.float64 or not action.is_contiguous() or action.shape != (self.B, 3) or action.device != self.state.device:
+            raise ValueError("action must be a contiguous float64 tensor [B, 3] on the simulator's device")
+        op, f64 = None, 0
+        if obs is not None:
+            if obs.dtype not in (torch.float32, torch.float64) or not obs.is_contiguous() or obs.shape != (self.B, 4, self.S, self.S):
+                raise ValueError("obs must be a contiguous float32/float64 tensor [B, 4, S, S]")
+            op, f64 = obs.data_ptr(), 1 if obs.dtype == torch.float64 else 0
+        _lib.check(self.L.wrsn_rollout_step(C.byref(self.dims), self.scen.data_ptr(), self.scen_id.data_ptr(),
+                                            self.state.data_ptr(), self._snap.data_ptr(), action.data_ptr(),
+                                            C.byref(self.req.c), op, f64, self._stream()), self.L)
         return self.req
 
     def get_state(self, agent_id=None, out=None, dtype=torch.float32):

@@ -57,6 +57,16 @@
 #else
 #define WRSN_GSZ(c) ((c).G)
 #endif
+/* Who stores the replicated scalar state (clock, charger records)?  Every thread computes it redundantly.  With one
+ * warp per environment ALL lanes store (same value, same address, one converged instruction: no branch, no
+ * divergence at the following barrier); with several warps only thread 0 does (a second warp could otherwise read
+ * a value the first one has already replaced). */
+#undef WRSN_LEAD
+#if WRSN_GFIX == 32
+#define WRSN_LEAD(c) true
+#else
+#define WRSN_LEAD(c) ((c).tid == 0)
+#endif
 
 /* ------------------------------------------------------------------ context */
 struct Ctx {
@@ -743,7 +753,7 @@ WRSN_D double charge_rate_xy(Ctx &c, double mx, double my, int node) {   /* alph
 /* schedule the slot's next event (all threads keep the clock, thread 0 stores) */
 WRSN_DI void slot_sched(Ctx &c, Clk &k, double *p, int pc, int prio, double delay) {
     double t = k.now + delay, key = take_seq(k) + (prio ? WRSN_KEY_NORMAL : 0.0);
-    if (c.tid == 0) { slot_i(p)[WRSN_PRI_PC] = pc; p[WRSN_PR_T] = t; p[WRSN_PR_KEY] = key; }
+    if (WRSN_LEAD(c)) { slot_i(p)[WRSN_PRI_PC] = pc; p[WRSN_PR_T] = t; p[WRSN_PR_KEY] = key; }
 }
 
 WRSN_DI void cond_check(Ctx &c, Clk &k, int j) {   /* simpy Condition._check for AnyOf (all threads; state read before) */
@@ -751,7 +761,7 @@ WRSN_DI void cond_check(Ctx &c, Clk &k, int j) {   /* simpy Condition._check for
     if (h[WRSN_H_COND_TRIG + j] != 0.0) return;
     double s = take_seq(k);
     gsync(c);
-    if (c.tid == 0) { h[WRSN_H_COND_TRIG + j] = 1.0; h[WRSN_H_COND_T + j] = k.now; h[WRSN_H_COND_KEY + j] = WRSN_KEY_NORMAL + s; }
+    if (WRSN_LEAD(c)) { h[WRSN_H_COND_TRIG + j] = 1.0; h[WRSN_H_COND_T + j] = k.now; h[WRSN_H_COND_KEY + j] = WRSN_KEY_NORMAL + s; }
     gsync(c);
 }
 WRSN_D void cond_check_h(Ctx &c, int j) {          /* leader-only variant used while building the chain */
@@ -771,7 +781,7 @@ WRSN_DI void ev_slot(Ctx &c, Clk &k, int s, double other_t) {
     double *m = mc_of(c, a);
     uint32_t *cm = c.conn + (size_t)a * c.W;
     const double *par = c.par;
-    const bool lead = c.tid == 0;
+    const bool lead = WRSN_LEAD(c);
     for (;;) {
         const int pc = slot_i(p)[WRSN_PRI_PC];
         k.nev += 1.0;
@@ -971,7 +981,7 @@ WRSN_DI void ev_cond(Ctx &c, Clk &k, int j) {
     /* _build_value: remove the check callbacks of this condition and, recursively, of the nested ones */
     if ((double)j > det) det = (double)j;
     gsync(c);
-    if (c.tid == 0) { h[WRSN_H_COND_T + j] = INFINITY; h[WRSN_H_CHAIN_DETACH] = det; }
+    if (WRSN_LEAD(c)) { h[WRSN_H_COND_T + j] = INFINITY; h[WRSN_H_CHAIN_DETACH] = det; }
     gsync(c);
     if (j + 1 < nch) { if ((double)(j + 1) > det) cond_check(c, k, j + 1); }
     else k.stop = 1;                                 /* StopSimulation */

@@ -6,6 +6,8 @@ __global__ void __launch_bounds__(WRSN_GFIX ? WRSN_GFIX : 256, WRSN_GFIX ? 16 : 
     char *smem = reinterpret_cast<char *>(smem_u4);
     const int b = blockIdx.x, tid = threadIdx.x, G = blockDim.x;
     if (P.mask && !P.mask[b]) return;
+    if (P.mask_mode == 1 && P.req.agent_id[b] < 0) return;
+    if (P.mask_mode == 2 && P.req.agent_id[b] >= 0) return;
     char *row = P.state + (size_t)b * P.L.total;
     const char *scen_row = P.scen + (size_t)P.scen_id[b] * P.L.scen_total;
     Ctx c;
@@ -20,6 +22,7 @@ __global__ void __launch_bounds__(WRSN_GFIX ? WRSN_GFIX : 256, WRSN_GFIX ? 16 : 
     for (int i = tid; i < c.Npad; i += G) c.own[i] = i < c.N ? (uint16_t)(c.tgt_ptr[i + 1] - c.tgt_ptr[i]) : (uint16_t)0;
     gsync(c);
 
+    const double now_before = c.hdr[WRSN_H_NOW];
     ReqOut r;
     r.agent = -3; r.terminal = 0; r.reward = 0; r.now = 0; r.flags = 0;
     r.act[0] = r.act[1] = r.act[2] = 0; r.detail[0] = r.detail[1] = 0;
@@ -41,6 +44,12 @@ __global__ void __launch_bounds__(WRSN_GFIX ? WRSN_GFIX : 256, WRSN_GFIX ? 16 : 
     }
     gsync(c);
     if (MODE != MODE_FITNESS) copy16(row, smem, P.L.resident, tid, G);
-    if ((MODE == MODE_RESET_FINISH || MODE == MODE_RESTORE_RESET || MODE == MODE_STEP) && tid == 0) write_request(P.req, b, r);
+    if ((MODE == MODE_RESET_FINISH || MODE == MODE_RESTORE_RESET || MODE == MODE_STEP) && tid == 0) {
+        write_request(P.req, b, r);
+        if (P.req.stats) {
+            if (r.agent >= 0) P.req.stats[2 * b] += 1.0;
+            if (MODE == MODE_STEP) P.req.stats[2 * b + 1] += r.now - now_before;
+        }
+    }
 }
 

@@ -25,6 +25,7 @@ struct KParams {
     char *state;
     const char *snap;
     const uint8_t *mask;
+    int mask_mode;                                   /* 0: mask[] (or all); 1: rows with req.agent_id >= 0; 2: rows with req.agent_id < 0 */
     const double *t_until;
     const int32_t *agent_in;
     const double *action_in;
@@ -346,6 +347,19 @@ int wrsn_step(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void
     KParams P = base_params(d, scen, scen_id, state, env_mask);
     P.agent_in = agent_id_in; P.action_in = action_in; P.req = *req;
     return launch_env<MODE_STEP>(P, stream);
+}
+
+int wrsn_rollout_step(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state, const void *snap,
+                      const double *action_in, wrsn_request *req, void *obs, int obs_f64, void *stream) {
+    if (!req || !req->agent_id || !snap || !action_in) WRSN_FAIL("req / req->agent_id / snap / action_in is NULL");
+    KParams P = base_params(d, scen, scen_id, state, nullptr);
+    P.req = *req; P.agent_in = req->agent_id; P.action_in = action_in; P.mask_mode = 1;
+    if (launch_env<MODE_STEP>(P, stream)) return -1;
+    KParams R = base_params(d, scen, scen_id, state, nullptr);
+    R.req = *req; R.snap = (const char *)snap; R.mask_mode = 2;
+    if (launch_env<MODE_RESTORE_RESET>(R, stream)) return -1;
+    if (obs) return wrsn_observe(d, scen, scen_id, state, req->agent_id, obs, obs_f64, stream);
+    return 0;
 }
 
 int wrsn_fitness(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state,

@@ -25,7 +25,7 @@ enum { MODE_INIT = 0, MODE_RUN_UNTIL, MODE_RESET_FINISH, MODE_RESTORE_RESET, MOD
 struct Args {
     const wrsn_dims *d; const char *scen; const int32_t *scen_id; char *state; const char *snap; const uint8_t *mask;
     const double *t_until; const int32_t *agent_in; const double *action_in; wrsn_request *req;
-    double *fitness, *fit_min; int with_reward;
+    double *fitness, *fit_min; int with_reward; int mask_mode;
 };
 
 static int run_mode(int mode, const Args &A) {
@@ -35,6 +35,8 @@ static int run_mode(int mode, const Args &A) {
     std::vector<char> smem((size_t)L.smem_total + 64);
     for (int b = 0; b < d.B; b++) {
         if (A.mask && !A.mask[b]) continue;
+        if (A.mask_mode == 1 && A.req->agent_id[b] < 0) continue;
+        if (A.mask_mode == 2 && A.req->agent_id[b] >= 0) continue;
         char *row = A.state + (size_t)b * L.total;
         const char *scen_row = A.scen + (size_t)A.scen_id[b] * L.scen_total;
         Ctx c;
@@ -45,6 +47,7 @@ static int run_mode(int mode, const Args &A) {
             memcpy(smem.data(), src, (size_t)L.resident);
         } else if (mode != MODE_INIT) memcpy(smem.data(), row, (size_t)L.resident);
         for (int i = 0; i < c.Npad; i++) c.own[i] = i < c.N ? (uint16_t)(c.tgt_ptr[i + 1] - c.tgt_ptr[i]) : 0;
+        const double now_before = c.hdr[WRSN_H_NOW];
         ReqOut r; memset(&r, 0, sizeof(r)); r.agent = -3;
         switch (mode) {
         case MODE_INIT: entry_init_network(c, A.with_reward); break;
@@ -67,6 +70,7 @@ static int run_mode(int mode, const Args &A) {
             if (q.action) for (int k = 0; k < 3; k++) q.action[3 * b + k] = r.act[k];
             if (q.detail) { q.detail[2 * b] = r.detail[0]; q.detail[2 * b + 1] = r.detail[1]; }
             if (q.flags) q.flags[b] = r.flags;
+            if (q.stats) { if (r.agent >= 0) q.stats[2 * b] += 1.0; if (mode == MODE_STEP) q.stats[2 * b + 1] += r.now - now_before; }
         }
     }
     return 0;
@@ -114,6 +118,14 @@ int wrsn_reset_from_snapshot(const wrsn_dims *d, const void *scen, const int32_t
 int wrsn_step(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state, const uint8_t *m, const int32_t *ag, const double *act, wrsn_request *req, void *) {
     Args A = {d, (const char *)scen, scen_id, (char *)state, nullptr, m, nullptr, ag, act, req, nullptr, nullptr, 0};
     return run_mode(MODE_STEP, A);
+}
+int wrsn_rollout_step(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state, const void *snap,
+                      const double *act, wrsn_request *req, void *obs, int, void *) {
+    if (obs) WRSN_FAIL("wrsn_observe is not available in the host emulation");
+    Args A = {d, (const char *)scen, scen_id, (char *)state, nullptr, nullptr, nullptr, req->agent_id, act, req, nullptr, nullptr, 0, 1};
+    if (run_mode(MODE_STEP, A)) return -1;
+    Args R = {d, (const char *)scen, scen_id, (char *)state, (const char *)snap, nullptr, nullptr, nullptr, nullptr, req, nullptr, nullptr, 0, 2};
+    return run_mode(MODE_RESTORE_RESET, R);
 }
 int wrsn_fitness(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state, double *fit, double *fmin_, void *) {
     Args A = {d, (const char *)scen, scen_id, (char *)state, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, fit, fmin_, 0};

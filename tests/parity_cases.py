@@ -192,3 +192,32 @@ def check_network_after_operate_stopped(scenario, device, horizon, every=50.0):
         np.testing.assert_allclose(_np(env.view("cs"))[0], nd["cs"], rtol=E_RTOL)
         t += every
     return env.counters(), int((nd["status"] == 0).sum())
+
+
+def check_rollout_step(scenarios, device, num_envs, steps, seed, with_obs):
+    """wrsn_rollout_step (step | reset-on-termination | observe in one call) == the same loop written with the
+    individual entry points, over several episode boundaries."""
+    rng = np.random.default_rng(seed)
+    acts = rng.uniform(0.0, 1.0, size=(steps, num_envs, 3))
+    acts[..., 2] *= 0.3                                  # long charges: episodes end inside the window
+    a = BatchedWRSN(scenarios, num_agent=3, num_envs=num_envs, device=device)
+    b = BatchedWRSN(scenarios, num_agent=3, num_envs=num_envs, device=device)
+    a.reset(); b.reset()
+    obs_a = torch.zeros((num_envs, 4, a.S, a.S), dtype=torch.float64, device=a.device) if with_obs else None
+    resets = 0
+    for k in range(steps):
+        act = torch.as_tensor(acts[k], device=a.device)
+        a.rollout_step(act, obs_a)
+        aid = b.req.agent_id.clone()
+        b.step(aid, act, mask=(aid >= 0))
+        done = b.req.agent_id < 0
+        resets += int(done.sum())
+        b.reset(mask=done)
+        for f in ("agent_id", "terminal", "now", "action"):
+            assert torch.equal(getattr(a.req, f), getattr(b.req, f)), (k, f)
+        ra, rb = _np(a.req.reward), _np(b.req.reward)
+        assert np.array_equal(ra, rb, equal_nan=True), k
+        assert torch.equal(a.state, b.state), k
+        if with_obs:
+            assert torch.equal(obs_a, b.get_state(dtype=torch.float64)) or bool((b.req.agent_id < 0).any()), k
+    return resets

@@ -69,3 +69,8 @@ def test_deaths_after_network_operate_stopped():
     sc = pc.sc_from_golden(golden("net_hanoi1000n50"))
     cnt, dead = pc.check_network_after_operate_stopped(sc, "cpu", horizon=12000.0, every=100.0)
     assert dead >= 5 and cnt["stale_rebuilds"] >= 4
+
+def test_rollout_step_equals_manual_loop():
+    scs = [synthetic(num_nodes=40, num_targets=120, seed=s, num_gateways=2) for s in (3, 4)]
+    resets = pc.check_rollout_step(scs, "cpu", num_envs=6, steps=120, seed=1, with_obs=False)
+    assert resets >= 3

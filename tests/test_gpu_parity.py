@@ -70,6 +70,12 @@ def test_deaths_after_network_operate_stopped():
     assert dead >= 5 and cnt["stale_rebuilds"] >= 4
 
 
+def test_rollout_step_equals_manual_loop():
+    scs = [synthetic(num_nodes=40, num_targets=120, seed=s, num_gateways=2) for s in (3, 4)]
+    resets = pc.check_rollout_step(scs, DEV, num_envs=16, steps=120, seed=1, with_obs=True)
+    assert resets >= 3
+
+
 @pytest.mark.parametrize("threads", [32, 64, 128])
 def test_group_size_independent(threads):
     """The result must not depend on how many threads share an environment."""
