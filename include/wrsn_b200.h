@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define WRSN_ABI_VERSION 5
+#define WRSN_ABI_VERSION 6
 #define WRSN_MAX_MC 16          /* chargers per environment */
 #define WRSN_RING 10            /* Node.operate keeps the last 10 per-second consumptions (Node.py:70-77) */
 
@@ -116,6 +116,8 @@ enum {
     WRSN_S_NBR_IDX,                                    /* int32[Emax]   neighbour ids in id order */
     WRSN_S_TGT_IDX,                                    /* int32[TEmax]  covered target ids in id order (Node.probe_targets :86) */
     WRSN_S_DIRECT,                                     /* uint8[Npad]   d(node, BS) <= com_range (BaseStation.probe_neighbors :20) */
+    WRSN_S_OBS_GX, WRSN_S_OBS_GY,                      /* float[Npad][obs_pitch]  exp(-(c_i - x_n)^2 / (2 hX^2)) of every node and map row /
+                                                          column: the node terms of get_state never change (wrsn_build_obs_tables) */
     WRSN_S_COUNT
 };
 
@@ -133,6 +135,7 @@ typedef struct wrsn_dims {
     int32_t Tw;       /* 32-bit words per target bitmask */
     int32_t n_slot;   /* charger process slots per environment */
     int32_t state_bytes, state_resident_bytes, scen_bytes, smem_bytes;
+    int32_t obs_pitch;  /* row pitch of the observation tables */
 } wrsn_dims;
 
 /* request record written by reset / step, device pointers, one row per environment */
@@ -155,6 +158,9 @@ int wrsn_dims_finalize(wrsn_dims *d);
 int wrsn_state_layout(const wrsn_dims *d, int64_t *offsets /* [WRSN_F_COUNT] */);
 int wrsn_scen_layout(const wrsn_dims *d, int64_t *offsets /* [WRSN_S_COUNT] */);
 int wrsn_device_ok(void);               /* 1 when a CUDA device of compute capability 10.x is usable */
+
+/* Fill WRSN_S_OBS_GX / WRSN_S_OBS_GY of every scenario record (once, after uploading `scen`; needs par, node_x, node_y). */
+int wrsn_build_obs_tables(const wrsn_dims *d, void *scen, void *stream);
 
 /* NetworkIO.makeNetwork + Network.operate start (NetworkIO.py:19-34, Network.py:69-73): node / clock state at
  * t = 0.  with_reward_process != 0 also starts WRSN.update_reward (WRSN.py:43).  env_mask (may be NULL) selects rows. */

@@ -21,7 +21,7 @@ _enums = None
 class Dims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "B", "N", "T", "M", "S", "Emax", "TEmax", "n_scen", "threads",
-        "Npad", "W", "Tw", "n_slot", "state_bytes", "state_resident_bytes", "scen_bytes", "smem_bytes")]
+        "Npad", "W", "Tw", "n_slot", "state_bytes", "state_resident_bytes", "scen_bytes", "smem_bytes", "obs_pitch")]
 
 
 class Request(C.Structure):
@@ -66,6 +66,7 @@ def _bind(L):
     L.wrsn_state_layout.argtypes = [dp, C.POINTER(C.c_int64)]
     L.wrsn_scen_layout.argtypes = [dp, C.POINTER(C.c_int64)]
     L.wrsn_device_ok.restype = ip
+    L.wrsn_build_obs_tables.argtypes = [dp, vp, vp]
     L.wrsn_init_network.argtypes = [dp, vp, vp, vp, vp, ip, vp]
     L.wrsn_run_until.argtypes = [dp, vp, vp, vp, vp, vp, vp]
     L.wrsn_reset_finish.argtypes = [dp, vp, vp, vp, vp, C.POINTER(Request), vp]

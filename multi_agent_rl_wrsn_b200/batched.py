@@ -91,6 +91,7 @@ class BatchedWRSN:
         _lib.check(self.L.wrsn_scen_layout(C.byref(d), self._soff), self.L)
 
         self.scen = torch.from_numpy(self._pack_scenarios(statics)).to(self.device)
+        _lib.check(self.L.wrsn_build_obs_tables(C.byref(d), self.scen.data_ptr(), self._stream()), self.L)
         if scenario_index is None:
             scenario_index = np.arange(B) % n_scen
         self.scen_id = torch.as_tensor(np.asarray(scenario_index, np.int32), device=self.device)

@@ -1,7 +1,7 @@
 /* wrsn_env_kernel.cuh — the one-CTA-per-environment kernel; included once per group-size specialisation (see
  * wrsn_engine.cuh), inside the same namespace. */
 template <int MODE>
-__global__ void __launch_bounds__(WRSN_GFIX ? WRSN_GFIX : 256, WRSN_GFIX ? 16 : 1) k_env(const KParams P) {
+__global__ void __launch_bounds__(WRSN_GFIX ? WRSN_GFIX : 256, WRSN_GFIX ? 20 : 1) k_env(const KParams P) {
     extern __shared__ uint4 smem_u4[];
     char *smem = reinterpret_cast<char *>(smem_u4);
     const int b = blockIdx.x, tid = threadIdx.x, G = blockDim.x;

@@ -76,19 +76,37 @@ namespace gany {                                     /* 64 ... 256 threads per e
 #define OBS_TI 4
 #define OBS_TJ 10
 
-struct ObsSrc { double x0, y0, hx, hy, w; int mode; };     /* mode 0: (w*gx)*gy ; 1: ((gx*gy)*w)/mtm */
+struct ObsSrc { double x0, y0, hx, hy, w; int mode; int node; };     /* mode 0: (w*gx)*gy ; 1: ((gx*gy)*w)/mtm ; node >= 0: table row */
+
+/* the node terms of get_state are static: one table row per node, float (the fp32 raster reads them, the fp64 parity
+ * raster evaluates its exponentials itself) */
+__global__ void k_obs_tables(const wrsn_dims d, const WrsnLayout L, char *scen) {
+    char *row = scen + (size_t)blockIdx.x * L.scen_total;
+    const double *par = (const double *)(row + L.soff[WRSN_S_PAR]);
+    const double *nx = (const double *)(row + L.soff[WRSN_S_NX]), *ny = (const double *)(row + L.soff[WRSN_S_NY]);
+    float *gx = (float *)(row + L.soff[WRSN_S_OBS_GX]), *gy = (float *)(row + L.soff[WRSN_S_OBS_GY]);
+    const int n = blockIdx.y, S = d.S, TP = d.obs_pitch;
+    const double f0 = par[WRSN_P_F0], f1 = par[WRSN_P_F1], f2 = par[WRSN_P_F2], f3 = par[WRSN_P_F3];
+    const double Wd = f1 - f0, Hd = f3 - f2, R = par[WRSN_P_MC_R];
+    const double unit = 1.0 / (double)S, start = unit / 2.0, delta = (start + unit) - start;
+    const double x0 = (nx[n] - f0) / Wd, y0 = (ny[n] - f2) / Hd, hx = R / Wd, hy = R / Hd;
+    for (int i = threadIdx.x; i < TP; i += blockDim.x) {
+        const double cc = start + (double)i * delta, ux = cc - x0, uy = cc - y0;
+        const bool in = i < S && n < d.N;
+        gx[(size_t)n * TP + i] = in ? (float)exp(ux * ux / (-2.0 * (hx * hx))) : 0.f;
+        gy[(size_t)n * TP + i] = in ? (float)exp(uy * uy / (-2.0 * (hy * hy))) : 0.f;
+    }
+}
 
 template <typename AccT>
-__global__ void __launch_bounds__(OBS_THREADS) k_observe(const KParams P, const int32_t *agent_id, AccT *obs) {
-    constexpr int CH = sizeof(AccT) == 4 ? 32 : 16;
+__global__ void __launch_bounds__(OBS_THREADS, sizeof(AccT) == 4 ? 3 : 1) k_observe(const KParams P, const int32_t *agent_id, AccT *obs) {
+    constexpr int CH = sizeof(AccT) == 4 ? 64 : 16;      /* sources staged per pass */
     extern __shared__ uint4 smem_u4[];
-    const int S = P.d.S, N = P.d.N, M = P.d.M;
+    const int S = P.d.S, N = P.d.N, M = P.d.M, TP = P.d.obs_pitch;
     const int tiles_i = (S + OBS_TI - 1) / OBS_TI, tiles_j = (S + OBS_TJ - 1) / OBS_TJ;
-    const int PI = tiles_i * OBS_TI, PJ = (tiles_j * OBS_TJ + 3) & ~3;        /* padded vector lengths */
-    AccT *gx = reinterpret_cast<AccT *>(smem_u4);                             /* [CH][PI] */
-    AccT *gy = gx + CH * PI;                                                  /* [CH][PJ] */
+    AccT *gx = reinterpret_cast<AccT *>(smem_u4);                             /* [CH][TP] */
+    AccT *gy = gx + CH * TP;                                                  /* [CH][TP] */
     __shared__ ObsSrc src[CH];
-    __shared__ int nsrc_s;
     const int b = blockIdx.x, tid = threadIdx.x;
     const int ag = agent_id[b];
     if (ag < 0) return;
@@ -101,6 +119,7 @@ __global__ void __launch_bounds__(OBS_THREADS) k_observe(const KParams P, const 
     const double *cs = (const double *)(row + P.L.off[WRSN_F_CS]);
     const uint8_t *status = (const uint8_t *)(row + P.L.off[WRSN_F_STATUS]);
     const double *mc = (const double *)(row + P.L.off[WRSN_F_MC]);
+    const float *tab_gx = (const float *)(scen_row + P.L.soff[WRSN_S_OBS_GX]), *tab_gy = (const float *)(scen_row + P.L.soff[WRSN_S_OBS_GY]);
     const double f0 = par[WRSN_P_F0], f1 = par[WRSN_P_F1], f2 = par[WRSN_P_F2], f3 = par[WRSN_P_F3];
     const double Wd = f1 - f0, Hd = f3 - f2;
     const double unit = 1.0 / (double)S, start = unit / 2.0, delta = (start + unit) - start;   /* np.arange(unit/2, 1.0, unit) */
@@ -123,66 +142,71 @@ __global__ void __launch_bounds__(OBS_THREADS) k_observe(const KParams P, const 
                 for (int q = 0; q < OBS_TJ; q++) acc[r][q] = (AccT)0;
             const int total = ch == 0 ? N : (ch == 1 ? 1 : M);
             for (int s0 = 0; s0 < total; s0 += CH) {
+                const int nq = total - s0 < CH ? total - s0 : CH;
                 __syncthreads();
-                if (tid < 32) {                      /* gather this chunk's sources, compacted in id order (CH <= 32) */
-                    const int s = s0 + tid;
-                    bool use = tid < CH && s < total;
-                    ObsSrc q; q.mode = 0; q.x0 = q.y0 = q.w = 0.0; q.hx = q.hy = 1.0;
-                    if (use) {
-                        if (ch == 0) {
-                            use = status[s] != 0;
-                            if (use) {
-                                q.x0 = (nx[s] - f0) / Wd; q.y0 = (ny[s] - f2) / Hd; q.hx = R / Wd; q.hy = R / Hd;
-                                q.w = (cs[s] / par[WRSN_P_MC_AB2]) / ((energy[s] - par[WRSN_P_THR]) / par[WRSN_P_CAPMTHR]);
-                            }
-                        } else if (ch == 1) {
-                            double tmp = fmin(Hd, Wd);
-                            q.x0 = (me[WRSN_MC_X] - f0) / Wd; q.y0 = (me[WRSN_MC_Y] - f2) / Hd;
-                            q.hx = 0.5 * tmp / Wd; q.hy = 0.5 * tmp / Hd;
-                            q.w = me[WRSN_MC_ENERGY] / par[WRSN_P_MC_CAP];
-                        } else {
-                            const double *an = mc + (size_t)s * WRSN_MC_LEN;
-                            const bool charging = an[WRSN_MC_TYPE] != 0.0;
-                            use = s != ag && (ch == 2 ? charging : !charging);
-                            if (use) {
-                                q.x0 = (an[WRSN_MC_CPA0] - f0) / Wd; q.y0 = (an[WRSN_MC_CPA1] - f2) / Hd; q.hx = R / Wd; q.hy = R / Hd;
-                                if (ch == 2) q.w = an[WRSN_MC_CPA2] / par[WRSN_P_CTM];
-                                else {               /* the observer's destination y */
-                                    double dx = an[WRSN_MC_X] - an[WRSN_MC_CPA0], dy = an[WRSN_MC_Y] - me[WRSN_MC_CPA1];
-                                    q.w = sqrt(dx * dx + dy * dy) / par[WRSN_P_MC_V];
-                                    q.mode = 1;
-                                }
+                /* the sources of this pass, one thread each, in id order; unused ones (dead node, wrong charger) get
+                   mode -1 and are skipped — the reference skips them too, and the sum order of the rest is unchanged */
+                for (int q = tid; q < nq; q += OBS_THREADS) {
+                    const int s = s0 + q;
+                    ObsSrc v; v.mode = -1; v.node = -1; v.x0 = v.y0 = v.w = 0.0; v.hx = v.hy = 1.0;
+                    if (ch == 0) {
+                        if (status[s] != 0) {
+                            v.mode = 0; v.node = s;
+                            v.x0 = (nx[s] - f0) / Wd; v.y0 = (ny[s] - f2) / Hd; v.hx = R / Wd; v.hy = R / Hd;
+                            v.w = (cs[s] / par[WRSN_P_MC_AB2]) / ((energy[s] - par[WRSN_P_THR]) / par[WRSN_P_CAPMTHR]);
+                        }
+                    } else if (ch == 1) {
+                        double tmp = fmin(Hd, Wd);
+                        v.mode = 0;
+                        v.x0 = (me[WRSN_MC_X] - f0) / Wd; v.y0 = (me[WRSN_MC_Y] - f2) / Hd;
+                        v.hx = 0.5 * tmp / Wd; v.hy = 0.5 * tmp / Hd;
+                        v.w = me[WRSN_MC_ENERGY] / par[WRSN_P_MC_CAP];
+                    } else {
+                        const double *an = mc + (size_t)s * WRSN_MC_LEN;
+                        const bool charging = an[WRSN_MC_TYPE] != 0.0;
+                        if (s != ag && (ch == 2 ? charging : !charging)) {
+                            v.x0 = (an[WRSN_MC_CPA0] - f0) / Wd; v.y0 = (an[WRSN_MC_CPA1] - f2) / Hd; v.hx = R / Wd; v.hy = R / Hd;
+                            if (ch == 2) { v.mode = 0; v.w = an[WRSN_MC_CPA2] / par[WRSN_P_CTM]; }
+                            else {                   /* the observer's destination y */
+                                double dx = an[WRSN_MC_X] - an[WRSN_MC_CPA0], dy = an[WRSN_MC_Y] - me[WRSN_MC_CPA1];
+                                v.w = sqrt(dx * dx + dy * dy) / par[WRSN_P_MC_V];
+                                v.mode = 1;
                             }
                         }
                     }
-                    const unsigned bal = __ballot_sync(0xffffffffu, use);
-                    if (use) src[__popc(bal & ((1u << tid) - 1u))] = q;
-                    if (tid == 0) nsrc_s = __popc(bal);
+                    src[q] = v;
                 }
                 __syncthreads();
-                const int n = nsrc_s;
-                if (n == 0) continue;
-                /* one exponential per (source, coordinate): threads [0, PI) fill gx, threads [PI, PI + PJ) fill gy */
-                for (int t = tid; t < PI + PJ; t += OBS_THREADS) {
-                    const bool isx = t < PI;
-                    const int i = isx ? t : t - PI;
-                    const double cc = start + (double)i * delta;
-                    for (int q = 0; q < n; q++) {
-                        const double u = cc - (isx ? src[q].x0 : src[q].y0), h = isx ? src[q].hx : src[q].hy;
-                        double e = i < S ? exp(u * u / (-2.0 * (h * h))) : 0.0;
-                        if (isx) gx[q * PI + i] = (AccT)(src[q].mode == 0 ? src[q].w * e : e);
-                        else gy[q * PJ + i] = (AccT)e;
+                /* expand every source into its two S-vectors.  Node sources of the fp32 raster are a scaled copy of the
+                   scenario's table (contiguous, independent loads); everything else is one fp64 exponential per entry. */
+                for (int k = tid; k < nq * TP; k += OBS_THREADS) {
+                    const int q = k / TP, i = k - q * TP;
+                    const int mode = src[q].mode;
+                    if (mode < 0) continue;
+                    if (sizeof(AccT) == 4 && src[q].node >= 0) {
+                        const size_t o = (size_t)src[q].node * TP + i;
+                        gx[k] = (AccT)((float)src[q].w * tab_gx[o]);
+                        gy[k] = (AccT)tab_gy[o];
+                    } else {
+                        const double cc = start + (double)i * delta;
+                        const double ux = cc - src[q].x0, uy = cc - src[q].y0;
+                        const double ax = ux * ux / (-2.0 * (src[q].hx * src[q].hx)), ay = uy * uy / (-2.0 * (src[q].hy * src[q].hy));
+                        const double ex = (i < S && ax > -745.2) ? exp(ax) : 0.0;   /* below: exp underflows to 0 anyway */
+                        const double ey = (i < S && ay > -745.2) ? exp(ay) : 0.0;
+                        gx[k] = (AccT)(mode == 0 ? src[q].w * ex : ex);
+                        gy[k] = (AccT)ey;
                     }
                 }
                 __syncthreads();
                 if (!has_tile) continue;
                 if (ch != 3) {
-                    for (int q = 0; q < n; q++) {
+                    for (int q = 0; q < nq; q++) {
+                        if (src[q].mode < 0) continue;
                         AccT a[OBS_TI], v[OBS_TJ];
 #pragma unroll
-                        for (int r = 0; r < OBS_TI; r++) a[r] = gx[q * PI + i0 + r];
+                        for (int r = 0; r < OBS_TI; r++) a[r] = gx[q * TP + i0 + r];
 #pragma unroll
-                        for (int x = 0; x < OBS_TJ; x++) v[x] = gy[q * PJ + j0 + x];
+                        for (int x = 0; x < OBS_TJ; x++) v[x] = gy[q * TP + j0 + x];
 #pragma unroll
                         for (int r = 0; r < OBS_TI; r++)
 #pragma unroll
@@ -192,13 +216,14 @@ __global__ void __launch_bounds__(OBS_THREADS) k_observe(const KParams P, const 
                             }
                     }
                 } else {
-                    for (int q = 0; q < n; q++) {
+                    for (int q = 0; q < nq; q++) {
+                        if (src[q].mode < 0) continue;
                         const AccT w = (AccT)src[q].w, d = (AccT)mtm;
 #pragma unroll
                         for (int r = 0; r < OBS_TI; r++)
 #pragma unroll
                             for (int x = 0; x < OBS_TJ; x++)
-                                acc[r][x] = acc[r][x] + gx[q * PI + i0 + r] * gy[q * PJ + j0 + x] * w / d;
+                                acc[r][x] = acc[r][x] + gx[q * TP + i0 + r] * gy[q * TP + j0 + x] * w / d;
                     }
                 }
             }
@@ -247,6 +272,11 @@ int wrsn_dims_finalize(wrsn_dims *d) {
         d->threads = t;
     }
     if (d->threads % 32 || d->threads > 256) WRSN_FAIL("threads must be a multiple of 32, at most 256");
+    {
+        const int ti = (d->S + OBS_TI - 1) / OBS_TI, tj = (d->S + OBS_TJ - 1) / OBS_TJ;
+        const int pi = ti * OBS_TI, pj = (tj * OBS_TJ + 3) & ~3;
+        d->obs_pitch = pi > pj ? pi : pj;
+    }
     WrsnLayout L;
     wrsn_make_layout(d, &L);
     d->state_bytes = (int32_t)L.total; d->state_resident_bytes = (int32_t)L.resident;
@@ -307,6 +337,15 @@ static KParams base_params(const wrsn_dims *d, const void *scen, const int32_t *
 }
 
 extern "C" {
+
+int wrsn_build_obs_tables(const wrsn_dims *d, void *scen, void *stream) {
+    if (check_dims(d)) return -1;
+    if (!scen) WRSN_FAIL("scen is NULL");
+    WrsnLayout L; wrsn_make_layout(d, &L);
+    k_obs_tables<<<dim3(d->n_scen, d->Npad), 128, 0, (cudaStream_t)stream>>>(*d, L, (char *)scen);
+    WRSN_CUDA(cudaGetLastError());
+    return 0;
+}
 
 int wrsn_init_network(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state,
                       const uint8_t *env_mask, int with_reward_process, void *stream) {
@@ -375,17 +414,16 @@ int wrsn_observe(const wrsn_dims *d, const void *scen, const int32_t *scen_id, c
     if (!agent_id || !obs || !scen || !scen_id || !state) WRSN_FAIL("NULL argument");
     KParams P = base_params(d, scen, scen_id, const_cast<void *>(state), nullptr);
     wrsn_make_layout(&P.d, &P.L);
-    const int tiles_i = (d->S + OBS_TI - 1) / OBS_TI, tiles_j = (d->S + OBS_TJ - 1) / OBS_TJ;
-    const size_t vec = (size_t)tiles_i * OBS_TI + (size_t)((tiles_j * OBS_TJ + 3) & ~3);
     if (obs_f64) {
-        size_t smem = sizeof(double) * 16 * vec;
+        size_t smem = sizeof(double) * 2 * 16 * (size_t)d->obs_pitch;
         if (smem > 200 * 1024) WRSN_FAIL("map_size too large");
         if (smem > 48 * 1024) WRSN_CUDA(cudaFuncSetAttribute(k_observe<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         k_observe<double><<<d->B, OBS_THREADS, smem, (cudaStream_t)stream>>>(P, agent_id, (double *)obs);
     } else {
-        size_t smem = sizeof(float) * 32 * vec;
+        size_t smem = sizeof(float) * 2 * 64 * (size_t)d->obs_pitch;
         if (smem > 200 * 1024) WRSN_FAIL("map_size too large");
-        if (smem > 48 * 1024) WRSN_CUDA(cudaFuncSetAttribute(k_observe<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        static bool attr = false;
+        if (!attr) { WRSN_CUDA(cudaFuncSetAttribute(k_observe<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
         k_observe<float><<<d->B, OBS_THREADS, smem, (cudaStream_t)stream>>>(P, agent_id, (float *)obs);
     }
     WRSN_CUDA(cudaGetLastError());

@@ -73,6 +73,9 @@ WRSN_HD void wrsn_make_layout(const wrsn_dims *d, WrsnLayout *L) {
     L->soff[WRSN_S_NBR_IDX] = o; o += wrsn_a16(4 * (int64_t)d->Emax);
     L->soff[WRSN_S_TGT_IDX] = o; o += wrsn_a16(4 * (int64_t)d->TEmax);
     L->soff[WRSN_S_DIRECT] = o; o += Np;
+    o = wrsn_a16(o);
+    L->soff[WRSN_S_OBS_GX] = o; o += 4 * Np * (int64_t)d->obs_pitch;
+    L->soff[WRSN_S_OBS_GY] = o; o += 4 * Np * (int64_t)d->obs_pitch;
     L->scen_total = wrsn_a16(o);
 }
 

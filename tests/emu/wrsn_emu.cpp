@@ -90,6 +90,7 @@ int wrsn_dims_finalize(wrsn_dims *d) {
     d->Npad = (d->N + 15) & ~15; d->W = (d->N + 31) / 32; d->Tw = (d->T + 31) / 32; if (d->Tw < 1) d->Tw = 1;
     d->n_slot = d->M + 3; if (d->Emax < 1) d->Emax = 1; if (d->TEmax < 1) d->TEmax = 1;
     d->threads = 32;
+    { const int ti = (d->S + 3) / 4, tj = (d->S + 9) / 10; const int pi = ti * 4, pj = (tj * 10 + 3) & ~3; d->obs_pitch = pi > pj ? pi : pj; }
     WrsnLayout L; wrsn_make_layout(d, &L);
     d->state_bytes = (int32_t)L.total; d->state_resident_bytes = (int32_t)L.resident;
     d->scen_bytes = (int32_t)L.scen_total; d->smem_bytes = (int32_t)L.smem_total;
@@ -98,6 +99,7 @@ int wrsn_dims_finalize(wrsn_dims *d) {
 int wrsn_state_layout(const wrsn_dims *d, int64_t *o) { WrsnLayout L; wrsn_make_layout(d, &L); for (int k = 0; k < WRSN_F_COUNT; k++) o[k] = L.off[k]; return 0; }
 int wrsn_scen_layout(const wrsn_dims *d, int64_t *o) { WrsnLayout L; wrsn_make_layout(d, &L); for (int k = 0; k < WRSN_S_COUNT; k++) o[k] = L.soff[k]; return 0; }
 int wrsn_device_ok(void) { return 0; }
+int wrsn_build_obs_tables(const wrsn_dims *, void *, void *) { return 0; }   /* only the CUDA raster reads them */
 
 int wrsn_init_network(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state, const uint8_t *m, int wr, void *) {
     Args A = {d, (const char *)scen, scen_id, (char *)state, nullptr, m, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, wr};
