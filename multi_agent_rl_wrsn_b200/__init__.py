@@ -5,5 +5,6 @@
 """
 from .scenario import Scenario, build_static, load_mc_type, synthetic  # noqa: F401
 from .batched import BatchedWRSN, Requests  # noqa: F401
+from .wrsn import WRSN  # noqa: F401
 
-__all__ = ["Scenario", "build_static", "load_mc_type", "synthetic", "BatchedWRSN", "Requests"]
+__all__ = ["Scenario", "build_static", "load_mc_type", "synthetic", "BatchedWRSN", "Requests", "WRSN"]

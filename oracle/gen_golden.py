@@ -245,6 +245,30 @@ def episode(R, case, scn, actions, num_agent=3, mc_yaml=None, max_decisions=10**
                                                              time.time() - t0), flush=True)
 
 
+def episode_density(R, case, scn, n_dec, num_agent=3):
+    """``density_map=True`` with the reference's RandomController rule (controller/random/RandomController.py:12-15:
+    dmap = s0 + s1 - 10 s2 + s3), i.e. runner/checkRL.py's loop: records the decoded action of every decision."""
+    t0 = time.time()
+    w = R.WRSN(os.path.join(R.scenario_dir, scn + ".yaml"), R.mc_type, num_agent, map_size=100, density_map=True)
+    req = w.reset()
+    rows = []
+    while len(rows) < n_dec and not req["terminal"]:
+        st = req["state"]
+        dmap = np.copy(st[0] + st[1] - 10 * st[2] + st[3])
+        aid = req["agent_id"]
+        req = w.step(aid, dmap)
+        rows.append(dict(fed_agent=aid, agent_id=-1 if req["agent_id"] is None else req["agent_id"], now=float(w.env.now),
+                         action=np.array(w.agents_action[aid], np.float64),
+                         reward=np.nan if req["reward"] is None else float(req["reward"]),
+                         energy=np.array([float(n.energy) for n in w.net.listNodes])))
+    out = dict(case=case, scenario=scn, num_agent=num_agent, n=len(rows))
+    out.update(_scenario_arrays(os.path.join(R.scenario_dir, scn + ".yaml")))
+    for k in rows[0]:
+        out[k] = np.stack([np.asarray(r[k]) for r in rows])
+    np.savez_compressed(os.path.join(OUT, "dmap_%s.npz" % case), **out)
+    print("dmap:%s decisions=%d now=%.4f (%.0fs)" % (case, len(rows), w.env.now, time.time() - t0), flush=True)
+
+
 def rand_actions(seed, n, scale2=0.05):
     rng = np.random.default_rng(seed)
     a = rng.uniform(0.0, 1.0, size=(n, 3))
@@ -289,11 +313,13 @@ NETS = ["hanoi1000n50", "hanoi1000n100", "hanoi1000n150", "hanoi1000n200", "sonl
 def main(argv):
     os.makedirs(OUT, exist_ok=True)
     R = load_reference()
-    todo = argv or (["net:" + s for s in NETS] + ["ep:" + c for c in CASES])
+    todo = argv or (["net:" + s for s in NETS] + ["ep:" + c for c in CASES] + ["dmap:random_n50"])
     for item in todo:
         kind, name = item.split(":")
         if kind == "net":
             pure_network(R, name)
+        elif kind == "dmap":
+            episode_density(R, name, "hanoi1000n50", 8)
         else:
             scn, actions, kw = CASES[name]
             episode(R, name, scn, actions, **kw)

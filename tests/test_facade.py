@@ -1,0 +1,75 @@
+"""The single-environment façade (multi_agent_rl_wrsn_b200.wrsn.WRSN) against the reference's request dicts."""
+import numpy as np
+import pytest
+import torch
+
+from multi_agent_rl_wrsn_b200 import _lib
+from tests import parity_cases as pc
+from tests.helpers import golden, mc_dict_of
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def cuda_library():
+    prev = _lib._lib
+    _lib._lib = None
+    _lib.lib()
+    yield
+    _lib._lib = prev
+
+
+def test_request_dict_matches_reference_episode():
+    from multi_agent_rl_wrsn_b200.wrsn import WRSN
+    g = golden("ep_edge_n50")
+    env = WRSN(pc.sc_from_golden(g), mc_dict_of(g), int(g["num_agent"]), map_size=100, device="cuda:0")
+    assert env.num_agent == 3 and env.observation_space.shape == (4, 100, 100) and env.action_space.shape == (3,)
+    req = env.reset()
+    full = {int(i): k for k, i in enumerate(g["full_state_idx"])}
+    for i in range(int(g["n"])):
+        if i > 0:
+            req = env.step(int(g["fed_agent"][i]), list(g["fed_action"][i]))
+        assert set(req) >= {"agent_id", "prev_state", "input_action", "action", "reward", "state", "terminal", "info", "detailed_rewards"}
+        assert req["agent_id"] == int(g["agent_id"][i]) and req["terminal"] == bool(g["terminal"][i])
+        assert env.env.now == float(g["now"][i])
+        assert env.net.targets_active == [int(v) for v in g["targets_active"][i]]
+        np.testing.assert_array_equal(req["action"], g["action"][i])
+        if i > 0:
+            np.testing.assert_allclose(req["reward"], float(g["reward"][i]), rtol=1e-9, atol=1e-18)
+            np.testing.assert_allclose(req["detailed_rewards"][2], req["reward"])
+        assert req["state"].shape == (4, 100, 100) and req["state"].dtype == np.float64
+        if i in full:
+            np.testing.assert_allclose(req["state"], g["full_state"][full[i]], rtol=1e-9, atol=1e-12)
+
+
+def test_prev_state_is_last_state_of_that_agent():
+    from multi_agent_rl_wrsn_b200.wrsn import WRSN
+    g = golden("ep_basic_n50")
+    env = WRSN(pc.sc_from_golden(g), mc_dict_of(g), 3, device="cuda:0")
+    req = env.reset()
+    want = {int(i): k for k, i in enumerate(g["full_prev_state_idx"])}
+    for i in range(1, max(want) + 1):
+        req = env.step(int(g["fed_agent"][i]), list(g["fed_action"][i]))
+        if i in want:
+            np.testing.assert_allclose(req["prev_state"], g["full_prev_state"][want[i]], rtol=1e-9, atol=1e-12)
+
+
+def test_density_map_actions_follow_the_reference():
+    """density_map=True with the RandomController rule (runner/checkRL.py): decoded actions, decision times and node
+    energies of the reference's first decisions.  The decode runs scipy's L-BFGS-B on a discontinuous objective, so
+    actions are compared at 1e-6 and the episode is only followed while it stays on the reference's trajectory."""
+    from multi_agent_rl_wrsn_b200.wrsn import WRSN
+    g = golden("dmap_random_n50")
+    env = WRSN(pc.sc_from_golden(g), None, int(g["num_agent"]), density_map=True, device="cuda:0")
+    req = env.reset()
+    for i in range(int(g["n"])):
+        st = req["state"]
+        aid = req["agent_id"]
+        assert aid == int(g["fed_agent"][i])
+        req = env.step(aid, np.copy(st[0] + st[1] - 10 * st[2] + st[3]))
+        np.testing.assert_allclose(env._b.mc("ACT0")[0, aid].item(), g["action"][i][0], rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(env._b.mc("ACT1")[0, aid].item(), g["action"][i][1], rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(env._b.mc("ACT2")[0, aid].item(), g["action"][i][2], rtol=1e-6, atol=1e-9)
+        assert req["agent_id"] == int(g["agent_id"][i])
+        np.testing.assert_allclose(env.env.now, float(g["now"][i]), rtol=1e-7)
+        np.testing.assert_allclose(env._b.view("energy")[0].cpu().numpy(), g["energy"][i], rtol=1e-5)
