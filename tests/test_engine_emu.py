@@ -74,3 +74,10 @@ def test_rollout_step_equals_manual_loop():
     scs = [synthetic(num_nodes=40, num_targets=120, seed=s, num_gateways=2) for s in (3, 4)]
     resets = pc.check_rollout_step(scs, "cpu", num_envs=6, steps=120, seed=1, with_obs=False)
     assert resets >= 3
+
+
+@pytest.mark.parametrize("nodes,targets,chargers,envs,steps", [(500, 500, 5, 2, 30), (1000, 1000, 10, 1, 45)])
+def test_large_configs_vs_oracle(nodes, targets, chargers, envs, steps):
+    sc = synthetic(num_nodes=nodes, num_targets=targets, seed=nodes, num_gateways=max(3, nodes // 40))
+    n_dec, cnt = pc.check_vs_oracle(sc, "cpu", num_envs=envs, steps=steps, seed=4, num_agent=chargers)
+    assert n_dec >= envs * 15

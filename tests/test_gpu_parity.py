@@ -126,3 +126,12 @@ def test_full_size_properties():
     obs = env.get_state()
     assert obs.shape == (B, 4, 100, 100) and bool(torch.isfinite(obs).all())
     assert bool((obs[0] == obs[1]).all())
+
+
+@pytest.mark.parametrize("nodes,targets,chargers,envs,steps", [(500, 500, 5, 3, 30), (1000, 1000, 10, 2, 45)])
+def test_large_configs_vs_oracle(nodes, targets, chargers, envs, steps):
+    """BASELINE configs 4 and 5 (500 nodes / 5 chargers, 1000 nodes / 10 chargers): the multi-warp build
+    (128 / 256 threads per environment) against the oracle on a few environments and decisions."""
+    sc = synthetic(num_nodes=nodes, num_targets=targets, seed=nodes, num_gateways=max(3, nodes // 40))
+    n_dec, cnt = pc.check_vs_oracle(sc, DEV, num_envs=envs, steps=steps, seed=4, num_agent=chargers, check_obs=(nodes == 500))
+    assert n_dec >= envs * 15
