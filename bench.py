@@ -338,6 +338,14 @@ def run_b200(a):
     obs_bytes = r_decisions * (4 * S * S * 4) / n_l
     step_gbs = step_bytes / (step_ms / n_l * 1e-3) / 1e9
     obs_gbs = obs_bytes / (obs_ms / n_l * 1e-3) / 1e9
+    traffic = None          # DRAM bytes per launch of the dominant kernel from the committed ncu capture, same launch shape only
+    try:
+        with open(os.path.join(REPO, "profiles", "traffic_r01.json")) as f:
+            tj = json.load(f)
+        if tj.get("nodes") == N and tj.get("chargers") == M and tj.get("envs_per_launch") == Bg:
+            traffic = tj
+    except Exception:
+        pass
     dominant = "k_env<MODE_STEP>" if step_ms >= obs_ms else "k_observe<float>"
     ach = step_gbs if step_ms >= obs_ms else obs_gbs
     line = dict(
@@ -357,7 +365,8 @@ def run_b200(a):
                  note="per step: actions from pinned host memory, rollout_step (step | reset | observe), request record "
                       "(agent_id, reward, terminal, now) read back on the host; observations stay in HBM for the policy networks"),
         gpu_launches=n_launch,
-        roofline=dict(bound="hbm", kernel=dominant, achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=None,
+        roofline=dict(bound="hbm", kernel=dominant, achieved=ach, peak=peak, unit="GB/s", frac=ach / peak,
+                      traffic=(traffic or {}).get(dominant), traffic_source=(traffic or {}).get("source"),
                       peak_source=peak_src,
                       how="serialized pass of %d launches per kernel on one stream right after the timed region" % n_l,
                       kernels={"k_env<MODE_STEP>": dict(ms_per_launch=step_ms / n_l, algorithmic_bytes=step_bytes, gbs=step_gbs,
