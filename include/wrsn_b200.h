@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define WRSN_ABI_VERSION 6
+#define WRSN_ABI_VERSION 7
 #define WRSN_MAX_MC 16          /* chargers per environment */
 #define WRSN_RING 10            /* Node.operate keeps the last 10 per-second consumptions (Node.py:70-77) */
 
@@ -60,11 +60,12 @@ enum {
     WRSN_H_NTICKS, WRSN_H_NEVENTS, WRSN_H_NSLOW, WRSN_H_NBFS, WRSN_H_NDECISIONS,
     WRSN_H_CHAIN_N, WRSN_H_CHAIN_DETACH,                            /* AnyOf chain of WRSN.step (:307-311) */
     WRSN_H_NSTALE,                                                  /* routing-tree rebuilds on stale levels (after Network.operate stopped) */
-    WRSN_H_CHAIN_SLOT = 32,                                         /* [WRSN_MAX_MC] process slot watched by member j */
+    WRSN_H_NLAZY,                                                   /* charger spans replayed lazily (slot_ff) */
+    WRSN_H_CHAIN_SLOT = 40,                                         /* [WRSN_MAX_MC] process slot watched by member j */
     WRSN_H_COND_TRIG = WRSN_H_CHAIN_SLOT + WRSN_MAX_MC,
     WRSN_H_COND_T = WRSN_H_COND_TRIG + WRSN_MAX_MC,                 /* time of the pending condition event, +inf when none */
     WRSN_H_COND_KEY = WRSN_H_COND_T + WRSN_MAX_MC,                  /* 2^40 + insertion counter */
-    WRSN_H_LEN = WRSN_H_COND_KEY + WRSN_MAX_MC                      /* 96 */
+    WRSN_H_LEN = WRSN_H_COND_KEY + WRSN_MAX_MC                      /* 104 */
 };
 
 /* ---- charger record  mc[M][WRSN_MC_LEN]  (MobileCharger.py:6-32 + WRSN per-agent lists) ---- */
@@ -81,15 +82,20 @@ enum {
 
 /* ---- charger process slot  proc[n_slot][WRSN_PR_LEN]  (one running MobileCharger.operate_step generator tree:
  *      operate_step -> move -> move_step / recharge / charge -> charge_step, flattened to one state machine with one
- *      pending event).  The first three doubles hold six int32 fields (WRSN_PRI_*); the rest are doubles. ---- */
-enum { WRSN_PRI_USED = 0, WRSN_PRI_PROCESSED, WRSN_PRI_CURRENT, WRSN_PRI_AGENT, WRSN_PRI_PC, WRSN_PRI_STAGE };
+ *      pending event).  The first four doubles hold eight int32 fields (WRSN_PRI_*); the rest are doubles.
+ *      A slot in the middle of a move (or of a charge without an alive connected node) only touches its own charger:
+ *      it is marked LAZY, the engine schedules just the instant TINT at which that run of spans ends, and the spans in
+ *      between are replayed in one tight loop when they are first needed. ---- */
+enum { WRSN_PRI_USED = 0, WRSN_PRI_PROCESSED, WRSN_PRI_CURRENT, WRSN_PRI_AGENT, WRSN_PRI_PC, WRSN_PRI_STAGE, WRSN_PRI_LAZY,
+       WRSN_PRI_SPARE };
 enum {
-    WRSN_PR_T = 3,                                     /* time of the pending event, +inf when none is pending */
+    WRSN_PR_T = 4,                                     /* time of the pending event, +inf when none is pending */
     WRSN_PR_KEY,                                       /* priority * 2^40 + insertion counter of the pending event */
     WRSN_PR_PHY0, WRSN_PR_PHY1, WRSN_PR_PHY2,
     WRSN_PR_DESTX, WRSN_PR_DESTY, WRSN_PR_MT, WRSN_PR_VX, WRSN_PR_VY, WRSN_PR_TOTAL, WRSN_PR_SPAN,
     WRSN_PR_SVX, WRSN_PR_SVY, WRSN_PR_CHTMP, WRSN_PR_CHSPAN,
-    WRSN_PR_LEN = 20
+    WRSN_PR_TINT,                                      /* LAZY: time of the span event that ends the run of private spans */
+    WRSN_PR_LEN = 22
 };
 
 /* ---- fields of one environment record (wrsn_state_layout) ---- */

@@ -352,9 +352,10 @@ WRSN_DI void mc_scan(Ctx &c, Clk &k) {
 #pragma unroll 1
     for (int s = 0; s < ns; s++) {
         const double *p = c.proc + s * WRSN_PR_LEN;
-        const double t = p[WRSN_PR_T];
+        const bool lazy = ((const int *)p)[WRSN_PRI_LAZY] != 0;
+        const double t = lazy ? p[WRSN_PR_TINT] : p[WRSN_PR_T];   /* a lazy slot next matters when its run of spans ends */
         if (t < INFINITY) {
-            const double key = p[WRSN_PR_KEY];
+            const double key = lazy ? WRSN_KEY_NORMAL * 2.0 : p[WRSN_PR_KEY];
             if (ev_before(t, key, bt, bkey)) { ot = bt; bi = s; bt = t; bkey = key; }
             else ot = fmin(ot, t);
         }
@@ -771,6 +772,134 @@ WRSN_D void cond_check_h(Ctx &c, int j) {          /* leader-only variant used w
     h[WRSN_H_COND_T + j] = h[WRSN_H_NOW]; h[WRSN_H_COND_KEY + j] = WRSN_KEY_NORMAL + take_seq_h(c);
 }
 
+/* ------------------------------------------------------------------ lazy charger spans
+ * A charger in the middle of a move repeats, once per second, "move_step fires; move() updates the remaining time and
+ * starts the next move_step" (MobileCharger.move :85-96); a charger charging where no alive node is in range repeats
+ * "charge_step fires; charge() counts the time down and starts the next charge_step" (:59-72, :40-50).  These events
+ * read and write only the charger's own record, so they commute with every grid event and with the other chargers.
+ * slot_ff() replays such a run of spans in registers — the reference's arithmetic, operation by operation, three
+ * insertion counters per span — up to a time limit, or (commit = false) just finds the instant at which the run ends
+ * (arrival, exhaustion, end of the charge, or a span landing exactly on the node grid, where the reference's insertion
+ * order against the grid events would matter).  Everything else about the slot stays with ev_slot(). */
+WRSN_DI bool on_grid(double t) {
+    const double f = floor(t);
+    return t == f || t == f + 0.5 || t == f + 0.1;
+}
+
+WRSN_DI bool conn_has_alive(Ctx &c, int a) {
+    const double *m = c.mc + a * WRSN_MC_LEN;
+    if (m[WRSN_MC_NCONN] == 0.0) return false;
+    const uint32_t *cm = c.conn + a * c.W;
+    for (int w = 0; w < c.W; w++)
+        for (uint32_t bits = cm[w]; bits; bits &= bits - 1u)
+            if (c.status[32 * w + wrsn_ctz(bits)] == 1) return true;
+    return false;
+}
+
+/* may the pending event of slot s start a lazy run? */
+WRSN_DI bool slot_lazy_ok(Ctx &c, int s) {
+    const double *p = slot_of(c, s);
+    const int *pi = (const int *)p;
+    const int pc = pi[WRSN_PRI_PC];
+    if (pc != PC_MS_FIRE && pc != PC_CS_FIRE) return false;
+    const int a = pi[WRSN_PRI_AGENT];
+    for (int q = 0; q < c.n_slot; q++)               /* a second running process of the same charger shares its record */
+        if (q != s && slot_i(slot_of(c, q))[WRSN_PRI_USED] != 0 && slot_i(slot_of(c, q))[WRSN_PRI_AGENT] == a &&
+            slot_of(c, q)[WRSN_PR_T] < INFINITY) return false;
+    const double *m = c.mc + a * WRSN_MC_LEN;
+    if (pc == PC_CS_FIRE) return m[WRSN_MC_RATE] == 0.0 && !conn_has_alive(c, a);
+    return m[WRSN_MC_TYPE] == 0.0 || !conn_has_alive(c, a);   /* update_reward reads a "charging" charger's position */
+}
+
+/* replay spans of slot s whose event time is < limit; returns the number replayed and, in *t_end, the time of the span
+ * event at which the run stops being private (or +inf if the limit came first) */
+WRSN_DI int slot_ff(Ctx &c, Clk &k, int s, double limit, bool commit, double *t_end) {
+    double *p = slot_of(c, s);
+    const int a = slot_i(p)[WRSN_PRI_AGENT], pc = slot_i(p)[WRSN_PRI_PC];
+    double *m = mc_of(c, a);
+    const double *par = c.par;
+    const double thr = par[WRSN_P_MC_THR];
+    double tf = p[WRSN_PR_T], ts_prev = tf;
+    int n = 0;
+    *t_end = INFINITY;
+    if (pc == PC_MS_FIRE) {
+        const double v = par[WRSN_P_MC_V], pm = par[WRSN_P_MC_PM], pmv = par[WRSN_P_MC_PMV];
+        const double destx = p[WRSN_PR_DESTX], desty = p[WRSN_PR_DESTY], vx = p[WRSN_PR_VX], vy = p[WRSN_PR_VY], total = p[WRSN_PR_TOTAL];
+        double x = m[WRSN_MC_X], y = m[WRSN_MC_Y], en = m[WRSN_MC_ENERGY];
+        double mt = p[WRSN_PR_MT], span = p[WRSN_PR_SPAN], svx = p[WRSN_PR_SVX], svy = p[WRSN_PR_SVY];
+        while (tf < limit) {
+            if (on_grid(tf)) { *t_end = tf; break; }
+            const double x1 = x + svx, y1 = y + svy, en1 = en - pm * span * v;     /* move_step :77-78 */
+            const double mt1 = mt - span;                                         /* move :95 */
+            if (mt1 <= 0.0 || en1 <= thr) { *t_end = tf; break; }                 /* arrival / exhaustion: ev_slot's business */
+            const double mt2 = euclid2(destx, desty, x1, y1) / v;                 /* move :91-94 */
+            const double span2 = fmin(fmin(mt2, 1.0), (en1 - thr) / pmv);
+            x = x1; y = y1; en = en1; mt = mt2; span = span2;
+            svx = vx / total * span2; svy = vy / total * span2;
+            ts_prev = tf; tf = tf + span2; n++;
+        }
+        if (commit && n > 0) {
+            gsync(c);
+            if (WRSN_LEAD(c)) {
+                m[WRSN_MC_X] = x; m[WRSN_MC_Y] = y; m[WRSN_MC_ENERGY] = en;
+                p[WRSN_PR_MT] = mt; p[WRSN_PR_SPAN] = span; p[WRSN_PR_SVX] = svx; p[WRSN_PR_SVY] = svy;
+            }
+        }
+    } else {                                         /* PC_CS_FIRE with charging rate 0 and nobody alive in range */
+        double en = m[WRSN_MC_ENERGY], cpa2 = m[WRSN_MC_CPA2], tmp = p[WRSN_PR_CHTMP], span = p[WRSN_PR_CHSPAN];
+        const double rate = m[WRSN_MC_RATE];
+        while (tf < limit) {
+            if (on_grid(tf)) { *t_end = tf; break; }
+            const double en1 = en - rate * span;                                   /* charge_step :45 */
+            const double cpa21 = fmax(0.0, cpa2 - span);                           /* :46 */
+            const double tmp1 = tmp - span;                                        /* charge :69 */
+            if (tmp1 == 0.0 || en1 <= thr) { *t_end = tf; break; }
+            en = en1; cpa2 = cpa21; tmp = tmp1; span = fmin(tmp1, 1.0);            /* :63 (rate is 0: no energy limiter) */
+            ts_prev = tf; tf = tf + span; n++;
+        }
+        if (commit && n > 0) {
+            gsync(c);
+            if (WRSN_LEAD(c)) {
+                m[WRSN_MC_ENERGY] = en; m[WRSN_MC_CPA2] = cpa2; m[WRSN_MC_CHTIME] = tmp;
+                p[WRSN_PR_CHTMP] = tmp; p[WRSN_PR_CHSPAN] = span;
+            }
+        }
+    }
+    if (commit && n > 0) {
+        /* every span drew three insertion counters (completion of the step, start of the next one, its timeout) */
+        const double key = k.seq + 3.0 * (double)n - 1.0;
+        k.seq += 3.0 * (double)n; k.nev += 3.0 * (double)n;
+        if (WRSN_LEAD(c)) { p[WRSN_PR_T] = tf; p[WRSN_PR_KEY] = WRSN_KEY_NORMAL + key; c.hdr[WRSN_H_NLAZY] += (double)n; }
+        gsync(c);
+    }
+    (void)ts_prev;
+    return n;
+}
+
+/* after an event of slot s: if its next event starts a private run of at least one span, make the slot lazy */
+WRSN_DI void slot_try_lazy(Ctx &c, Clk &k, int s) {
+    double *p = slot_of(c, s);
+    if (!(p[WRSN_PR_T] < INFINITY) || !slot_lazy_ok(c, s)) return;
+    double t_end;
+    const int n = slot_ff(c, k, s, INFINITY, false, &t_end);
+    if (n < 1) return;
+    gsync(c);
+    if (WRSN_LEAD(c)) { slot_i(p)[WRSN_PRI_LAZY] = 1; p[WRSN_PR_TINT] = t_end; }
+    gsync(c);
+}
+
+/* bring a lazy slot up to date: replay its spans before `limit`; wake = it becomes an ordinary slot again */
+WRSN_DI void slot_catch_up(Ctx &c, Clk &k, int s, double limit, bool wake) {
+    double *p = slot_of(c, s);
+    double t_end;
+    slot_ff(c, k, s, limit, true, &t_end);
+    if (wake) {
+        gsync(c);
+        if (WRSN_LEAD(c)) slot_i(p)[WRSN_PRI_LAZY] = 0;
+        gsync(c);
+    }
+}
+
 /* Events of one charger process slot, starting with the pending one.  Zero-delay follow-up events of the same slot
  * (process start / completion hops of the generator tree) are executed back to back as long as NO other event of the
  * environment is due at the current instant (`other_t` > now): then the (time, priority, counter) order would pick
@@ -1004,8 +1133,11 @@ WRSN_DI void run_loop(Ctx &c) {
         if (ev_before(k.mc_t, k.mc_key, gt, gkey)) {
             k.now = k.mc_t;
             if (k.mc_idx < c.n_slot) {
+                const int s = k.mc_idx;
+                if (slot_i(slot_of(c, s))[WRSN_PRI_LAZY] != 0) slot_catch_up(c, k, s, k.mc_t, true);   /* its run of private spans ends now */
                 double other = fmin(fmin(k.mc_other_t, k.nodes_t), fmin(fmin(k.net_t, k.ur_t), k.until_t));
-                ev_slot(c, k, k.mc_idx, other);
+                ev_slot(c, k, s, other);
+                slot_try_lazy(c, k, s);
             } else ev_cond(c, k, k.mc_idx - c.n_slot);
             rescan = true;
         } else {
@@ -1030,6 +1162,9 @@ WRSN_DI void run_loop(Ctx &c) {
         }
         if (k.stop) break;
     }
+    /* whoever looks at the chargers next (decider scan, observation, the next step) sees them as of now */
+    for (int s = 0; s < c.n_slot; s++)
+        if (slot_i(slot_of(c, s))[WRSN_PRI_LAZY] != 0) slot_catch_up(c, k, s, k.now, false);
     clk_store(c, k);
 }
 
@@ -1161,6 +1296,7 @@ WRSN_D void entry_step(Ctx &c, int agent_id, const double *input_action, ReqOut 
             if (old >= 0) {
                 int *po = slot_i(slot_of(c, old));
                 po[WRSN_PRI_CURRENT] = 0;
+                po[WRSN_PRI_LAZY] = 0;               /* two processes now share this charger's record: no private runs */
                 if (po[WRSN_PRI_PROCESSED] != 0) po[WRSN_PRI_USED] = 0;
             }
             m[WRSN_MC_SLOT] = new_slot_h(c, agent_id, phy0, phy1, phy2);
