@@ -68,24 +68,49 @@
 #define WRSN_LEAD(c) ((c).tid == 0)
 #endif
 
-/* ------------------------------------------------------------------ context */
+#undef WRSN_SMEM_BASE
+#if defined(WRSN_HOST_EMU)
+#define WRSN_SMEM_BASE wrsn_smem_host              /* set per environment by the emulation driver */
+#else
+#define WRSN_SMEM_BASE (reinterpret_cast<char *>(wrsn_smem_u4))
+#endif
+
+/* ------------------------------------------------------------------ context
+ * The environment's shared-memory image is addressed as 32-bit offsets from the CTA's dynamic shared memory (SArr):
+ * the compiler then knows the address space (LDS / STS with immediate offsets instead of generic 64-bit loads), the
+ * context stays small, and nothing has to be re-derived from 64-bit pointers in the hot loop. */
+#undef WRSN_M
+#if defined(WRSN_HOST_EMU)
+#define WRSN_M inline
+#else
+#define WRSN_M __device__ __forceinline__
+#endif
+template <typename T>
+struct SArr {
+    uint32_t off;
+    WRSN_M T *ptr() const { return reinterpret_cast<T *>(WRSN_SMEM_BASE + off); }
+    WRSN_M operator T *() const { return ptr(); }
+    template <typename I> WRSN_M T &operator[](I i) const { return ptr()[i]; }
+};
+
 struct Ctx {
     int tid, G;
     int N, T, M, W, Tw, Npad, n_slot, scr_len;
     /* shared-memory image */
-    double *hdr, *mc, *proc;
-    double *energy, *rr, *cs, *esend, *logc;
-    uint16_t *nbef, *naft, *own;
-    int16_t *level, *parent;
-    uint8_t *status;
-    uint32_t *tact, *conn;
-    double *scr0, *scr1;
-    int *bcast;
-    double *red;
+    SArr<double> hdr, mc, proc;
+    SArr<double> energy, rr, cs, esend, logc;
+    SArr<uint16_t> nbef, naft, own;
+    SArr<int16_t> level, parent;
+    SArr<uint8_t> status;
+    SArr<uint32_t> tact, conn;
+    SArr<double> scr0, scr1;
+    SArr<int> bcast;
+    SArr<double> red;
+    SArr<double> par;                                /* scenario constants, copied next to the state */
     /* global, per environment */
     double *logtick, *ring;
     /* global, per scenario */
-    const double *par, *nx, *ny, *bs_esend, *nbr_dist, *nbr_esend;
+    const double *nx, *ny, *bs_esend, *nbr_dist, *nbr_esend;
     const int32_t *nbr_ptr, *tgt_ptr, *nbr_idx, *tgt_idx;
     const uint8_t *direct;
 };
@@ -99,37 +124,23 @@ enum {   /* program counter of a charger process slot */
 };
 
 WRSN_D void ctx_bind(Ctx &c, const wrsn_dims &d, const WrsnLayout &L, const char *scen_row, char *state_row,
-                     char *smem, int tid, int G) {
+                     int tid, int G) {
     c.tid = tid; c.G = G;
     c.N = d.N; c.T = d.T; c.M = d.M; c.W = d.W; c.Tw = d.Tw; c.Npad = d.Npad; c.n_slot = d.n_slot;
     c.scr_len = L.scr_len;
-    c.hdr = (double *)(smem + L.off[WRSN_F_HDR]);
-    c.mc = (double *)(smem + L.off[WRSN_F_MC]);
-    c.proc = (double *)(smem + L.off[WRSN_F_PROC]);
-    c.energy = (double *)(smem + L.off[WRSN_F_ENERGY]);
-    c.rr = (double *)(smem + L.off[WRSN_F_RR]);
-    c.cs = (double *)(smem + L.off[WRSN_F_CS]);
-    c.esend = (double *)(smem + L.off[WRSN_F_ESEND]);
-    c.logc = (double *)(smem + L.off[WRSN_F_LOGC]);
-    c.nbef = (uint16_t *)(smem + L.off[WRSN_F_NBEF]);
-    c.naft = (uint16_t *)(smem + L.off[WRSN_F_NAFT]);
-    c.level = (int16_t *)(smem + L.off[WRSN_F_LEVEL]);
-    c.parent = (int16_t *)(smem + L.off[WRSN_F_PARENT]);
-    c.status = (uint8_t *)(smem + L.off[WRSN_F_STATUS]);
-    c.tact = (uint32_t *)(smem + L.off[WRSN_F_TACT]);
-    c.conn = (uint32_t *)(smem + L.off[WRSN_F_CONN]);
-    c.own = (uint16_t *)(smem + L.s_own);
-    c.scr0 = (double *)(smem + L.s_scr0);
-    c.scr1 = (double *)(smem + L.s_scr1);
-    c.bcast = (int *)(smem + L.s_bcast);
-    c.red = (double *)(smem + L.s_red);
+    c.hdr.off = (uint32_t)L.off[WRSN_F_HDR]; c.mc.off = (uint32_t)L.off[WRSN_F_MC]; c.proc.off = (uint32_t)L.off[WRSN_F_PROC];
+    c.energy.off = (uint32_t)L.off[WRSN_F_ENERGY]; c.rr.off = (uint32_t)L.off[WRSN_F_RR]; c.cs.off = (uint32_t)L.off[WRSN_F_CS];
+    c.esend.off = (uint32_t)L.off[WRSN_F_ESEND]; c.logc.off = (uint32_t)L.off[WRSN_F_LOGC];
+    c.nbef.off = (uint32_t)L.off[WRSN_F_NBEF]; c.naft.off = (uint32_t)L.off[WRSN_F_NAFT];
+    c.level.off = (uint32_t)L.off[WRSN_F_LEVEL]; c.parent.off = (uint32_t)L.off[WRSN_F_PARENT];
+    c.status.off = (uint32_t)L.off[WRSN_F_STATUS]; c.tact.off = (uint32_t)L.off[WRSN_F_TACT]; c.conn.off = (uint32_t)L.off[WRSN_F_CONN];
+    c.own.off = (uint32_t)L.s_own; c.scr0.off = (uint32_t)L.s_scr0; c.scr1.off = (uint32_t)L.s_scr1;
+    c.bcast.off = (uint32_t)L.s_bcast; c.red.off = (uint32_t)L.s_red; c.par.off = (uint32_t)L.s_par;
     c.logtick = (double *)(state_row + L.off[WRSN_F_LOGTICK]);
     c.ring = (double *)(state_row + L.off[WRSN_F_RING]);
     {
         const double *gpar = (const double *)(scen_row + L.soff[WRSN_S_PAR]);
-        double *spar = (double *)(smem + L.s_par);
-        for (int k = tid; k < WRSN_P_LEN; k += G) spar[k] = gpar[k];   /* visible after the caller's first barrier */
-        c.par = spar;
+        for (int k = tid; k < WRSN_P_LEN; k += G) c.par[k] = gpar[k];   /* visible after the caller's first barrier */
     }
     c.nx = (const double *)(scen_row + L.soff[WRSN_S_NX]);
     c.ny = (const double *)(scen_row + L.soff[WRSN_S_NY]);
@@ -395,7 +406,7 @@ WRSN_NOINLINE void leave_uniform(Ctx &c) {
  * its children send, forwards nothing (e_send = 0) and sends nothing itself — as the reference does. */
 WRSN_NOINLINE void build_tree(Ctx &c) {
     const int N = c.N;
-    int *cnt = (int *)c.scr0;                       /* 2 ints per node: relayed packets from lower / higher ids */
+    int *cnt = (int *)c.scr0.ptr();                       /* 2 ints per node: relayed packets from lower / higher ids */
     for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
         cnt[2 * i] = 0; cnt[2 * i + 1] = 0;
         int par = -1; double es = 0.0;
@@ -817,7 +828,7 @@ WRSN_DI int slot_ff(Ctx &c, Clk &k, int s, double limit, bool commit, double *t_
     double *p = slot_of(c, s);
     const int a = slot_i(p)[WRSN_PRI_AGENT], pc = slot_i(p)[WRSN_PRI_PC];
     double *m = mc_of(c, a);
-    const double *par = c.par;
+    const double *par = c.par.ptr();
     const double thr = par[WRSN_P_MC_THR];
     double tf = p[WRSN_PR_T], ts_prev = tf;
     int n = 0;
@@ -909,7 +920,7 @@ WRSN_DI void ev_slot(Ctx &c, Clk &k, int s, double other_t) {
     const int a = slot_i(p)[WRSN_PRI_AGENT];
     double *m = mc_of(c, a);
     uint32_t *cm = c.conn + (size_t)a * c.W;
-    const double *par = c.par;
+    const double *par = c.par.ptr();
     const bool lead = WRSN_LEAD(c);
     for (;;) {
         const int pc = slot_i(p)[WRSN_PRI_PC];
@@ -920,7 +931,7 @@ WRSN_DI void ev_slot(Ctx &c, Clk &k, int s, double other_t) {
         switch (pc) {
         case PC_OP_INIT: {                           /* MobileCharger.operate_step :105-132, up to the first yield */
             const double dx = p[WRSN_PR_PHY0], dy = p[WRSN_PR_PHY1], ct = p[WRSN_PR_PHY2];
-            uint32_t *near = (uint32_t *)c.scr1;
+            uint32_t *near = (uint32_t *)c.scr1.ptr();
             near_mask(c, dx, dy, near);
             const double pm = par[WRSN_P_MC_PM], beta = par[WRSN_P_MC_BETA], alpha = par[WRSN_P_MC_ALPHA];
             double used = euclid2(dx, dy, m[WRSN_MC_X], m[WRSN_MC_Y]) * pm;

@@ -2,8 +2,7 @@
  * wrsn_engine.cuh), inside the same namespace. */
 template <int MODE>
 __global__ void __launch_bounds__(WRSN_GFIX ? WRSN_GFIX : 256, WRSN_GFIX ? 20 : 1) k_env(const KParams P) {
-    extern __shared__ uint4 smem_u4[];
-    char *smem = reinterpret_cast<char *>(smem_u4);
+    char *smem = reinterpret_cast<char *>(wrsn_smem_u4);
     const int b = blockIdx.x, tid = threadIdx.x, G = blockDim.x;
     if (P.mask && !P.mask[b]) return;
     if (P.mask_mode == 1 && P.req.agent_id[b] < 0) return;
@@ -11,7 +10,7 @@ __global__ void __launch_bounds__(WRSN_GFIX ? WRSN_GFIX : 256, WRSN_GFIX ? 20 : 
     char *row = P.state + (size_t)b * P.L.total;
     const char *scen_row = P.scen + (size_t)P.scen_id[b] * P.L.scen_total;
     Ctx c;
-    ctx_bind(c, P.d, P.L, scen_row, row, smem, tid, G);
+    ctx_bind(c, P.d, P.L, scen_row, row, tid, G);
     if (MODE == MODE_RESTORE_RESET) {
         const char *src = P.snap + (size_t)P.scen_id[b] * P.L.total;
         copy16(row + P.L.resident, src + P.L.resident, P.L.total - P.L.resident, tid, G);

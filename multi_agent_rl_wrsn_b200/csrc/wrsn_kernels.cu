@@ -51,6 +51,8 @@ __device__ __forceinline__ void write_request(const wrsn_request &q, int b, cons
     if (q.flags) q.flags[b] = r.flags;
 }
 
+extern __shared__ uint4 wrsn_smem_u4[];             /* the environment's image (k_env), addressed by 32-bit offsets */
+
 namespace g32 {                                      /* one warp per environment (N <= 128) */
 #define WRSN_GFIX 32
 #include "wrsn_engine.cuh"

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "wrsn_layout.h"
+static thread_local char *wrsn_smem_host = nullptr;
 #define WRSN_GFIX 1
 #include "wrsn_engine.cuh"
 
@@ -40,7 +41,8 @@ static int run_mode(int mode, const Args &A) {
         char *row = A.state + (size_t)b * L.total;
         const char *scen_row = A.scen + (size_t)A.scen_id[b] * L.scen_total;
         Ctx c;
-        ctx_bind(c, d, L, scen_row, row, smem.data(), 0, 1);
+        wrsn_smem_host = smem.data();
+        ctx_bind(c, d, L, scen_row, row, 0, 1);
         if (mode == MODE_RESTORE_RESET) {
             const char *src = A.snap + (size_t)A.scen_id[b] * L.total;
             memcpy(row + L.resident, src + L.resident, (size_t)(L.total - L.resident));
