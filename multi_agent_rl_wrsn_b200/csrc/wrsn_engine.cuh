@@ -624,6 +624,124 @@ WRSN_D void ev_nodes_book(Ctx &c) {
     gsync(c);
 }
 
+/* ------------------------------------------------------------------ whole-cycle batches
+ * While no charger event, no death and no active update_reward lies ahead, one simulated second of the grid is the
+ * same five events over and over: drain (k+0.5), update_reward / Network.operate exit check / bookkeeping (k+1.0),
+ * Network.operate connectivity (k+1.1, levels unchanged).  Nobody looks at the node rows in between, so n such cycles
+ * are applied at once, node-parallel, with the reference's fp64 results:
+ *   - a node that is not being charged (energyRR == 0) loses the same integer number of ulps every cycle while it
+ *     stays inside its binade (see sub_chain), so n cycles are ONE exact multiply-subtract;
+ *   - any other node replays its cycles one by one in registers;
+ *   - energyCS under a constant per-second consumption reaches the fixed point of (cs*10 - lg + lg)/10 after one or
+ *     two applications; the loop stops there.
+ * A batch never contains a cycle the event-by-event path would send down the serial (possible death) path: the
+ * number of cycles is cut to the safe prefix and the rest runs event by event.
+ * Returns the number of cycles applied (0: nothing changed). */
+WRSN_NOINLINE int replay_cycles(double e, double rr, double es, double er, int nb, int ow, int na, double thr, double cap,
+                                int n, double *e_out) {
+    const double slack = 1e-6;
+    int done = 0;
+    for (; done < n; done++) {
+        const double e1 = sub_chain(e, es, 0, er, nb);
+        if (nb > 0 && !(e1 - thr >= slack)) break;
+        const double e2 = fmin(e1 + rr * 0.5, cap);
+        const double e3 = sub_chain(e2, es, ow, er, na);
+        if (ow + na > 0 && !(e3 - thr >= slack)) break;
+        e = fmin(e3 + rr * 0.5, cap);
+    }
+    *e_out = e;
+    return done;
+}
+
+WRSN_D bool reward_pairs(Ctx &c);
+
+WRSN_NOINLINE int nodes_batch(Ctx &c, int n_max, int ur_on) {
+    const int N = c.N;
+    const double thr = c.par[WRSN_P_THR], cap = c.par[WRSN_P_CAP], er = c.par[WRSN_P_ERECV];
+    const double slack = 1e-6;
+    const double *h = c.hdr;
+    if (h[WRSN_H_OPT_NOBATCH] != 0.0 || h[WRSN_H_BFS_DIRTY] != 0.0 || h[WRSN_H_LOG_LITERAL] != 0.0 ||
+        h[WRSN_H_LOG_LEN] < (double)WRSN_RING || h[WRSN_H_LOG_UNIFORM] < 10.0 || h[WRSN_H_ALIVE] == 0.0) return 0;
+    if (ur_on && reward_pairs(c)) return 0;
+    /* pass 1: per node, the per-cycle decrement (scr0; NaN = replay cycle by cycle) and the number of safe cycles */
+    int n_safe = n_max;
+    _Pragma("unroll 1")
+    for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
+        if (c.status[i] != 1) continue;
+        const double e = c.energy[i], es = c.esend[i], rr = c.rr[i];
+        const int nb = c.nbef[i], na = c.naft[i];
+        const int ow = c.parent[i] != -1 ? (int)c.own[i] : 0;
+        const int n_a = nb + ow + na, n_b = nb + na;
+        double dec = NAN;
+        int m = 0;
+        if (rr == 0.0 && n_a == 0) { dec = 0.0; m = n_max; }
+        else if (rr == 0.0) {
+            const int ex = wrsn_biased_exp(e);
+            if (e > 0.0 && ex > 60 && ex < 1900) {
+                const double lo = wrsn_pow2_biased(ex), inv_u = wrsn_pow2_biased(2098 - ex), u = wrsn_pow2_biased(ex - 52);
+                const double qa = es * inv_u, qb = er * inv_u;
+                const double ra = rint(qa), rb = rint(qb);
+                const bool tie = (fabs(qa - ra) == 0.5) || (n_b > 0 && fabs(qb - rb) == 0.5);
+                const double K = ra * (double)n_a + rb * (double)n_b;      /* ulps per cycle */
+                if (!tie && K * (double)n_max < 4503599627370496.0) {
+                    dec = K * u;
+                    if (K == 0.0) m = n_max;
+                    else {
+                        const double room = e - fmax(lo, thr + 2.0 * slack);
+                        double q = room > 0.0 ? floor(room / dec) - 1.0 : 0.0;
+                        q = fmin(fmax(q, 0.0), (double)n_max);
+                        m = (int)q;
+                        if (m > 0) { const double r = e - dec * (double)m; if (!(r >= lo) || !(r - thr >= slack)) m = 0; }
+                    }
+                }
+            }
+            if (m == 0) dec = NAN;
+        }
+        if (dec != dec) {                            /* charged, near a binade edge or near the threshold: literal cycles */
+            double e_end;
+            m = replay_cycles(e, rr, es, er, nb, ow, na, thr, cap, n_safe, &e_end);
+        }
+        c.scr0[i] = dec;
+        if (m < n_safe) n_safe = m;
+    }
+    gsync(c);
+    n_safe = (int)red_min(c, (double)n_safe);
+    if (n_safe <= 0) return 0;
+    /* pass 2 */
+    const double L = (double)WRSN_RING;
+    _Pragma("unroll 1")
+    for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
+        if (c.status[i] != 1) continue;
+        const double dec = c.scr0[i];
+        if (dec == dec) c.energy[i] = c.energy[i] - dec * (double)n_safe;
+        else {
+            double e_end;
+            const int nb = c.nbef[i], na = c.naft[i];
+            const int ow = c.parent[i] != -1 ? (int)c.own[i] : 0;
+            replay_cycles(c.energy[i], c.rr[i], c.esend[i], er, nb, ow, na, thr, cap, n_safe, &e_end);
+            c.energy[i] = e_end;
+        }
+        const double lg = c.logc[i];
+        double cs = c.cs[i];
+        for (int t = 0; t < n_safe; t++) {           /* Node.py:75 with log[0] == log_energy */
+            const double nx = (cs * L - lg + lg) / L;
+            if (nx == cs) break;
+            cs = nx;
+        }
+        c.cs[i] = cs;
+    }
+    gsync(c);
+    if (c.tid == 0) {
+        double *hw = c.hdr;
+        hw[WRSN_H_LOG_HEAD] = (double)(((int)hw[WRSN_H_LOG_HEAD] + n_safe) % WRSN_RING);
+        if (hw[WRSN_H_LOG_UNIFORM] < 1e9) hw[WRSN_H_LOG_UNIFORM] = fmin(hw[WRSN_H_LOG_UNIFORM] + (double)n_safe, 1e9);
+        hw[WRSN_H_NTICKS] += (double)n_safe;
+        hw[WRSN_H_NBATCH] += (double)n_safe;
+    }
+    gsync(c);
+    return n_safe;
+}
+
 /* ------------------------------------------------------------------ WRSN.update_reward (WRSN.py:100-127) */
 WRSN_D double charge_rate_to(Ctx &c, const double *m, int node) {   /* alpha / (d + beta) ** 2 */
     double t = euclid2(c.nx[node], c.ny[node], m[WRSN_MC_X], m[WRSN_MC_Y]) + c.par[WRSN_P_MC_BETA];
@@ -633,8 +751,8 @@ WRSN_D double charge_rate_to(Ctx &c, const double *m, int node) {   /* alpha / (
 /* the softmax priority + incentive sums; only reached when some incentive sum is non-empty */
 WRSN_NOINLINE void update_reward_body(Ctx &c);
 
-WRSN_D void ev_update_reward(Ctx &c) {
-    bool any = false;                                /* is there any (charging charger, connected alive node) pair? */
+WRSN_D bool reward_pairs(Ctx &c) {                 /* is there any (charging charger, connected alive node) pair? */
+    bool any = false;
     for (int a = 0; a < c.M; a++) {
         const double *m = c.mc + a * WRSN_MC_LEN;
         if (m[WRSN_MC_STATUS] == 0.0 || m[WRSN_MC_TYPE] == 0.0 || m[WRSN_MC_NCONN] == 0.0) continue;
@@ -643,7 +761,11 @@ WRSN_D void ev_update_reward(Ctx &c) {
             for (uint32_t bits = cm[w]; bits; bits &= bits - 1u)
                 if (c.status[32 * w + wrsn_ctz(bits)] == 1) any = true;
     }
-    if (any) update_reward_body(c);                  /* otherwise every incentive sum is empty: excl += 0 */
+    return any;
+}
+
+WRSN_D void ev_update_reward(Ctx &c) {
+    if (reward_pairs(c)) update_reward_body(c);      /* otherwise every incentive sum is empty: excl += 0 */
 }
 
 WRSN_NOINLINE void update_reward_body(Ctx &c) {
@@ -1155,9 +1277,38 @@ WRSN_DI void run_loop(Ctx &c) {
             k.now = gt;
             k.nev += 1.0;
             if (gk == K_NODES) {
-                if (k.nodes_phase == 1) { ev_nodes_drain(c); k.nodes_phase = 2; }
-                else { ev_nodes_book(c); k.nodes_phase = 1; }
-                k.nodes_t = gt + 0.5; k.nodes_key = WRSN_KEY_NORMAL + take_seq(k);
+                int batched = 0;
+                if (k.nodes_phase == 1) {
+                    /* whole cycles strictly before the next charger / condition / until event: the canonical pending set
+                       is {drain now, update_reward and the exit check of Network.operate at +0.5 (in that order)} */
+                    const double H = fmin(fmin(k.mc_t, k.until_t), maxtime - 2.0);
+                    const bool ur_on = k.ur_t < INFINITY;
+                    if (gt + 1.0 <= H && k.net_state == 2 && k.net_t == gt + 0.5 &&
+                        (!ur_on || (k.ur_t == gt + 0.5 && k.ur_key < k.net_key))) {
+                        const double span = fmin(H - gt, 1048576.0);
+                        int n = (int)span;
+                        while (n > 0 && !(gt + (double)n <= H)) n--;
+                        if (n > 0) batched = nodes_batch(c, n, ur_on ? 1 : 0);
+                        if (batched > 0) {
+                            /* the clock after `batched` cycles: every cycle drew 5 (4 without update_reward) insertion counters
+                               in the order drain, [update_reward,] exit check, bookkeeping, connectivity */
+                            const double nb = (double)batched, per = ur_on ? 5.0 : 4.0;
+                            const double s0 = k.seq + per * (nb - 1.0);
+                            if (ur_on) {
+                                k.ur_key = WRSN_KEY_NORMAL + (s0 + 1.0); k.net_key = WRSN_KEY_NORMAL + (s0 + 4.0);
+                                k.nodes_key = WRSN_KEY_NORMAL + (s0 + 3.0); k.ur_t += nb;
+                            } else { k.net_key = WRSN_KEY_NORMAL + (s0 + 3.0); k.nodes_key = WRSN_KEY_NORMAL + (s0 + 2.0); }
+                            k.seq += per * nb; k.nev += per * nb - 1.0;
+                            k.net_t += nb; k.nodes_t = gt + nb;
+                            k.now = (k.net_t - 1.0) + 0.1;
+                        }
+                    }
+                }
+                if (!batched) {
+                    if (k.nodes_phase == 1) { ev_nodes_drain(c); k.nodes_phase = 2; }
+                    else { ev_nodes_book(c); k.nodes_phase = 1; }
+                    k.nodes_t = gt + 0.5; k.nodes_key = WRSN_KEY_NORMAL + take_seq(k);
+                }
             } else if (gk == K_NET) {                /* Network.operate :74-80 */
                 if (k.net_state == 1) {
                     if (c.hdr[WRSN_H_BFS_DIRTY] != 0.0) do_bfs(c);

@@ -221,3 +221,61 @@ def check_rollout_step(scenarios, device, num_envs, steps, seed, with_obs):
         if with_obs:
             assert torch.equal(obs_a, b.get_state(dtype=torch.float64)) or bool((b.req.agent_id < 0).any()), k
     return resets
+
+
+def _disable_batches(env):
+    """TEST SWITCH hdr[OPT_NOBATCH]: every simulated second runs event by event (the path the batches must equal)."""
+    env.hdr("OPT_NOBATCH")[:] = 1.0
+    env.view("hdr", env._snap)[:, env.E["WRSN_H_OPT_NOBATCH"]] = 1.0
+
+
+def _states_equal_but_switch(a, b):
+    ha, hb = a.view("hdr").clone(), b.view("hdr").clone()
+    for f in ("OPT_NOBATCH", "NBATCH"):
+        ha[:, a.E["WRSN_H_" + f]] = 0.0
+        hb[:, b.E["WRSN_H_" + f]] = 0.0
+    if not torch.equal(ha, hb):
+        return False
+    off = int(a._foff[a.E["WRSN_F_HDR"]]) + 8 * a.E["WRSN_H_LEN"]
+    return torch.equal(a.state[:, off:], b.state[:, off:])
+
+
+def check_batches_equal_event_path(scenarios, device, num_envs, steps, seed, num_agent=3, scale2=0.3, threads=0):
+    """Whole-cycle batches (nodes_batch) leave EVERY byte of the environment record — node rows, event clock with its
+    insertion counters, charger records — exactly as the event-by-event path does, over several episodes."""
+    rng = np.random.default_rng(seed)
+    acts = rng.uniform(0.0, 1.0, size=(steps, num_envs, 3))
+    acts[..., 2] *= scale2
+    a = BatchedWRSN(scenarios, num_agent=num_agent, num_envs=num_envs, device=device, threads=threads)
+    b = BatchedWRSN(scenarios, num_agent=num_agent, num_envs=num_envs, device=device, threads=threads)
+    _disable_batches(b)
+    a.reset(); b.reset()
+    ends = 0
+    for k in range(steps):
+        act = torch.as_tensor(acts[k], device=a.device)
+        a.rollout_step(act); b.rollout_step(act)
+        ends += int((a.req.now == a.warm_up_time).sum())           # rows that were just reset
+        for f in ("agent_id", "terminal", "now", "action"):
+            assert torch.equal(getattr(a.req, f), getattr(b.req, f)), (k, f)
+        assert np.array_equal(_np(a.req.reward), _np(b.req.reward), equal_nan=True), k
+        assert _states_equal_but_switch(a, b), k
+    ca, cb = a.counters(), b.counters()
+    # (the warm-up snapshot of `b` was simulated before the switch was set: its counter is not zero)
+    assert ca["batched_ticks"] > cb["batched_ticks"] and ca["ticks"] == cb["ticks"] and ca["events"] == cb["events"]
+    ca["batched_ticks"] -= cb["batched_ticks"]
+    ca["episode_ends"] = ends
+    return ca
+
+
+def check_pure_network_batches(scenario, device, horizon, every):
+    """Pure network (no chargers, no update_reward: four events per cycle) with and without batches."""
+    a = BatchedWRSN(scenario, num_agent=0, num_envs=1, device=device)
+    b = BatchedWRSN(scenario, num_agent=0, num_envs=1, device=device)
+    a.init_network(with_reward_process=False); b.init_network(with_reward_process=False)
+    b.hdr("OPT_NOBATCH")[:] = 1.0
+    t = 0.25
+    while t < horizon:
+        a.run_until(t); b.run_until(t)
+        assert _states_equal_but_switch(a, b), t
+        t += every
+    return a.counters()

@@ -76,6 +76,25 @@ def test_rollout_step_equals_manual_loop():
     assert resets >= 3
 
 
+def test_batches_equal_event_path():
+    scs = [synthetic(num_nodes=40, num_targets=120, seed=s, num_gateways=2) for s in (3, 4)]
+    cnt = pc.check_batches_equal_event_path(scs, "cpu", num_envs=6, steps=150, seed=1)
+    assert cnt["batched_ticks"] > 0.1 * cnt["ticks"] and cnt["episode_ends"] >= 3
+
+
+def test_batches_equal_event_path_short_charges():
+    sc = synthetic(num_nodes=60, num_targets=70, seed=11)
+    cnt = pc.check_batches_equal_event_path(sc, "cpu", num_envs=4, steps=120, seed=2, scale2=0.05)
+    assert cnt["batched_ticks"] > 0.25 * cnt["ticks"]
+
+
+def test_pure_network_batches():
+    from tests.helpers import golden
+    sc = pc.sc_from_golden(golden("net_hanoi1000n50"))
+    cnt = pc.check_pure_network_batches(sc, "cpu", horizon=6000.0, every=37.0)
+    assert cnt["batched_ticks"] > 0.6 * cnt["ticks"]      # Network.operate (and with it the batches) ends at t = 4048
+
+
 @pytest.mark.parametrize("nodes,targets,chargers,envs,steps", [(500, 500, 5, 2, 30), (1000, 1000, 10, 1, 45)])
 def test_large_configs_vs_oracle(nodes, targets, chargers, envs, steps):
     sc = synthetic(num_nodes=nodes, num_targets=targets, seed=nodes, num_gateways=max(3, nodes // 40))

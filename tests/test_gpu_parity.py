@@ -76,6 +76,24 @@ def test_rollout_step_equals_manual_loop():
     assert resets >= 3
 
 
+@pytest.mark.parametrize("threads", [32, 128])
+def test_batches_equal_event_path(threads):
+    """Whole-cycle batches == the event-by-event path, byte for byte (node rows, clock, insertion counters)."""
+    scs = [synthetic(num_nodes=100, num_targets=100, seed=1000 + s) for s in range(4)]
+    a = pc.check_batches_equal_event_path(scs, DEV, num_envs=64, steps=300, seed=1, scale2=0.05, threads=threads)
+    assert a["batched_ticks"] > 0.25 * a["ticks"]
+    scs = [synthetic(num_nodes=40, num_targets=120, seed=s, num_gateways=2) for s in (3, 4)]
+    b = pc.check_batches_equal_event_path(scs, DEV, num_envs=32, steps=150, seed=1, threads=threads)
+    assert b["episode_ends"] >= 8
+
+
+def test_pure_network_batches():
+    from tests.helpers import golden
+    sc = pc.sc_from_golden(golden("net_hanoi1000n50"))
+    cnt = pc.check_pure_network_batches(sc, DEV, horizon=6000.0, every=37.0)
+    assert cnt["batched_ticks"] > 0.6 * cnt["ticks"]
+
+
 @pytest.mark.parametrize("threads", [32, 64, 128])
 def test_group_size_independent(threads):
     """The result must not depend on how many threads share an environment."""
