@@ -654,6 +654,15 @@ WRSN_NOINLINE int replay_cycles(double e, double rr, double es, double er, int n
 }
 
 WRSN_D bool reward_pairs(Ctx &c);
+WRSN_NOINLINE void update_reward_body(Ctx &c);
+
+/* one node's k+0.5 tick on the fast path (no death possible): relayed packets of lower ids, top-up, own packets,
+ * relayed packets of higher ids */
+WRSN_NOINLINE double drain_node(double e, double rr, double es, double er, int nb, int ow, int na, double cap) {
+    const double e1 = sub_chain(e, es, 0, er, nb);
+    const double e2 = fmin(e1 + rr * 0.5, cap);
+    return sub_chain(e2, es, ow, er, na);
+}
 
 WRSN_NOINLINE int nodes_batch(Ctx &c, int n_max, int ur_on) {
     const int N = c.N;
@@ -662,8 +671,8 @@ WRSN_NOINLINE int nodes_batch(Ctx &c, int n_max, int ur_on) {
     const double *h = c.hdr;
     if (h[WRSN_H_OPT_NOBATCH] != 0.0 || h[WRSN_H_BFS_DIRTY] != 0.0 || h[WRSN_H_LOG_LITERAL] != 0.0 ||
         h[WRSN_H_LOG_LEN] < (double)WRSN_RING || h[WRSN_H_LOG_UNIFORM] < 10.0 || h[WRSN_H_ALIVE] == 0.0) return 0;
-    if (ur_on && reward_pairs(c)) return 0;
-    /* pass 1: per node, the per-cycle decrement (scr0; NaN = replay cycle by cycle) and the number of safe cycles */
+    const bool active = ur_on && reward_pairs(c);    /* update_reward looks at every node every second */
+    /* pass 1: per node, the per-cycle decrement (scr1; NaN = replay cycle by cycle) and the number of safe cycles */
     int n_safe = n_max;
     _Pragma("unroll 1")
     for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
@@ -701,36 +710,69 @@ WRSN_NOINLINE int nodes_batch(Ctx &c, int n_max, int ur_on) {
             double e_end;
             m = replay_cycles(e, rr, es, er, nb, ow, na, thr, cap, n_safe, &e_end);
         }
-        c.scr0[i] = dec;
+        c.scr1[i] = dec;
         if (m < n_safe) n_safe = m;
     }
     gsync(c);
     n_safe = (int)red_min(c, (double)n_safe);
     if (n_safe <= 0) return 0;
-    /* pass 2 */
     const double L = (double)WRSN_RING;
-    _Pragma("unroll 1")
-    for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
-        if (c.status[i] != 1) continue;
-        const double dec = c.scr0[i];
-        if (dec == dec) c.energy[i] = c.energy[i] - dec * (double)n_safe;
-        else {
-            double e_end;
-            const int nb = c.nbef[i], na = c.naft[i];
-            const int ow = c.parent[i] != -1 ? (int)c.own[i] : 0;
-            replay_cycles(c.energy[i], c.rr[i], c.esend[i], er, nb, ow, na, thr, cap, n_safe, &e_end);
-            c.energy[i] = e_end;
+    if (!active) {
+        /* pass 2: all cycles at once */
+        _Pragma("unroll 1")
+        for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
+            if (c.status[i] != 1) continue;
+            const double dec = c.scr1[i];
+            if (dec == dec) c.energy[i] = c.energy[i] - dec * (double)n_safe;
+            else {
+                double e_end;
+                const int nb = c.nbef[i], na = c.naft[i];
+                const int ow = c.parent[i] != -1 ? (int)c.own[i] : 0;
+                replay_cycles(c.energy[i], c.rr[i], c.esend[i], er, nb, ow, na, thr, cap, n_safe, &e_end);
+                c.energy[i] = e_end;
+            }
+            const double lg = c.logc[i];
+            double cs = c.cs[i];
+            for (int t = 0; t < n_safe; t++) {       /* Node.py:75 with log[0] == log_energy */
+                const double nx = (cs * L - lg + lg) / L;
+                if (nx == cs) break;
+                cs = nx;
+            }
+            c.cs[i] = cs;
         }
-        const double lg = c.logc[i];
-        double cs = c.cs[i];
-        for (int t = 0; t < n_safe; t++) {           /* Node.py:75 with log[0] == log_energy */
-            const double nx = (cs * L - lg + lg) / L;
-            if (nx == cs) break;
-            cs = nx;
+        gsync(c);
+    } else {
+        /* pass 2: cycle by cycle, because update_reward reads every node at every k+1.0 (before the bookkeeping) */
+        uint32_t fixed = 0u;                         /* node slots of this thread whose energyCS has reached its fixed point */
+        _Pragma("unroll 1")
+        for (int j = 0; j < n_safe; j++) {
+            _Pragma("unroll 1")
+            for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
+                if (c.status[i] != 1) continue;
+                const double dec = c.scr1[i];
+                if (dec == dec) c.energy[i] = c.energy[i] - dec;
+                else {
+                    const int ow = c.parent[i] != -1 ? (int)c.own[i] : 0;
+                    c.energy[i] = drain_node(c.energy[i], c.rr[i], c.esend[i], er, c.nbef[i], ow, c.naft[i], cap);
+                }
+            }
+            gsync(c);
+            update_reward_body(c);
+            int sl = 0;
+            _Pragma("unroll 1")
+            for (int i = c.tid; i < N; i += WRSN_GSZ(c), sl++) {
+                if (c.status[i] != 1) continue;
+                const double rr = c.rr[i];
+                if (rr != 0.0) c.energy[i] = fmin(c.energy[i] + rr * 0.5, cap);
+                if (sl < 32 && ((fixed >> sl) & 1u)) continue;
+                const double lg = c.logc[i], cs = c.cs[i];
+                const double nx = (cs * L - lg + lg) / L;
+                if (nx == cs) { if (sl < 32) fixed |= 1u << sl; }
+                else c.cs[i] = nx;
+            }
+            gsync(c);
         }
-        c.cs[i] = cs;
     }
-    gsync(c);
     if (c.tid == 0) {
         double *hw = c.hdr;
         hw[WRSN_H_LOG_HEAD] = (double)(((int)hw[WRSN_H_LOG_HEAD] + n_safe) % WRSN_RING);
@@ -749,8 +791,6 @@ WRSN_D double charge_rate_to(Ctx &c, const double *m, int node) {   /* alpha / (
 }
 
 /* the softmax priority + incentive sums; only reached when some incentive sum is non-empty */
-WRSN_NOINLINE void update_reward_body(Ctx &c);
-
 WRSN_D bool reward_pairs(Ctx &c) {                 /* is there any (charging charger, connected alive node) pair? */
     bool any = false;
     for (int a = 0; a < c.M; a++) {
@@ -866,6 +906,8 @@ WRSN_NOINLINE double do_fitness(Ctx &c, double *per_target /* global, may be NUL
 /* ------------------------------------------------------------------ chargers (MobileCharger.py) */
 /* all threads: bitmask of nodes with d(node, (x, y)) <= charging_range */
 WRSN_NOINLINE void near_mask(Ctx &c, double x, double y, uint32_t *mask) {
+    gsync(c);                                        /* `mask` may be a charger's connection mask that another warp is still
+                                                        reading (reward_pairs / rr_invariant of the previous event) */
     for (int w = c.tid; w < c.W; w += WRSN_GSZ(c)) mask[w] = 0u;
     gsync(c);
     const double R = c.par[WRSN_P_MC_R];
@@ -929,6 +971,27 @@ WRSN_DI bool conn_has_alive(Ctx &c, int a) {
     return false;
 }
 
+/* A charging charger disconnects and reconnects its nodes once per span (charge_step :40-50, Node.charger_connection /
+ * charger_disconnection :134-146): energyRR -= r, then energyRR += r with the same r.  If that leaves every connected
+ * alive node's energyRR exactly where it was — always the case for a node charged by this charger alone: (r - r) + r —
+ * the spans of the charge are private to the charger (its own energy and countdown) and can be replayed lazily: the
+ * charging rate, re-accumulated from zero over the same alive nodes in the same order, repeats as well.  A death, or
+ * another charger connecting to / disconnecting from a shared node, ends the run (wake_lazy_*). */
+WRSN_DI bool rr_invariant(Ctx &c, int a) {
+    const double *m = c.mc + a * WRSN_MC_LEN;
+    if (m[WRSN_MC_NCONN] == 0.0) return true;
+    const double mx = m[WRSN_MC_X], my = m[WRSN_MC_Y];
+    const uint32_t *cm = c.conn + a * c.W;
+    for (int w = 0; w < c.W; w++)
+        for (uint32_t bits = cm[w]; bits; bits &= bits - 1u) {
+            const int i = 32 * w + wrsn_ctz(bits);
+            if (c.status[i] == 0) continue;
+            const double r = charge_rate_xy(c, mx, my, i), rr = c.rr[i];
+            if ((rr - r) + r != rr) return false;
+        }
+    return true;
+}
+
 /* may the pending event of slot s start a lazy run? */
 WRSN_DI bool slot_lazy_ok(Ctx &c, int s) {
     const double *p = slot_of(c, s);
@@ -940,7 +1003,7 @@ WRSN_DI bool slot_lazy_ok(Ctx &c, int s) {
         if (q != s && slot_i(slot_of(c, q))[WRSN_PRI_USED] != 0 && slot_i(slot_of(c, q))[WRSN_PRI_AGENT] == a &&
             slot_of(c, q)[WRSN_PR_T] < INFINITY) return false;
     const double *m = c.mc + a * WRSN_MC_LEN;
-    if (pc == PC_CS_FIRE) return m[WRSN_MC_RATE] == 0.0 && !conn_has_alive(c, a);
+    if (pc == PC_CS_FIRE) return rr_invariant(c, a);
     return m[WRSN_MC_TYPE] == 0.0 || !conn_has_alive(c, a);   /* update_reward reads a "charging" charger's position */
 }
 
@@ -1030,6 +1093,25 @@ WRSN_DI void slot_catch_up(Ctx &c, Clk &k, int s, double limit, bool wake) {
         gsync(c);
         if (WRSN_LEAD(c)) slot_i(p)[WRSN_PRI_LAZY] = 0;
         gsync(c);
+    }
+}
+
+/* a death: every lazy run ends (the alive set of a charge, hence its rate, changes from the next connection on) */
+WRSN_DI void wake_lazy_all(Ctx &c, Clk &k) {
+    for (int q = 0; q < c.n_slot; q++)
+        if (slot_i(slot_of(c, q))[WRSN_PRI_LAZY] != 0) slot_catch_up(c, k, q, k.now, true);
+}
+/* charger `a` (slot s, not lazy) is about to change the energyRR of its connected nodes: lazy charges that share one of
+ * them must re-validate rr_invariant() at the new value */
+WRSN_DI void wake_lazy_sharing(Ctx &c, Clk &k, int s, int a) {
+    const uint32_t *cm = c.conn + a * c.W;
+    for (int q = 0; q < c.n_slot; q++) {
+        const int *qi = slot_i(slot_of(c, q));
+        if (q == s || qi[WRSN_PRI_LAZY] == 0 || qi[WRSN_PRI_PC] != PC_CS_FIRE) continue;
+        const uint32_t *cq = c.conn + qi[WRSN_PRI_AGENT] * c.W;
+        uint32_t both = 0u;
+        for (int w = 0; w < c.W; w++) both |= cm[w] & cq[w];
+        if (both) slot_catch_up(c, k, q, k.now, true);
     }
 }
 
@@ -1193,6 +1275,7 @@ WRSN_DI void ev_slot(Ctx &c, Clk &k, int s, double other_t) {
             double rate = m[WRSN_MC_RATE], en = m[WRSN_MC_ENERGY], cpa2 = m[WRSN_MC_CPA2];
             const bool connect = pc == PC_CS_INIT;
             if (!connect) { en = en - rate * span; cpa2 = fmax(0.0, cpa2 - span); }
+            wake_lazy_sharing(c, k, s, a);
             gsync(c);
             WRSN_FOR_BITS(cm, c.W, i) {
                 if (c.status[i] == 0) continue;
@@ -1305,7 +1388,10 @@ WRSN_DI void run_loop(Ctx &c) {
                     }
                 }
                 if (!batched) {
-                    if (k.nodes_phase == 1) { ev_nodes_drain(c); k.nodes_phase = 2; }
+                    if (k.nodes_phase == 1) {
+                        ev_nodes_drain(c); k.nodes_phase = 2;
+                        if (c.hdr[WRSN_H_BFS_DIRTY] != 0.0) { wake_lazy_all(c, k); rescan = true; }
+                    }
                     else { ev_nodes_book(c); k.nodes_phase = 1; }
                     k.nodes_t = gt + 0.5; k.nodes_key = WRSN_KEY_NORMAL + take_seq(k);
                 }

@@ -17,6 +17,9 @@ __global__ void __launch_bounds__(WRSN_GFIX ? WRSN_GFIX : 256, WRSN_GFIX ? 20 : 
         copy16(smem, src, P.L.resident, tid, G);
     } else if (MODE != MODE_INIT) {
         copy16(smem, row, P.L.resident, tid, G);
+    } else {                                         /* alignment gaps between the fields: defined bytes in the record */
+        uint4 *z = reinterpret_cast<uint4 *>(smem);
+        for (int i = tid; i < (int)(P.L.resident >> 4); i += G) z[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     for (int i = tid; i < c.Npad; i += G) c.own[i] = i < c.N ? (uint16_t)(c.tgt_ptr[i + 1] - c.tgt_ptr[i]) : (uint16_t)0;
     gsync(c);

@@ -48,6 +48,7 @@ static int run_mode(int mode, const Args &A) {
             memcpy(row + L.resident, src + L.resident, (size_t)(L.total - L.resident));
             memcpy(smem.data(), src, (size_t)L.resident);
         } else if (mode != MODE_INIT) memcpy(smem.data(), row, (size_t)L.resident);
+        else memset(smem.data(), 0, (size_t)L.resident);
         for (int i = 0; i < c.Npad; i++) c.own[i] = i < c.N ? (uint16_t)(c.tgt_ptr[i + 1] - c.tgt_ptr[i]) : 0;
         const double now_before = c.hdr[WRSN_H_NOW];
         ReqOut r; memset(&r, 0, sizeof(r)); r.agent = -3;

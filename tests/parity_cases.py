@@ -229,15 +229,29 @@ def _disable_batches(env):
     env.view("hdr", env._snap)[:, env.E["WRSN_H_OPT_NOBATCH"]] = 1.0
 
 
-def _states_equal_but_switch(a, b):
+_STATE_FIELDS = ("hdr", "mc", "proc", "energy", "rr", "cs", "esend", "logc", "nbef", "naft", "level", "parent", "status",
+                 "tact_words", "conn_words", "logtick", "ring")
+
+
+def _state_diff_but_switch(a, b):
+    """'' when the two simulators' records are identical byte for byte (apart from the test switch and its counter),
+    else a description of the first differing field."""
     ha, hb = a.view("hdr").clone(), b.view("hdr").clone()
     for f in ("OPT_NOBATCH", "NBATCH"):
         ha[:, a.E["WRSN_H_" + f]] = 0.0
         hb[:, b.E["WRSN_H_" + f]] = 0.0
-    if not torch.equal(ha, hb):
-        return False
     off = int(a._foff[a.E["WRSN_F_HDR"]]) + 8 * a.E["WRSN_H_LEN"]
-    return torch.equal(a.state[:, off:], b.state[:, off:])
+    if torch.equal(ha.view(torch.int64), hb.view(torch.int64)) and torch.equal(a.state[:, off:], b.state[:, off:]):
+        return ""
+    for f in _STATE_FIELDS:
+        x, y = (ha, hb) if f == "hdr" else (a.view(f), b.view(f))
+        x, y = x.contiguous().view(torch.uint8).reshape(a.B, -1), y.contiguous().view(torch.uint8).reshape(a.B, -1)
+        neq = x != y
+        if bool(neq.any()):
+            rows = torch.nonzero(neq.any(1)).flatten().tolist()
+            cols = torch.nonzero(neq[rows[0]]).flatten().tolist()
+            return "field %s envs %s byte columns %s" % (f, rows[:8], cols[:16])
+    return "padding bytes differ"
 
 
 def check_batches_equal_event_path(scenarios, device, num_envs, steps, seed, num_agent=3, scale2=0.3, threads=0):
@@ -258,7 +272,8 @@ def check_batches_equal_event_path(scenarios, device, num_envs, steps, seed, num
         for f in ("agent_id", "terminal", "now", "action"):
             assert torch.equal(getattr(a.req, f), getattr(b.req, f)), (k, f)
         assert np.array_equal(_np(a.req.reward), _np(b.req.reward), equal_nan=True), k
-        assert _states_equal_but_switch(a, b), k
+        diff = _state_diff_but_switch(a, b)
+        assert not diff, (k, diff)
     ca, cb = a.counters(), b.counters()
     # (the warm-up snapshot of `b` was simulated before the switch was set: its counter is not zero)
     assert ca["batched_ticks"] > cb["batched_ticks"] and ca["ticks"] == cb["ticks"] and ca["events"] == cb["events"]
@@ -276,6 +291,7 @@ def check_pure_network_batches(scenario, device, horizon, every):
     t = 0.25
     while t < horizon:
         a.run_until(t); b.run_until(t)
-        assert _states_equal_but_switch(a, b), t
+        diff = _state_diff_but_switch(a, b)
+        assert not diff, (t, diff)
         t += every
     return a.counters()
