@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define WRSN_ABI_VERSION 8
+#define WRSN_ABI_VERSION 9
 #define WRSN_MAX_MC 16          /* chargers per environment */
 #define WRSN_RING 10            /* Node.operate keeps the last 10 per-second consumptions (Node.py:70-77) */
 
@@ -63,6 +63,8 @@ enum {
     WRSN_H_NLAZY,                                                   /* charger spans replayed lazily (slot_ff) */
     WRSN_H_NBATCH,                                                  /* simulated seconds advanced by whole-cycle batches (nodes_batch) */
     WRSN_H_OPT_NOBATCH,                                             /* TEST SWITCH: != 0 disables the batches (every second runs event by event) */
+    WRSN_H_PROF0, WRSN_H_PROF1, WRSN_H_PROF2, WRSN_H_PROF3, WRSN_H_PROF4, /* SM cycles of the last launch (builds with -DWRSN_PROF only):
+                                                                       total, serial ticks, batches, BFS + tree, fitness */
     WRSN_H_CHAIN_SLOT = 40,                                         /* [WRSN_MAX_MC] process slot watched by member j */
     WRSN_H_COND_TRIG = WRSN_H_CHAIN_SLOT + WRSN_MAX_MC,
     WRSN_H_COND_T = WRSN_H_COND_TRIG + WRSN_MAX_MC,                 /* time of the pending condition event, +inf when none */
@@ -97,6 +99,7 @@ enum {
     WRSN_PR_DESTX, WRSN_PR_DESTY, WRSN_PR_MT, WRSN_PR_VX, WRSN_PR_VY, WRSN_PR_TOTAL, WRSN_PR_SPAN,
     WRSN_PR_SVX, WRSN_PR_SVY, WRSN_PR_CHTMP, WRSN_PR_CHSPAN,
     WRSN_PR_TINT,                                      /* LAZY: time of the span event that ends the run of private spans */
+    WRSN_PR_OWED,                                      /* LAZY: insertion counters drawn by the replayed spans, taken at wake-up */
     WRSN_PR_LEN = 22
 };
 

@@ -75,6 +75,16 @@
 #define WRSN_SMEM_BASE (reinterpret_cast<char *>(wrsn_smem_u4))
 #endif
 
+#undef WRSN_PROF_BEGIN
+#undef WRSN_PROF_END
+#if defined(WRSN_PROF) && !defined(WRSN_HOST_EMU)
+#define WRSN_PROF_BEGIN() const long long prof_t0_ = clock64()
+#define WRSN_PROF_END(c, slot) do { if ((c).tid == 0) (c).hdr[slot] += (double)(clock64() - prof_t0_); } while (0)
+#else
+#define WRSN_PROF_BEGIN() do { } while (0)
+#define WRSN_PROF_END(c, slot) do { } while (0)
+#endif
+
 /* ------------------------------------------------------------------ context
  * The environment's shared-memory image is addressed as 32-bit offsets from the CTA's dynamic shared memory (SArr):
  * the compiler then knows the address space (LDS / STS with immediate offsets instead of generic 64-bit loads), the
@@ -452,6 +462,7 @@ WRSN_NOINLINE void build_tree(Ctx &c) {
 /* ------------------------------------------------------------------ Network.setLevels + check_targets (Network.py:37-66,84),
  * then the routing tree the drain tick replays. */
 WRSN_NOINLINE void do_bfs(Ctx &c) {
+    WRSN_PROF_BEGIN();
     leave_uniform(c);
     const int N = c.N;
     for (int i = c.tid; i < N; i += WRSN_GSZ(c)) c.level[i] = (c.status[i] == 1 && c.direct[i]) ? 1 : -1;
@@ -488,6 +499,7 @@ WRSN_NOINLINE void do_bfs(Ctx &c) {
         c.hdr[WRSN_H_NBFS] += 1.0;
     }
     gsync(c);
+    WRSN_PROF_END(c, WRSN_H_PROF3);
 }
 
 /* ------------------------------------------------------------------ Node.operate, k+0.5 tick (Node.py:57-62,92-132) */
@@ -583,6 +595,7 @@ WRSN_D void ev_nodes_drain(Ctx &c) {
         return;
     }
     leave_uniform(c);
+    WRSN_PROF_BEGIN();
     if (c.tid == 0) {
         int deaths = drain_serial(c);
         c.hdr[WRSN_H_LOG_LITERAL] = 1.0;
@@ -590,6 +603,7 @@ WRSN_D void ev_nodes_drain(Ctx &c) {
         if (deaths > 0) c.hdr[WRSN_H_BFS_DIRTY] = 1.0;
     }
     gsync(c);
+    WRSN_PROF_END(c, WRSN_H_PROF1);
 }
 
 /* ------------------------------------------------------------------ Node.operate, k+1.0 tick (Node.py:65-77) */
@@ -624,166 +638,6 @@ WRSN_D void ev_nodes_book(Ctx &c) {
     gsync(c);
 }
 
-/* ------------------------------------------------------------------ whole-cycle batches
- * While no charger event, no death and no active update_reward lies ahead, one simulated second of the grid is the
- * same five events over and over: drain (k+0.5), update_reward / Network.operate exit check / bookkeeping (k+1.0),
- * Network.operate connectivity (k+1.1, levels unchanged).  Nobody looks at the node rows in between, so n such cycles
- * are applied at once, node-parallel, with the reference's fp64 results:
- *   - a node that is not being charged (energyRR == 0) loses the same integer number of ulps every cycle while it
- *     stays inside its binade (see sub_chain), so n cycles are ONE exact multiply-subtract;
- *   - any other node replays its cycles one by one in registers;
- *   - energyCS under a constant per-second consumption reaches the fixed point of (cs*10 - lg + lg)/10 after one or
- *     two applications; the loop stops there.
- * A batch never contains a cycle the event-by-event path would send down the serial (possible death) path: the
- * number of cycles is cut to the safe prefix and the rest runs event by event.
- * Returns the number of cycles applied (0: nothing changed). */
-WRSN_NOINLINE int replay_cycles(double e, double rr, double es, double er, int nb, int ow, int na, double thr, double cap,
-                                int n, double *e_out) {
-    const double slack = 1e-6;
-    int done = 0;
-    for (; done < n; done++) {
-        const double e1 = sub_chain(e, es, 0, er, nb);
-        if (nb > 0 && !(e1 - thr >= slack)) break;
-        const double e2 = fmin(e1 + rr * 0.5, cap);
-        const double e3 = sub_chain(e2, es, ow, er, na);
-        if (ow + na > 0 && !(e3 - thr >= slack)) break;
-        e = fmin(e3 + rr * 0.5, cap);
-    }
-    *e_out = e;
-    return done;
-}
-
-WRSN_D bool reward_pairs(Ctx &c);
-WRSN_NOINLINE void update_reward_body(Ctx &c);
-
-/* one node's k+0.5 tick on the fast path (no death possible): relayed packets of lower ids, top-up, own packets,
- * relayed packets of higher ids */
-WRSN_NOINLINE double drain_node(double e, double rr, double es, double er, int nb, int ow, int na, double cap) {
-    const double e1 = sub_chain(e, es, 0, er, nb);
-    const double e2 = fmin(e1 + rr * 0.5, cap);
-    return sub_chain(e2, es, ow, er, na);
-}
-
-WRSN_NOINLINE int nodes_batch(Ctx &c, int n_max, int ur_on) {
-    const int N = c.N;
-    const double thr = c.par[WRSN_P_THR], cap = c.par[WRSN_P_CAP], er = c.par[WRSN_P_ERECV];
-    const double slack = 1e-6;
-    const double *h = c.hdr;
-    if (h[WRSN_H_OPT_NOBATCH] != 0.0 || h[WRSN_H_BFS_DIRTY] != 0.0 || h[WRSN_H_LOG_LITERAL] != 0.0 ||
-        h[WRSN_H_LOG_LEN] < (double)WRSN_RING || h[WRSN_H_LOG_UNIFORM] < 10.0 || h[WRSN_H_ALIVE] == 0.0) return 0;
-    const bool active = ur_on && reward_pairs(c);    /* update_reward looks at every node every second */
-    /* pass 1: per node, the per-cycle decrement (scr1; NaN = replay cycle by cycle) and the number of safe cycles */
-    int n_safe = n_max;
-    _Pragma("unroll 1")
-    for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
-        if (c.status[i] != 1) continue;
-        const double e = c.energy[i], es = c.esend[i], rr = c.rr[i];
-        const int nb = c.nbef[i], na = c.naft[i];
-        const int ow = c.parent[i] != -1 ? (int)c.own[i] : 0;
-        const int n_a = nb + ow + na, n_b = nb + na;
-        double dec = NAN;
-        int m = 0;
-        if (rr == 0.0 && n_a == 0) { dec = 0.0; m = n_max; }
-        else if (rr == 0.0) {
-            const int ex = wrsn_biased_exp(e);
-            if (e > 0.0 && ex > 60 && ex < 1900) {
-                const double lo = wrsn_pow2_biased(ex), inv_u = wrsn_pow2_biased(2098 - ex), u = wrsn_pow2_biased(ex - 52);
-                const double qa = es * inv_u, qb = er * inv_u;
-                const double ra = rint(qa), rb = rint(qb);
-                const bool tie = (fabs(qa - ra) == 0.5) || (n_b > 0 && fabs(qb - rb) == 0.5);
-                const double K = ra * (double)n_a + rb * (double)n_b;      /* ulps per cycle */
-                if (!tie && K * (double)n_max < 4503599627370496.0) {
-                    dec = K * u;
-                    if (K == 0.0) m = n_max;
-                    else {
-                        const double room = e - fmax(lo, thr + 2.0 * slack);
-                        double q = room > 0.0 ? floor(room / dec) - 1.0 : 0.0;
-                        q = fmin(fmax(q, 0.0), (double)n_max);
-                        m = (int)q;
-                        if (m > 0) { const double r = e - dec * (double)m; if (!(r >= lo) || !(r - thr >= slack)) m = 0; }
-                    }
-                }
-            }
-            if (m == 0) dec = NAN;
-        }
-        if (dec != dec) {                            /* charged, near a binade edge or near the threshold: literal cycles */
-            double e_end;
-            m = replay_cycles(e, rr, es, er, nb, ow, na, thr, cap, n_safe, &e_end);
-        }
-        c.scr1[i] = dec;
-        if (m < n_safe) n_safe = m;
-    }
-    gsync(c);
-    n_safe = (int)red_min(c, (double)n_safe);
-    if (n_safe <= 0) return 0;
-    const double L = (double)WRSN_RING;
-    if (!active) {
-        /* pass 2: all cycles at once */
-        _Pragma("unroll 1")
-        for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
-            if (c.status[i] != 1) continue;
-            const double dec = c.scr1[i];
-            if (dec == dec) c.energy[i] = c.energy[i] - dec * (double)n_safe;
-            else {
-                double e_end;
-                const int nb = c.nbef[i], na = c.naft[i];
-                const int ow = c.parent[i] != -1 ? (int)c.own[i] : 0;
-                replay_cycles(c.energy[i], c.rr[i], c.esend[i], er, nb, ow, na, thr, cap, n_safe, &e_end);
-                c.energy[i] = e_end;
-            }
-            const double lg = c.logc[i];
-            double cs = c.cs[i];
-            for (int t = 0; t < n_safe; t++) {       /* Node.py:75 with log[0] == log_energy */
-                const double nx = (cs * L - lg + lg) / L;
-                if (nx == cs) break;
-                cs = nx;
-            }
-            c.cs[i] = cs;
-        }
-        gsync(c);
-    } else {
-        /* pass 2: cycle by cycle, because update_reward reads every node at every k+1.0 (before the bookkeeping) */
-        uint32_t fixed = 0u;                         /* node slots of this thread whose energyCS has reached its fixed point */
-        _Pragma("unroll 1")
-        for (int j = 0; j < n_safe; j++) {
-            _Pragma("unroll 1")
-            for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
-                if (c.status[i] != 1) continue;
-                const double dec = c.scr1[i];
-                if (dec == dec) c.energy[i] = c.energy[i] - dec;
-                else {
-                    const int ow = c.parent[i] != -1 ? (int)c.own[i] : 0;
-                    c.energy[i] = drain_node(c.energy[i], c.rr[i], c.esend[i], er, c.nbef[i], ow, c.naft[i], cap);
-                }
-            }
-            gsync(c);
-            update_reward_body(c);
-            int sl = 0;
-            _Pragma("unroll 1")
-            for (int i = c.tid; i < N; i += WRSN_GSZ(c), sl++) {
-                if (c.status[i] != 1) continue;
-                const double rr = c.rr[i];
-                if (rr != 0.0) c.energy[i] = fmin(c.energy[i] + rr * 0.5, cap);
-                if (sl < 32 && ((fixed >> sl) & 1u)) continue;
-                const double lg = c.logc[i], cs = c.cs[i];
-                const double nx = (cs * L - lg + lg) / L;
-                if (nx == cs) { if (sl < 32) fixed |= 1u << sl; }
-                else c.cs[i] = nx;
-            }
-            gsync(c);
-        }
-    }
-    if (c.tid == 0) {
-        double *hw = c.hdr;
-        hw[WRSN_H_LOG_HEAD] = (double)(((int)hw[WRSN_H_LOG_HEAD] + n_safe) % WRSN_RING);
-        if (hw[WRSN_H_LOG_UNIFORM] < 1e9) hw[WRSN_H_LOG_UNIFORM] = fmin(hw[WRSN_H_LOG_UNIFORM] + (double)n_safe, 1e9);
-        hw[WRSN_H_NTICKS] += (double)n_safe;
-        hw[WRSN_H_NBATCH] += (double)n_safe;
-    }
-    gsync(c);
-    return n_safe;
-}
-
 /* ------------------------------------------------------------------ WRSN.update_reward (WRSN.py:100-127) */
 WRSN_D double charge_rate_to(Ctx &c, const double *m, int node) {   /* alpha / (d + beta) ** 2 */
     double t = euclid2(c.nx[node], c.ny[node], m[WRSN_MC_X], m[WRSN_MC_Y]) + c.par[WRSN_P_MC_BETA];
@@ -791,6 +645,8 @@ WRSN_D double charge_rate_to(Ctx &c, const double *m, int node) {   /* alpha / (
 }
 
 /* the softmax priority + incentive sums; only reached when some incentive sum is non-empty */
+WRSN_NOINLINE void update_reward_body(Ctx &c);
+
 WRSN_D bool reward_pairs(Ctx &c) {                 /* is there any (charging charger, connected alive node) pair? */
     bool any = false;
     for (int a = 0; a < c.M; a++) {
@@ -856,6 +712,7 @@ WRSN_NOINLINE double do_fitness(Ctx &c, double *per_target /* global, may be NUL
     const int N = c.N;
     const double thr = c.par[WRSN_P_THR];
     double *node_t = c.scr0, *lt = c.scr1;
+    WRSN_PROF_BEGIN();
     for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
         double v = -1.0, l = 0.0;
         if (c.status[i] == 1) {
@@ -900,6 +757,7 @@ WRSN_NOINLINE double do_fitness(Ctx &c, double *per_target /* global, may be NUL
     }
     mn = red_min(c, mn);
     gsync(c);
+    WRSN_PROF_END(c, WRSN_H_PROF4);
     return mn;
 }
 
@@ -954,8 +812,8 @@ WRSN_D void cond_check_h(Ctx &c, int j) {          /* leader-only variant used w
  * read and write only the charger's own record, so they commute with every grid event and with the other chargers.
  * slot_ff() replays such a run of spans in registers — the reference's arithmetic, operation by operation, three
  * insertion counters per span — up to a time limit, or (commit = false) just finds the instant at which the run ends
- * (arrival, exhaustion, end of the charge, or a span landing exactly on the node grid, where the reference's insertion
- * order against the grid events would matter).  Everything else about the slot stays with ev_slot(). */
+ * (arrival, exhaustion, end of the charge, or a charge span landing exactly on the node grid, where the reference's
+ * insertion order against the grid events would matter).  Everything else about the slot stays with ev_slot(). */
 WRSN_DI bool on_grid(double t) {
     const double f = floor(t);
     return t == f || t == f + 0.5 || t == f + 0.1;
@@ -992,24 +850,30 @@ WRSN_DI bool rr_invariant(Ctx &c, int a) {
     return true;
 }
 
-/* may the pending event of slot s start a lazy run? */
-WRSN_DI bool slot_lazy_ok(Ctx &c, int s) {
+/* may the pending event of slot s start a lazy run?  0 no, 1 private, 2 private except that update_reward reads the
+ * charger's position every second (the orphan process of agent 0 marks it "charging", with the nodes around
+ * the base station connected, while it is moving): update_reward then brings the slot up to date first. */
+WRSN_DI int slot_lazy_ok(Ctx &c, const Clk &k, int s) {
     const double *p = slot_of(c, s);
     const int *pi = (const int *)p;
     const int pc = pi[WRSN_PRI_PC];
-    if (pc != PC_MS_FIRE && pc != PC_CS_FIRE) return false;
+    if (pc != PC_MS_FIRE && pc != PC_CS_FIRE) return 0;
     const int a = pi[WRSN_PRI_AGENT];
     for (int q = 0; q < c.n_slot; q++)               /* a second running process of the same charger shares its record */
         if (q != s && slot_i(slot_of(c, q))[WRSN_PRI_USED] != 0 && slot_i(slot_of(c, q))[WRSN_PRI_AGENT] == a &&
-            slot_of(c, q)[WRSN_PR_T] < INFINITY) return false;
+            slot_of(c, q)[WRSN_PR_T] < INFINITY) return 0;
     const double *m = c.mc + a * WRSN_MC_LEN;
-    if (pc == PC_CS_FIRE) return rr_invariant(c, a);
-    return m[WRSN_MC_TYPE] == 0.0 || !conn_has_alive(c, a);   /* update_reward reads a "charging" charger's position */
+    if (pc == PC_CS_FIRE) return rr_invariant(c, a) ? 1 : 0;
+    if (m[WRSN_MC_TYPE] == 0.0 || !conn_has_alive(c, a)) return 1;
+    /* spans that fire at the very instant of an update_reward: from the second such span on update_reward always comes
+       first (its timeout was inserted earlier); the first one must already be in that order */
+    if (p[WRSN_PR_T] == k.ur_t && p[WRSN_PR_KEY] < k.ur_key) return 0;
+    return 2;
 }
 
 /* replay spans of slot s whose event time is < limit; returns the number replayed and, in *t_end, the time of the span
  * event at which the run stops being private (or +inf if the limit came first) */
-WRSN_DI int slot_ff(Ctx &c, Clk &k, int s, double limit, bool commit, double *t_end) {
+WRSN_DI int slot_ff(Ctx &c, int s, double limit, bool commit, double *t_end) {
     double *p = slot_of(c, s);
     const int a = slot_i(p)[WRSN_PRI_AGENT], pc = slot_i(p)[WRSN_PRI_PC];
     double *m = mc_of(c, a);
@@ -1024,7 +888,8 @@ WRSN_DI int slot_ff(Ctx &c, Clk &k, int s, double limit, bool commit, double *t_
         double x = m[WRSN_MC_X], y = m[WRSN_MC_Y], en = m[WRSN_MC_ENERGY];
         double mt = p[WRSN_PR_MT], span = p[WRSN_PR_SPAN], svx = p[WRSN_PR_SVX], svy = p[WRSN_PR_SVY];
         while (tf < limit) {
-            if (on_grid(tf)) { *t_end = tf; break; }
+            /* (a span that fires exactly on the node grid is still private: a moving charger is not "charging", so no
+               grid event reads or writes its record; slot_try_lazy() refuses runs whose LAST event lands on the grid) */
             const double x1 = x + svx, y1 = y + svy, en1 = en - pm * span * v;     /* move_step :77-78 */
             const double mt1 = mt - span;                                         /* move :95 */
             if (mt1 <= 0.0 || en1 <= thr) { *t_end = tf; break; }                 /* arrival / exhaustion: ev_slot's business */
@@ -1062,10 +927,9 @@ WRSN_DI int slot_ff(Ctx &c, Clk &k, int s, double limit, bool commit, double *t_
         }
     }
     if (commit && n > 0) {
-        /* every span drew three insertion counters (completion of the step, start of the next one, its timeout) */
-        const double key = k.seq + 3.0 * (double)n - 1.0;
-        k.seq += 3.0 * (double)n; k.nev += 3.0 * (double)n;
-        if (WRSN_LEAD(c)) { p[WRSN_PR_T] = tf; p[WRSN_PR_KEY] = WRSN_KEY_NORMAL + key; c.hdr[WRSN_H_NLAZY] += (double)n; }
+        /* every span drew three insertion counters (completion of the step, start of the next one, its timeout); they are
+           owed until the slot wakes up: only the ORDER of pending events matters, and a lazy slot has none that ties */
+        if (WRSN_LEAD(c)) { p[WRSN_PR_T] = tf; p[WRSN_PR_OWED] += 3.0 * (double)n; c.hdr[WRSN_H_NLAZY] += (double)n; }
         gsync(c);
     }
     (void)ts_prev;
@@ -1075,25 +939,40 @@ WRSN_DI int slot_ff(Ctx &c, Clk &k, int s, double limit, bool commit, double *t_
 /* after an event of slot s: if its next event starts a private run of at least one span, make the slot lazy */
 WRSN_DI void slot_try_lazy(Ctx &c, Clk &k, int s) {
     double *p = slot_of(c, s);
-    if (!(p[WRSN_PR_T] < INFINITY) || !slot_lazy_ok(c, s)) return;
+    if (!(p[WRSN_PR_T] < INFINITY)) return;
+    const int kind = slot_lazy_ok(c, k, s);
+    if (kind == 0) return;
     double t_end;
-    const int n = slot_ff(c, k, s, INFINITY, false, &t_end);
-    if (n < 1) return;
+    const int n = slot_ff(c, s, INFINITY, false, &t_end);
+    if (n < 1 || on_grid(t_end)) return;             /* arrival / exhaustion on the grid: its order against the grid events
+                                                        of that instant is decided by insertion counters — event by event */
     gsync(c);
-    if (WRSN_LEAD(c)) { slot_i(p)[WRSN_PRI_LAZY] = 1; p[WRSN_PR_TINT] = t_end; }
+    if (WRSN_LEAD(c)) { slot_i(p)[WRSN_PRI_LAZY] = kind; p[WRSN_PR_TINT] = t_end; p[WRSN_PR_OWED] = 0.0; }
     gsync(c);
 }
 
-/* bring a lazy slot up to date: replay its spans before `limit`; wake = it becomes an ordinary slot again */
+/* bring a lazy slot up to date: replay its spans before `limit`; wake = it becomes an ordinary slot again, and its
+ * pending event gets the last of the insertion counters its spans drew */
 WRSN_DI void slot_catch_up(Ctx &c, Clk &k, int s, double limit, bool wake) {
     double *p = slot_of(c, s);
     double t_end;
-    slot_ff(c, k, s, limit, true, &t_end);
+    slot_ff(c, s, limit, true, &t_end);
     if (wake) {
+        const double owed = p[WRSN_PR_OWED];
+        const double key = k.seq + owed - 1.0;
+        k.seq += owed; k.nev += owed;
         gsync(c);
-        if (WRSN_LEAD(c)) slot_i(p)[WRSN_PRI_LAZY] = 0;
+        if (WRSN_LEAD(c)) {
+            slot_i(p)[WRSN_PRI_LAZY] = 0;
+            if (owed > 0.0) { p[WRSN_PR_KEY] = WRSN_KEY_NORMAL + key; p[WRSN_PR_OWED] = 0.0; }
+        }
         gsync(c);
     }
+}
+/* update_reward is about to read the chargers' positions */
+WRSN_D void catch_up_for_reward(Ctx &c, double t_reward) {
+    for (int q = 0; q < c.n_slot; q++)
+        if (slot_i(slot_of(c, q))[WRSN_PRI_LAZY] == 2) { double t_end; slot_ff(c, q, t_reward, true, &t_end); }
 }
 
 /* a death: every lazy run ends (the alive set of a charge, hence its rate, changes from the next connection on) */
@@ -1275,8 +1154,15 @@ WRSN_DI void ev_slot(Ctx &c, Clk &k, int s, double other_t) {
             double rate = m[WRSN_MC_RATE], en = m[WRSN_MC_ENERGY], cpa2 = m[WRSN_MC_CPA2];
             const bool connect = pc == PC_CS_INIT;
             if (!connect) { en = en - rate * span; cpa2 = fmax(0.0, cpa2 - span); }
-            wake_lazy_sharing(c, k, s, a);
+            /* lazy charges of other chargers that share a node re-validate when this event changes energyRR for good:
+               the first connection, the last disconnection, or a disconnect / reconnect pair that does not restore the
+               value.  A "quiet" pair (the charge goes on and rr_invariant holds) leaves them alone. */
+            bool quiet;
+            if (connect) quiet = slot_i(p)[WRSN_PRI_SPARE] != 0;
+            else quiet = (p[WRSN_PR_CHTMP] - span != 0.0) && en > par[WRSN_P_MC_THR] && rr_invariant(c, a);
+            if (!quiet) wake_lazy_sharing(c, k, s, a);
             gsync(c);
+            if (lead) slot_i(p)[WRSN_PRI_SPARE] = (!connect && quiet) ? 1 : 0;
             WRSN_FOR_BITS(cm, c.W, i) {
                 if (c.status[i] == 0) continue;
                 double r = charge_rate_xy(c, mx, my, i);
@@ -1332,6 +1218,166 @@ WRSN_DI void ev_cond(Ctx &c, Clk &k, int j) {
     else k.stop = 1;                                 /* StopSimulation */
 }
 
+/* ------------------------------------------------------------------ whole-cycle batches
+ * While no charger event, no death and no active update_reward lies ahead, one simulated second of the grid is the
+ * same five events over and over: drain (k+0.5), update_reward / Network.operate exit check / bookkeeping (k+1.0),
+ * Network.operate connectivity (k+1.1, levels unchanged).  Nobody looks at the node rows in between, so n such cycles
+ * are applied at once, node-parallel, with the reference's fp64 results:
+ *   - a node that is not being charged (energyRR == 0) loses the same integer number of ulps every cycle while it
+ *     stays inside its binade (see sub_chain), so n cycles are ONE exact multiply-subtract;
+ *   - any other node replays its cycles one by one in registers;
+ *   - energyCS under a constant per-second consumption reaches the fixed point of (cs*10 - lg + lg)/10 after one or
+ *     two applications; the loop stops there.
+ * A batch never contains a cycle the event-by-event path would send down the serial (possible death) path: the
+ * number of cycles is cut to the safe prefix and the rest runs event by event.
+ * Returns the number of cycles applied (0: nothing changed). */
+WRSN_NOINLINE int replay_cycles(double e, double rr, double es, double er, int nb, int ow, int na, double thr, double cap,
+                                int n, double *e_out) {
+    const double slack = 1e-6;
+    int done = 0;
+    for (; done < n; done++) {
+        const double e1 = sub_chain(e, es, 0, er, nb);
+        if (nb > 0 && !(e1 - thr >= slack)) break;
+        const double e2 = fmin(e1 + rr * 0.5, cap);
+        const double e3 = sub_chain(e2, es, ow, er, na);
+        if (ow + na > 0 && !(e3 - thr >= slack)) break;
+        e = fmin(e3 + rr * 0.5, cap);
+    }
+    *e_out = e;
+    return done;
+}
+
+/* one node's k+0.5 tick on the fast path (no death possible): relayed packets of lower ids, top-up, own packets,
+ * relayed packets of higher ids */
+WRSN_NOINLINE double drain_node(double e, double rr, double es, double er, int nb, int ow, int na, double cap) {
+    const double e1 = sub_chain(e, es, 0, er, nb);
+    const double e2 = fmin(e1 + rr * 0.5, cap);
+    return sub_chain(e2, es, ow, er, na);
+}
+
+WRSN_NOINLINE int nodes_batch(Ctx &c, int n_max, int ur_on, double t_reward) {
+    const int N = c.N;
+    const double thr = c.par[WRSN_P_THR], cap = c.par[WRSN_P_CAP], er = c.par[WRSN_P_ERECV];
+    const double slack = 1e-6;
+    const double *h = c.hdr;
+    WRSN_PROF_BEGIN();
+    if (h[WRSN_H_OPT_NOBATCH] != 0.0 || h[WRSN_H_BFS_DIRTY] != 0.0 || h[WRSN_H_LOG_LITERAL] != 0.0 ||
+        h[WRSN_H_LOG_LEN] < (double)WRSN_RING || h[WRSN_H_LOG_UNIFORM] < 10.0) return 0;
+    const bool active = ur_on && reward_pairs(c);    /* update_reward looks at every node every second */
+    /* pass 1: per node, the per-cycle decrement (scr1; NaN = replay cycle by cycle) and the number of safe cycles */
+    int n_safe = n_max;
+    _Pragma("unroll 1")
+    for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
+        if (c.status[i] != 1) continue;
+        const double e = c.energy[i], es = c.esend[i], rr = c.rr[i];
+        const int nb = c.nbef[i], na = c.naft[i];
+        const int ow = c.parent[i] != -1 ? (int)c.own[i] : 0;
+        const int n_a = nb + ow + na, n_b = nb + na;
+        double dec = NAN;
+        int m = 0;
+        if (rr == 0.0 && n_a == 0) { dec = 0.0; m = n_max; }
+        else if (rr == 0.0) {
+            const int ex = wrsn_biased_exp(e);
+            if (e > 0.0 && ex > 60 && ex < 1900) {
+                const double lo = wrsn_pow2_biased(ex), inv_u = wrsn_pow2_biased(2098 - ex), u = wrsn_pow2_biased(ex - 52);
+                const double qa = es * inv_u, qb = er * inv_u;
+                const double ra = rint(qa), rb = rint(qb);
+                const bool tie = (fabs(qa - ra) == 0.5) || (n_b > 0 && fabs(qb - rb) == 0.5);
+                const double K = ra * (double)n_a + rb * (double)n_b;      /* ulps per cycle */
+                if (!tie && K * (double)n_max < 4503599627370496.0) {
+                    dec = K * u;
+                    if (K == 0.0) m = n_max;
+                    else {
+                        const double room = e - fmax(lo, thr + 2.0 * slack);
+                        double q = room > 0.0 ? floor(room / dec) - 1.0 : 0.0;
+                        q = fmin(fmax(q, 0.0), (double)n_max);
+                        m = (int)q;
+                        if (m > 0) { const double r = e - dec * (double)m; if (!(r >= lo) || !(r - thr >= slack)) m = 0; }
+                    }
+                }
+            }
+            if (m == 0) dec = NAN;
+        }
+        if (dec != dec) {                            /* charged, near a binade edge or near the threshold: literal cycles */
+            double e_end;
+            m = replay_cycles(e, rr, es, er, nb, ow, na, thr, cap, n_safe, &e_end);
+        }
+        c.scr1[i] = dec;
+        if (m < n_safe) n_safe = m;
+    }
+    gsync(c);
+    n_safe = (int)red_min(c, (double)n_safe);
+    if (n_safe <= 0) return 0;
+    const double L = (double)WRSN_RING;
+    if (!active) {
+        /* pass 2: all cycles at once */
+        _Pragma("unroll 1")
+        for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
+            if (c.status[i] != 1) continue;
+            const double dec = c.scr1[i];
+            if (dec == dec) c.energy[i] = c.energy[i] - dec * (double)n_safe;
+            else {
+                double e_end;
+                const int nb = c.nbef[i], na = c.naft[i];
+                const int ow = c.parent[i] != -1 ? (int)c.own[i] : 0;
+                replay_cycles(c.energy[i], c.rr[i], c.esend[i], er, nb, ow, na, thr, cap, n_safe, &e_end);
+                c.energy[i] = e_end;
+            }
+            const double lg = c.logc[i];
+            double cs = c.cs[i];
+            for (int t = 0; t < n_safe; t++) {       /* Node.py:75 with log[0] == log_energy */
+                const double nx = (cs * L - lg + lg) / L;
+                if (nx == cs) break;
+                cs = nx;
+            }
+            c.cs[i] = cs;
+        }
+        gsync(c);
+    } else {
+        /* pass 2: cycle by cycle, because update_reward reads every node at every k+1.0 (before the bookkeeping) */
+        uint32_t fixed = 0u;                         /* node slots of this thread whose energyCS has reached its fixed point */
+        _Pragma("unroll 1")
+        for (int j = 0; j < n_safe; j++) {
+            _Pragma("unroll 1")
+            for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
+                if (c.status[i] != 1) continue;
+                const double dec = c.scr1[i];
+                if (dec == dec) c.energy[i] = c.energy[i] - dec;
+                else {
+                    const int ow = c.parent[i] != -1 ? (int)c.own[i] : 0;
+                    c.energy[i] = drain_node(c.energy[i], c.rr[i], c.esend[i], er, c.nbef[i], ow, c.naft[i], cap);
+                }
+            }
+            gsync(c);
+            catch_up_for_reward(c, t_reward + (double)j);
+            update_reward_body(c);
+            int sl = 0;
+            _Pragma("unroll 1")
+            for (int i = c.tid; i < N; i += WRSN_GSZ(c), sl++) {
+                if (c.status[i] != 1) continue;
+                const double rr = c.rr[i];
+                if (rr != 0.0) c.energy[i] = fmin(c.energy[i] + rr * 0.5, cap);
+                if (sl < 32 && ((fixed >> sl) & 1u)) continue;
+                const double lg = c.logc[i], cs = c.cs[i];
+                const double nx = (cs * L - lg + lg) / L;
+                if (nx == cs) { if (sl < 32) fixed |= 1u << sl; }
+                else c.cs[i] = nx;
+            }
+            gsync(c);
+        }
+    }
+    if (c.tid == 0) {
+        double *hw = c.hdr;
+        hw[WRSN_H_LOG_HEAD] = (double)(((int)hw[WRSN_H_LOG_HEAD] + n_safe) % WRSN_RING);
+        if (hw[WRSN_H_LOG_UNIFORM] < 1e9) hw[WRSN_H_LOG_UNIFORM] = fmin(hw[WRSN_H_LOG_UNIFORM] + (double)n_safe, 1e9);
+        hw[WRSN_H_NTICKS] += (double)n_safe;
+        hw[WRSN_H_NBATCH] += (double)n_safe;
+    }
+    gsync(c);
+    WRSN_PROF_END(c, WRSN_H_PROF2);
+    return n_safe;
+}
+
 /* ------------------------------------------------------------------ the event loop: env.run(...) */
 WRSN_DI void run_loop(Ctx &c) {
     Clk k;
@@ -1365,25 +1411,25 @@ WRSN_DI void run_loop(Ctx &c) {
                     /* whole cycles strictly before the next charger / condition / until event: the canonical pending set
                        is {drain now, update_reward and the exit check of Network.operate at +0.5 (in that order)} */
                     const double H = fmin(fmin(k.mc_t, k.until_t), maxtime - 2.0);
-                    const bool ur_on = k.ur_t < INFINITY;
-                    if (gt + 1.0 <= H && k.net_state == 2 && k.net_t == gt + 0.5 &&
-                        (!ur_on || (k.ur_t == gt + 0.5 && k.ur_key < k.net_key))) {
+                    const bool ur_on = k.ur_t < INFINITY, net_on = k.net_t < INFINITY;
+                    if (gt + 1.0 <= H && (!net_on || (k.net_state == 2 && k.net_t == gt + 0.5 && c.hdr[WRSN_H_ALIVE] != 0.0)) &&
+                        (!ur_on || (k.ur_t == gt + 0.5 && (!net_on || k.ur_key < k.net_key)))) {
                         const double span = fmin(H - gt, 1048576.0);
                         int n = (int)span;
                         while (n > 0 && !(gt + (double)n <= H)) n--;
-                        if (n > 0) batched = nodes_batch(c, n, ur_on ? 1 : 0);
+                        if (n > 0) batched = nodes_batch(c, n, ur_on ? 1 : 0, gt + 0.5);
                         if (batched > 0) {
-                            /* the clock after `batched` cycles: every cycle drew 5 (4 without update_reward) insertion counters
-                               in the order drain, [update_reward,] exit check, bookkeeping, connectivity */
-                            const double nb = (double)batched, per = ur_on ? 5.0 : 4.0;
-                            const double s0 = k.seq + per * (nb - 1.0);
-                            if (ur_on) {
-                                k.ur_key = WRSN_KEY_NORMAL + (s0 + 1.0); k.net_key = WRSN_KEY_NORMAL + (s0 + 4.0);
-                                k.nodes_key = WRSN_KEY_NORMAL + (s0 + 3.0); k.ur_t += nb;
-                            } else { k.net_key = WRSN_KEY_NORMAL + (s0 + 3.0); k.nodes_key = WRSN_KEY_NORMAL + (s0 + 2.0); }
+                            /* the clock after `batched` cycles: every cycle drew its insertion counters in the order drain,
+                               [update_reward,] [exit check,] bookkeeping, [connectivity] (Network.operate may have ended, Q1) */
+                            const double nb = (double)batched;
+                            const double per = 2.0 + (ur_on ? 1.0 : 0.0) + (net_on ? 2.0 : 0.0);
+                            double s0 = k.seq + per * (nb - 1.0);
+                            if (ur_on) { s0 += 1.0; k.ur_key = WRSN_KEY_NORMAL + s0; k.ur_t += nb; }
+                            if (net_on) { s0 += 1.0; k.net_key = WRSN_KEY_NORMAL + (s0 + 2.0); k.net_t += nb; }
+                            k.nodes_key = WRSN_KEY_NORMAL + (s0 + 1.0);
                             k.seq += per * nb; k.nev += per * nb - 1.0;
-                            k.net_t += nb; k.nodes_t = gt + nb;
-                            k.now = (k.net_t - 1.0) + 0.1;
+                            k.nodes_t = gt + nb;
+                            k.now = net_on ? (k.net_t - 1.0) + 0.1 : gt + (nb - 0.5);
                         }
                     }
                 }
@@ -1402,6 +1448,7 @@ WRSN_DI void run_loop(Ctx &c) {
                 } else if (c.hdr[WRSN_H_ALIVE] == 0.0 || gt >= maxtime) k.net_t = INFINITY;
                 else { k.net_t = gt + 0.1; k.net_key = WRSN_KEY_NORMAL + take_seq(k); k.net_state = 1; }
             } else if (gk == K_UR) {
+                catch_up_for_reward(c, gt);
                 ev_update_reward(c);
                 k.ur_t = gt + 1.0; k.ur_key = WRSN_KEY_NORMAL + take_seq(k);
             } else {                                 /* K_UNTIL */

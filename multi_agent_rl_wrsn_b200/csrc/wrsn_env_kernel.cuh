@@ -25,6 +25,10 @@ __global__ void __launch_bounds__(WRSN_GFIX ? WRSN_GFIX : 256, WRSN_GFIX ? 20 : 
     gsync(c);
 
     const double now_before = c.hdr[WRSN_H_NOW];
+#if defined(WRSN_PROF)
+    const long long prof_start = clock64();
+    if (MODE == MODE_STEP) { gsync(c); if (tid == 0) for (int q = WRSN_H_PROF0; q <= WRSN_H_PROF4; q++) c.hdr[q] = 0.0; gsync(c); }
+#endif
     ReqOut r;
     r.agent = -3; r.terminal = 0; r.reward = 0; r.now = 0; r.flags = 0;
     r.act[0] = r.act[1] = r.act[2] = 0; r.detail[0] = r.detail[1] = 0;
@@ -45,6 +49,9 @@ __global__ void __launch_bounds__(WRSN_GFIX ? WRSN_GFIX : 256, WRSN_GFIX ? 20 : 
     case MODE_K_REWARD: ev_update_reward(c); break;
     }
     gsync(c);
+#if defined(WRSN_PROF)
+    if (MODE == MODE_STEP) { if (tid == 0) c.hdr[WRSN_H_PROF0] = (double)(clock64() - prof_start); gsync(c); }
+#endif
     if (MODE != MODE_FITNESS) copy16(row, smem, P.L.resident, tid, G);
     if ((MODE == MODE_RESET_FINISH || MODE == MODE_RESTORE_RESET || MODE == MODE_STEP) && tid == 0) {
         write_request(P.req, b, r);

@@ -1,0 +1,35 @@
+"""Where do the SM cycles of a step launch go?  Needs the profiling build:
+    nvcc ... -DWRSN_PROF -o multi_agent_rl_wrsn_b200/csrc/libwrsn_b200_prof.so   (tools/build_prof.sh)
+Prints, per rollout step of B environments, the mean and the maximum over environments of the cycles spent in the
+whole step kernel, the serial (possible death) ticks, the whole-cycle batches, BFS + routing tree, and fitness."""
+import os, sys
+import numpy as np, torch
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+from multi_agent_rl_wrsn_b200 import _lib, BatchedWRSN, synthetic
+_lib.use_library(os.path.join(REPO, "multi_agent_rl_wrsn_b200", "csrc", "libwrsn_b200_prof.so"))
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 200
+scs = [synthetic(num_nodes=100, num_targets=100, seed=1000 + k) for k in range(64)]
+env = BatchedWRSN(scs, num_agent=3, num_envs=B, device="cuda:0")
+env.reset()
+g = torch.Generator(device="cuda:0"); g.manual_seed(0)
+names = ["total", "serial", "batch", "bfs", "fitness"]
+idx = [env.E["WRSN_H_PROF%d" % k] for k in range(5)]
+acc = []
+for k in range(steps):
+    a = torch.rand((B, 3), dtype=torch.float64, device="cuda:0", generator=g); a[:, 2] *= 0.05
+    env.rollout_step(a)
+    if k >= steps - 50:
+        h = env.view("hdr")[:, idx].cpu().numpy()
+        acc.append(h)
+acc = np.stack(acc)            # [steps, B, 5]
+print("per-step mean over envs (kcycles):", dict(zip(names, np.round(acc.mean((0, 1)) / 1e3, 1))))
+print("per-step MAX over envs, averaged over steps (kcycles):", dict(zip(names, np.round(acc.max(1).mean(0) / 1e3, 1))))
+tot = acc[..., 0]
+print("total kcycles percentiles 50/90/99/99.9/max:", np.round(np.percentile(tot, [50, 90, 99, 99.9, 100]) / 1e3, 1))
+srt = np.argsort(-tot.reshape(-1))[:10]
+print("slowest rows (total, serial, batch, bfs, fitness kcycles):")
+for r in srt:
+    print("   ", np.round(acc.reshape(-1, 5)[r] / 1e3, 1))
+print(env.counters())
