@@ -75,14 +75,32 @@
 #define WRSN_SMEM_BASE (reinterpret_cast<char *>(wrsn_smem_u4))
 #endif
 
+/* cycle counters of the profiling builds (tools/build_prof.sh): -DWRSN_PROF=1 counts serial ticks / batches / BFS / fitness,
+ * -DWRSN_PROF=2 charger events / lazy replays / event-path grid events / the slot scan, into hdr[WRSN_H_PROF1..4] */
 #undef WRSN_PROF_BEGIN
 #undef WRSN_PROF_END
+#undef WRSN_PROFB_BEGIN
+#undef WRSN_PROFB_END
 #if defined(WRSN_PROF) && !defined(WRSN_HOST_EMU)
-#define WRSN_PROF_BEGIN() const long long prof_t0_ = clock64()
-#define WRSN_PROF_END(c, slot) do { if ((c).tid == 0) (c).hdr[slot] += (double)(clock64() - prof_t0_); } while (0)
+#define WRSN_PROF_T0_() const long long prof_t0_ = clock64()
+#define WRSN_PROF_ADD_(c, slot) do { if ((c).tid == 0) (c).hdr[slot] += (double)(clock64() - prof_t0_); } while (0)
+#else
+#define WRSN_PROF_T0_() do { } while (0)
+#define WRSN_PROF_ADD_(c, slot) do { } while (0)
+#endif
+#if defined(WRSN_PROF) && WRSN_PROF == 1
+#define WRSN_PROF_BEGIN() WRSN_PROF_T0_()
+#define WRSN_PROF_END(c, slot) WRSN_PROF_ADD_(c, slot)
 #else
 #define WRSN_PROF_BEGIN() do { } while (0)
 #define WRSN_PROF_END(c, slot) do { } while (0)
+#endif
+#if defined(WRSN_PROF) && WRSN_PROF == 2
+#define WRSN_PROFB_BEGIN() WRSN_PROF_T0_()
+#define WRSN_PROFB_END(c, slot) WRSN_PROF_ADD_(c, slot)
+#else
+#define WRSN_PROFB_BEGIN() do { } while (0)
+#define WRSN_PROFB_END(c, slot) do { } while (0)
 #endif
 
 /* ------------------------------------------------------------------ context
@@ -665,30 +683,33 @@ WRSN_D void ev_update_reward(Ctx &c) {
 }
 
 WRSN_NOINLINE void update_reward_body(Ctx &c) {
-    const int N = c.N;
+    const int N = c.N, G = WRSN_GSZ(c);
     const double thr = c.par[WRSN_P_THR], cap = c.par[WRSN_P_CAP], eps = c.par[WRSN_P_EPSENV];
-    double s = 0.0;
-    _Pragma("unroll 1")
-    for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
-        double p = c.status[i] != 0 ? c.cs[i] / (c.energy[i] - thr + eps) : 0.0;
-        c.scr0[i] = p; s += p;
+    double tot;
+    {   /* rolled on purpose: the step kernel is bound by instruction fetch, one compact loop body beats four unrolled
+           division / exp expansions */
+        double s = 0.0;
+        _Pragma("unroll 1")
+        for (int i = c.tid; i < N; i += G) {
+            double p = c.status[i] != 0 ? c.cs[i] / (c.energy[i] - thr + eps) : 0.0;
+            c.scr0[i] = p; s += p;
+        }
+        const double mean = red_sum(c, s) / (double)N;
+        s = 0.0;
+        _Pragma("unroll 1")
+        for (int i = c.tid; i < N; i += G) { double x = c.scr0[i] - mean; s += x * x; }
+        double sd = sqrt(red_sum(c, s) / (double)N);
+        if (sd == 0.0) sd = eps;
+        s = 0.0;
+        _Pragma("unroll 1")
+        for (int i = c.tid; i < N; i += G) { double q = exp((c.scr0[i] - mean) / sd); c.scr0[i] = q; s += q; }
+        tot = red_sum(c, s);
     }
-    double mean = red_sum(c, s) / (double)N;
-    s = 0.0;
-    _Pragma("unroll 1")
-    for (int i = c.tid; i < N; i += WRSN_GSZ(c)) { double x = c.scr0[i] - mean; s += x * x; }
-    double sd = sqrt(red_sum(c, s) / (double)N);
-    if (sd == 0.0) sd = eps;
-    s = 0.0;
-    _Pragma("unroll 1")
-    for (int i = c.tid; i < N; i += WRSN_GSZ(c)) { double q = exp((c.scr0[i] - mean) / sd); c.scr0[i] = q; s += q; }
-    double tot = red_sum(c, s);
     if (tot == 0.0) tot = eps;
     gsync(c);
-    if (c.tid == 0) {
-        for (int a = 0; a < c.M; a++) {
-            double *m = c.mc + (size_t)a * WRSN_MC_LEN;
-            if (m[WRSN_MC_STATUS] == 0.0 || m[WRSN_MC_TYPE] == 0.0) continue;
+    for (int a = c.tid; a < c.M; a += G) {           /* one thread per charger: the incentive sums run side by side */
+        double *m = c.mc + (size_t)a * WRSN_MC_LEN;
+        if (m[WRSN_MC_STATUS] != 0.0 && m[WRSN_MC_TYPE] != 0.0) {
             double incentive = 0.0;
             const uint32_t *cm = c.conn + (size_t)a * c.W;
             for (int w = 0; w < c.W; w++) {
@@ -714,12 +735,31 @@ WRSN_NOINLINE double do_fitness(Ctx &c, double *per_target /* global, may be NUL
     double *node_t = c.scr0, *lt = c.scr1;
     WRSN_PROF_BEGIN();
     for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
-        double v = -1.0, l = 0.0;
+        double l = 0.0;
+        if (c.status[i] == 1) l = (c.cs[i] == 0.0) ? INFINITY : (c.energy[i] - thr) / c.cs[i];
+        lt[i] = l;
+    }
+    gsync(c);
+    /* start from the bottleneck of the node's own routing path (receiver by receiver to the base station): a real
+       path, hence a valid lower bound of the widest one and usually the widest already, so the relaxation below has
+       little or nothing left to do instead of walking the network depth hop by hop */
+    for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
+        double v = -1.0;
         if (c.status[i] == 1) {
-            l = (c.cs[i] == 0.0) ? INFINITY : (c.energy[i] - thr) / c.cs[i];
-            if (c.direct[i]) v = l;
+            if (c.direct[i]) v = lt[i];
+            else {
+                double mn = lt[i];
+                int h = c.parent[i], hops = 0;
+                while (h >= 0 && hops++ < N) {
+                    if (c.status[h] != 1) { h = -1; break; }     /* a death the tree does not know yet */
+                    mn = fmin(mn, lt[h]);
+                    if (c.direct[h]) { h = -2; break; }
+                    h = c.parent[h];
+                }
+                if (h == -2) v = mn;
+            }
         }
-        node_t[i] = v; lt[i] = l;
+        node_t[i] = v;
     }
     gsync(c);
     for (;;) {                                       /* widest path to the base station; only min / max, so any order is exact */
@@ -853,7 +893,7 @@ WRSN_DI bool rr_invariant(Ctx &c, int a) {
 /* may the pending event of slot s start a lazy run?  0 no, 1 private, 2 private except that update_reward reads the
  * charger's position every second (the orphan process of agent 0 marks it "charging", with the nodes around
  * the base station connected, while it is moving): update_reward then brings the slot up to date first. */
-WRSN_DI int slot_lazy_ok(Ctx &c, const Clk &k, int s) {
+WRSN_D int slot_lazy_ok(Ctx &c, double ur_t, double ur_key, int s) {
     const double *p = slot_of(c, s);
     const int *pi = (const int *)p;
     const int pc = pi[WRSN_PRI_PC];
@@ -867,19 +907,31 @@ WRSN_DI int slot_lazy_ok(Ctx &c, const Clk &k, int s) {
     if (m[WRSN_MC_TYPE] == 0.0 || !conn_has_alive(c, a)) return 1;
     /* spans that fire at the very instant of an update_reward: from the second such span on update_reward always comes
        first (its timeout was inserted earlier); the first one must already be in that order */
-    if (p[WRSN_PR_T] == k.ur_t && p[WRSN_PR_KEY] < k.ur_key) return 0;
+    if (p[WRSN_PR_T] == ur_t && p[WRSN_PR_KEY] < ur_key) return 0;
     return 2;
 }
 
 /* replay spans of slot s whose event time is < limit; returns the number replayed and, in *t_end, the time of the span
- * event at which the run stops being private (or +inf if the limit came first) */
-WRSN_DI int slot_ff(Ctx &c, int s, double limit, bool commit, double *t_end) {
+ * event at which the run stops being private (or +inf if the limit came first).
+ * mode FF_DRY: nothing is stored.  FF_ALL: every thread of the environment makes the same call, the leader stores.
+ * FF_OWN: only the calling thread works on this slot (other threads replay other slots at the same time) and stores;
+ * the caller puts barriers around the whole group of calls. */
+enum { FF_DRY = 0, FF_ALL = 1, FF_OWN = 2 };
+WRSN_D void atomic_add_f64(double *p, double v) {
+#if !defined(WRSN_HOST_EMU)
+    atomicAdd(p, v);
+#else
+    *p += v;
+#endif
+}
+WRSN_NOINLINE int slot_ff(Ctx &c, int s, double limit, int mode, double *t_end) {
     double *p = slot_of(c, s);
     const int a = slot_i(p)[WRSN_PRI_AGENT], pc = slot_i(p)[WRSN_PRI_PC];
     double *m = mc_of(c, a);
     const double *par = c.par.ptr();
     const double thr = par[WRSN_P_MC_THR];
-    double tf = p[WRSN_PR_T], ts_prev = tf;
+    const bool store = mode == FF_OWN || (mode == FF_ALL && WRSN_LEAD(c));
+    double tf = p[WRSN_PR_T];
     int n = 0;
     *t_end = INFINITY;
     if (pc == PC_MS_FIRE) {
@@ -887,26 +939,40 @@ WRSN_DI int slot_ff(Ctx &c, int s, double limit, bool commit, double *t_end) {
         const double destx = p[WRSN_PR_DESTX], desty = p[WRSN_PR_DESTY], vx = p[WRSN_PR_VX], vy = p[WRSN_PR_VY], total = p[WRSN_PR_TOTAL];
         double x = m[WRSN_MC_X], y = m[WRSN_MC_Y], en = m[WRSN_MC_ENERGY];
         double mt = p[WRSN_PR_MT], span = p[WRSN_PR_SPAN], svx = p[WRSN_PR_SVX], svy = p[WRSN_PR_SVY];
+        /* Far from the destination and from exhaustion a span is always 1 s: min(mt, 1.0, (energy - threshold) / (pm v))
+           with mt >= 1 and energy - threshold >= pm v (x / y >= 1 exactly when x >= y).  Then neither the square root nor
+           the two divisions are needed to know the span, and the remaining time `mt` is only needed once, for the
+           position the replay stops at (it is a pure function of the position: move :91).  `far` is a safe margin above
+           v^2; anything closer takes the literal arithmetic. */
+        const double ux = vx / total, uy = vy / total;                            /* move_step :77 (vec / total) * span */
+        const double far = v * v * 1.000001;
+        bool mt_known = true;
         while (tf < limit) {
             /* (a span that fires exactly on the node grid is still private: a moving charger is not "charging", so no
                grid event reads or writes its record; slot_try_lazy() refuses runs whose LAST event lands on the grid) */
             const double x1 = x + svx, y1 = y + svy, en1 = en - pm * span * v;     /* move_step :77-78 */
-            const double mt1 = mt - span;                                         /* move :95 */
-            if (mt1 <= 0.0 || en1 <= thr) { *t_end = tf; break; }                 /* arrival / exhaustion: ev_slot's business */
-            const double mt2 = euclid2(destx, desty, x1, y1) / v;                 /* move :91-94 */
-            const double span2 = fmin(fmin(mt2, 1.0), (en1 - thr) / pmv);
-            x = x1; y = y1; en = en1; mt = mt2; span = span2;
-            svx = vx / total * span2; svy = vy / total * span2;
-            ts_prev = tf; tf = tf + span2; n++;
+            if (mt_known) { if (mt - span <= 0.0) { *t_end = tf; break; } }       /* move :95 (unknown mt: > 1 = span) */
+            if (en1 <= thr) { *t_end = tf; break; }                               /* arrival / exhaustion: ev_slot's business */
+            const double dx = destx - x1, dy = desty - y1, d2 = dx * dx + dy * dy;
+            double span2;
+            if (d2 > far && en1 - thr >= pmv) { span2 = 1.0; mt_known = false; }
+            else {
+                mt = sqrt(d2) / v; mt_known = true;                               /* move :91-94 */
+                span2 = fmin(fmin(mt, 1.0), (en1 - thr) / pmv);
+            }
+            x = x1; y = y1; en = en1; span = span2;
+            svx = ux * span2; svy = uy * span2;
+            tf = tf + span2; n++;
         }
-        if (commit && n > 0) {
-            gsync(c);
-            if (WRSN_LEAD(c)) {
+        if (!mt_known) mt = euclid2(destx, desty, x, y) / v;
+        if (mode != FF_DRY && n > 0) {
+            if (mode == FF_ALL) gsync(c);
+            if (store) {
                 m[WRSN_MC_X] = x; m[WRSN_MC_Y] = y; m[WRSN_MC_ENERGY] = en;
                 p[WRSN_PR_MT] = mt; p[WRSN_PR_SPAN] = span; p[WRSN_PR_SVX] = svx; p[WRSN_PR_SVY] = svy;
             }
         }
-    } else {                                         /* PC_CS_FIRE with charging rate 0 and nobody alive in range */
+    } else {                                         /* PC_CS_FIRE: a charge whose disconnect / reconnect pairs change nothing */
         double en = m[WRSN_MC_ENERGY], cpa2 = m[WRSN_MC_CPA2], tmp = p[WRSN_PR_CHTMP], span = p[WRSN_PR_CHSPAN];
         const double rate = m[WRSN_MC_RATE];
         while (tf < limit) {
@@ -915,35 +981,36 @@ WRSN_DI int slot_ff(Ctx &c, int s, double limit, bool commit, double *t_end) {
             const double cpa21 = fmax(0.0, cpa2 - span);                           /* :46 */
             const double tmp1 = tmp - span;                                        /* charge :69 */
             if (tmp1 == 0.0 || en1 <= thr) { *t_end = tf; break; }
-            en = en1; cpa2 = cpa21; tmp = tmp1; span = fmin(tmp1, 1.0);            /* :63 (rate is 0: no energy limiter) */
-            ts_prev = tf; tf = tf + span; n++;
+            en = en1; cpa2 = cpa21; tmp = tmp1; span = fmin(tmp1, 1.0);            /* :63-68 (the rate is 0 there: no energy limiter, Q3) */
+            tf = tf + span; n++;
         }
-        if (commit && n > 0) {
-            gsync(c);
-            if (WRSN_LEAD(c)) {
+        if (mode != FF_DRY && n > 0) {
+            if (mode == FF_ALL) gsync(c);
+            if (store) {
                 m[WRSN_MC_ENERGY] = en; m[WRSN_MC_CPA2] = cpa2; m[WRSN_MC_CHTIME] = tmp;
                 p[WRSN_PR_CHTMP] = tmp; p[WRSN_PR_CHSPAN] = span;
             }
         }
     }
-    if (commit && n > 0) {
+    if (mode != FF_DRY && n > 0) {
         /* every span drew three insertion counters (completion of the step, start of the next one, its timeout); they are
            owed until the slot wakes up: only the ORDER of pending events matters, and a lazy slot has none that ties */
-        if (WRSN_LEAD(c)) { p[WRSN_PR_T] = tf; p[WRSN_PR_OWED] += 3.0 * (double)n; c.hdr[WRSN_H_NLAZY] += (double)n; }
-        gsync(c);
+        if (store) { p[WRSN_PR_T] = tf; p[WRSN_PR_OWED] += 3.0 * (double)n; }
+        if (mode == FF_OWN) atomic_add_f64(&c.hdr[WRSN_H_NLAZY], (double)n);
+        else if (store) c.hdr[WRSN_H_NLAZY] += (double)n;
+        if (mode == FF_ALL) gsync(c);
     }
-    (void)ts_prev;
     return n;
 }
 
 /* after an event of slot s: if its next event starts a private run of at least one span, make the slot lazy */
-WRSN_DI void slot_try_lazy(Ctx &c, Clk &k, int s) {
+WRSN_NOINLINE void slot_try_lazy(Ctx &c, double ur_t, double ur_key, int s) {
     double *p = slot_of(c, s);
     if (!(p[WRSN_PR_T] < INFINITY)) return;
-    const int kind = slot_lazy_ok(c, k, s);
+    const int kind = slot_lazy_ok(c, ur_t, ur_key, s);
     if (kind == 0) return;
     double t_end;
-    const int n = slot_ff(c, s, INFINITY, false, &t_end);
+    const int n = slot_ff(c, s, INFINITY, FF_DRY, &t_end);
     if (n < 1 || on_grid(t_end)) return;             /* arrival / exhaustion on the grid: its order against the grid events
                                                         of that instant is decided by insertion counters — event by event */
     gsync(c);
@@ -952,28 +1019,38 @@ WRSN_DI void slot_try_lazy(Ctx &c, Clk &k, int s) {
 }
 
 /* bring a lazy slot up to date: replay its spans before `limit`; wake = it becomes an ordinary slot again, and its
- * pending event gets the last of the insertion counters its spans drew */
-WRSN_DI void slot_catch_up(Ctx &c, Clk &k, int s, double limit, bool wake) {
+ * pending event gets the last of the insertion counters its spans drew (returned: how many the clock owes) */
+WRSN_NOINLINE double slot_catch_up_core(Ctx &c, int s, double limit, bool wake, double seq) {
     double *p = slot_of(c, s);
     double t_end;
-    slot_ff(c, s, limit, true, &t_end);
-    if (wake) {
-        const double owed = p[WRSN_PR_OWED];
-        const double key = k.seq + owed - 1.0;
-        k.seq += owed; k.nev += owed;
-        gsync(c);
-        if (WRSN_LEAD(c)) {
-            slot_i(p)[WRSN_PRI_LAZY] = 0;
-            if (owed > 0.0) { p[WRSN_PR_KEY] = WRSN_KEY_NORMAL + key; p[WRSN_PR_OWED] = 0.0; }
-        }
-        gsync(c);
+    slot_ff(c, s, limit, FF_ALL, &t_end);
+    if (!wake) return 0.0;
+    const double owed = p[WRSN_PR_OWED];
+    gsync(c);
+    if (WRSN_LEAD(c)) {
+        slot_i(p)[WRSN_PRI_LAZY] = 0;
+        if (owed > 0.0) { p[WRSN_PR_KEY] = WRSN_KEY_NORMAL + (seq + owed - 1.0); p[WRSN_PR_OWED] = 0.0; }
     }
+    gsync(c);
+    return owed;
+}
+WRSN_DI void slot_catch_up(Ctx &c, Clk &k, int s, double limit, bool wake) {
+    const double owed = slot_catch_up_core(c, s, limit, wake, k.seq);
+    k.seq += owed; k.nev += owed;
+}
+/* bring several lazy slots up to date at once, one thread per slot (they stay lazy): kind 2 = the slots whose position
+ * update_reward reads, 1 = every lazy slot */
+WRSN_D void catch_up_many(Ctx &c, double limit, int kind) {
+    bool any = false;
+    for (int q = 0; q < c.n_slot; q++) any = any || slot_i(slot_of(c, q))[WRSN_PRI_LAZY] >= kind;
+    if (!any) return;
+    gsync(c);
+    for (int q = c.tid; q < c.n_slot; q += WRSN_GSZ(c))
+        if (slot_i(slot_of(c, q))[WRSN_PRI_LAZY] >= kind) { double t_end; slot_ff(c, q, limit, FF_OWN, &t_end); }
+    gsync(c);
 }
 /* update_reward is about to read the chargers' positions */
-WRSN_D void catch_up_for_reward(Ctx &c, double t_reward) {
-    for (int q = 0; q < c.n_slot; q++)
-        if (slot_i(slot_of(c, q))[WRSN_PRI_LAZY] == 2) { double t_end; slot_ff(c, q, t_reward, true, &t_end); }
-}
+WRSN_D void catch_up_for_reward(Ctx &c, double t_reward) { catch_up_many(c, t_reward, 2); }
 
 /* a death: every lazy run ends (the alive set of a charge, hence its rate, changes from the next connection on) */
 WRSN_DI void wake_lazy_all(Ctx &c, Clk &k) {
@@ -1336,6 +1413,8 @@ WRSN_NOINLINE int nodes_batch(Ctx &c, int n_max, int ur_on, double t_reward) {
     } else {
         /* pass 2: cycle by cycle, because update_reward reads every node at every k+1.0 (before the bookkeeping) */
         uint32_t fixed = 0u;                         /* node slots of this thread whose energyCS has reached its fixed point */
+        bool watched = false;                        /* is there a lazy move whose position update_reward reads (Q2)? */
+        for (int q = 0; q < c.n_slot; q++) watched = watched || slot_i(slot_of(c, q))[WRSN_PRI_LAZY] == 2;
         _Pragma("unroll 1")
         for (int j = 0; j < n_safe; j++) {
             _Pragma("unroll 1")
@@ -1349,7 +1428,7 @@ WRSN_NOINLINE int nodes_batch(Ctx &c, int n_max, int ur_on, double t_reward) {
                 }
             }
             gsync(c);
-            catch_up_for_reward(c, t_reward + (double)j);
+            if (watched) catch_up_for_reward(c, t_reward + (double)j);
             update_reward_body(c);
             int sl = 0;
             _Pragma("unroll 1")
@@ -1385,7 +1464,7 @@ WRSN_DI void run_loop(Ctx &c) {
     const double maxtime = c.par[WRSN_P_MAXTIME];
     bool rescan = true;
     for (long guard = 0; guard < 400000000L; guard++) {
-        if (rescan) { mc_scan(c, k); rescan = false; }
+        if (rescan) { WRSN_PROFB_BEGIN(); mc_scan(c, k); rescan = false; WRSN_PROFB_END(c, WRSN_H_PROF4); }
         /* earliest of the grid items (Network.operate, update_reward, the node block, run(until=t)) */
         int gk = K_NODES;
         double gt = k.nodes_t, gkey = k.nodes_key;
@@ -1396,10 +1475,14 @@ WRSN_DI void run_loop(Ctx &c) {
             k.now = k.mc_t;
             if (k.mc_idx < c.n_slot) {
                 const int s = k.mc_idx;
+                { WRSN_PROFB_BEGIN();
                 if (slot_i(slot_of(c, s))[WRSN_PRI_LAZY] != 0) slot_catch_up(c, k, s, k.mc_t, true);   /* its run of private spans ends now */
+                WRSN_PROFB_END(c, WRSN_H_PROF2); }
                 double other = fmin(fmin(k.mc_other_t, k.nodes_t), fmin(fmin(k.net_t, k.ur_t), k.until_t));
+                { WRSN_PROFB_BEGIN();
                 ev_slot(c, k, s, other);
-                slot_try_lazy(c, k, s);
+                slot_try_lazy(c, k.ur_t, k.ur_key, s);
+                WRSN_PROFB_END(c, WRSN_H_PROF1); }
             } else ev_cond(c, k, k.mc_idx - c.n_slot);
             rescan = true;
         } else {
@@ -1434,12 +1517,14 @@ WRSN_DI void run_loop(Ctx &c) {
                     }
                 }
                 if (!batched) {
+                    WRSN_PROFB_BEGIN();
                     if (k.nodes_phase == 1) {
                         ev_nodes_drain(c); k.nodes_phase = 2;
                         if (c.hdr[WRSN_H_BFS_DIRTY] != 0.0) { wake_lazy_all(c, k); rescan = true; }
                     }
                     else { ev_nodes_book(c); k.nodes_phase = 1; }
                     k.nodes_t = gt + 0.5; k.nodes_key = WRSN_KEY_NORMAL + take_seq(k);
+                    WRSN_PROFB_END(c, WRSN_H_PROF3);
                 }
             } else if (gk == K_NET) {                /* Network.operate :74-80 */
                 if (k.net_state == 1) {
@@ -1448,8 +1533,10 @@ WRSN_DI void run_loop(Ctx &c) {
                 } else if (c.hdr[WRSN_H_ALIVE] == 0.0 || gt >= maxtime) k.net_t = INFINITY;
                 else { k.net_t = gt + 0.1; k.net_key = WRSN_KEY_NORMAL + take_seq(k); k.net_state = 1; }
             } else if (gk == K_UR) {
+                WRSN_PROFB_BEGIN();
                 catch_up_for_reward(c, gt);
                 ev_update_reward(c);
+                WRSN_PROFB_END(c, WRSN_H_PROF3);
                 k.ur_t = gt + 1.0; k.ur_key = WRSN_KEY_NORMAL + take_seq(k);
             } else {                                 /* K_UNTIL */
                 k.until_t = INFINITY; k.stop = 1;
@@ -1458,8 +1545,9 @@ WRSN_DI void run_loop(Ctx &c) {
         if (k.stop) break;
     }
     /* whoever looks at the chargers next (decider scan, observation, the next step) sees them as of now */
-    for (int s = 0; s < c.n_slot; s++)
-        if (slot_i(slot_of(c, s))[WRSN_PRI_LAZY] != 0) slot_catch_up(c, k, s, k.now, false);
+    { WRSN_PROFB_BEGIN();
+    catch_up_many(c, k.now, 1);
+    WRSN_PROFB_END(c, WRSN_H_PROF2); }
     clk_store(c, k);
 }
 

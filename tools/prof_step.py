@@ -7,14 +7,15 @@ import numpy as np, torch
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 from multi_agent_rl_wrsn_b200 import _lib, BatchedWRSN, synthetic
-_lib.use_library(os.path.join(REPO, "multi_agent_rl_wrsn_b200", "csrc", "libwrsn_b200_prof.so"))
+VARIANT = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+_lib.use_library(os.path.join(REPO, "multi_agent_rl_wrsn_b200", "csrc", "libwrsn_b200_prof%d.so" % VARIANT))
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 200
 scs = [synthetic(num_nodes=100, num_targets=100, seed=1000 + k) for k in range(64)]
 env = BatchedWRSN(scs, num_agent=3, num_envs=B, device="cuda:0")
 env.reset()
 g = torch.Generator(device="cuda:0"); g.manual_seed(0)
-names = ["total", "serial", "batch", "bfs", "fitness"]
+names = ["total", "serial", "batch", "bfs", "fitness"] if VARIANT == 1 else ["total", "charger_events", "lazy_replay", "grid_events", "slot_scan"]
 idx = [env.E["WRSN_H_PROF%d" % k] for k in range(5)]
 acc = []
 for k in range(steps):
@@ -29,7 +30,7 @@ print("per-step MAX over envs, averaged over steps (kcycles):", dict(zip(names, 
 tot = acc[..., 0]
 print("total kcycles percentiles 50/90/99/99.9/max:", np.round(np.percentile(tot, [50, 90, 99, 99.9, 100]) / 1e3, 1))
 srt = np.argsort(-tot.reshape(-1))[:10]
-print("slowest rows (total, serial, batch, bfs, fitness kcycles):")
+print("slowest rows (kcycles, same columns):")
 for r in srt:
     print("   ", np.round(acc.reshape(-1, 5)[r] / 1e3, 1))
 print(env.counters())
