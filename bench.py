@@ -39,7 +39,7 @@ def parse():
     p.add_argument("--topologies", type=int, default=64, help="distinct synthetic scenarios per GPU")
     p.add_argument("--threads", type=int, default=0)
     p.add_argument("--preroll", type=int, default=160, help="untimed steps before warm-up that desynchronise the episodes")
-    p.add_argument("--groups", type=int, default=4, help="asynchronous environment groups (CUDA streams) per GPU")
+    p.add_argument("--groups", type=int, default=8, help="asynchronous environment groups (CUDA streams) per GPU")
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")

@@ -102,6 +102,15 @@
 #define WRSN_PROFB_BEGIN() do { } while (0)
 #define WRSN_PROFB_END(c, slot) do { } while (0)
 #endif
+#undef WRSN_PROFC_BEGIN
+#undef WRSN_PROFC_END
+#if defined(WRSN_PROF) && WRSN_PROF == 3                /* inside the batches: pass 1 / all-at-once pass 2 / cycle loop / update_reward */
+#define WRSN_PROFC_BEGIN(v) const long long v = clock64()
+#define WRSN_PROFC_END(c, slot, v) do { if ((c).tid == 0) (c).hdr[slot] += (double)(clock64() - v); } while (0)
+#else
+#define WRSN_PROFC_BEGIN(v) do { } while (0)
+#define WRSN_PROFC_END(c, slot, v) do { } while (0)
+#endif
 
 /* ------------------------------------------------------------------ context
  * The environment's shared-memory image is addressed as 32-bit offsets from the CTA's dynamic shared memory (SArr):
@@ -281,6 +290,10 @@ WRSN_D int wrsn_popc(uint32_t v) {
     return __builtin_popcount(v);
 #endif
 }
+
+/* num / den for den > 0 and num >= 0.  A zero numerator (a node without traffic: energyCS == 0) would send CUDA's fp64
+ * division down its special-case subroutine for the whole warp; the quotient is the (signed) zero itself. */
+WRSN_D double div_pos(double num, double den) { return num == 0.0 ? num : num / den; }
 
 WRSN_NOINLINE double euclid2(double ax, double ay, double bx, double by) {
     /* scipy.spatial.distance.euclidean == sqrt(dot(u - v, u - v)) for 2-vectors */
@@ -641,7 +654,7 @@ WRSN_D void ev_nodes_book(Ctx &c) {
             c.ring[(size_t)L * c.Npad + i] = lg;
         } else {
             double old = uni ? lg : c.ring[(size_t)head * c.Npad + i];
-            c.cs[i] = (c.cs[i] * (double)L - old + lg) / (double)L;
+            c.cs[i] = div_pos(c.cs[i] * (double)L - old + lg, (double)L);
             if (!uni) c.ring[(size_t)head * c.Npad + i] = lg;
         }
     }
@@ -691,7 +704,7 @@ WRSN_NOINLINE void update_reward_body(Ctx &c) {
         double s = 0.0;
         _Pragma("unroll 1")
         for (int i = c.tid; i < N; i += G) {
-            double p = c.status[i] != 0 ? c.cs[i] / (c.energy[i] - thr + eps) : 0.0;
+            double p = c.status[i] != 0 ? div_pos(c.cs[i], c.energy[i] - thr + eps) : 0.0;
             c.scr0[i] = p; s += p;
         }
         const double mean = red_sum(c, s) / (double)N;
@@ -700,9 +713,11 @@ WRSN_NOINLINE void update_reward_body(Ctx &c) {
         for (int i = c.tid; i < N; i += G) { double x = c.scr0[i] - mean; s += x * x; }
         double sd = sqrt(red_sum(c, s) / (double)N);
         if (sd == 0.0) sd = eps;
+        const double inv_sd = 1.0 / sd;              /* one division instead of N: (x - mean) * (1 / sd) is within 2 ulp of the
+                                                        reference's (x - mean) / sd, i.e. ~1e-15 relative on the softmax weight */
         s = 0.0;
         _Pragma("unroll 1")
-        for (int i = c.tid; i < N; i += G) { double q = exp((c.scr0[i] - mean) / sd); c.scr0[i] = q; s += q; }
+        for (int i = c.tid; i < N; i += G) { double q = exp((c.scr0[i] - mean) * inv_sd); c.scr0[i] = q; s += q; }
         tot = red_sum(c, s);
     }
     if (tot == 0.0) tot = eps;
@@ -1342,6 +1357,7 @@ WRSN_NOINLINE int nodes_batch(Ctx &c, int n_max, int ur_on, double t_reward) {
         h[WRSN_H_LOG_LEN] < (double)WRSN_RING || h[WRSN_H_LOG_UNIFORM] < 10.0) return 0;
     const bool active = ur_on && reward_pairs(c);    /* update_reward looks at every node every second */
     /* pass 1: per node, the per-cycle decrement (scr1; NaN = replay cycle by cycle) and the number of safe cycles */
+    WRSN_PROFC_BEGIN(pc1);
     int n_safe = n_max;
     _Pragma("unroll 1")
     for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
@@ -1376,16 +1392,21 @@ WRSN_NOINLINE int nodes_batch(Ctx &c, int n_max, int ur_on, double t_reward) {
             if (m == 0) dec = NAN;
         }
         if (dec != dec) {                            /* charged, near a binade edge or near the threshold: literal cycles */
-            double e_end;
-            m = replay_cycles(e, rr, es, er, nb, ow, na, thr, cap, n_safe, &e_end);
+            /* without any charging the node loses at most `cons` per cycle (plus a few ulps of rounding); if that cannot
+               bring it within a joule of the threshold, no cycle of the batch can take the serial path because of it */
+            const double cons = ((double)n_a * es + (double)n_b * er) * 1.000001 + 1e-9;
+            if (e - thr - 1.0 > cons * (double)n_safe) m = n_safe;
+            else { double e_end; m = replay_cycles(e, rr, es, er, nb, ow, na, thr, cap, n_safe, &e_end); }
         }
         c.scr1[i] = dec;
         if (m < n_safe) n_safe = m;
     }
     gsync(c);
     n_safe = (int)red_min(c, (double)n_safe);
+    WRSN_PROFC_END(c, WRSN_H_PROF1, pc1);
     if (n_safe <= 0) return 0;
     const double L = (double)WRSN_RING;
+    WRSN_PROFC_BEGIN(pc2);
     if (!active) {
         /* pass 2: all cycles at once */
         _Pragma("unroll 1")
@@ -1403,13 +1424,14 @@ WRSN_NOINLINE int nodes_batch(Ctx &c, int n_max, int ur_on, double t_reward) {
             const double lg = c.logc[i];
             double cs = c.cs[i];
             for (int t = 0; t < n_safe; t++) {       /* Node.py:75 with log[0] == log_energy */
-                const double nx = (cs * L - lg + lg) / L;
+                const double nx = div_pos(cs * L - lg + lg, L);
                 if (nx == cs) break;
                 cs = nx;
             }
             c.cs[i] = cs;
         }
         gsync(c);
+        WRSN_PROFC_END(c, WRSN_H_PROF2, pc2);
     } else {
         /* pass 2: cycle by cycle, because update_reward reads every node at every k+1.0 (before the bookkeeping) */
         uint32_t fixed = 0u;                         /* node slots of this thread whose energyCS has reached its fixed point */
@@ -1429,7 +1451,7 @@ WRSN_NOINLINE int nodes_batch(Ctx &c, int n_max, int ur_on, double t_reward) {
             }
             gsync(c);
             if (watched) catch_up_for_reward(c, t_reward + (double)j);
-            update_reward_body(c);
+            { WRSN_PROFC_BEGIN(pc4); update_reward_body(c); WRSN_PROFC_END(c, WRSN_H_PROF4, pc4); }
             int sl = 0;
             _Pragma("unroll 1")
             for (int i = c.tid; i < N; i += WRSN_GSZ(c), sl++) {
@@ -1438,12 +1460,13 @@ WRSN_NOINLINE int nodes_batch(Ctx &c, int n_max, int ur_on, double t_reward) {
                 if (rr != 0.0) c.energy[i] = fmin(c.energy[i] + rr * 0.5, cap);
                 if (sl < 32 && ((fixed >> sl) & 1u)) continue;
                 const double lg = c.logc[i], cs = c.cs[i];
-                const double nx = (cs * L - lg + lg) / L;
+                const double nx = div_pos(cs * L - lg + lg, L);
                 if (nx == cs) { if (sl < 32) fixed |= 1u << sl; }
                 else c.cs[i] = nx;
             }
             gsync(c);
         }
+        WRSN_PROFC_END(c, WRSN_H_PROF3, pc2);
     }
     if (c.tid == 0) {
         double *hw = c.hdr;

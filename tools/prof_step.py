@@ -15,7 +15,9 @@ scs = [synthetic(num_nodes=100, num_targets=100, seed=1000 + k) for k in range(6
 env = BatchedWRSN(scs, num_agent=3, num_envs=B, device="cuda:0")
 env.reset()
 g = torch.Generator(device="cuda:0"); g.manual_seed(0)
-names = ["total", "serial", "batch", "bfs", "fitness"] if VARIANT == 1 else ["total", "charger_events", "lazy_replay", "grid_events", "slot_scan"]
+names = ["total", "serial", "batch", "bfs", "fitness"] if VARIANT == 1 else (
+    ["total", "charger_events", "lazy_replay", "grid_events", "slot_scan"] if VARIANT == 2 else
+    ["total", "batch_pass1", "batch_all_at_once", "batch_cycle_loop", "update_reward_in_loop"])
 idx = [env.E["WRSN_H_PROF%d" % k] for k in range(5)]
 acc = []
 for k in range(steps):
