@@ -543,7 +543,8 @@ WRSN_NOINLINE int drain_serial(Ctx &c) {
     const int N = c.N;
     const double thr = c.par[WRSN_P_THR], cap = c.par[WRSN_P_CAP], er = c.par[WRSN_P_ERECV];
     int deaths = 0;
-    for (int i = 0; i < N; i++) c.logtick[i] = 0.0;
+    double *lt = c.scr1;                             /* this tick's log_energy, in shared memory: the leader adds to it at every hop;
+                                                        the caller zeroes it before and copies it to the record afterwards */
     for (int i = 0; i < N; i++) {
         if (c.status[i] == 0) continue;
         c.energy[i] = fmin(c.energy[i] + c.rr[i] * 0.5, cap);
@@ -551,14 +552,17 @@ WRSN_NOINLINE int drain_serial(Ctx &c) {
         for (int k = 0; k < ow; k++) {
             int h = i; bool pay_recv = false;
             for (;;) {
+                /* one hop; the node's energy lives in a register from the receive to the death check (the leader is alone
+                   here, and every shared-memory access is ~30 dependent cycles on this single thread) */
+                double e = c.energy[h];
                 if (pay_recv) {                      /* receive_package */
-                    if (c.energy[h] - thr < er) {
+                    if (e - thr < er) {
                         c.energy[h] = thr;
                         if (c.status[h] == 1) deaths++;
-                        check_status_node(c, h);
+                        c.status[h] = 0; c.cs[h] = 0.0;          /* check_status: energy == threshold */
                         break;
                     }
-                    c.energy[h] -= er;
+                    e -= er;
                 }
                 /* send_package: find_receiver() = the tree's receiver unless that node died earlier in this very tick
                    (a death can only remove candidates, never bring a nearer one), then the literal neighbour scan */
@@ -566,23 +570,30 @@ WRSN_NOINLINE int drain_serial(Ctx &c) {
                 if (recv >= 0 && c.status[recv] != 1) {
                     recv = -1; es = 0.0;
                     double bd = 0.0; int lv = c.level[h];
-                    for (int e = c.nbr_ptr[h]; e < c.nbr_ptr[h + 1]; e++) {
-                        int j = c.nbr_idx[e];
+                    for (int q = c.nbr_ptr[h]; q < c.nbr_ptr[h + 1]; q++) {
+                        int j = c.nbr_idx[q];
                         if (c.level[j] < lv && c.status[j] == 1) {
-                            double dd = c.nbr_dist[e];
-                            if (recv < 0 || dd < bd) { recv = j; bd = dd; es = c.nbr_esend[e]; }
+                            double dd = c.nbr_dist[q];
+                            if (recv < 0 || dd < bd) { recv = j; bd = dd; es = c.nbr_esend[q]; }
                         }
                     }
                 }
                 bool sent = false;
                 if (recv != -1) {
-                    if (c.energy[h] - thr < es) c.energy[h] = thr;
-                    else { c.energy[h] -= es; sent = true; }
+                    if (e - thr < es) e = thr;
+                    else { e -= es; sent = true; }
                 }
-                if (sent) c.logtick[h] += es;
-                if (pay_recv) c.logtick[h] += er;
-                if (c.status[h] == 1 && c.energy[h] <= thr) deaths++;
-                check_status_node(c, h);
+                c.energy[h] = e;
+                if (sent || pay_recv) {
+                    double l = lt[h];
+                    if (sent) l += es;
+                    if (pay_recv) l += er;
+                    lt[h] = l;
+                }
+                if (e <= thr) {                      /* check_status */
+                    if (c.status[h] == 1) deaths++;
+                    c.status[h] = 0; c.cs[h] = 0.0;
+                }
                 if (!sent || recv == -2) break;
                 h = recv; pay_recv = true;
             }
@@ -627,12 +638,16 @@ WRSN_D void ev_nodes_drain(Ctx &c) {
     }
     leave_uniform(c);
     WRSN_PROF_BEGIN();
+    for (int i = c.tid; i < N; i += WRSN_GSZ(c)) c.scr1[i] = 0.0;
+    gsync(c);
     if (c.tid == 0) {
         int deaths = drain_serial(c);
         c.hdr[WRSN_H_LOG_LITERAL] = 1.0;
         c.hdr[WRSN_H_NSLOW] += 1.0;
         if (deaths > 0) c.hdr[WRSN_H_BFS_DIRTY] = 1.0;
     }
+    gsync(c);
+    for (int i = c.tid; i < N; i += WRSN_GSZ(c)) c.logtick[i] = c.scr1[i];
     gsync(c);
     WRSN_PROF_END(c, WRSN_H_PROF1);
 }
