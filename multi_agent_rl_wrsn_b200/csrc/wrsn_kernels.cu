@@ -182,27 +182,34 @@ __global__ void __launch_bounds__(OBS_THREADS, sizeof(AccT) == 4 ? 3 : 1) k_obse
                 __syncthreads();
                 /* expand every source into its two S-vectors.  Node sources of the fp32 raster are a scaled copy of the
                    scenario's table (contiguous, independent loads); everything else is one fp64 exponential per entry. */
-                for (int k = tid; k < nq * TP; k += OBS_THREADS) {
-                    const int q = k / TP, i = k - q * TP;
+                for (int q = tid >> 5; q < nq; q += OBS_THREADS / 32) {        /* one warp per source row: no index division */
                     const int mode = src[q].mode;
                     if (mode < 0) continue;
-                    if (sizeof(AccT) == 4 && src[q].node >= 0) {
-                        const size_t o = (size_t)src[q].node * TP + i;
-                        gx[k] = (AccT)((float)src[q].w * tab_gx[o]);
-                        gy[k] = (AccT)tab_gy[o];
+                    const int node = src[q].node;
+                    if (sizeof(AccT) == 4 && node >= 0) {
+                        const float wq = (float)src[q].w;
+                        const float *rx = tab_gx + (size_t)node * TP, *ry = tab_gy + (size_t)node * TP;
+                        for (int i = tid & 31; i < TP; i += 32) { gx[q * TP + i] = (AccT)(wq * rx[i]); gy[q * TP + i] = (AccT)ry[i]; }
                     } else {
-                        const double cc = start + (double)i * delta;
-                        const double ux = cc - src[q].x0, uy = cc - src[q].y0;
-                        const double ax = ux * ux / (-2.0 * (src[q].hx * src[q].hx)), ay = uy * uy / (-2.0 * (src[q].hy * src[q].hy));
-                        const double ex = (i < S && ax > -745.2) ? exp(ax) : 0.0;   /* below: exp underflows to 0 anyway */
-                        const double ey = (i < S && ay > -745.2) ? exp(ay) : 0.0;
-                        gx[k] = (AccT)(mode == 0 ? src[q].w * ex : ex);
-                        gy[k] = (AccT)ey;
+                        const double x0 = src[q].x0, y0 = src[q].y0;
+                        const double dnx = -2.0 * (src[q].hx * src[q].hx), dny = -2.0 * (src[q].hy * src[q].hy);
+                        /* fp32 raster: the constant factor of the source (w, or w / moving_time_max for the travel-time
+                           channel) is folded into the x-vector, so every channel shares the FFMA loop below */
+                        const double fold = mode == 0 ? src[q].w : (sizeof(AccT) == 4 ? src[q].w / mtm : 1.0);
+                        for (int i = tid & 31; i < TP; i += 32) {
+                            const double cc = start + (double)i * delta;
+                            const double ux = cc - x0, uy = cc - y0;
+                            const double ax = ux * ux / dnx, ay = uy * uy / dny;
+                            const double ex = (i < S && ax > -745.2) ? exp(ax) : 0.0;   /* below: exp underflows to 0 anyway */
+                            const double ey = (i < S && ay > -745.2) ? exp(ay) : 0.0;
+                            gx[q * TP + i] = (AccT)((mode == 0 || sizeof(AccT) == 4) ? fold * ex : ex);
+                            gy[q * TP + i] = (AccT)ey;
+                        }
                     }
                 }
                 __syncthreads();
                 if (!has_tile) continue;
-                if (ch != 3) {
+                if (ch != 3 || sizeof(AccT) == 4) {
                     for (int q = 0; q < nq; q++) {
                         if (src[q].mode < 0) continue;
                         AccT a[OBS_TI], v[OBS_TJ];
@@ -231,11 +238,21 @@ __global__ void __launch_bounds__(OBS_THREADS, sizeof(AccT) == 4 ? 3 : 1) k_obse
                 }
             }
             if (has_tile) {
+                if (sizeof(AccT) == 4 && (S & 1) == 0 && j0 + OBS_TJ <= S) {  /* even map size: every row segment is 8-byte aligned */
 #pragma unroll
-                for (int r = 0; r < OBS_TI; r++)
+                    for (int r = 0; r < OBS_TI; r++) {
+                        if (i0 + r >= S) continue;
+                        float2 *o2 = reinterpret_cast<float2 *>(out + (size_t)ch * SS + (size_t)(i0 + r) * S + j0);
 #pragma unroll
-                    for (int x = 0; x < OBS_TJ; x++)
-                        if (i0 + r < S && j0 + x < S) out[(size_t)ch * SS + (size_t)(i0 + r) * S + j0 + x] = acc[r][x];
+                        for (int x = 0; x < OBS_TJ; x += 2) o2[x >> 1] = make_float2((float)acc[r][x], (float)acc[r][x + 1]);
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < OBS_TI; r++)
+#pragma unroll
+                        for (int x = 0; x < OBS_TJ; x++)
+                            if (i0 + r < S && j0 + x < S) out[(size_t)ch * SS + (size_t)(i0 + r) * S + j0 + x] = acc[r][x];
+                }
             }
         }
     }
