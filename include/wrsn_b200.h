@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define WRSN_ABI_VERSION 9
+#define WRSN_ABI_VERSION 10
 #define WRSN_MAX_MC 16          /* chargers per environment */
 #define WRSN_RING 10            /* Node.operate keeps the last 10 per-second consumptions (Node.py:70-77) */
 
@@ -205,6 +205,12 @@ int wrsn_rollout_step(const wrsn_dims *d, const void *scen, const int32_t *scen_
  * obs[b][4][S][S] as float (obs_f64 == 0) or double.  Rows with agent_id[b] < 0 are left untouched. */
 int wrsn_observe(const wrsn_dims *d, const void *scen, const int32_t *scen_id, const void *state,
                  const int32_t *agent_id, void *obs, int obs_f64, void *stream);
+/* WRSN.density_map_to_action (:229-287) with the map normalisation of WRSN.step (:293-296): dmap[b][S][S] (float, or
+ * double when dmap_f64 != 0) -> action_out[b][3] = (x-frac, y-frac, charge-time frac) for every row with
+ * agent_id[b] >= 0; other rows are left untouched.  The location search replaces scipy's L-BFGS-B (see the kernel's
+ * comment for what is reproduced exactly and what within tolerance). */
+int wrsn_decode_density_map(const wrsn_dims *d, const void *scen, const int32_t *scen_id, const void *state,
+                            const int32_t *agent_id, const void *dmap, int dmap_f64, double *action_out, void *stream);
 /* WRSN.get_network_fitness (:188-220): per-target values fitness[B][T] (may be NULL) and their minimum fit_min[B]. */
 int wrsn_fitness(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state,
                  double *fitness, double *fit_min, void *stream);

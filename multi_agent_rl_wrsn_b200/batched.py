@@ -211,6 +211,27 @@ class BatchedWRSN:
                                        1 if out.dtype == torch.float64 else 0, self._stream()), self.L)
         return out
 
+    def density_map_to_action(self, dmap, agent_id=None, out=None):
+        """``WRSN.density_map_to_action`` (:229-287) with the map normalisation of ``WRSN.step`` (:293-296) for every
+        environment with ``agent_id[b] >= 0`` (default: the deciding charger of the last request): ``dmap`` [B, S, S]
+        float32 / float64 in HBM -> actions [B, 3] float64 (x-frac, y-frac, charge-time frac), ready for ``step`` /
+        ``rollout_step``.  One streaming pass over the maps, no host round trip."""
+        if agent_id is None:
+            agent_id = self.req.agent_id
+        a = torch.as_tensor(agent_id, device=self.device).to(torch.int32).contiguous()
+        if dmap.dtype not in (torch.float32, torch.float64) or not dmap.is_contiguous() or dmap.shape != (self.B, self.S, self.S) \
+                or dmap.device != self.state.device:
+            raise ValueError("dmap must be a contiguous float32/float64 tensor [B, S, S] on the simulator's device")
+        if out is None:
+            out = torch.zeros((self.B, 3), dtype=torch.float64, device=self.device)
+        if out.dtype != torch.float64 or not out.is_contiguous() or out.shape != (self.B, 3):
+            raise ValueError("out must be a contiguous float64 tensor [B, 3]")
+        _lib.check(self.L.wrsn_decode_density_map(C.byref(self.dims), self.scen.data_ptr(), self.scen_id.data_ptr(),
+                                                  self.state.data_ptr(), a.data_ptr(), dmap.data_ptr(),
+                                                  1 if dmap.dtype == torch.float64 else 0, out.data_ptr(), self._stream()),
+                   self.L)
+        return out
+
     def get_network_fitness(self):
         """``WRSN.get_network_fitness`` (:188-220): per-target values [B, T] and their minimum [B]."""
         fit = torch.zeros((self.B, max(self.T, 1)), dtype=torch.float64, device=self.device)

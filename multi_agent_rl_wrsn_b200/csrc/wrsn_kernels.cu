@@ -258,6 +258,158 @@ __global__ void __launch_bounds__(OBS_THREADS, sizeof(AccT) == 4 ? 3 : 1) k_obse
     }
 }
 
+
+/* ------------------------------------------------------------------ WRSN.density_map_to_action (rl_env/WRSN.py:229-287)
+ * and the map normalisation of WRSN.step (:293-296): an S x S density map -> (x-frac, y-frac, charge-time frac).
+ * One CTA per environment, one pass over the map in HBM (the only traffic that matters: S*S values in, 24 bytes out).
+ *   - the map is staged in shared memory as doubles (exp(x) of it when the map is not already a distribution: the
+ *     reference then divides by sum + epsilon, a common factor that cancels in everything computed here);
+ *   - np.argmax (first maximum in row-major order) and np.percentile(flat, 99.9) (linear interpolation between two order
+ *     statistics near the top) come from a few rounds of block-wide "largest remaining value, smallest index";
+ *   - third component = map[argmax] / sum of the values >= that percentile;
+ *   - location: the reference maximises  sum_{alive n, d_n <= R} energyCS_n / (E_n - thr) * alpha / (d_n + beta)^2  inside
+ *     the +-R box around the argmax cell with scipy's L-BFGS-B from the box centre.  With the magnitudes of this model
+ *     L-BFGS-B stops at once (projected gradient <= pgtol = 1e-5: the centre itself is returned, bit for bit) in most
+ *     calls, takes one unit step along the gradient and stops on its ftol in most of the others, and otherwise climbs
+ *     to the nearest cusp (a node).  Warp 0 runs the same three regimes: scipy's two stopping rules with their default
+ *     constants, a unit first step, then spectral (Barzilai-Borwein, the L-BFGS scaling) steps with backtracking.  The
+ *     objective is discontinuous and scipy's answer depends on its version: parity is tolerance-based
+ *     (tests/test_decode.py), exact whenever scipy returns the centre. */
+#define DEC_THREADS 256
+template <typename MapT>
+__global__ void __launch_bounds__(DEC_THREADS) k_decode_map(const KParams P, const int32_t *agent_id, const MapT *dmap, double *action) {
+    extern __shared__ uint4 smem_u4[];
+    double *val = reinterpret_cast<double *>(smem_u4);                      /* [S*S] */
+    __shared__ double red_v[DEC_THREADS / 32];
+    __shared__ int red_i[DEC_THREADS / 32];
+    __shared__ double red_s[3][DEC_THREADS / 32];
+    __shared__ double top_v[32];
+    __shared__ int top_i[32];
+    __shared__ double bc[4];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (agent_id[b] < 0) return;
+    const int S = P.d.S, n = S * S, N = P.d.N;
+    const MapT *src = dmap + (size_t)b * n;
+    /* pass 1: stage, min / max / sum */
+    double mn = INFINITY, mx = -INFINITY, sm = 0.0;
+    for (int k = tid; k < n; k += DEC_THREADS) { const double v = (double)src[k]; val[k] = v; mn = fmin(mn, v); mx = fmax(mx, v); sm += v; }
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o)); sm += __shfl_xor_sync(0xffffffffu, sm, o);
+    }
+    if (lane == 0) { red_s[0][wid] = mn; red_s[1][wid] = mx; red_s[2][wid] = sm; }
+    __syncthreads();
+    mn = red_s[0][0]; mx = red_s[1][0]; sm = red_s[2][0];
+    for (int w = 1; w < DEC_THREADS / 32; w++) { mn = fmin(mn, red_s[0][w]); mx = fmax(mx, red_s[1][w]); sm += red_s[2][w]; }
+    /* WRSN.step :294: np.all((a >= 0) & (a <= 1)) and np.isclose(np.sum(a), 1)  (rtol 1e-5, atol 1e-8) */
+    const bool is_dist = mn >= 0.0 && mx <= 1.0 && fabs(sm - 1.0) <= 1e-8 + 1e-5;
+    if (!is_dist) {
+        __syncthreads();
+        for (int k = tid; k < n; k += DEC_THREADS) val[k] = exp(val[k]);
+    }
+    __syncthreads();
+    /* order statistics from the top: np.percentile(., 99.9), method "linear" */
+    const double vidx = (double)(n - 1) * (99.9 / 100.0);
+    const int lo_idx = (int)floor(vidx);
+    const double tq = vidx - (double)lo_idx;
+    int rounds = n - lo_idx;                         /* the (n - lo_idx)-th largest value is sorted[lo_idx] */
+    if (rounds > 32) rounds = 32;                    /* map sizes up to ~175 x 175 */
+    for (int r = 0; r < rounds; r++) {
+        double bv = -INFINITY; int bi = 0x7fffffff;
+        for (int k = tid; k < n; k += DEC_THREADS) { const double v = val[k]; if (v > bv || (v == bv && k < bi)) { bv = v; bi = k; } }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { red_v[wid] = bv; red_i[wid] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < DEC_THREADS / 32; w++) if (red_v[w] > bv || (red_v[w] == bv && red_i[w] < bi)) { bv = red_v[w]; bi = red_i[w]; }
+            top_v[r] = bv; top_i[r] = bi;
+            if (bi < n) val[bi] = -INFINITY;         /* taken */
+        }
+        __syncthreads();
+    }
+    const double a_q = top_v[rounds - 1], b_q = rounds >= 2 ? top_v[rounds - 2] : top_v[rounds - 1];
+    double thr_q = a_q + (b_q - a_q) * tq;           /* numpy _lerp */
+    if (tq >= 0.5) thr_q = b_q - (b_q - a_q) * (1.0 - tq);
+    if (lo_idx + 1 > n - 1) thr_q = a_q;
+    /* sum of the kept values: the taken ones individually (in index order of taking), the rest from the staged map */
+    double keep = 0.0;
+    for (int k = tid; k < n; k += DEC_THREADS) { const double v = val[k]; if (v >= thr_q) keep += v; }
+    for (int o = 16; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+    if (lane == 0) red_s[0][wid] = keep;
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < DEC_THREADS / 32; w++) tot += red_s[0][w];
+        for (int r = 0; r < rounds; r++) if (top_v[r] >= thr_q) tot += top_v[r];
+        bc[0] = top_v[0] / tot;                      /* prob[max_index] after thresholding and renormalising */
+    }
+    /* ---- location (warp 0) */
+    if (wid == 0) {
+        const char *row = P.state + (size_t)b * P.L.total;
+        const char *scen_row = P.scen + (size_t)P.scen_id[b] * P.L.scen_total;
+        const double *par = (const double *)(scen_row + P.L.soff[WRSN_S_PAR]);
+        const double *nx = (const double *)(scen_row + P.L.soff[WRSN_S_NX]), *ny = (const double *)(scen_row + P.L.soff[WRSN_S_NY]);
+        const double *energy = (const double *)(row + P.L.off[WRSN_F_ENERGY]), *cs = (const double *)(row + P.L.off[WRSN_F_CS]);
+        const uint8_t *status = (const uint8_t *)(row + P.L.off[WRSN_F_STATUS]);
+        const double f0 = par[WRSN_P_F0], f1 = par[WRSN_P_F1], f2 = par[WRSN_P_F2], f3 = par[WRSN_P_F3];
+        const double R = par[WRSN_P_MC_R], alpha = par[WRSN_P_MC_ALPHA], beta = par[WRSN_P_MC_BETA], thr = par[WRSN_P_THR];
+        const double unit = 1.0 / (double)S;
+        const int flat = top_i[0], m0 = flat / S, m1 = flat - m0 * S;
+        const double cx = ((double)m0 + 0.5) * unit, cy = ((double)m1 + 0.5) * unit;
+        const double rx = R / (f1 - f0), ry = R / (f3 - f2);
+        const double lox = (cx - rx) * (f1 - f0) + f0, loy = (cy - ry) * (f3 - f2) + f2;      /* up_mapping :91-93 */
+        const double hix = (cx + rx) * (f1 - f0) + f0, hiy = (cy + ry) * (f3 - f2) + f2;
+        double x = (lox + hix) / 2.0, y = (loy + hiy) / 2.0;
+        /* value and gradient of the (positive) objective at (px, py): every lane its nodes, shuffle-tree sums */
+        auto eval = [&](double px, double py, double &F, double &gx, double &gy) {
+            double f = 0.0, ax = 0.0, ay = 0.0;
+            for (int i = lane; i < N; i += 32) {
+                if (status[i] == 0) continue;
+                const double dx = px - nx[i], dy = py - ny[i];
+                const double d = sqrt(dx * dx + dy * dy);
+                if (d <= R) {
+                    const double w = cs[i] / (energy[i] - thr) * alpha, t = d + beta;
+                    f += w / (t * t);
+                    if (d > 0.0) { const double c = -2.0 * w / (t * t * t) / d; ax += c * dx; ay += c * dy; }
+                }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                f += __shfl_xor_sync(0xffffffffu, f, o); ax += __shfl_xor_sync(0xffffffffu, ax, o); ay += __shfl_xor_sync(0xffffffffu, ay, o);
+            }
+            F = f; gx = ax; gy = ay;
+        };
+        double F, gx, gy;
+        eval(x, y, F, gx, gy);
+        double t = 1.0;                              /* L-BFGS-B's first step: the Cauchy point of the unit-Hessian model */
+        for (int it = 0; it < 100; it++) {
+            double px = gx, py = gy;                 /* projected gradient */
+            if ((x <= lox && px < 0.0) || (x >= hix && px > 0.0)) px = 0.0;
+            if ((y <= loy && py < 0.0) || (y >= hiy && py > 0.0)) py = 0.0;
+            if (fmax(fabs(px), fabs(py)) <= 1e-5) break;                      /* pgtol */
+            double tt = t, xn = x, yn = y, Fn = F, gxn = gx, gyn = gy;
+            bool ok = false;
+            for (int ls = 0; ls < 40; ls++) {
+                xn = fmin(fmax(x + tt * px, lox), hix); yn = fmin(fmax(y + tt * py, loy), hiy);
+                eval(xn, yn, Fn, gxn, gyn);
+                if (Fn > F) { ok = true; break; }
+                tt *= 0.5;
+            }
+            if (!ok) break;
+            const double sx = xn - x, sy = yn - y, yx = -(gxn - gx), yy = -(gyn - gy);     /* s, y of the minimised -F */
+            const double s_y = sx * yx + sy * yy, y_y = yx * yx + yy * yy;
+            const bool done = (Fn - F) <= 2.220446049250313e-09 * fmax(fmax(fabs(F), fabs(Fn)), 1.0);   /* ftol = factr * epsmch */
+            x = xn; y = yn; F = Fn; gx = gxn; gy = gyn;
+            if (done) break;
+            t = (s_y > 0.0 && y_y > 0.0) ? s_y / y_y : tt * 4.0;
+        }
+        if (lane == 0) { bc[1] = (x - f0) / (f1 - f0); bc[2] = (y - f2) / (f3 - f2); }       /* down_mapping :86-88 */
+    }
+    __syncthreads();
+    if (tid < 3) action[3 * (size_t)b + tid] = tid == 0 ? bc[1] : (tid == 1 ? bc[2] : bc[0]);
+}
+
 /* ------------------------------------------------------------------ host side of the C ABI */
 static int check_dims(const wrsn_dims *d) {
     if (!d) WRSN_FAIL("dims is NULL");
@@ -451,6 +603,26 @@ int wrsn_observe(const wrsn_dims *d, const void *scen, const int32_t *scen_id, c
         if (!attr) { WRSN_CUDA(cudaFuncSetAttribute(k_observe<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
         k_observe<float><<<d->B, OBS_THREADS, smem, (cudaStream_t)stream>>>(P, agent_id, (float *)obs);
     }
+    WRSN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int wrsn_decode_density_map(const wrsn_dims *d, const void *scen, const int32_t *scen_id, const void *state,
+                            const int32_t *agent_id, const void *dmap, int dmap_f64, double *action_out, void *stream) {
+    if (check_dims(d)) return -1;
+    if (!agent_id || !dmap || !action_out || !scen || !scen_id || !state) WRSN_FAIL("NULL argument");
+    KParams P = base_params(d, scen, scen_id, const_cast<void *>(state), nullptr);
+    wrsn_make_layout(&P.d, &P.L);
+    const size_t smem = sizeof(double) * (size_t)d->S * (size_t)d->S;
+    if (smem > 200 * 1024) WRSN_FAIL("map_size too large for the density-map decoder");
+    static bool attr = false;
+    if (!attr) {
+        WRSN_CUDA(cudaFuncSetAttribute(k_decode_map<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        WRSN_CUDA(cudaFuncSetAttribute(k_decode_map<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr = true;
+    }
+    if (dmap_f64) k_decode_map<double><<<d->B, DEC_THREADS, smem, (cudaStream_t)stream>>>(P, agent_id, (const double *)dmap, action_out);
+    else k_decode_map<float><<<d->B, DEC_THREADS, smem, (cudaStream_t)stream>>>(P, agent_id, (const float *)dmap, action_out);
     WRSN_CUDA(cudaGetLastError());
     return 0;
 }

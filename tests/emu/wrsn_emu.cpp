@@ -139,6 +139,9 @@ int wrsn_fitness(const wrsn_dims *d, const void *scen, const int32_t *scen_id, v
 int wrsn_observe(const wrsn_dims *, const void *, const int32_t *, const void *, const int32_t *, void *, int, void *) {
     WRSN_FAIL("wrsn_observe is not available in the host emulation");
 }
+int wrsn_decode_density_map(const wrsn_dims *, const void *, const int32_t *, const void *, const int32_t *, const void *, int, double *, void *) {
+    WRSN_FAIL("wrsn_decode_density_map is not available in the host emulation");
+}
 #define EMU_K(NAME, MODE) int NAME(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state, void *) { \
     Args A = {d, (const char *)scen, scen_id, (char *)state, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0}; return run_mode(MODE, A); }
 EMU_K(wrsn_k_bfs, MODE_K_BFS)
