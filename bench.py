@@ -309,14 +309,64 @@ def run_b200(a):
     rd1, rs1 = totals()
     r_decisions, r_ticks = rd1 - rd0, rs1 - rs0
 
+    # ---- the density-map decoder, the one streaming kernel of the path: every launch reads another group's
+    # maps (G x Bg x S x S float32 = 164 MB at the default sizes, more than the 126 MB L2)
+    maps = [torch.rand((Bg, S, S), generator=gen, dtype=torch.float32, device=dev) for _ in range(G)]
+    dec_out = torch.zeros((Bg, 3), dtype=torch.float64, device=dev)
+    all_agents = torch.zeros(Bg, dtype=torch.int32, device=dev)
+    for g in range(G):
+        groups[g].density_map_to_action(maps[g], agent_id=all_agents, out=dec_out)
+    dev_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(3 * G)]
+    sync_all()
+    for k in range(3 * G):
+        dev_ev[k][0].record()
+        groups[k % G].density_map_to_action(maps[k % G], agent_id=all_agents, out=dec_out)
+        dev_ev[k][1].record()
+    sync_all()
+    dec_ms = sum(x[0].elapsed_time(x[1]) for x in dev_ev) / len(dev_ev)
+    dec_bytes = Bg * (S * S * 4 + 24)
+    del maps
+
+    # ---- the reference's RandomController (controller/random/RandomController.py:12: map = s0 + s1 - 10 s2 + s3) as the
+    # action source: torch forms the map from the observation in HBM, the decoder turns it into the action, rollout_step
+    # consumes it.  A short device-timed run, reported beside the headline (which feeds 3-vector actions).
+    K2 = min(a.steps, 30)
+    act_buf = [torch.zeros((Bg, 3), dtype=torch.float64, device=dev) for _ in range(G)]
+
+    def map_step(g):
+        with torch.cuda.stream(streams[g]):
+            o = obs[g]
+            dm = o[:, 0] + o[:, 1] - 10.0 * o[:, 2] + o[:, 3]
+            groups[g].density_map_to_action(dm, out=act_buf[g])
+            groups[g].rollout_step(act_buf[g], obs[g])
+
+    for k in range(3):
+        for g in range(G):
+            map_step(g)
+    sync_all()
+    md0, _ = totals()
+    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    m0.record(torch.cuda.current_stream(dev))
+    for st in streams:
+        st.wait_stream(torch.cuda.current_stream(dev))
+    for k in range(K2):
+        for g in range(G):
+            map_step(g)
+    for st in streams:
+        torch.cuda.current_stream(dev).wait_stream(st)
+    m1.record(torch.cuda.current_stream(dev))
+    sync_all()
+    md1, _ = totals()
+    map_ms, map_dec = m0.elapsed_time(m1), md1 - md0
+
     # ---- reduce over ranks: max time, summed work
-    t = torch.tensor([elapsed_ms, e2e_ms], dtype=torch.float64, device=dev)
-    w = torch.tensor([decisions, ticks, float(e2e_dec)], dtype=torch.float64, device=dev)
+    t = torch.tensor([elapsed_ms, e2e_ms, map_ms], dtype=torch.float64, device=dev)
+    w = torch.tensor([decisions, ticks, float(e2e_dec), map_dec], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(w, op=dist.ReduceOp.SUM)
-    elapsed_ms, e2e_ms = [float(x) for x in t.tolist()]
-    decisions_all, ticks_all, e2e_dec_all = [float(x) for x in w.tolist()]
+    elapsed_ms, e2e_ms, map_ms = [float(x) for x in t.tolist()]
+    decisions_all, ticks_all, e2e_dec_all, map_dec_all = [float(x) for x in w.tolist()]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -359,7 +409,11 @@ def run_b200(a):
                     l2="working set (state %.0f MB + observations %.0f MB per GPU) exceeds the 126 MB L2; no explicit flush"
                        % (B * groups[0].dims.state_bytes / 1e6, B * 4 * S * S * 4 / 1e6),
                     sim_seconds_per_decision=ticks_all / max(decisions_all, 1.0),
-                    env_ticks_per_s=ticks_all / (elapsed_ms * 1e-3)),
+                    env_ticks_per_s=ticks_all / (elapsed_ms * 1e-3),
+                    random_controller_map=dict(value=map_dec_all / (map_ms * 1e-3), unit=UNIT, steps=K2,
+                                               note="same environments driven by the reference's RandomController density map "
+                                                    "(s0 + s1 - 10 s2 + s3), decoded on the device by wrsn_decode_density_map; "
+                                                    "device-resident, not the headline workload")),
         clocks=clocks,
         e2e=dict(value=e2e_dec_all / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                  note="per step: actions from pinned host memory, rollout_step (step | reset | observe), request record "
@@ -372,7 +426,12 @@ def run_b200(a):
                       kernels={"k_env<MODE_STEP>": dict(ms_per_launch=step_ms / n_l, algorithmic_bytes=step_bytes, gbs=step_gbs,
                                                         share=step_ms / (step_ms + obs_ms)),
                                "k_observe<float>": dict(ms_per_launch=obs_ms / n_l, algorithmic_bytes=obs_bytes, gbs=obs_gbs,
-                                                        share=obs_ms / (step_ms + obs_ms))}),
+                                                        share=obs_ms / (step_ms + obs_ms)),
+                               "k_decode_map<float>": dict(ms_per_launch=dec_ms, algorithmic_bytes=dec_bytes,
+                                                           gbs=dec_bytes / (dec_ms * 1e-3) / 1e9,
+                                                           frac=dec_bytes / (dec_ms * 1e-3) / 1e9 / peak,
+                                                           share=0.0, note="not launched by the headline workload (3-vector actions); "
+                                                                           "timed alone on maps larger than L2")}),
     )
     if world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = {k: v for k, v in cpu_baseline(a, 1, a.cpu_seconds).items() if k != "wall_s"}
