@@ -316,14 +316,18 @@ def run_b200(a):
     all_agents = torch.zeros(Bg, dtype=torch.int32, device=dev)
     for g in range(G):
         groups[g].density_map_to_action(maps[g], agent_id=all_agents, out=dec_out)
-    dev_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(3 * G)]
+    # (a launch lasts ~10 us, less than the host needs to issue it: the launches are queued behind a spin kernel so that the
+    # events bracket back-to-back device execution, not host latency)
+    n_dec = 6 * G
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
-    for k in range(3 * G):
-        dev_ev[k][0].record()
+    torch.cuda._sleep(int(2e7))                        # ~10 ms at 1.9 GHz
+    d0.record()
+    for k in range(n_dec):
         groups[k % G].density_map_to_action(maps[k % G], agent_id=all_agents, out=dec_out)
-        dev_ev[k][1].record()
+    d1.record()
     sync_all()
-    dec_ms = sum(x[0].elapsed_time(x[1]) for x in dev_ev) / len(dev_ev)
+    dec_ms = d0.elapsed_time(d1) / n_dec
     dec_bytes = Bg * (S * S * 4 + 24)
     del maps
 

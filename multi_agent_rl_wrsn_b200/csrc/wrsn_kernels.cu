@@ -261,12 +261,17 @@ __global__ void __launch_bounds__(OBS_THREADS, sizeof(AccT) == 4 ? 3 : 1) k_obse
 
 /* ------------------------------------------------------------------ WRSN.density_map_to_action (rl_env/WRSN.py:229-287)
  * and the map normalisation of WRSN.step (:293-296): an S x S density map -> (x-frac, y-frac, charge-time frac).
- * One CTA per environment, one pass over the map in HBM (the only traffic that matters: S*S values in, 24 bytes out).
- *   - the map is staged in shared memory as doubles (exp(x) of it when the map is not already a distribution: the
- *     reference then divides by sum + epsilon, a common factor that cancels in everything computed here);
- *   - np.argmax (first maximum in row-major order) and np.percentile(flat, 99.9) (linear interpolation between two order
- *     statistics near the top) come from a few rounds of block-wide "largest remaining value, smallest index";
- *   - third component = map[argmax] / sum of the values >= that percentile;
+ * One CTA per environment, ONE streaming pass over the map in HBM (the only traffic that matters: S*S values in, 24
+ * bytes out); nothing but a few scalars is staged on chip.
+ *   - every thread keeps min / max / sum and the two largest values of its (strided) share of the map in registers;
+ *   - np.argmax (first maximum in row-major order) and the order statistics around np.percentile(flat, 99.9) come from
+ *     n - floor(0.999 (n - 1)) + 1 rounds (12 for a 100 x 100 map) of block-wide "largest remaining head, smallest
+ *     index"; a thread whose two heads are both taken rescans its share (rare: neighbouring cells belong to different
+ *     threads).  If the map is not a distribution the reference replaces it by exp(map) / (sum + eps): monotone, so the
+ *     ORDER is taken from the raw values, exp() is applied to the handful of selected ones only, and the common divisor
+ *     cancels in everything computed here;
+ *   - third component = map[argmax] / sum of the values >= that percentile: the selected values — unless values tie
+ *     with the percentile beyond the selected ones (uniform or one-hot maps), then a second pass over the map sums them;
  *   - location: the reference maximises  sum_{alive n, d_n <= R} energyCS_n / (E_n - thr) * alpha / (d_n + beta)^2  inside
  *     the +-R box around the argmax cell with scipy's L-BFGS-B from the box centre.  With the magnitudes of this model
  *     L-BFGS-B stops at once (projected gradient <= pgtol = 1e-5: the centre itself is returned, bit for bit) in most
@@ -276,74 +281,118 @@ __global__ void __launch_bounds__(OBS_THREADS, sizeof(AccT) == 4 ? 3 : 1) k_obse
  *     objective is discontinuous and scipy's answer depends on its version: parity is tolerance-based
  *     (tests/test_decode.py), exact whenever scipy returns the centre. */
 #define DEC_THREADS 256
+#define DEC_MAXR 34
+#define DEC_MAXC 64
 template <typename MapT>
-__global__ void __launch_bounds__(DEC_THREADS) k_decode_map(const KParams P, const int32_t *agent_id, const MapT *dmap, double *action) {
-    extern __shared__ uint4 smem_u4[];
-    double *val = reinterpret_cast<double *>(smem_u4);                      /* [S*S] */
-    __shared__ double red_v[DEC_THREADS / 32];
-    __shared__ int red_i[DEC_THREADS / 32];
+__global__ void __launch_bounds__(DEC_THREADS, 4) k_decode_map(const KParams P, const int32_t *agent_id, const MapT *dmap, double *action) {
+    __shared__ double cand_v[(DEC_THREADS / 32) * DEC_MAXR];
+    __shared__ int cand_i[(DEC_THREADS / 32) * DEC_MAXR];
     __shared__ double red_s[3][DEC_THREADS / 32];
-    __shared__ double top_v[32];
-    __shared__ int top_i[32];
+    __shared__ double top_v[DEC_MAXR];
+    __shared__ int top_i[DEC_MAXR];
     __shared__ double bc[4];
+    __shared__ double cn_x[DEC_MAXC], cn_y[DEC_MAXC], cn_w[DEC_MAXC];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (agent_id[b] < 0) return;
     const int S = P.d.S, n = S * S, N = P.d.N;
     const MapT *src = dmap + (size_t)b * n;
-    /* pass 1: stage, min / max / sum */
-    double mn = INFINITY, mx = -INFINITY, sm = 0.0;
-    for (int k = tid; k < n; k += DEC_THREADS) { const double v = (double)src[k]; val[k] = v; mn = fmin(mn, v); mx = fmax(mx, v); sm += v; }
+    /* pass 1: min / max / sum and this thread's two heads (value descending, index ascending; k only grows here) */
+    MapT mn = (MapT)INFINITY, mx = (MapT)-INFINITY; double sm = 0.0;
+    MapT h1v = (MapT)-INFINITY, h2v = (MapT)-INFINITY; int h1i = 0x7fffffff, h2i = 0x7fffffff;
+#pragma unroll 4
+    for (int k = tid; k < n; k += DEC_THREADS) {
+        const MapT v = src[k];
+        mn = v < mn ? v : mn; mx = v > mx ? v : mx; sm += (double)v;
+        if (v > h1v) { h2v = h1v; h2i = h1i; h1v = v; h1i = k; }
+        else if (v > h2v) { h2v = v; h2i = k; }
+    }
+    double dmn = (double)mn, dmx = (double)mx;
     for (int o = 16; o > 0; o >>= 1) {
-        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o)); sm += __shfl_xor_sync(0xffffffffu, sm, o);
+        dmn = fmin(dmn, __shfl_xor_sync(0xffffffffu, dmn, o)); dmx = fmax(dmx, __shfl_xor_sync(0xffffffffu, dmx, o)); sm += __shfl_xor_sync(0xffffffffu, sm, o);
     }
-    if (lane == 0) { red_s[0][wid] = mn; red_s[1][wid] = mx; red_s[2][wid] = sm; }
-    __syncthreads();
-    mn = red_s[0][0]; mx = red_s[1][0]; sm = red_s[2][0];
-    for (int w = 1; w < DEC_THREADS / 32; w++) { mn = fmin(mn, red_s[0][w]); mx = fmax(mx, red_s[1][w]); sm += red_s[2][w]; }
-    /* WRSN.step :294: np.all((a >= 0) & (a <= 1)) and np.isclose(np.sum(a), 1)  (rtol 1e-5, atol 1e-8) */
-    const bool is_dist = mn >= 0.0 && mx <= 1.0 && fabs(sm - 1.0) <= 1e-8 + 1e-5;
-    if (!is_dist) {
-        __syncthreads();
-        for (int k = tid; k < n; k += DEC_THREADS) val[k] = exp(val[k]);
-    }
-    __syncthreads();
-    /* order statistics from the top: np.percentile(., 99.9), method "linear" */
-    const double vidx = (double)(n - 1) * (99.9 / 100.0);
+    if (lane == 0) { red_s[0][wid] = dmn; red_s[1][wid] = dmx; red_s[2][wid] = sm; }
+    /* np.percentile(., 99.9), method "linear": virtual index n q + (alpha + q (1 - alpha - beta)) - 1 with alpha = beta = 1 */
+    const double qf = 99.9 / 100.0;
+    const double vidx = (double)n * qf + (1.0 + qf * (1.0 - 1.0 - 1.0)) - 1.0;
     const int lo_idx = (int)floor(vidx);
     const double tq = vidx - (double)lo_idx;
-    int rounds = n - lo_idx;                         /* the (n - lo_idx)-th largest value is sorted[lo_idx] */
-    if (rounds > 32) rounds = 32;                    /* map sizes up to ~175 x 175 */
-    for (int r = 0; r < rounds; r++) {
-        double bv = -INFINITY; int bi = 0x7fffffff;
-        for (int k = tid; k < n; k += DEC_THREADS) { const double v = val[k]; if (v > bv || (v == bv && k < bi)) { bv = v; bi = k; } }
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    int R = n - lo_idx;                              /* the R-th largest value is sorted[lo_idx] */
+    if (R > DEC_MAXR - 2) R = DEC_MAXR - 2;          /* map sizes up to ~175 x 175 */
+    const int rounds = R + 1 < n ? R + 1 : n;        /* one more: does anything tie with sorted[lo_idx] beyond the selection? */
+    /* every warp selects ITS `rounds` largest (shuffles only): the block's `rounds` largest are among those */
+    {
+        int taken = 0; MapT lastv = (MapT)INFINITY; int lasti = -1;
+        for (int r = 0; r < rounds; r++) {
+            if (taken == 2) {                        /* both heads gone: the next two of this thread's share after (lastv, lasti) */
+                h1v = h2v = (MapT)-INFINITY; h1i = h2i = 0x7fffffff;
+                for (int k = tid; k < n; k += DEC_THREADS) {
+                    const MapT v = src[k];
+                    if (!(v < lastv || (v == lastv && k > lasti))) continue;
+                    if (v > h1v) { h2v = h1v; h2i = h1i; h1v = v; h1i = k; }
+                    else if (v > h2v) { h2v = v; h2i = k; }
+                }
+                taken = 0;
+            }
+            const MapT pv = taken == 0 ? h1v : h2v; const int pi = taken == 0 ? h1i : h2i;
+            MapT bv = pv; int bi = pi;
+            for (int o = 16; o > 0; o >>= 1) {
+                const MapT ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (lane == 0) { cand_v[wid * DEC_MAXR + r] = (double)bv; cand_i[wid * DEC_MAXR + r] = bi; }
+            if (pi == bi && bi != 0x7fffffff) { taken++; lastv = pv; lasti = pi; }
         }
-        if (lane == 0) { red_v[wid] = bv; red_i[wid] = bi; }
-        __syncthreads();
-        if (tid == 0) {
-            for (int w = 1; w < DEC_THREADS / 32; w++) if (red_v[w] > bv || (red_v[w] == bv && red_i[w] < bi)) { bv = red_v[w]; bi = red_i[w]; }
-            top_v[r] = bv; top_i[r] = bi;
-            if (bi < n) val[bi] = -INFINITY;         /* taken */
-        }
-        __syncthreads();
     }
-    const double a_q = top_v[rounds - 1], b_q = rounds >= 2 ? top_v[rounds - 2] : top_v[rounds - 1];
+    __syncthreads();
+    double mn_d = red_s[0][0], mx_d = red_s[1][0]; sm = red_s[2][0];
+    for (int w = 1; w < DEC_THREADS / 32; w++) { mn_d = fmin(mn_d, red_s[0][w]); mx_d = fmax(mx_d, red_s[1][w]); sm += red_s[2][w]; }
+    /* WRSN.step :294: np.all((a >= 0) & (a <= 1)) and np.isclose(np.sum(a), 1)  (rtol 1e-5, atol 1e-8) */
+    const bool is_dist = mn_d >= 0.0 && mx_d <= 1.0 && fabs(sm - 1.0) <= 1e-8 + 1e-5;
+    /* warp 0 merges the 8 sorted lists: `rounds` times the largest list head */
+    if (wid == 0) {
+        int pos = 0;                                 /* lane w < 8 walks list w */
+        for (int r = 0; r < rounds; r++) {
+            double bv = -INFINITY; int bi = 0x7fffffff;
+            if (lane < DEC_THREADS / 32 && pos < rounds) { bv = cand_v[lane * DEC_MAXR + pos]; bi = cand_i[lane * DEC_MAXR + pos]; }
+            const int mine = bi;
+            for (int o = 4; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            bv = __shfl_sync(0xffffffffu, bv, 0); bi = __shfl_sync(0xffffffffu, bi, 0);
+            if (lane == 0) { top_v[r] = bv; top_i[r] = bi; }
+            if (mine == bi && bi != 0x7fffffff) pos++;
+        }
+    }
+    __syncthreads();
+    /* the transformed values of the selection (exp only here), threshold, kept mass */
+    if (R > rounds) R = rounds;
+    const double a_x = top_v[R - 1];
+    const double a_q = is_dist ? a_x : exp(a_x);
+    const double b_q = R >= 2 ? (is_dist ? top_v[R - 2] : exp(top_v[R - 2])) : a_q;
     double thr_q = a_q + (b_q - a_q) * tq;           /* numpy _lerp */
     if (tq >= 0.5) thr_q = b_q - (b_q - a_q) * (1.0 - tq);
     if (lo_idx + 1 > n - 1) thr_q = a_q;
-    /* sum of the kept values: the taken ones individually (in index order of taking), the rest from the staged map */
+    const bool ties_beyond = a_q >= thr_q && rounds > R && top_v[R] == a_x;
     double keep = 0.0;
-    for (int k = tid; k < n; k += DEC_THREADS) { const double v = val[k]; if (v >= thr_q) keep += v; }
-    for (int o = 16; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
-    if (lane == 0) red_s[0][wid] = keep;
-    __syncthreads();
-    if (tid == 0) {
-        double tot = 0.0;
-        for (int w = 0; w < DEC_THREADS / 32; w++) tot += red_s[0][w];
-        for (int r = 0; r < rounds; r++) if (top_v[r] >= thr_q) tot += top_v[r];
-        bc[0] = top_v[0] / tot;                      /* prob[max_index] after thresholding and renormalising */
+    if (!ties_beyond) {
+        if (tid == 0) {
+            for (int r = 0; r < R; r++) { const double v = is_dist ? top_v[r] : exp(top_v[r]); if (v >= thr_q) keep += v; }
+            bc[0] = (is_dist ? top_v[0] : exp(top_v[0])) / keep;
+        }
+    } else {                                         /* values equal to the percentile all over the map: sum them in a second pass */
+        for (int k = tid; k < n; k += DEC_THREADS) {
+            const double x = (double)src[k];
+            if (x >= a_x) { const double v = is_dist ? x : exp(x); if (v >= thr_q) keep += v; }
+        }
+        for (int o = 16; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+        if (lane == 0) red_s[0][wid] = keep;
+        __syncthreads();
+        if (tid == 0) {
+            double tot = 0.0;
+            for (int w = 0; w < DEC_THREADS / 32; w++) tot += red_s[0][w];
+            bc[0] = (is_dist ? top_v[0] : exp(top_v[0])) / tot;
+        }
     }
     /* ---- location (warp 0) */
     if (wid == 0) {
@@ -362,17 +411,48 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode_map(const KParams P, con
         const double lox = (cx - rx) * (f1 - f0) + f0, loy = (cy - ry) * (f3 - f2) + f2;      /* up_mapping :91-93 */
         const double hix = (cx + rx) * (f1 - f0) + f0, hiy = (cy + ry) * (f3 - f2) + f2;
         double x = (lox + hix) / 2.0, y = (loy + hiy) / 2.0;
+        /* only nodes within R of SOME point of the box can ever count: collect them once (id order) with their weights;
+           the climb then evaluates the objective from shared memory instead of walking all N nodes in HBM per trial */
+        const double reach = R * 2.4143 + 1e-6;      /* R + half diagonal of the +-R box */
+        int cnt = 0;
+        for (int base = 0; base < N; base += 32) {
+            const int i = base + lane;
+            bool c = false; double wx = 0.0, wy = 0.0, ww = 0.0;
+            if (i < N && status[i] != 0) {
+                wx = nx[i]; wy = ny[i];
+                const double dx = x - wx, dy = y - wy;
+                if (dx * dx + dy * dy <= reach * reach) { c = true; ww = cs[i] / (energy[i] - thr) * alpha; }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, c);
+            const int slot = cnt + __popc(m & ((1u << lane) - 1u));
+            if (c && slot < DEC_MAXC) { cn_x[slot] = wx; cn_y[slot] = wy; cn_w[slot] = ww; }
+            cnt += __popc(m);
+        }
+        __syncwarp();
+        const bool listed = cnt <= DEC_MAXC;
         /* value and gradient of the (positive) objective at (px, py): every lane its nodes, shuffle-tree sums */
         auto eval = [&](double px, double py, double &F, double &gx, double &gy) {
             double f = 0.0, ax = 0.0, ay = 0.0;
-            for (int i = lane; i < N; i += 32) {
-                if (status[i] == 0) continue;
-                const double dx = px - nx[i], dy = py - ny[i];
-                const double d = sqrt(dx * dx + dy * dy);
-                if (d <= R) {
-                    const double w = cs[i] / (energy[i] - thr) * alpha, t = d + beta;
-                    f += w / (t * t);
-                    if (d > 0.0) { const double c = -2.0 * w / (t * t * t) / d; ax += c * dx; ay += c * dy; }
+            if (listed) {
+                for (int j = lane; j < cnt; j += 32) {
+                    const double dx = px - cn_x[j], dy = py - cn_y[j];
+                    const double d = sqrt(dx * dx + dy * dy);
+                    if (d <= R) {
+                        const double w = cn_w[j], t = d + beta;
+                        f += w / (t * t);
+                        if (d > 0.0) { const double c = -2.0 * w / (t * t * t) / d; ax += c * dx; ay += c * dy; }
+                    }
+                }
+            } else {
+                for (int i = lane; i < N; i += 32) {
+                    if (status[i] == 0) continue;
+                    const double dx = px - nx[i], dy = py - ny[i];
+                    const double d = sqrt(dx * dx + dy * dy);
+                    if (d <= R) {
+                        const double w = cs[i] / (energy[i] - thr) * alpha, t = d + beta;
+                        f += w / (t * t);
+                        if (d > 0.0) { const double c = -2.0 * w / (t * t * t) / d; ax += c * dx; ay += c * dy; }
+                    }
                 }
             }
             for (int o = 16; o > 0; o >>= 1) {
@@ -613,16 +693,9 @@ int wrsn_decode_density_map(const wrsn_dims *d, const void *scen, const int32_t 
     if (!agent_id || !dmap || !action_out || !scen || !scen_id || !state) WRSN_FAIL("NULL argument");
     KParams P = base_params(d, scen, scen_id, const_cast<void *>(state), nullptr);
     wrsn_make_layout(&P.d, &P.L);
-    const size_t smem = sizeof(double) * (size_t)d->S * (size_t)d->S;
-    if (smem > 200 * 1024) WRSN_FAIL("map_size too large for the density-map decoder");
-    static bool attr = false;
-    if (!attr) {
-        WRSN_CUDA(cudaFuncSetAttribute(k_decode_map<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        WRSN_CUDA(cudaFuncSetAttribute(k_decode_map<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr = true;
-    }
-    if (dmap_f64) k_decode_map<double><<<d->B, DEC_THREADS, smem, (cudaStream_t)stream>>>(P, agent_id, (const double *)dmap, action_out);
-    else k_decode_map<float><<<d->B, DEC_THREADS, smem, (cudaStream_t)stream>>>(P, agent_id, (const float *)dmap, action_out);
+    if ((int64_t)d->S * d->S > (1 << 30)) WRSN_FAIL("map_size too large for the density-map decoder");
+    if (dmap_f64) k_decode_map<double><<<d->B, DEC_THREADS, 0, (cudaStream_t)stream>>>(P, agent_id, (const double *)dmap, action_out);
+    else k_decode_map<float><<<d->B, DEC_THREADS, 0, (cudaStream_t)stream>>>(P, agent_id, (const float *)dmap, action_out);
     WRSN_CUDA(cudaGetLastError());
     return 0;
 }
