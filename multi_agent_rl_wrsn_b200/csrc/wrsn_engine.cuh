@@ -720,7 +720,8 @@ WRSN_D double charge_rate_to(Ctx &c, const double *m, int node) {   /* alpha / (
 }
 
 /* the softmax priority + incentive sums; only reached when some incentive sum is non-empty */
-WRSN_NOINLINE void update_reward_body(Ctx &c);
+WRSN_NOINLINE void update_reward_body(Ctx &c, const double *dec);
+WRSN_NOINLINE double drain_node(double e, double rr, double es, double er, int nb, int ow, int na, double cap);
 
 WRSN_D bool reward_pairs(Ctx &c) {                 /* is there any (charging charger, connected alive node) pair? */
     bool any = false;
@@ -736,10 +737,12 @@ WRSN_D bool reward_pairs(Ctx &c) {                 /* is there any (charging cha
 }
 
 WRSN_D void ev_update_reward(Ctx &c) {
-    if (reward_pairs(c)) update_reward_body(c);      /* otherwise every incentive sum is empty: excl += 0 */
+    if (reward_pairs(c)) update_reward_body(c, (const double *)0);   /* otherwise every incentive sum is empty: excl += 0 */
 }
 
-WRSN_NOINLINE void update_reward_body(Ctx &c) {
+/* `dec` != NULL (whole-cycle batches): this second's k+0.5 drain is applied on the way — the per-second decrement of an
+ * uncharged node, or the node's literal tick where dec[i] is NaN — so the batch needs no separate pass over the nodes */
+WRSN_NOINLINE void update_reward_body(Ctx &c, const double *dec) {
     const int N = c.N, G = WRSN_GSZ(c);
     const double thr = c.par[WRSN_P_THR], cap = c.par[WRSN_P_CAP], eps = c.par[WRSN_P_EPSENV];
     double tot;
@@ -748,7 +751,20 @@ WRSN_NOINLINE void update_reward_body(Ctx &c) {
         double s = 0.0;
         _Pragma("unroll 1")
         for (int i = c.tid; i < N; i += G) {
-            double p = c.status[i] != 0 ? div_pos(c.cs[i], c.energy[i] - thr + eps) : 0.0;
+            double p = 0.0;
+            if (c.status[i] != 0) {
+                double e = c.energy[i];
+                if (dec) {
+                    const double d = dec[i];
+                    if (d == d) e = e - d;
+                    else {
+                        const int ow = c.parent[i] != -1 ? (int)c.own[i] : 0;
+                        e = drain_node(e, c.rr[i], c.esend[i], c.par[WRSN_P_ERECV], c.nbef[i], ow, c.naft[i], cap);
+                    }
+                    c.energy[i] = e;
+                }
+                p = div_pos(c.cs[i], e - thr + eps);
+            }
             c.scr0[i] = p; s += p;
         }
         const double mean = red_sum(c, s) / (double)N;
@@ -1483,19 +1499,8 @@ WRSN_NOINLINE int nodes_batch(Ctx &c, int n_max, int ur_on, double t_reward) {
         for (int q = 0; q < c.n_slot; q++) watched = watched || slot_i(slot_of(c, q))[WRSN_PRI_LAZY] == 2;
         _Pragma("unroll 1")
         for (int j = 0; j < n_safe; j++) {
-            _Pragma("unroll 1")
-            for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
-                if (c.status[i] != 1) continue;
-                const double dec = c.scr1[i];
-                if (dec == dec) c.energy[i] = c.energy[i] - dec;
-                else {
-                    const int ow = c.parent[i] != -1 ? (int)c.own[i] : 0;
-                    c.energy[i] = drain_node(c.energy[i], c.rr[i], c.esend[i], er, c.nbef[i], ow, c.naft[i], cap);
-                }
-            }
-            gsync(c);
             if (watched) catch_up_for_reward(c, t_reward + (double)j);
-            { WRSN_PROFC_BEGIN(pc4); update_reward_body(c); WRSN_PROFC_END(c, WRSN_H_PROF4, pc4); }
+            { WRSN_PROFC_BEGIN(pc4); update_reward_body(c, c.scr1.ptr()); WRSN_PROFC_END(c, WRSN_H_PROF4, pc4); }   /* drain + update_reward */
             int sl = 0;
             _Pragma("unroll 1")
             for (int i = c.tid; i < N; i += WRSN_GSZ(c), sl++) {
