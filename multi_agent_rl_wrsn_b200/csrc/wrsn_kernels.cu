@@ -189,7 +189,14 @@ __global__ void __launch_bounds__(OBS_THREADS, sizeof(AccT) == 4 ? 3 : 1) k_obse
                     if (sizeof(AccT) == 4 && node >= 0) {
                         const float wq = (float)src[q].w;
                         const float *rx = tab_gx + (size_t)node * TP, *ry = tab_gy + (size_t)node * TP;
-                        for (int i = tid & 31; i < TP; i += 32) { gx[q * TP + i] = (AccT)(wq * rx[i]); gy[q * TP + i] = (AccT)ry[i]; }
+                        /* TP is a multiple of 4 and every row starts 16-byte aligned: four entries per lane and instruction */
+                        const float4 *rx4 = reinterpret_cast<const float4 *>(rx), *ry4 = reinterpret_cast<const float4 *>(ry);
+                        float4 *gx4 = reinterpret_cast<float4 *>(gx + q * TP), *gy4 = reinterpret_cast<float4 *>(gy + q * TP);
+                        for (int i = tid & 31; i < (TP >> 2); i += 32) {
+                            float4 vx = rx4[i];
+                            vx.x *= wq; vx.y *= wq; vx.z *= wq; vx.w *= wq;
+                            gx4[i] = vx; gy4[i] = ry4[i];
+                        }
                     } else {
                         const double x0 = src[q].x0, y0 = src[q].y0;
                         const double dnx = -2.0 * (src[q].hx * src[q].hx), dny = -2.0 * (src[q].hy * src[q].hy);
@@ -213,10 +220,18 @@ __global__ void __launch_bounds__(OBS_THREADS, sizeof(AccT) == 4 ? 3 : 1) k_obse
                     for (int q = 0; q < nq; q++) {
                         if (src[q].mode < 0) continue;
                         AccT a[OBS_TI], v[OBS_TJ];
+                        if (sizeof(AccT) == 4) {     /* i0 is a multiple of 4, j0 of 2: one 16-byte and five 8-byte loads */
+                            const float4 a4 = *reinterpret_cast<const float4 *>(gx + q * TP + i0);
+                            a[0] = (AccT)a4.x; a[1] = (AccT)a4.y; a[2] = (AccT)a4.z; a[3] = (AccT)a4.w;
+                            const float2 *v2 = reinterpret_cast<const float2 *>(gy + q * TP + j0);
 #pragma unroll
-                        for (int r = 0; r < OBS_TI; r++) a[r] = gx[q * TP + i0 + r];
+                            for (int x = 0; x < OBS_TJ; x += 2) { const float2 t2 = v2[x >> 1]; v[x] = (AccT)t2.x; v[x + 1] = (AccT)t2.y; }
+                        } else {
 #pragma unroll
-                        for (int x = 0; x < OBS_TJ; x++) v[x] = gy[q * TP + j0 + x];
+                            for (int r = 0; r < OBS_TI; r++) a[r] = gx[q * TP + i0 + r];
+#pragma unroll
+                            for (int x = 0; x < OBS_TJ; x++) v[x] = gy[q * TP + j0 + x];
+                        }
 #pragma unroll
                         for (int r = 0; r < OBS_TI; r++)
 #pragma unroll
