@@ -75,9 +75,11 @@ namespace gany {                                     /* 64 ... 256 threads per e
  * IN SOURCE ORDER.  AccT = double: multiply and add rounded separately, exactly the reference's `map += w*gx*gy`
  * (parity path, float64 out).  AccT = float: the vectors are rounded to fp32 once and accumulated with FFMA (the
  * observation the policy networks consume is float32; error ~1e-6 of the channel maximum). */
-#define OBS_THREADS 256
 #define OBS_TI 4
-#define OBS_TJ 10
+#define OBS_TJ64 10                 /* fp64 parity raster: 4 x 10 tiles, 256 threads */
+#define OBS_THREADS64 256
+#define OBS_TJ32 20                 /* fp32 raster: 4 x 20 tiles, 128 threads */
+#define OBS_THREADS32 128
 
 struct ObsSrc { double x0, y0, hx, hy, w; int mode; int node; };     /* mode 0: (w*gx)*gy ; 1: ((gx*gy)*w)/mtm ; node >= 0: table row */
 
@@ -101,12 +103,14 @@ __global__ void k_obs_tables(const wrsn_dims d, const WrsnLayout L, char *scen) 
     }
 }
 
-template <typename AccT>
-__global__ void __launch_bounds__(OBS_THREADS, sizeof(AccT) == 4 ? 3 : 1) k_observe(const KParams P, const int32_t *agent_id, AccT *obs) {
+/* tile = OBS_TI rows x TJ columns of output cells per thread.  fp64 parity raster: 4 x 10 on 256 threads; fp32 raster: 4 x 20 on
+ * 128 threads (125 tiles of a 100 x 100 map: 80 FFMA per source against one 16-byte and five 16-byte shared-memory loads) */
+template <typename AccT, int TJ, int THREADS>
+__global__ void __launch_bounds__(THREADS, sizeof(AccT) == 4 ? 3 : 1) k_observe(const KParams P, const int32_t *agent_id, AccT *obs) {
     constexpr int CH = sizeof(AccT) == 4 ? 64 : 16;      /* sources staged per pass */
     extern __shared__ uint4 smem_u4[];
     const int S = P.d.S, N = P.d.N, M = P.d.M, TP = P.d.obs_pitch;
-    const int tiles_i = (S + OBS_TI - 1) / OBS_TI, tiles_j = (S + OBS_TJ - 1) / OBS_TJ;
+    const int tiles_i = (S + OBS_TI - 1) / OBS_TI, tiles_j = (S + TJ - 1) / TJ;
     AccT *gx = reinterpret_cast<AccT *>(smem_u4);                             /* [CH][TP] */
     AccT *gy = gx + CH * TP;                                                  /* [CH][TP] */
     __shared__ ObsSrc src[CH];
@@ -132,24 +136,24 @@ __global__ void __launch_bounds__(OBS_THREADS, sizeof(AccT) == 4 ? 3 : 1) k_obse
     AccT *out = obs + (size_t)b * 4 * SS;
     const int n_tiles = tiles_i * tiles_j;
 
-    for (int tbase = 0; tbase < n_tiles; tbase += OBS_THREADS) {
+    for (int tbase = 0; tbase < n_tiles; tbase += THREADS) {
         const int tile = tbase + tid;
         const bool has_tile = tile < n_tiles;
         const int ti = has_tile ? tile / tiles_j : 0, tj = has_tile ? tile - ti * tiles_j : 0;
-        const int i0 = ti * OBS_TI, j0 = tj * OBS_TJ;
+        const int i0 = ti * OBS_TI, j0 = tj * TJ;
         for (int ch = 0; ch < 4; ch++) {
-            AccT acc[OBS_TI][OBS_TJ];
+            AccT acc[OBS_TI][TJ];
 #pragma unroll
             for (int r = 0; r < OBS_TI; r++)
 #pragma unroll
-                for (int q = 0; q < OBS_TJ; q++) acc[r][q] = (AccT)0;
+                for (int q = 0; q < TJ; q++) acc[r][q] = (AccT)0;
             const int total = ch == 0 ? N : (ch == 1 ? 1 : M);
             for (int s0 = 0; s0 < total; s0 += CH) {
                 const int nq = total - s0 < CH ? total - s0 : CH;
                 __syncthreads();
                 /* the sources of this pass, one thread each, in id order; unused ones (dead node, wrong charger) get
                    mode -1 and are skipped — the reference skips them too, and the sum order of the rest is unchanged */
-                for (int q = tid; q < nq; q += OBS_THREADS) {
+                for (int q = tid; q < nq; q += THREADS) {
                     const int s = s0 + q;
                     ObsSrc v; v.mode = -1; v.node = -1; v.x0 = v.y0 = v.w = 0.0; v.hx = v.hy = 1.0;
                     if (ch == 0) {
@@ -182,7 +186,7 @@ __global__ void __launch_bounds__(OBS_THREADS, sizeof(AccT) == 4 ? 3 : 1) k_obse
                 __syncthreads();
                 /* expand every source into its two S-vectors.  Node sources of the fp32 raster are a scaled copy of the
                    scenario's table (contiguous, independent loads); everything else is one fp64 exponential per entry. */
-                for (int q = tid >> 5; q < nq; q += OBS_THREADS / 32) {        /* one warp per source row: no index division */
+                for (int q = tid >> 5; q < nq; q += THREADS / 32) {        /* one warp per source row: no index division */
                     const int mode = src[q].mode;
                     if (mode < 0) continue;
                     const int node = src[q].node;
@@ -219,23 +223,32 @@ __global__ void __launch_bounds__(OBS_THREADS, sizeof(AccT) == 4 ? 3 : 1) k_obse
                 if (ch != 3 || sizeof(AccT) == 4) {
                     for (int q = 0; q < nq; q++) {
                         if (src[q].mode < 0) continue;
-                        AccT a[OBS_TI], v[OBS_TJ];
+                        AccT a[OBS_TI], v[TJ];
                         if (sizeof(AccT) == 4) {     /* i0 is a multiple of 4, j0 of 2: one 16-byte and five 8-byte loads */
                             const float4 a4 = *reinterpret_cast<const float4 *>(gx + q * TP + i0);
                             a[0] = (AccT)a4.x; a[1] = (AccT)a4.y; a[2] = (AccT)a4.z; a[3] = (AccT)a4.w;
-                            const float2 *v2 = reinterpret_cast<const float2 *>(gy + q * TP + j0);
+                            if (TJ % 4 == 0) {           /* j0 is a multiple of 4 */
+                                const float4 *v4 = reinterpret_cast<const float4 *>(gy + q * TP + j0);
 #pragma unroll
-                            for (int x = 0; x < OBS_TJ; x += 2) { const float2 t2 = v2[x >> 1]; v[x] = (AccT)t2.x; v[x + 1] = (AccT)t2.y; }
+                                for (int x = 0; x < TJ; x += 4) {
+                                    const float4 t4 = v4[x >> 2];
+                                    v[x] = (AccT)t4.x; v[x + 1] = (AccT)t4.y; v[x + 2] = (AccT)t4.z; v[x + 3] = (AccT)t4.w;
+                                }
+                            } else {
+                                const float2 *v2 = reinterpret_cast<const float2 *>(gy + q * TP + j0);
+#pragma unroll
+                                for (int x = 0; x < TJ; x += 2) { const float2 t2 = v2[x >> 1]; v[x] = (AccT)t2.x; v[x + 1] = (AccT)t2.y; }
+                            }
                         } else {
 #pragma unroll
                             for (int r = 0; r < OBS_TI; r++) a[r] = gx[q * TP + i0 + r];
 #pragma unroll
-                            for (int x = 0; x < OBS_TJ; x++) v[x] = gy[q * TP + j0 + x];
+                            for (int x = 0; x < TJ; x++) v[x] = gy[q * TP + j0 + x];
                         }
 #pragma unroll
                         for (int r = 0; r < OBS_TI; r++)
 #pragma unroll
-                            for (int x = 0; x < OBS_TJ; x++) {
+                            for (int x = 0; x < TJ; x++) {
                                 if (sizeof(AccT) == 4) acc[r][x] = fmaf((float)a[r], (float)v[x], (float)acc[r][x]);
                                 else acc[r][x] = acc[r][x] + a[r] * v[x];       /* -fmad=false: two roundings, as numpy */
                             }
@@ -247,25 +260,34 @@ __global__ void __launch_bounds__(OBS_THREADS, sizeof(AccT) == 4 ? 3 : 1) k_obse
 #pragma unroll
                         for (int r = 0; r < OBS_TI; r++)
 #pragma unroll
-                            for (int x = 0; x < OBS_TJ; x++)
+                            for (int x = 0; x < TJ; x++)
                                 acc[r][x] = acc[r][x] + gx[q * TP + i0 + r] * gy[q * TP + j0 + x] * w / d;
                     }
                 }
             }
             if (has_tile) {
-                if (sizeof(AccT) == 4 && (S & 1) == 0 && j0 + OBS_TJ <= S) {  /* even map size: every row segment is 8-byte aligned */
+                if (sizeof(AccT) == 4 && TJ % 4 == 0 && (S & 3) == 0 && j0 + TJ <= S) {   /* 16-byte aligned row segments */
+#pragma unroll
+                    for (int r = 0; r < OBS_TI; r++) {
+                        if (i0 + r >= S) continue;
+                        float4 *o4 = reinterpret_cast<float4 *>(out + (size_t)ch * SS + (size_t)(i0 + r) * S + j0);
+#pragma unroll
+                        for (int x = 0; x < TJ; x += 4)
+                            o4[x >> 2] = make_float4((float)acc[r][x], (float)acc[r][x + 1], (float)acc[r][x + 2], (float)acc[r][x + 3]);
+                    }
+                } else if (sizeof(AccT) == 4 && (S & 1) == 0 && j0 + TJ <= S) {  /* even map size: every row segment is 8-byte aligned */
 #pragma unroll
                     for (int r = 0; r < OBS_TI; r++) {
                         if (i0 + r >= S) continue;
                         float2 *o2 = reinterpret_cast<float2 *>(out + (size_t)ch * SS + (size_t)(i0 + r) * S + j0);
 #pragma unroll
-                        for (int x = 0; x < OBS_TJ; x += 2) o2[x >> 1] = make_float2((float)acc[r][x], (float)acc[r][x + 1]);
+                        for (int x = 0; x < TJ; x += 2) o2[x >> 1] = make_float2((float)acc[r][x], (float)acc[r][x + 1]);
                     }
                 } else {
 #pragma unroll
                     for (int r = 0; r < OBS_TI; r++)
 #pragma unroll
-                        for (int x = 0; x < OBS_TJ; x++)
+                        for (int x = 0; x < TJ; x++)
                             if (i0 + r < S && j0 + x < S) out[(size_t)ch * SS + (size_t)(i0 + r) * S + j0 + x] = acc[r][x];
                 }
             }
@@ -542,8 +564,11 @@ int wrsn_dims_finalize(wrsn_dims *d) {
     }
     if (d->threads % 32 || d->threads > 256) WRSN_FAIL("threads must be a multiple of 32, at most 256");
     {
-        const int ti = (d->S + OBS_TI - 1) / OBS_TI, tj = (d->S + OBS_TJ - 1) / OBS_TJ;
-        const int pi = ti * OBS_TI, pj = (tj * OBS_TJ + 3) & ~3;
+        const int ti = (d->S + OBS_TI - 1) / OBS_TI;
+        const int tj = (d->S + OBS_TJ64 - 1) / OBS_TJ64, tk = (d->S + OBS_TJ32 - 1) / OBS_TJ32;
+        const int pk = (tk * OBS_TJ32 + 3) & ~3;
+        int pi = ti * OBS_TI, pj = (tj * OBS_TJ64 + 3) & ~3;
+        if (pk > pj) pj = pk;
         d->obs_pitch = pi > pj ? pi : pj;
     }
     WrsnLayout L;
@@ -689,14 +714,14 @@ int wrsn_observe(const wrsn_dims *d, const void *scen, const int32_t *scen_id, c
     if (obs_f64) {
         size_t smem = sizeof(double) * 2 * 16 * (size_t)d->obs_pitch;
         if (smem > 200 * 1024) WRSN_FAIL("map_size too large");
-        if (smem > 48 * 1024) WRSN_CUDA(cudaFuncSetAttribute(k_observe<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        k_observe<double><<<d->B, OBS_THREADS, smem, (cudaStream_t)stream>>>(P, agent_id, (double *)obs);
+        if (smem > 48 * 1024) WRSN_CUDA(cudaFuncSetAttribute(k_observe<double, OBS_TJ64, OBS_THREADS64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        k_observe<double, OBS_TJ64, OBS_THREADS64><<<d->B, OBS_THREADS64, smem, (cudaStream_t)stream>>>(P, agent_id, (double *)obs);
     } else {
         size_t smem = sizeof(float) * 2 * 64 * (size_t)d->obs_pitch;
         if (smem > 200 * 1024) WRSN_FAIL("map_size too large");
         static bool attr = false;
-        if (!attr) { WRSN_CUDA(cudaFuncSetAttribute(k_observe<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
-        k_observe<float><<<d->B, OBS_THREADS, smem, (cudaStream_t)stream>>>(P, agent_id, (float *)obs);
+        if (!attr) { WRSN_CUDA(cudaFuncSetAttribute(k_observe<float, OBS_TJ32, OBS_THREADS32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+        k_observe<float, OBS_TJ32, OBS_THREADS32><<<d->B, OBS_THREADS32, smem, (cudaStream_t)stream>>>(P, agent_id, (float *)obs);
     }
     WRSN_CUDA(cudaGetLastError());
     return 0;

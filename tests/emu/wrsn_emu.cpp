@@ -93,7 +93,7 @@ int wrsn_dims_finalize(wrsn_dims *d) {
     d->Npad = (d->N + 15) & ~15; d->W = (d->N + 31) / 32; d->Tw = (d->T + 31) / 32; if (d->Tw < 1) d->Tw = 1;
     d->n_slot = d->M + 3; if (d->Emax < 1) d->Emax = 1; if (d->TEmax < 1) d->TEmax = 1;
     d->threads = 32;
-    { const int ti = (d->S + 3) / 4, tj = (d->S + 9) / 10; const int pi = ti * 4, pj = (tj * 10 + 3) & ~3; d->obs_pitch = pi > pj ? pi : pj; }
+    { const int ti = (d->S + 3) / 4, tj = (d->S + 9) / 10, tk = (d->S + 19) / 20; const int pi = ti * 4, pk = (tk * 20 + 3) & ~3; int pj = (tj * 10 + 3) & ~3; if (pk > pj) pj = pk; d->obs_pitch = pi > pj ? pi : pj; }
     WrsnLayout L; wrsn_make_layout(d, &L);
     d->state_bytes = (int32_t)L.total; d->state_resident_bytes = (int32_t)L.resident;
     d->scen_bytes = (int32_t)L.scen_total; d->smem_bytes = (int32_t)L.smem_total;
