@@ -11,8 +11,11 @@ VARIANT = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 _lib.use_library(os.path.join(REPO, "multi_agent_rl_wrsn_b200", "csrc", "libwrsn_b200_prof%d.so" % VARIANT))
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 200
-scs = [synthetic(num_nodes=100, num_targets=100, seed=1000 + k) for k in range(64)]
-env = BatchedWRSN(scs, num_agent=3, num_envs=B, device="cuda:0")
+NODES = int(sys.argv[4]) if len(sys.argv) > 4 else 100
+CHARGERS = int(sys.argv[5]) if len(sys.argv) > 5 else 3
+scs = [synthetic(num_nodes=NODES, num_targets=NODES, seed=1000 + k, num_gateways=max(3, NODES // 40)) if NODES > 100 else
+       synthetic(num_nodes=NODES, num_targets=NODES, seed=1000 + k) for k in range(64 if NODES <= 100 else 8)]
+env = BatchedWRSN(scs, num_agent=CHARGERS, num_envs=B, device="cuda:0")
 env.reset()
 g = torch.Generator(device="cuda:0"); g.manual_seed(0)
 names = ["total", "serial", "batch", "bfs", "fitness"] if VARIANT == 1 else (
