@@ -43,6 +43,7 @@ def parse():
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--engine-switch", type=int, default=0, help="diagnostic: hdr[OPT_NOBATCH] of every environment (see include/wrsn_b200.h)")
     return p.parse_args()
 
 
@@ -185,6 +186,10 @@ def run_b200(a):
     groups = [BatchedWRSN(scs, num_agent=M, num_envs=Bg, device=dev, threads=a.threads, map_size=S,
                           scenario_index=(np.arange(Bg) + g * Bg) % len(scs)) for g in range(G)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(G)]
+    if a.engine_switch:
+        for env in groups:
+            env.hdr("OPT_NOBATCH")[:] = float(a.engine_switch)
+            env.view("hdr", env._snap)[:, env.E["WRSN_H_OPT_NOBATCH"]] = float(a.engine_switch)
     N, T = groups[0].N, groups[0].T
     obs = [torch.zeros((Bg, 4, S, S), dtype=torch.float32, device=dev) for _ in range(G)]
     gen = torch.Generator(device=dev)

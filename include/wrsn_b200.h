@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define WRSN_ABI_VERSION 10
+#define WRSN_ABI_VERSION 11
 #define WRSN_MAX_MC 16          /* chargers per environment */
 #define WRSN_RING 10            /* Node.operate keeps the last 10 per-second consumptions (Node.py:70-77) */
 
@@ -62,14 +62,16 @@ enum {
     WRSN_H_NSTALE,                                                  /* routing-tree rebuilds on stale levels (after Network.operate stopped) */
     WRSN_H_NLAZY,                                                   /* charger spans replayed lazily (slot_ff) */
     WRSN_H_NBATCH,                                                  /* simulated seconds advanced by whole-cycle batches (nodes_batch) */
-    WRSN_H_OPT_NOBATCH,                                             /* TEST SWITCH: != 0 disables the batches (every second runs event by event) */
+    WRSN_H_OPT_NOBATCH,                                             /* TEST SWITCH: 1 disables the batches (every second runs event by event) and the split
+                                                                       death tick; 2 disables the split death tick only */
     WRSN_H_PROF0, WRSN_H_PROF1, WRSN_H_PROF2, WRSN_H_PROF3, WRSN_H_PROF4, /* SM cycles of the last launch (builds with -DWRSN_PROF only):
                                                                        total, serial ticks, batches, BFS + tree, fitness */
-    WRSN_H_CHAIN_SLOT = 40,                                         /* [WRSN_MAX_MC] process slot watched by member j */
+    WRSN_H_NSPLIT,                                                  /* death ticks handled by drain_split (clean load in closed form) */
+    WRSN_H_CHAIN_SLOT = 48,                                         /* [WRSN_MAX_MC] process slot watched by member j */
     WRSN_H_COND_TRIG = WRSN_H_CHAIN_SLOT + WRSN_MAX_MC,
     WRSN_H_COND_T = WRSN_H_COND_TRIG + WRSN_MAX_MC,                 /* time of the pending condition event, +inf when none */
     WRSN_H_COND_KEY = WRSN_H_COND_T + WRSN_MAX_MC,                  /* 2^40 + insertion counter */
-    WRSN_H_LEN = WRSN_H_COND_KEY + WRSN_MAX_MC                      /* 104 */
+    WRSN_H_LEN = WRSN_H_COND_KEY + WRSN_MAX_MC                      /* 112 */
 };
 
 /* ---- charger record  mc[M][WRSN_MC_LEN]  (MobileCharger.py:6-32 + WRSN per-agent lists) ---- */
@@ -115,6 +117,7 @@ enum {
     WRSN_F_CONN,                                       /* uint32[M][W]  MobileCharger.connected_nodes as bitmasks */
     WRSN_F_LOGTICK,                                    /* double[Npad]  literal log_energy of a death tick */
     WRSN_F_RING,                                       /* double[WRSN_RING][Npad]  Node.log */
+    WRSN_F_SCRATCH,                                    /* engine scratch: backup of energy / energyCS / status during a death tick */
     WRSN_F_COUNT
 };
 

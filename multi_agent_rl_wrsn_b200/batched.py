@@ -318,5 +318,5 @@ class BatchedWRSN:
         E = self.E
         return {k: float(h[:, E["WRSN_H_" + n]].sum().item()) for k, n in
                 (("ticks", "NTICKS"), ("events", "NEVENTS"), ("serial_ticks", "NSLOW"), ("bfs", "NBFS"),
-                 ("stale_rebuilds", "NSTALE"), ("lazy_spans", "NLAZY"), ("batched_ticks", "NBATCH"),
+                 ("stale_rebuilds", "NSTALE"), ("lazy_spans", "NLAZY"), ("batched_ticks", "NBATCH"), ("split_death_ticks", "NSPLIT"),
                  ("decisions", "NDECISIONS"))}

@@ -146,6 +146,7 @@ struct Ctx {
     SArr<double> par;                                /* scenario constants, copied next to the state */
     /* global, per environment */
     double *logtick, *ring;
+    char *gscratch;
     /* global, per scenario */
     const double *nx, *ny, *bs_esend, *nbr_dist, *nbr_esend;
     const int32_t *nbr_ptr, *tgt_ptr, *nbr_idx, *tgt_idx;
@@ -175,6 +176,7 @@ WRSN_D void ctx_bind(Ctx &c, const wrsn_dims &d, const WrsnLayout &L, const char
     c.bcast.off = (uint32_t)L.s_bcast; c.red.off = (uint32_t)L.s_red; c.par.off = (uint32_t)L.s_par;
     c.logtick = (double *)(state_row + L.off[WRSN_F_LOGTICK]);
     c.ring = (double *)(state_row + L.off[WRSN_F_RING]);
+    c.gscratch = state_row + L.off[WRSN_F_SCRATCH];
     {
         const double *gpar = (const double *)(scen_row + L.soff[WRSN_S_PAR]);
         for (int k = tid; k < WRSN_P_LEN; k += G) c.par[k] = gpar[k];   /* visible after the caller's first barrier */
@@ -621,6 +623,175 @@ WRSN_NOINLINE int drain_serial(Ctx &c) {
     return deaths;
 }
 
+/* ------------------------------------------------------------------ death tick, split
+ * A death tick must replay packets one by one — but only the packets that can meet the death.  A node is ENDANGERED
+ * when the no-death closed form leaves it within the slack of the threshold.  Sources whose routing path contains no
+ * endangered node are CLEAN: until something reroutes onto them their packets cannot fail, and inside a binade the order
+ * in which a node's subtractions happen does not matter (sub_chain), so their whole contribution is applied node-parallel
+ * in closed form.  The DIRTY sources (an endangered node and everything routed through it) are then replayed by the
+ * leader exactly as drain_serial() does, hop by hop, with deaths and re-routing.  Nodes of dirty subtrees see only
+ * serial packets (exact order).  A SHARED node — a clean node that also relays dirty or re-routed packets — is only
+ * allowed if it is not being charged, stays in one binade and never fails a check with the clean load already applied
+ * (it then holds at least as much energy at that point in the reference's order); anything else restores the backup and
+ * the caller falls back to drain_serial().  Per-tick log_energy of shared / clean nodes = the literal sum over the packets
+ * that actually arrived (before / after the node's own turn), as in build_tree(). */
+#define WRSN_CNT_MASK 0x0fffffffu
+#define WRSN_CNT_DIRTY 0x80000000u
+enum { CLS_OK = 0, CLS_SENS = 1, CLS_END = 2 };
+WRSN_NOINLINE int drain_split(Ctx &c) {            /* returns the number of deaths, or -1: nothing changed, use drain_serial */
+    const int N = c.N, G = WRSN_GSZ(c);
+    const double thr = c.par[WRSN_P_THR], cap = c.par[WRSN_P_CAP], er = c.par[WRSN_P_ERECV];
+    const double slack = 1e-6;
+    uint32_t *cnt = (uint32_t *)c.scr0.ptr();        /* [2N]: clean relays from lower / higher ids; flags in the high bits */
+    double *lt = c.scr1;                             /* zeroed by the caller */
+    double *bk_e = (double *)c.gscratch, *bk_cs = bk_e + c.Npad;
+    uint8_t *bk_st = (uint8_t *)(bk_cs + c.Npad);
+    /* 1. classes */
+    for (int i = c.tid; i < N; i += G) {
+        uint32_t cls = CLS_OK;
+        if (c.status[i] == 1) {
+            const double e = c.energy[i], es = c.esend[i], rr = c.rr[i];
+            const int nb = c.nbef[i], na = c.naft[i];
+            const int ow = c.parent[i] != -1 ? (int)c.own[i] : 0;
+            double e3 = rr == 0.0 ? sub_chain_fast(e, es, ow, er, nb + na) : NAN;
+            if (e3 == e3) { if (nb + ow + na > 0 && !(e3 - thr >= slack)) cls = CLS_END; }
+            else {
+                cls = CLS_SENS;
+                const double e1 = sub_chain(e, es, 0, er, nb);
+                if (nb > 0 && !(e1 - thr >= slack)) cls = CLS_END;
+                const double e2 = fmin(e1 + rr * 0.5, cap);
+                e3 = sub_chain(e2, es, ow, er, na);
+                if (ow + na > 0 && !(e3 - thr >= slack)) cls = CLS_END;
+            }
+        }
+        cnt[2 * i] = 0u; cnt[2 * i + 1] = cls << 30;
+    }
+    gsync(c);
+    /* 2. dirty = routed through an endangered node (or one itself) */
+    for (int s = c.tid; s < N; s += G) {
+        if (c.status[s] != 1) continue;
+        bool dirty = false; int hops = 0;
+        for (int h = s; h >= 0 && hops++ <= N; h = c.parent[h]) if ((cnt[2 * h + 1] >> 30) == CLS_END) { dirty = true; break; }
+        if (dirty) cnt[2 * s] = WRSN_CNT_DIRTY;
+    }
+    gsync(c);
+    /* 3. clean relay counts; a dirty packet's regular path may only cross shared nodes of class OK */
+    int fail = 0;
+    for (int s = c.tid; s < N; s += G) {
+        const int ow = c.own[s];
+        if (c.status[s] != 1 || ow == 0 || c.parent[s] == -1) continue;
+        const bool dirty = (cnt[2 * s] & WRSN_CNT_DIRTY) != 0u;
+        for (int h = c.parent[s]; h >= 0; h = c.parent[h]) {
+            if (!dirty) {
+#if !defined(WRSN_HOST_EMU)
+                atomicAdd(&cnt[2 * h + (s < h ? 0 : 1)], (uint32_t)ow);
+#else
+                cnt[2 * h + (s < h ? 0 : 1)] += (uint32_t)ow;
+#endif
+            } else if ((cnt[2 * h] & WRSN_CNT_DIRTY) == 0u && (cnt[2 * h + 1] >> 30) != CLS_OK) fail = 1;
+        }
+    }
+    gsync(c);
+    if (red_or(c, fail)) return -1;
+    /* 4. backup, 5. the clean load in closed form (exact three-step form: top-up between the two chains) */
+    for (int i = c.tid; i < N; i += G) {
+        bk_e[i] = c.energy[i]; bk_cs[i] = c.cs[i]; bk_st[i] = c.status[i];
+        if (c.status[i] != 1 || (cnt[2 * i] & WRSN_CNT_DIRTY)) continue;
+        const int cb = (int)(cnt[2 * i] & WRSN_CNT_MASK), ca = (int)(cnt[2 * i + 1] & WRSN_CNT_MASK);
+        const int ow = c.parent[i] != -1 ? (int)c.own[i] : 0;
+        const double es = c.esend[i];
+        const double e1 = sub_chain(c.energy[i], es, 0, er, cb);
+        const double e2 = fmin(e1 + c.rr[i] * 0.5, cap);
+        c.energy[i] = sub_chain(e2, es, ow, er, ca);
+    }
+    gsync(c);
+    /* 6. the dirty sources, serially (leader) */
+    if (c.tid == 0) {
+        int deaths = 0; bool ok = true;
+        for (int i = 0; i < N && ok; i++) {
+            if (!(cnt[2 * i] & WRSN_CNT_DIRTY) || c.status[i] == 0) continue;
+            c.energy[i] = fmin(c.energy[i] + c.rr[i] * 0.5, cap);
+            const int ow = c.own[i];
+            for (int k = 0; k < ow && ok; k++) {
+                int h = i; bool pay_recv = false;
+                for (;;) {
+                    const bool serial = (cnt[2 * h] & WRSN_CNT_DIRTY) != 0u;
+                    if (!serial && (cnt[2 * h + 1] >> 30) != CLS_OK) { ok = false; break; }      /* re-routed onto a charged / edge node */
+                    double e = c.energy[h];
+                    if (pay_recv) {
+                        if (e - thr < er) {
+                            if (!serial) { ok = false; break; }
+                            c.energy[h] = thr;
+                            if (c.status[h] == 1) deaths++;
+                            c.status[h] = 0; c.cs[h] = 0.0;
+                            break;
+                        }
+                        e -= er;
+                    }
+                    int recv = c.parent[h]; double es = c.esend[h];
+                    if (recv >= 0 && c.status[recv] != 1) {
+                        recv = -1; es = 0.0;
+                        double bd = 0.0; int lv = c.level[h];
+                        for (int q = c.nbr_ptr[h]; q < c.nbr_ptr[h + 1]; q++) {
+                            int j = c.nbr_idx[q];
+                            if (c.level[j] < lv && c.status[j] == 1) {
+                                double dd = c.nbr_dist[q];
+                                if (recv < 0 || dd < bd) { recv = j; bd = dd; es = c.nbr_esend[q]; }
+                            }
+                        }
+                        if (!serial) { ok = false; break; }      /* a shared node's own receiver died: its clean load was applied with the old one */
+                    }
+                    bool sent = false;
+                    if (recv != -1) {
+                        if (e - thr < es) { if (!serial) { ok = false; break; } e = thr; }
+                        else { e -= es; sent = true; }
+                    }
+                    c.energy[h] = e;
+                    if (serial) {
+                        if (sent || pay_recv) { double l = lt[h]; if (sent) l += es; if (pay_recv) l += er; lt[h] = l; }
+                    } else cnt[2 * h + (i < h ? 0 : 1)] += 1u;                                 /* one more relayed packet arrived */
+                    if (e <= thr) {
+                        if (!serial) { ok = false; break; }
+                        if (c.status[h] == 1) deaths++;
+                        c.status[h] = 0; c.cs[h] = 0.0;
+                    }
+                    if (!sent || recv == -2) break;
+                    h = recv; pay_recv = true;
+                }
+            }
+        }
+        c.bcast[0] = ok ? deaths : -1;
+    }
+    gsync(c);
+    int res = c.bcast[0];
+    /* 7. shared nodes must have stayed inside their binade; then the per-tick log of every clean / shared node */
+    fail = 0;
+    if (res >= 0)
+        for (int i = c.tid; i < N; i += G) {
+            if (bk_st[i] != 1 || (cnt[2 * i] & WRSN_CNT_DIRTY)) continue;
+            if ((cnt[2 * i + 1] >> 30) == CLS_OK && wrsn_biased_exp(c.energy[i]) != wrsn_biased_exp(bk_e[i])) fail = 1;
+        }
+    gsync(c);
+    if (res < 0 || red_or(c, fail)) {
+        for (int i = c.tid; i < N; i += G) { c.energy[i] = bk_e[i]; c.cs[i] = bk_cs[i]; c.status[i] = bk_st[i]; lt[i] = 0.0; }
+        gsync(c);
+        return -1;
+    }
+    for (int i = c.tid; i < N; i += G) {
+        if (bk_st[i] != 1 || (cnt[2 * i] & WRSN_CNT_DIRTY)) continue;
+        const int cb = (int)(cnt[2 * i] & WRSN_CNT_MASK), ca = (int)(cnt[2 * i + 1] & WRSN_CNT_MASK);
+        const int ow = c.parent[i] != -1 ? (int)c.own[i] : 0;
+        const double es = c.esend[i];
+        double lg = 0.0;
+        for (int k = 0; k < cb; k++) { lg += es; lg += er; }
+        for (int k = 0; k < ow; k++) lg += es;
+        for (int k = 0; k < ca; k++) { lg += es; lg += er; }
+        lt[i] = lg;
+    }
+    gsync(c);
+    return res;
+}
+
 WRSN_D void ev_nodes_drain(Ctx &c) {
     const int N = c.N;
     const double thr = c.par[WRSN_P_THR], cap = c.par[WRSN_P_CAP], er = c.par[WRSN_P_ERECV];
@@ -669,10 +840,12 @@ WRSN_D void ev_nodes_drain(Ctx &c) {
     WRSN_PROF_BEGIN();
     for (int i = c.tid; i < N; i += WRSN_GSZ(c)) c.scr1[i] = 0.0;
     gsync(c);
+    int split_deaths = c.hdr[WRSN_H_OPT_NOBATCH] != 0.0 ? -1 : drain_split(c);   /* (the test switch also forces the plain serial tick) */
     if (c.tid == 0) {
-        int deaths = drain_serial(c);
+        int deaths = split_deaths >= 0 ? split_deaths : drain_serial(c);
         c.hdr[WRSN_H_LOG_LITERAL] = 1.0;
         c.hdr[WRSN_H_NSLOW] += 1.0;
+        if (split_deaths >= 0) c.hdr[WRSN_H_NSPLIT] += 1.0;
         if (deaths > 0) c.hdr[WRSN_H_BFS_DIRTY] = 1.0;
     }
     gsync(c);
@@ -1413,7 +1586,7 @@ WRSN_NOINLINE int nodes_batch(Ctx &c, int n_max, int ur_on, double t_reward) {
     const double slack = 1e-6;
     const double *h = c.hdr;
     WRSN_PROF_BEGIN();
-    if (h[WRSN_H_OPT_NOBATCH] != 0.0 || h[WRSN_H_BFS_DIRTY] != 0.0 || h[WRSN_H_LOG_LITERAL] != 0.0 ||
+    if (h[WRSN_H_OPT_NOBATCH] == 1.0 || h[WRSN_H_BFS_DIRTY] != 0.0 || h[WRSN_H_LOG_LITERAL] != 0.0 ||
         h[WRSN_H_LOG_LEN] < (double)WRSN_RING || h[WRSN_H_LOG_UNIFORM] < 10.0) return 0;
     const bool active = ur_on && reward_pairs(c);    /* update_reward looks at every node every second */
     /* pass 1: per node, the per-cycle decrement (scr1; NaN = replay cycle by cycle) and the number of safe cycles */

@@ -48,6 +48,7 @@ WRSN_HD void wrsn_make_layout(const wrsn_dims *d, WrsnLayout *L) {
     L->resident = o;
     L->off[WRSN_F_LOGTICK] = o; o += 8 * Np;
     L->off[WRSN_F_RING] = o; o += 8 * Np * WRSN_RING;
+    L->off[WRSN_F_SCRATCH] = o; o += wrsn_a16(17 * Np);
     L->total = o;
     /* shared-memory extras behind the resident image */
     int64_t Tp = ((int64_t)d->T + 15) & ~(int64_t)15;

@@ -230,18 +230,19 @@ def _disable_batches(env):
 
 
 _STATE_FIELDS = ("hdr", "mc", "proc", "energy", "rr", "cs", "esend", "logc", "nbef", "naft", "level", "parent", "status",
-                 "tact_words", "conn_words", "logtick", "ring")
+                 "tact_words", "conn_words", "logtick", "ring")          # (the engine's scratch field is not state)
 
 
 def _state_diff_but_switch(a, b):
     """'' when the two simulators' records are identical byte for byte (apart from the test switch and its counter),
     else a description of the first differing field."""
     ha, hb = a.view("hdr").clone(), b.view("hdr").clone()
-    for f in ("OPT_NOBATCH", "NBATCH"):
+    for f in ("OPT_NOBATCH", "NBATCH", "NSPLIT"):
         ha[:, a.E["WRSN_H_" + f]] = 0.0
         hb[:, b.E["WRSN_H_" + f]] = 0.0
     off = int(a._foff[a.E["WRSN_F_HDR"]]) + 8 * a.E["WRSN_H_LEN"]
-    if torch.equal(ha.view(torch.int64), hb.view(torch.int64)) and torch.equal(a.state[:, off:], b.state[:, off:]):
+    end = int(a._foff[a.E["WRSN_F_SCRATCH"]])            # the engine's scratch field (last in the record) is not state
+    if torch.equal(ha.view(torch.int64), hb.view(torch.int64)) and torch.equal(a.state[:, off:end], b.state[:, off:end]):
         return ""
     for f in _STATE_FIELDS:
         x, y = (ha, hb) if f == "hdr" else (a.view(f), b.view(f))
