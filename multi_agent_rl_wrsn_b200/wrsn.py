@@ -127,7 +127,13 @@ class _AgentView:
 
 class WRSN:
     def __init__(self, scenario_path, agent_type_path, num_agent, map_size=100, warm_up_time=100, density_map=False,
-                 device=None):
+                 device=None, decode="host"):
+        """Same arguments as the reference's constructor (``rl_env/WRSN.py:22``).  ``decode``: where a density-map action
+        is turned into the 3-vector — ``"host"`` (scipy's L-BFGS-B, as the reference does it) or ``"device"``
+        (``wrsn_decode_density_map``: no host round trip; see DESIGN §4.4 for what is reproduced exactly)."""
+        if decode not in ("host", "device"):
+            raise ValueError("decode must be 'host' or 'device'")
+        self.decode = decode
         scenario = scenario_path if isinstance(scenario_path, Scenario) else Scenario.load_yaml(scenario_path)
         if isinstance(agent_type_path, dict) or agent_type_path is None:
             self.agent_phy_para = agent_type_path
@@ -243,7 +249,11 @@ class WRSN:
         if agent_id is not None:
             action = np.array(input_action)
             self.agents_input_action[agent_id] = action.copy()
-            if self.density_map:
+            if self.density_map and self.decode == "device":
+                dm = torch.as_tensor(np.ascontiguousarray(action, np.float64).reshape(1, self.map_size, self.map_size), device=dev)
+                aid = torch.tensor([agent_id], dtype=torch.int32, device=dev)
+                action = self._b.density_map_to_action(dm, agent_id=aid)[0].cpu().numpy()
+            elif self.density_map:
                 if not (np.all((action >= 0) & (action <= 1)) and np.isclose(np.sum(action), 1)):
                     action = np.exp(action)
                     action = action / (np.sum(action) + self.epsilon)

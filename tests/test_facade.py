@@ -73,3 +73,23 @@ def test_density_map_actions_follow_the_reference():
         assert req["agent_id"] == int(g["agent_id"][i])
         np.testing.assert_allclose(env.env.now, float(g["now"][i]), rtol=1e-7)
         np.testing.assert_allclose(env._b.view("energy")[0].cpu().numpy(), g["energy"][i], rtol=1e-5)
+
+
+def test_density_map_device_decode_follows_the_reference():
+    """The same golden density-map episode with the map decoded on the device (wrsn_decode_density_map): the reference's
+    decoded actions at 1e-6 wherever scipy's L-BFGS-B stops at (or one gradient step from) the box centre — every decision
+    of this fixture — and the episode stays on the reference's trajectory."""
+    from multi_agent_rl_wrsn_b200.wrsn import WRSN
+    g = golden("dmap_random_n50")
+    env = WRSN(pc.sc_from_golden(g), None, int(g["num_agent"]), density_map=True, device="cuda:0", decode="device")
+    req = env.reset()
+    for i in range(int(g["n"])):
+        st = req["state"]
+        aid = req["agent_id"]
+        assert aid == int(g["fed_agent"][i])
+        req = env.step(aid, np.copy(st[0] + st[1] - 10 * st[2] + st[3]))
+        for k, name in enumerate(("ACT0", "ACT1", "ACT2")):
+            np.testing.assert_allclose(env._b.mc(name)[0, aid].item(), g["action"][i][k], rtol=1e-6, atol=1e-9)
+        assert req["agent_id"] == int(g["agent_id"][i])
+        np.testing.assert_allclose(env.env.now, float(g["now"][i]), rtol=1e-7)
+        np.testing.assert_allclose(env._b.view("energy")[0].cpu().numpy(), g["energy"][i], rtol=1e-5)
