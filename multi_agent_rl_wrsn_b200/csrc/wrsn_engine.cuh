@@ -560,17 +560,20 @@ WRSN_D void check_status_node(Ctx &c, int i) {     /* Node.py:148-151 */
 }
 
 /* exact serial tick: packet by packet, hop by hop, as the reference does it (leader only) */
-WRSN_NOINLINE int drain_serial(Ctx &c) {
+/* Starts with packet k0 of source s0 and handles `max_packets` packets at most (a whole tick: 0, 0, false, INT_MAX);
+ * `begun`: the turn of s0 has begun already (its top-up is done). */
+WRSN_NOINLINE int drain_serial(Ctx &c, int s0, int k0, bool begun, int max_packets) {
     const int N = c.N;
     const double thr = c.par[WRSN_P_THR], cap = c.par[WRSN_P_CAP], er = c.par[WRSN_P_ERECV];
     int deaths = 0;
     double *lt = c.scr1;                             /* this tick's log_energy, in shared memory: the leader adds to it at every hop;
                                                         the caller zeroes it before and copies it to the record afterwards */
-    for (int i = 0; i < N; i++) {
+    for (int i = s0; i < N && max_packets > 0; i++) {
         if (c.status[i] == 0) continue;
-        c.energy[i] = fmin(c.energy[i] + c.rr[i] * 0.5, cap);
+        const bool resumed = i == s0 && begun;
+        if (!resumed) c.energy[i] = fmin(c.energy[i] + c.rr[i] * 0.5, cap);
         int ow = c.own[i];
-        for (int k = 0; k < ow; k++) {
+        for (int k = resumed ? k0 : 0; k < ow && max_packets > 0; k++, max_packets--) {
             int h = i; bool pay_recv = false;
             for (;;) {
                 /* one hop; the node's energy lives in a register from the receive to the death check (the leader is alone
@@ -623,173 +626,177 @@ WRSN_NOINLINE int drain_serial(Ctx &c) {
     return deaths;
 }
 
-/* ------------------------------------------------------------------ death tick, split
- * A death tick must replay packets one by one — but only the packets that can meet the death.  A node is ENDANGERED
- * when the no-death closed form leaves it within the slack of the threshold.  Sources whose routing path contains no
- * endangered node are CLEAN: until something reroutes onto them their packets cannot fail, and inside a binade the order
- * in which a node's subtractions happen does not matter (sub_chain), so their whole contribution is applied node-parallel
- * in closed form.  The DIRTY sources (an endangered node and everything routed through it) are then replayed by the
- * leader exactly as drain_serial() does, hop by hop, with deaths and re-routing.  Nodes of dirty subtrees see only
- * serial packets (exact order).  A SHARED node — a clean node that also relays dirty or re-routed packets — is only
- * allowed if it is not being charged, stays in one binade and never fails a check with the clean load already applied
- * (it then holds at least as much energy at that point in the reference's order); anything else restores the backup and
- * the caller falls back to drain_serial().  Per-tick log_energy of shared / clean nodes = the literal sum over the packets
- * that actually arrived (before / after the node's own turn), as in build_tree(). */
-#define WRSN_CNT_MASK 0x0fffffffu
-#define WRSN_CNT_DIRTY 0x80000000u
-enum { CLS_OK = 0, CLS_SENS = 1, CLS_END = 2 };
-WRSN_NOINLINE int drain_split(Ctx &c) {            /* returns the number of deaths, or -1: nothing changed, use drain_serial */
+/* ------------------------------------------------------------------ death tick in pieces
+ * A death tick must replay packets one by one — but only around the death.  Until the first node fails nothing is
+ * irregular: all packets of the sources before the death packet (s*, k*) are applied node-parallel in the exact
+ * three-step closed form (relays of lower sources, top-up, own packets, relays of higher sources — restricted to the
+ * sources < s*, plus the first k* packets of s*).  The death packet itself runs through the literal hop code.  After it
+ * the routing is rebuilt (same rule as the reference's find_receiver on the stale levels) and, if no node is endangered
+ * under the remaining load, the remaining packets are applied in closed form as well; otherwise the rest of the tick is
+ * replayed serially.  (s*, k*) is found by replaying, literally and on one thread, the operation sequence of every
+ * ENDANGERED node alone (a node the no-death closed form leaves within the slack of the threshold): before the first
+ * death no other node can fail.  The per-tick log_energy is accumulated in the same order (piece 1, death packet,
+ * piece 2). */
+#define WRSN_MAX_ENDANGERED 4
+WRSN_D void count_relays(Ctx &c, uint32_t *cnt, int s_lo, int k_lo, int s_hi, int k_hi) {
+    /* relays per node from the packets (s, k) with (s_lo, k_lo) <= (s, k) < (s_hi, k_hi), split by s < node / s > node */
+    const int N = c.N, G = WRSN_GSZ(c);
+    for (int i = c.tid; i < N; i += G) { cnt[2 * i] = 0u; cnt[2 * i + 1] = 0u; }
+    gsync(c);
+    for (int s = c.tid; s < N; s += G) {
+        int ow = c.own[s];
+        if (c.status[s] != 1 || ow == 0 || c.parent[s] == -1 || s < s_lo || s > s_hi) continue;
+        int first = s == s_lo ? k_lo : 0, last = s == s_hi ? k_hi : ow;
+        if (last > ow) last = ow;
+        const int n = last - first;
+        if (n <= 0) continue;
+        for (int h = c.parent[s]; h >= 0; h = c.parent[h]) {
+#if !defined(WRSN_HOST_EMU)
+            atomicAdd(&cnt[2 * h + (s < h ? 0 : 1)], (uint32_t)n);
+#else
+            cnt[2 * h + (s < h ? 0 : 1)] += (uint32_t)n;
+#endif
+        }
+    }
+    gsync(c);
+}
+
+WRSN_NOINLINE int drain_pieces(Ctx &c) {           /* returns the number of deaths, or -1: nothing changed, use drain_serial */
     const int N = c.N, G = WRSN_GSZ(c);
     const double thr = c.par[WRSN_P_THR], cap = c.par[WRSN_P_CAP], er = c.par[WRSN_P_ERECV];
     const double slack = 1e-6;
-    uint32_t *cnt = (uint32_t *)c.scr0.ptr();        /* [2N]: clean relays from lower / higher ids; flags in the high bits */
+    uint32_t *cnt = (uint32_t *)c.scr0.ptr();
     double *lt = c.scr1;                             /* zeroed by the caller */
-    double *bk_e = (double *)c.gscratch, *bk_cs = bk_e + c.Npad;
-    uint8_t *bk_st = (uint8_t *)(bk_cs + c.Npad);
-    /* 1. classes */
+    int *bc = c.bcast;                               /* [0] number of endangered nodes, [1..4] their ids, [5] s*, [6] k*, [7] deaths */
+    if (c.tid == 0) { bc[0] = 0; bc[5] = N; bc[6] = 0; bc[7] = 0; }
+    gsync(c);
+    /* endangered nodes under the full load of the tick */
     for (int i = c.tid; i < N; i += G) {
-        uint32_t cls = CLS_OK;
-        if (c.status[i] == 1) {
-            const double e = c.energy[i], es = c.esend[i], rr = c.rr[i];
-            const int nb = c.nbef[i], na = c.naft[i];
-            const int ow = c.parent[i] != -1 ? (int)c.own[i] : 0;
-            double e3 = rr == 0.0 ? sub_chain_fast(e, es, ow, er, nb + na) : NAN;
-            if (e3 == e3) { if (nb + ow + na > 0 && !(e3 - thr >= slack)) cls = CLS_END; }
-            else {
-                cls = CLS_SENS;
-                const double e1 = sub_chain(e, es, 0, er, nb);
-                if (nb > 0 && !(e1 - thr >= slack)) cls = CLS_END;
-                const double e2 = fmin(e1 + rr * 0.5, cap);
-                e3 = sub_chain(e2, es, ow, er, na);
-                if (ow + na > 0 && !(e3 - thr >= slack)) cls = CLS_END;
-            }
-        }
-        cnt[2 * i] = 0u; cnt[2 * i + 1] = cls << 30;
-    }
-    gsync(c);
-    /* 2. dirty = routed through an endangered node (or one itself) */
-    for (int s = c.tid; s < N; s += G) {
-        if (c.status[s] != 1) continue;
-        bool dirty = false; int hops = 0;
-        for (int h = s; h >= 0 && hops++ <= N; h = c.parent[h]) if ((cnt[2 * h + 1] >> 30) == CLS_END) { dirty = true; break; }
-        if (dirty) cnt[2 * s] = WRSN_CNT_DIRTY;
-    }
-    gsync(c);
-    /* 3. clean relay counts; a dirty packet's regular path may only cross shared nodes of class OK */
-    int fail = 0;
-    for (int s = c.tid; s < N; s += G) {
-        const int ow = c.own[s];
-        if (c.status[s] != 1 || ow == 0 || c.parent[s] == -1) continue;
-        const bool dirty = (cnt[2 * s] & WRSN_CNT_DIRTY) != 0u;
-        for (int h = c.parent[s]; h >= 0; h = c.parent[h]) {
-            if (!dirty) {
-#if !defined(WRSN_HOST_EMU)
-                atomicAdd(&cnt[2 * h + (s < h ? 0 : 1)], (uint32_t)ow);
-#else
-                cnt[2 * h + (s < h ? 0 : 1)] += (uint32_t)ow;
-#endif
-            } else if ((cnt[2 * h] & WRSN_CNT_DIRTY) == 0u && (cnt[2 * h + 1] >> 30) != CLS_OK) fail = 1;
-        }
-    }
-    gsync(c);
-    if (red_or(c, fail)) return -1;
-    /* 4. backup, 5. the clean load in closed form (exact three-step form: top-up between the two chains) */
-    for (int i = c.tid; i < N; i += G) {
-        bk_e[i] = c.energy[i]; bk_cs[i] = c.cs[i]; bk_st[i] = c.status[i];
-        if (c.status[i] != 1 || (cnt[2 * i] & WRSN_CNT_DIRTY)) continue;
-        const int cb = (int)(cnt[2 * i] & WRSN_CNT_MASK), ca = (int)(cnt[2 * i + 1] & WRSN_CNT_MASK);
+        if (c.status[i] != 1) continue;
+        const double e = c.energy[i], es = c.esend[i], rr = c.rr[i];
+        const int nb = c.nbef[i], na = c.naft[i];
         const int ow = c.parent[i] != -1 ? (int)c.own[i] : 0;
-        const double es = c.esend[i];
-        const double e1 = sub_chain(c.energy[i], es, 0, er, cb);
-        const double e2 = fmin(e1 + c.rr[i] * 0.5, cap);
-        c.energy[i] = sub_chain(e2, es, ow, er, ca);
+        bool end = false;
+        const double e1 = sub_chain(e, es, 0, er, nb);
+        if (nb > 0 && !(e1 - thr >= slack)) end = true;
+        const double e2 = fmin(e1 + rr * 0.5, cap);
+        const double e3 = sub_chain(e2, es, ow, er, na);
+        if (ow + na > 0 && !(e3 - thr >= slack)) end = true;
+        if (end) {
+#if !defined(WRSN_HOST_EMU)
+            const int slot = atomicAdd(&bc[0], 1);
+#else
+            const int slot = bc[0]++;
+#endif
+            if (slot < WRSN_MAX_ENDANGERED) bc[1 + slot] = i;
+        }
     }
     gsync(c);
-    /* 6. the dirty sources, serially (leader) */
-    if (c.tid == 0) {
-        int deaths = 0; bool ok = true;
-        for (int i = 0; i < N && ok; i++) {
-            if (!(cnt[2 * i] & WRSN_CNT_DIRTY) || c.status[i] == 0) continue;
-            c.energy[i] = fmin(c.energy[i] + c.rr[i] * 0.5, cap);
-            const int ow = c.own[i];
-            for (int k = 0; k < ow && ok; k++) {
-                int h = i; bool pay_recv = false;
-                for (;;) {
-                    const bool serial = (cnt[2 * h] & WRSN_CNT_DIRTY) != 0u;
-                    if (!serial && (cnt[2 * h + 1] >> 30) != CLS_OK) { ok = false; break; }      /* re-routed onto a charged / edge node */
-                    double e = c.energy[h];
-                    if (pay_recv) {
-                        if (e - thr < er) {
-                            if (!serial) { ok = false; break; }
-                            c.energy[h] = thr;
-                            if (c.status[h] == 1) deaths++;
-                            c.status[h] = 0; c.cs[h] = 0.0;
-                            break;
-                        }
+    const int n_end = bc[0];
+    if (n_end < 1 || n_end > WRSN_MAX_ENDANGERED) return -1;
+    /* the first packet at which an endangered node fails or is left at the threshold: its own operation sequence, literally */
+    for (int q = 0; q < n_end; q++) {
+        const int h = bc[1 + q];
+        for (int s = c.tid; s < N; s += G) {         /* packets of source s that pass through h */
+            uint32_t w = 0u;
+            if (c.status[s] == 1 && s != h && c.parent[s] != -1) {
+                int hops = 0;
+                for (int a = c.parent[s]; a >= 0 && hops++ <= N; a = c.parent[a]) if (a == h) { w = c.own[s]; break; }
+            }
+            cnt[s] = w;
+        }
+        gsync(c);
+        if (c.tid == 0) {
+            double e = c.energy[h];
+            const double es = c.esend[h];
+            const bool can_send = c.parent[h] != -1;
+            int fs = N, fk = 0;
+            for (int s2 = 0; s2 < N && fs == N; s2++) {
+                if (s2 == h) {
+                    e = fmin(e + c.rr[h] * 0.5, cap);
+                    const int ow = c.own[h];
+                    for (int k = 0; k < ow; k++) {
+                        if (can_send) { if (e - thr < es) { fs = s2; fk = k; break; } e -= es; }
+                        if (e <= thr) { fs = s2; fk = k; break; }
+                    }
+                } else {
+                    const int w = (int)cnt[s2];
+                    for (int k = 0; k < w; k++) {
+                        if (e - thr < er) { fs = s2; fk = k; break; }
                         e -= er;
+                        if (can_send) { if (e - thr < es) { fs = s2; fk = k; break; } e -= es; }
+                        if (e <= thr) { fs = s2; fk = k; break; }
                     }
-                    int recv = c.parent[h]; double es = c.esend[h];
-                    if (recv >= 0 && c.status[recv] != 1) {
-                        recv = -1; es = 0.0;
-                        double bd = 0.0; int lv = c.level[h];
-                        for (int q = c.nbr_ptr[h]; q < c.nbr_ptr[h + 1]; q++) {
-                            int j = c.nbr_idx[q];
-                            if (c.level[j] < lv && c.status[j] == 1) {
-                                double dd = c.nbr_dist[q];
-                                if (recv < 0 || dd < bd) { recv = j; bd = dd; es = c.nbr_esend[q]; }
-                            }
-                        }
-                        if (!serial) { ok = false; break; }      /* a shared node's own receiver died: its clean load was applied with the old one */
-                    }
-                    bool sent = false;
-                    if (recv != -1) {
-                        if (e - thr < es) { if (!serial) { ok = false; break; } e = thr; }
-                        else { e -= es; sent = true; }
-                    }
-                    c.energy[h] = e;
-                    if (serial) {
-                        if (sent || pay_recv) { double l = lt[h]; if (sent) l += es; if (pay_recv) l += er; lt[h] = l; }
-                    } else cnt[2 * h + (i < h ? 0 : 1)] += 1u;                                 /* one more relayed packet arrived */
-                    if (e <= thr) {
-                        if (!serial) { ok = false; break; }
-                        if (c.status[h] == 1) deaths++;
-                        c.status[h] = 0; c.cs[h] = 0.0;
-                    }
-                    if (!sent || recv == -2) break;
-                    h = recv; pay_recv = true;
                 }
             }
+            if (fs < bc[5] || (fs == bc[5] && fk < bc[6])) { bc[5] = fs; bc[6] = fk; }
         }
-        c.bcast[0] = ok ? deaths : -1;
-    }
-    gsync(c);
-    int res = c.bcast[0];
-    /* 7. shared nodes must have stayed inside their binade; then the per-tick log of every clean / shared node */
-    fail = 0;
-    if (res >= 0)
-        for (int i = c.tid; i < N; i += G) {
-            if (bk_st[i] != 1 || (cnt[2 * i] & WRSN_CNT_DIRTY)) continue;
-            if ((cnt[2 * i + 1] >> 30) == CLS_OK && wrsn_biased_exp(c.energy[i]) != wrsn_biased_exp(bk_e[i])) fail = 1;
-        }
-    gsync(c);
-    if (res < 0 || red_or(c, fail)) {
-        for (int i = c.tid; i < N; i += G) { c.energy[i] = bk_e[i]; c.cs[i] = bk_cs[i]; c.status[i] = bk_st[i]; lt[i] = 0.0; }
         gsync(c);
-        return -1;
     }
-    for (int i = c.tid; i < N; i += G) {
-        if (bk_st[i] != 1 || (cnt[2 * i] & WRSN_CNT_DIRTY)) continue;
-        const int cb = (int)(cnt[2 * i] & WRSN_CNT_MASK), ca = (int)(cnt[2 * i + 1] & WRSN_CNT_MASK);
-        const int ow = c.parent[i] != -1 ? (int)c.own[i] : 0;
-        const double es = c.esend[i];
+    const int s_star = bc[5], k_star = bc[6];
+    if (s_star >= N) return -1;                      /* nobody fails after all (slack): the caller's serial path settles it */
+    /* piece 1: every packet before (s*, k*) */
+    count_relays(c, cnt, 0, 0, s_star, k_star);
+    for (int j = c.tid; j < N; j += G) {
+        if (c.status[j] != 1) continue;
+        const int cb = (int)cnt[2 * j], ca = (int)cnt[2 * j + 1];
+        const int ow_full = c.parent[j] != -1 ? (int)c.own[j] : 0;
+        const int ow = j < s_star ? ow_full : (j == s_star ? (k_star < ow_full ? k_star : ow_full) : 0);
+        const double es = c.esend[j];
+        const double e1 = sub_chain(c.energy[j], es, 0, er, cb);
+        const double e2 = j <= s_star ? fmin(e1 + c.rr[j] * 0.5, cap) : e1;
+        c.energy[j] = sub_chain(e2, es, ow, er, ca);
         double lg = 0.0;
         for (int k = 0; k < cb; k++) { lg += es; lg += er; }
         for (int k = 0; k < ow; k++) lg += es;
         for (int k = 0; k < ca; k++) { lg += es; lg += er; }
-        lt[i] = lg;
+        lt[j] = lg;
     }
     gsync(c);
-    return res;
+    /* the death packet, literally */
+    if (c.tid == 0) bc[7] = drain_serial(c, s_star, k_star, true, 1);
+    gsync(c);
+    /* piece 2: new receivers (stale or fresh levels alike: Node.find_receiver), remaining packets */
+    build_tree(c);                                   /* parent / esend of the survivors; its counts are not used here */
+    count_relays(c, cnt, s_star, k_star + 1, N - 1, 1 << 30);
+    int end2 = 0;
+    for (int j = c.tid; j < N; j += G) {
+        if (c.status[j] != 1) continue;
+        const int cb = (int)cnt[2 * j], ca = (int)cnt[2 * j + 1];
+        const int ow_full = c.parent[j] != -1 ? (int)c.own[j] : 0;
+        int ow = j > s_star ? ow_full : (j == s_star ? ow_full - (k_star + 1) : 0);
+        if (ow < 0) ow = 0;
+        const double es = c.esend[j];
+        const double e1 = sub_chain(c.energy[j], es, 0, er, cb);
+        if (cb > 0 && !(e1 - thr >= slack)) end2 = 1;
+        const double e2 = j > s_star ? fmin(e1 + c.rr[j] * 0.5, cap) : e1;
+        const double e3 = sub_chain(e2, es, ow, er, ca);
+        if (ow + ca > 0 && !(e3 - thr >= slack)) end2 = 1;
+        /* stash the result; committed below if nobody is endangered */
+        ((double *)c.gscratch)[j] = e3;
+    }
+    gsync(c);
+    if (red_or(c, end2)) {                           /* a second death is possible: the rest of the tick literally */
+        if (c.tid == 0) bc[7] += drain_serial(c, s_star, k_star + 1, true, 1 << 30);
+        gsync(c);
+        return bc[7];
+    }
+    for (int j = c.tid; j < N; j += G) {
+        if (c.status[j] != 1) continue;
+        const int cb = (int)cnt[2 * j], ca = (int)cnt[2 * j + 1];
+        const int ow_full = c.parent[j] != -1 ? (int)c.own[j] : 0;
+        int ow = j > s_star ? ow_full : (j == s_star ? ow_full - (k_star + 1) : 0);
+        if (ow < 0) ow = 0;
+        const double es = c.esend[j];
+        c.energy[j] = ((double *)c.gscratch)[j];
+        double lg = lt[j];
+        for (int k = 0; k < cb; k++) { lg += es; lg += er; }
+        for (int k = 0; k < ow; k++) lg += es;
+        for (int k = 0; k < ca; k++) { lg += es; lg += er; }
+        lt[j] = lg;
+    }
+    gsync(c);
+    return bc[7];
 }
 
 WRSN_D void ev_nodes_drain(Ctx &c) {
@@ -840,15 +847,18 @@ WRSN_D void ev_nodes_drain(Ctx &c) {
     WRSN_PROF_BEGIN();
     for (int i = c.tid; i < N; i += WRSN_GSZ(c)) c.scr1[i] = 0.0;
     gsync(c);
-    int split_deaths = c.hdr[WRSN_H_OPT_NOBATCH] != 0.0 ? -1 : drain_split(c);   /* (the test switch also forces the plain serial tick) */
+    const int pieces = c.hdr[WRSN_H_OPT_NOBATCH] != 0.0 ? -1 : drain_pieces(c);   /* (the test switch also forces the plain serial tick) */
     if (c.tid == 0) {
-        int deaths = split_deaths >= 0 ? split_deaths : drain_serial(c);
+        const int deaths = pieces >= 0 ? pieces : drain_serial(c, 0, 0, false, 1 << 30);
+        c.bcast[7] = deaths;
         c.hdr[WRSN_H_LOG_LITERAL] = 1.0;
         c.hdr[WRSN_H_NSLOW] += 1.0;
-        if (split_deaths >= 0) c.hdr[WRSN_H_NSPLIT] += 1.0;
+        if (pieces >= 0) c.hdr[WRSN_H_NSPLIT] += 1.0;
         if (deaths > 0) c.hdr[WRSN_H_BFS_DIRTY] = 1.0;
     }
     gsync(c);
+    if (c.bcast[7] > 0) build_tree(c);               /* receivers of the survivors (levels as they are; Network.setLevels follows at
+                                                        k+1.1 if Network.operate is still running) */
     for (int i = c.tid; i < N; i += WRSN_GSZ(c)) c.logtick[i] = c.scr1[i];
     gsync(c);
     WRSN_PROF_END(c, WRSN_H_PROF1);

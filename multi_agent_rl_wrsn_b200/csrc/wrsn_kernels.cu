@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(THREADS, sizeof(AccT) == 4 ? 3 : 1) k_observe(
                             v.mode = 0; v.node = s;
                             v.x0 = (nx[s] - f0) / Wd; v.y0 = (ny[s] - f2) / Hd; v.hx = R / Wd; v.hy = R / Hd;
                             v.w = (cs[s] / par[WRSN_P_MC_AB2]) / ((energy[s] - par[WRSN_P_THR]) / par[WRSN_P_CAPMTHR]);
+                            if (v.w == 0.0) v.mode = -1;     /* a node without traffic (energyCS == 0) adds exact zeros: skip it */
                         }
                     } else if (ch == 1) {
                         double tmp = fmin(Hd, Wd);
