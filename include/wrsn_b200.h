@@ -44,6 +44,7 @@ enum {
     WRSN_P_EPSENV,                                     /* WRSN.epsilon = 1e-9 */
     WRSN_P_CAPMTHR,                                    /* capacity - threshold */
     WRSN_P_ESMAX,                                      /* largest per-hop cost in the scenario (slack of the no-death test) */
+    WRSN_P_INVN,                                       /* 1 / number of nodes (mean and variance of update_reward's priorities) */
     WRSN_P_LEN = 32
 };
 

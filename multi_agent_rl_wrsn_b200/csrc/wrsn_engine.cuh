@@ -950,11 +950,12 @@ WRSN_NOINLINE void update_reward_body(Ctx &c, const double *dec) {
             }
             c.scr0[i] = p; s += p;
         }
-        const double mean = red_sum(c, s) / (double)N;
+        const double inv_n = c.par[WRSN_P_INVN];     /* 1 / N from the host: mean and variance by multiplication (1 ulp) */
+        const double mean = red_sum(c, s) * inv_n;
         s = 0.0;
         _Pragma("unroll 1")
         for (int i = c.tid; i < N; i += G) { double x = c.scr0[i] - mean; s += x * x; }
-        double sd = sqrt(red_sum(c, s) / (double)N);
+        double sd = sqrt(red_sum(c, s) * inv_n);
         if (sd == 0.0) sd = eps;
         const double inv_sd = 1.0 / sd;              /* one division instead of N: (x - mean) * (1 / sd) is within 2 ulp of the
                                                         reference's (x - mean) / sd, i.e. ~1e-15 relative on the softmax weight */
