@@ -87,6 +87,14 @@ def test_batches_equal_event_path(threads):
     assert b["episode_ends"] >= 8
 
 
+def test_batches_and_death_ticks_equal_event_path_300_nodes():
+    """Several nodes per thread (300 nodes on 64 threads), long charges, episodes that end in deaths: batches and the
+    piecewise death tick against the event-by-event path with the plain serial tick, byte for byte."""
+    scs = [synthetic(num_nodes=300, num_targets=300, seed=40 + s, num_gateways=5) for s in range(2)]
+    c = pc.check_batches_equal_event_path(scs, DEV, num_envs=24, steps=260, seed=3, num_agent=4, scale2=0.2, threads=64)
+    assert c["split_death_ticks"] >= 1 or c["episode_ends"] >= 1
+
+
 def test_pure_network_batches():
     from tests.helpers import golden
     sc = pc.sc_from_golden(golden("net_hanoi1000n50"))
