@@ -205,13 +205,13 @@ WRSN_D void gsync(const Ctx &c) {
 }
 
 #if !defined(WRSN_HOST_EMU)
-WRSN_NOINLINE double warp_sum(double v) {
-#pragma unroll 1
+WRSN_NOINLINE double warp_sum(double v) {            /* one copy, five unrolled shuffle steps (called once per reduction) */
+#pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
 WRSN_NOINLINE double warp_min(double v) {
-#pragma unroll 1
+#pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
