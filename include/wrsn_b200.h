@@ -64,10 +64,10 @@ enum {
     WRSN_H_NLAZY,                                                   /* charger spans replayed lazily (slot_ff) */
     WRSN_H_NBATCH,                                                  /* simulated seconds advanced by whole-cycle batches (nodes_batch) */
     WRSN_H_OPT_NOBATCH,                                             /* TEST SWITCH: 1 disables the batches (every second runs event by event) and the split
-                                                                       death tick; 2 disables the split death tick only */
+                                                                       death tick in pieces; 2 disables only the latter (plain serial death ticks) */
     WRSN_H_PROF0, WRSN_H_PROF1, WRSN_H_PROF2, WRSN_H_PROF3, WRSN_H_PROF4, /* SM cycles of the last launch (builds with -DWRSN_PROF only):
                                                                        total, serial ticks, batches, BFS + tree, fitness */
-    WRSN_H_NSPLIT,                                                  /* death ticks handled by drain_split (clean load in closed form) */
+    WRSN_H_NSPLIT,                                                  /* death ticks handled in pieces (drain_pieces: closed form around the death packet) */
     WRSN_H_CHAIN_SLOT = 48,                                         /* [WRSN_MAX_MC] process slot watched by member j */
     WRSN_H_COND_TRIG = WRSN_H_CHAIN_SLOT + WRSN_MAX_MC,
     WRSN_H_COND_T = WRSN_H_COND_TRIG + WRSN_MAX_MC,                 /* time of the pending condition event, +inf when none */

@@ -51,7 +51,7 @@ def test_heterogeneous_scenarios_vs_oracle():
 
 
 def test_long_charging_and_deaths_vs_oracle():
-    # long charge phases (capacity clamp, Q19) and episodes that run into node deaths (split death ticks vs the oracle)
+    # long charge phases (capacity clamp, Q19) and episodes that run into node deaths (death ticks in pieces vs the oracle)
     sc = synthetic(num_nodes=40, num_targets=120, seed=3, num_gateways=2)
     n_dec, cnt = pc.check_vs_oracle(sc, "cpu", num_envs=4, steps=60, seed=9, scale2=0.5)
     assert cnt["serial_ticks"] >= 1 and cnt["split_death_ticks"] >= 1
