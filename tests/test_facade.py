@@ -93,3 +93,31 @@ def test_density_map_device_decode_follows_the_reference():
         assert req["agent_id"] == int(g["agent_id"][i])
         np.testing.assert_allclose(env.env.now, float(g["now"][i]), rtol=1e-7)
         np.testing.assert_allclose(env._b.view("energy")[0].cpu().numpy(), g["energy"][i], rtol=1e-5)
+
+
+def test_batched_random_controller_rollout_equals_the_single_environment_loop():
+    """runner/checkRL.py's loop (RandomController map -> step) through the batched caller-side helpers: every
+    environment of a replicated batch walks exactly the trajectory of the single-environment façade with the device
+    decoder (same kernels, deterministic), and the returned statistics count its decisions."""
+    import torch
+    from multi_agent_rl_wrsn_b200 import BatchedWRSN, BatchedRandomController, rollout
+    from multi_agent_rl_wrsn_b200.wrsn import WRSN
+    g = golden("dmap_random_n50")
+    sc = pc.sc_from_golden(g)
+    steps = 6
+    single = WRSN(sc, None, 3, density_map=True, device="cuda:0", decode="device")
+    req = single.reset()
+    nows, agents = [], []
+    for _ in range(steps):
+        st = req["state"]
+        req = single.step(req["agent_id"], np.copy(st[0] + st[1] - 10 * st[2] + st[3]))
+        nows.append(single.env.now); agents.append(req["agent_id"])
+    env = BatchedWRSN(sc, num_agent=3, num_envs=5, device="cuda:0")
+    env.reset()
+    obs = torch.zeros((5, 4, env.S, env.S), dtype=torch.float64, device="cuda:0")     # float64 maps, as the façade feeds them
+    env.get_state(out=obs)
+    ctl = BatchedRandomController()
+    for k in range(steps):
+        obs, stats = rollout(env, ctl, 1, obs=obs)
+        assert stats["decisions"] == 5.0
+        assert bool((env.req.now == nows[k]).all()) and bool((env.req.agent_id == agents[k]).all())
