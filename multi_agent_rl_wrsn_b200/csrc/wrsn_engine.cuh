@@ -68,6 +68,13 @@
 #define WRSN_LEAD(c) ((c).tid == 0)
 #endif
 
+#undef WRSN_LDG                                     /* read-only scenario data (CSR graph, flags): the non-coherent L1 path */
+#if defined(WRSN_HOST_EMU)
+#define WRSN_LDG(p) (*(p))
+#else
+#define WRSN_LDG(p) __ldg(p)
+#endif
+
 #undef WRSN_SMEM_BASE
 #if defined(WRSN_HOST_EMU)
 #define WRSN_SMEM_BASE wrsn_smem_host              /* set per environment by the emulation driver */
@@ -1005,14 +1012,14 @@ WRSN_NOINLINE double do_fitness(Ctx &c, double *per_target /* global, may be NUL
     for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
         double v = -1.0;
         if (c.status[i] == 1) {
-            if (c.direct[i]) v = lt[i];
+            if (c.parent[i] == -2) v = lt[i];                      /* direct node: its receiver is the base station */
             else {
+                /* (shared memory only: an alive node whose receiver is the base station, parent == -2, is a direct node) */
                 double mn = lt[i];
                 int h = c.parent[i], hops = 0;
                 while (h >= 0 && hops++ < N) {
                     if (c.status[h] != 1) { h = -1; break; }     /* a death the tree does not know yet */
                     mn = fmin(mn, lt[h]);
-                    if (c.direct[h]) { h = -2; break; }
                     h = c.parent[h];
                 }
                 if (h == -2) v = mn;
@@ -1024,10 +1031,11 @@ WRSN_NOINLINE double do_fitness(Ctx &c, double *per_target /* global, may be NUL
     for (;;) {                                       /* widest path to the base station; only min / max, so any order is exact */
         int changed = 0;
         for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
-            if (c.status[i] != 1 || c.direct[i]) continue;
+            if (c.status[i] != 1 || c.parent[i] == -2) continue;     /* dead, or direct (receiver = base station) */
             double best = -1.0;
-            for (int e = c.nbr_ptr[i]; e < c.nbr_ptr[i + 1]; e++) {
-                int j = c.nbr_idx[e];
+            const int e1 = WRSN_LDG(c.nbr_ptr + i + 1);
+            for (int e = WRSN_LDG(c.nbr_ptr + i); e < e1; e++) {
+                int j = WRSN_LDG(c.nbr_idx + e);
                 if (c.status[j] == 1) { double v = node_t[j]; if (v > best) best = v; }
             }
             if (best >= 0.0) {
