@@ -91,8 +91,19 @@ def test_batches_equal_event_path_short_charges():
 def test_pure_network_batches():
     from tests.helpers import golden
     sc = pc.sc_from_golden(golden("net_hanoi1000n50"))
-    cnt = pc.check_pure_network_batches(sc, "cpu", horizon=6000.0, every=37.0)
-    assert cnt["batched_ticks"] > 0.6 * cnt["ticks"]      # Network.operate (and with it the batches) ends at t = 4048
+    cnt = pc.check_pure_network_batches(sc, "cpu", horizon=12500.0, every=37.0)
+    assert cnt["batched_ticks"] > 0.6 * cnt["ticks"]
+    # Network.operate ends at t = 4048; later deaths re-route on stale levels: the piecewise death tick against the serial one
+    assert cnt["split_death_ticks"] >= 5 and cnt["stale_rebuilds"] >= 4
+
+
+@pytest.mark.parametrize("seed", [3, 4, 5])
+def test_fragile_networks_die_out_identically(seed):
+    """Two gateways for 120 targets: node after node dies (also in the same second, also after Network.operate has ended);
+    the piecewise death tick and the batches against the event-by-event path with the plain serial tick, all the way."""
+    sc = synthetic(num_nodes=40, num_targets=120, seed=seed, num_gateways=2)
+    cnt = pc.check_pure_network_batches(sc, "cpu", horizon=20000.0, every=211.0)
+    assert cnt["serial_ticks"] >= 2 and cnt["split_death_ticks"] >= 1
 
 
 @pytest.mark.parametrize("nodes,targets,chargers,envs,steps", [(500, 500, 5, 2, 30), (1000, 1000, 10, 1, 45)])

@@ -98,8 +98,8 @@ def test_batches_and_death_ticks_equal_event_path_300_nodes():
 def test_pure_network_batches():
     from tests.helpers import golden
     sc = pc.sc_from_golden(golden("net_hanoi1000n50"))
-    cnt = pc.check_pure_network_batches(sc, DEV, horizon=6000.0, every=37.0)
-    assert cnt["batched_ticks"] > 0.6 * cnt["ticks"]
+    cnt = pc.check_pure_network_batches(sc, DEV, horizon=12500.0, every=37.0)
+    assert cnt["batched_ticks"] > 0.6 * cnt["ticks"] and cnt["split_death_ticks"] >= 5
 
 
 @pytest.mark.parametrize("threads", [32, 64, 128])
