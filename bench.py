@@ -219,6 +219,9 @@ def run_b200(a):
         st = torch.stack([env.req.stats.sum(0) for env in groups]).sum(0)
         return float(st[0].item()), float(st[1].item())
 
+    def resets():
+        return float(sum(env.req.stats[:, 2].sum().item() for env in groups))
+
     # untimed pre-roll: all episodes start at the same instant; run long enough for their phases to spread out, so the
     # timed window sees the steady state of a rollout (resets, death ticks and charging phases mixed) whatever K is
     for k in range(a.preroll):
@@ -233,6 +236,7 @@ def run_b200(a):
         time.sleep(0.3)
     sync_all()
     dec0, sim0 = totals()
+    ep0 = resets()
     t_wall0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(torch.cuda.current_stream(dev))
@@ -250,6 +254,7 @@ def run_b200(a):
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     dec1, sim1 = totals()
     decisions, ticks = dec1 - dec0, sim1 - sim0
+    episodes = resets() - ep0
     n_launch = 3 * G * a.steps
 
     # ---- end-to-end run (e2e): per step and group, actions come from pinned host memory and the request record is
@@ -370,12 +375,12 @@ def run_b200(a):
 
     # ---- reduce over ranks: max time, summed work
     t = torch.tensor([elapsed_ms, e2e_ms, map_ms], dtype=torch.float64, device=dev)
-    w = torch.tensor([decisions, ticks, float(e2e_dec), map_dec], dtype=torch.float64, device=dev)
+    w = torch.tensor([decisions, ticks, float(e2e_dec), map_dec, episodes], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(w, op=dist.ReduceOp.SUM)
     elapsed_ms, e2e_ms, map_ms = [float(x) for x in t.tolist()]
-    decisions_all, ticks_all, e2e_dec_all, map_dec_all = [float(x) for x in w.tolist()]
+    decisions_all, ticks_all, e2e_dec_all, map_dec_all, episodes_all = [float(x) for x in w.tolist()]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -419,6 +424,8 @@ def run_b200(a):
                        % (B * groups[0].dims.state_bytes / 1e6, B * 4 * S * S * 4 / 1e6),
                     sim_seconds_per_decision=ticks_all / max(decisions_all, 1.0),
                     env_ticks_per_s=ticks_all / (elapsed_ms * 1e-3),
+                    episodes_per_s=episodes_all / (elapsed_ms * 1e-3),
+                    resets="finished episodes are reset inside the timed step (wrsn_rollout_step: step | reset | observe)",
                     random_controller_map=dict(value=map_dec_all / (map_ms * 1e-3), unit=UNIT, steps=K2,
                                                note="same environments driven by the reference's RandomController density map "
                                                     "(s0 + s1 - 10 s2 + s3), decoded on the device by wrsn_decode_density_map; "

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define WRSN_ABI_VERSION 11
+#define WRSN_ABI_VERSION 12
 #define WRSN_MAX_MC 16          /* chargers per environment */
 #define WRSN_RING 10            /* Node.operate keeps the last 10 per-second consumptions (Node.py:70-77) */
 
@@ -162,8 +162,8 @@ typedef struct wrsn_request {
     double *action;                     /* [B][3] agents_action[agent_id] */
     double *detail;                     /* [B][2] term_all, term_exclusive of get_reward (WRSN.py:225-226) */
     int32_t *flags;                     /* [B]  bit0 = every charger dead (the reference would never return, Q1), bit1 = engine error */
-    double *stats;                      /* [B][2] running totals, never cleared by the library (may be NULL): requests handed out
-                                           with a deciding charger; simulated seconds advanced by step */
+    double *stats;                      /* [B][3] running totals, never cleared by the library (may be NULL): requests handed out
+                                           with a deciding charger; simulated seconds advanced by step; resets (episodes begun) */
 } wrsn_request;
 
 const char *wrsn_last_error(void);

@@ -37,7 +37,7 @@ class Requests:
         self.action = torch.zeros((B, 3), dtype=torch.float64, device=device)
         self.detail = torch.zeros((B, 2), dtype=torch.float64, device=device)
         self.flags = torch.zeros((B,), dtype=torch.int32, device=device)
-        self.stats = torch.zeros((B, 2), dtype=torch.float64, device=device)   # running totals: decisions, simulated seconds
+        self.stats = torch.zeros((B, 3), dtype=torch.float64, device=device)   # running totals: decisions, simulated seconds, resets
         self.c = _lib.Request(self.agent_id.data_ptr(), self.terminal.data_ptr(), self.reward.data_ptr(),
                               self.now.data_ptr(), self.action.data_ptr(), self.detail.data_ptr(), self.flags.data_ptr(),
                               self.stats.data_ptr())

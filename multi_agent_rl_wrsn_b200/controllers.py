@@ -31,6 +31,7 @@ def rollout(env, controller, steps, obs=None, group=None):
         env.get_state(out=obs)
     action = torch.zeros((B, 3), dtype=torch.float64, device=dev)
     local = torch.zeros(2, dtype=torch.float64, device=dev)               # episodes finished, sum of rewards
+    resets0 = env.req.stats[:, 2].sum()
     dec0, sim0 = reduce_stats(env, group)
     for _ in range(int(steps)):
         a = controller.make_action(env.req.agent_id, obs)
@@ -38,11 +39,9 @@ def rollout(env, controller, steps, obs=None, group=None):
             env.density_map_to_action(a.contiguous(), out=action)
         else:
             action.copy_(a)
-        before = env.req.agent_id >= 0
         env.rollout_step(action, obs)
-        req = env.req
-        local[0] += (before & (req.now == env.warm_up_time)).sum()        # rows whose episode ended and was reset in this call
-        local[1] += torch.nan_to_num(req.reward, nan=0.0).sum()
+        local[1] += torch.nan_to_num(env.req.reward, nan=0.0).sum()
+    local[0] = env.req.stats[:, 2].sum() - resets0                        # episodes that ended (and were reset) in these steps
     if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size(group) > 1:
         torch.distributed.all_reduce(local, group=group)
     dec1, sim1 = reduce_stats(env, group)

@@ -56,8 +56,9 @@ __global__ void __launch_bounds__(WRSN_GFIX ? WRSN_GFIX : 256, WRSN_GFIX ? 20 : 
     if ((MODE == MODE_RESET_FINISH || MODE == MODE_RESTORE_RESET || MODE == MODE_STEP) && tid == 0) {
         write_request(P.req, b, r);
         if (P.req.stats) {
-            if (r.agent >= 0) P.req.stats[2 * b] += 1.0;
-            if (MODE == MODE_STEP) P.req.stats[2 * b + 1] += r.now - now_before;
+            if (r.agent >= 0) P.req.stats[3 * b] += 1.0;
+            if (MODE == MODE_STEP) P.req.stats[3 * b + 1] += r.now - now_before;
+            if (MODE == MODE_RESTORE_RESET || MODE == MODE_RESET_FINISH) P.req.stats[3 * b + 2] += 1.0;
         }
     }
 }

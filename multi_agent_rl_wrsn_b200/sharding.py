@@ -25,7 +25,8 @@ def shard_scenario_index(num_envs, num_scenarios, rank, world_size):
 
 
 def reduce_stats(env, group=None):
-    """Job-wide (decisions, simulated seconds): sum of the kernels' running totals over environments and ranks."""
+    """Job-wide (decisions, simulated seconds): sum of the kernels' running totals over environments and ranks
+    (the third total, resets, is ``env.req.stats[:, 2]``)."""
     s = env.req.stats.sum(0).clone()
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
