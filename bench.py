@@ -12,6 +12,7 @@ Environments shard across ranks by index with no data-path collective (weak scal
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -358,7 +359,7 @@ def run_b200(a):
         for g in range(G):
             map_step(g)
     sync_all()
-    md0, _ = totals()
+    md0, ms0 = totals()
     m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     m0.record(torch.cuda.current_stream(dev))
     for st in streams:
@@ -370,17 +371,57 @@ def run_b200(a):
         torch.cuda.current_stream(dev).wait_stream(st)
     m1.record(torch.cuda.current_stream(dev))
     sync_all()
-    md1, _ = totals()
-    map_ms, map_dec = m0.elapsed_time(m1), md1 - md0
+    md1, ms1 = totals()
+    map_ms, map_dec, map_sim = m0.elapsed_time(m1), md1 - md0, ms1 - ms0
+
+    # ---- the rollout loop of the reference's IPPO trainer (controller/ippo/IPPO.py:128-155) with its transition record
+    # kept in HBM (controllers.IPPORollout): a Gaussian policy around the RandomController map stands in
+    # for the actors (map, sample, log-probability by torch), the decoder and rollout_step do the rest.  Windows of T3 steps.
+    from multi_agent_rl_wrsn_b200.controllers import IPPORollout
+    T3, W3 = 6, 3
+    sigma = 1e-3
+
+    def gauss_policy(agent_id, o):
+        mean = o[:, 0] + o[:, 1] - 10.0 * o[:, 2] + o[:, 3]
+        x = torch.randn_like(mean).mul_(sigma).add_(mean)
+        lp = (-0.5 * ((x - mean) / sigma) ** 2).sum((1, 2)) - S * S * (math.log(sigma) + 0.5 * math.log(2.0 * math.pi))
+        return x, lp
+
+    ros = [IPPORollout(groups[g], T3) for g in range(G)]
+    sync_all()                                   # the records were initialised on the current stream; the groups' streams follow
+
+    def ippo_window():
+        for g in range(G):
+            with torch.cuda.stream(streams[g]):
+                ros[g].carry_over()
+                ros[g].collect(gauss_policy)
+
+    ippo_window()
+    sync_all()
+    id0, is0 = totals()
+    i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    i0.record(torch.cuda.current_stream(dev))
+    for st in streams:
+        st.wait_stream(torch.cuda.current_stream(dev))
+    for k in range(W3):
+        ippo_window()
+    for st in streams:
+        torch.cuda.current_stream(dev).wait_stream(st)
+    i1.record(torch.cuda.current_stream(dev))
+    sync_all()
+    id1, is1 = totals()
+    ippo_ms, ippo_dec, ippo_sim = i0.elapsed_time(i1), id1 - id0, is1 - is0
+    ippo_tr = float(sum(sum(int(r.transitions(i)[0].numel()) for i in range(M)) for r in ros))   # of the last window
+    del ros
 
     # ---- reduce over ranks: max time, summed work
-    t = torch.tensor([elapsed_ms, e2e_ms, map_ms], dtype=torch.float64, device=dev)
-    w = torch.tensor([decisions, ticks, float(e2e_dec), map_dec, episodes], dtype=torch.float64, device=dev)
+    t = torch.tensor([elapsed_ms, e2e_ms, map_ms, ippo_ms], dtype=torch.float64, device=dev)
+    w = torch.tensor([decisions, ticks, float(e2e_dec), map_dec, episodes, ippo_dec, ippo_tr, map_sim, ippo_sim], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(w, op=dist.ReduceOp.SUM)
-    elapsed_ms, e2e_ms, map_ms = [float(x) for x in t.tolist()]
-    decisions_all, ticks_all, e2e_dec_all, map_dec_all, episodes_all = [float(x) for x in w.tolist()]
+    elapsed_ms, e2e_ms, map_ms, ippo_ms = [float(x) for x in t.tolist()]
+    decisions_all, ticks_all, e2e_dec_all, map_dec_all, episodes_all, ippo_dec_all, ippo_tr_all, map_sim_all, ippo_sim_all = [float(x) for x in w.tolist()]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -427,9 +468,17 @@ def run_b200(a):
                     episodes_per_s=episodes_all / (elapsed_ms * 1e-3),
                     resets="finished episodes are reset inside the timed step (wrsn_rollout_step: step | reset | observe)",
                     random_controller_map=dict(value=map_dec_all / (map_ms * 1e-3), unit=UNIT, steps=K2,
+                                               sim_seconds_per_decision=map_sim_all / max(map_dec_all, 1.0),
                                                note="same environments driven by the reference's RandomController density map "
                                                     "(s0 + s1 - 10 s2 + s3), decoded on the device by wrsn_decode_density_map; "
-                                                    "device-resident, not the headline workload")),
+                                                    "device-resident, not the headline workload"),
+                    ippo_rollout_record=dict(value=ippo_dec_all / (ippo_ms * 1e-3), unit=UNIT, steps=T3 * W3,
+                                             sim_seconds_per_decision=ippo_sim_all / max(ippo_dec_all, 1.0),
+                                             transitions_last_window=ippo_tr_all,
+                                             note="IPPO.roll_out's loop (IPPO.py:128-155) with the per-agent transition record "
+                                                  "(state, map action, log-probability, reward, next state) kept in HBM by "
+                                                  "controllers.IPPORollout; Gaussian policy around the RandomController map as "
+                                                  "the stand-in actor, maps decoded on the device; windows of %d steps" % T3)),
         clocks=clocks,
         e2e=dict(value=e2e_dec_all / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                  note="per step: actions from pinned host memory, rollout_step (step | reset | observe), request record "

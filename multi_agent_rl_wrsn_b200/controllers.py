@@ -47,3 +47,162 @@ def rollout(env, controller, steps, obs=None, group=None):
     dec1, sim1 = reduce_stats(env, group)
     return obs, dict(decisions=dec1 - dec0, simulated_seconds=sim1 - sim0, episodes=float(local[0].item()),
                      reward_sum=float(local[1].item()))
+
+
+class IPPORollout:
+    """``IPPO.roll_out`` (``controller/ippo/IPPO.py:119-210``; ``PPO.roll_out`` is the same loop with one shared
+    network) for B environments at once, with the record kept in HBM.
+
+    The reference loops ``get_action -> step`` on one environment and, per agent, appends a transition
+    ``(prev_state, input_action, log_prob, reward, state, terminal)`` whenever a request names an agent that has
+    already acted in the current episode (``:141-155``); ``prev_state`` is the observation that agent was last handed.
+    Here the T rollout steps are stored time-major (``obs[t]`` = the observation handed out at step t, one request per
+    environment and step) and a transition is a *link*: ``link[t, b]`` is the earlier step at which environment b
+    asked the same agent in the same episode, or -1.  Nothing is copied twice and nothing leaves the device:
+
+        state = obs[link[t, b], b]   action, log_prob = act / logp[link[t, b], b]
+        next_state = obs[t, b]       reward = reward[t, b]        terminal = False  (the reference breaks on terminal
+                                                                                     before it records, ``:143-144``)
+
+    ``policy(agent_id, obs)`` -> ``(input_action, log_prob)`` with ``agent_id`` int32 [B], ``obs`` [B, 4, S, S];
+    ``input_action`` is a [B, S, S] density map (``density_map=True``, the runners' setting) or a [B, 3] action.
+    """
+
+    def __init__(self, env, steps, action_shape=None, obs_dtype=torch.float32, with_obs=True):
+        """``with_obs=False`` keeps no observations (``policy`` is handed None; ``batch`` has no states): for policies that
+        do not look at the map, and for the CPU tests of the record, whose host emulation has no raster."""
+        B, S, M, dev = env.B, env.S, env.M, env.device
+        self.env, self.T = env, int(steps)
+        action_shape = (S, S) if action_shape is None else tuple(action_shape)
+        self.obs = torch.zeros((self.T + 1, B, 4, S, S), dtype=obs_dtype, device=dev) if with_obs else None
+        self.now = torch.zeros((self.T + 1, B), dtype=torch.float64, device=dev)   # env.now of every request
+        self.act = torch.zeros((self.T, B) + action_shape, dtype=torch.float32, device=dev)
+        self.logp = torch.zeros((self.T, B), dtype=torch.float32, device=dev)
+        self.reward = torch.zeros((self.T + 1, B), dtype=torch.float64, device=dev)
+        self.agent = torch.full((self.T + 1, B), -1, dtype=torch.int64, device=dev)
+        self.link = torch.full((self.T + 1, B), -1, dtype=torch.int64, device=dev)
+        self.new_episode = torch.zeros((self.T + 1, B), dtype=torch.bool, device=dev)
+        self.last = torch.full((B, M), -1, dtype=torch.int64, device=dev)   # step of each agent's open decision
+        self.action = torch.zeros((B, 3), dtype=torch.float64, device=dev)
+        self.terminal_factor = None
+        self._collected = False
+        if bool((env.req.agent_id == -3).all()):                          # never reset: start the first episodes
+            env.reset()
+        if bool((env.req.agent_id < 0).any()):
+            raise RuntimeError("IPPORollout needs an open request (a deciding charger) in every environment")
+        if with_obs:
+            env.get_state(out=self.obs[0])
+        self.agent[0] = env.req.agent_id.to(torch.int64)
+        self.now[0] = env.req.now
+
+    def collect(self, policy):
+        """T rollout steps.  Row t of the record is the request answered at step t; row T is the request left open
+        (its observation starts the next ``collect`` after ``carry_over``)."""
+        env = self.env
+        for t in range(self.T):
+            a = self.agent[t]
+            x, lp = policy(a.to(torch.int32), None if self.obs is None else self.obs[t])
+            self.act[t].copy_(x)
+            self.logp[t].copy_(lp)
+            self.last.scatter_(1, a[:, None], t)                          # log_probs_pre[agent] = log_prob (:140)
+            if x.dim() == 3:                                              # WRSN.step :293-297 on the device
+                env.density_map_to_action(self.act[t], out=self.action)
+            else:
+                self.action.copy_(x)
+            resets = env.req.stats[:, 2].clone()
+            env.rollout_step(self.action, None if self.obs is None else self.obs[t + 1])
+            ended = env.req.stats[:, 2] != resets                         # terminal -> env.reset() (:137, :143)
+            self.last.masked_fill_(ended[:, None], -1)                    # log_probs_pre = [None] * num_agent (:138)
+            nxt = env.req.agent_id.to(torch.int64).clamp_min(0)           # < 0 only with flags bit0 (every charger dead)
+            self.agent[t + 1] = nxt
+            self.new_episode[t + 1] = ended
+            self.link[t + 1] = self.last.gather(1, nxt[:, None])[:, 0]    # -1: `continue` (:145-146)
+            self.reward[t + 1] = torch.nan_to_num(env.req.reward, nan=0.0)
+            self.now[t + 1] = env.req.now
+        self._collected = True
+        return self
+
+    def carry_over(self):
+        """Start the next window from the open requests: links into the finished window are dropped (the reference
+        starts every ``roll_out`` with ``env.reset()``; a continuing batch keeps its episodes instead).  No-op on a fresh record."""
+        if not self._collected:
+            return
+        self._collected = False
+        if self.obs is not None:
+            self.obs[0].copy_(self.obs[self.T])
+        self.agent[0] = self.agent[self.T]
+        self.now[0] = self.now[self.T]
+        self.last.fill_(-1)
+        self.link.fill_(-1)
+        self.new_episode.zero_()
+
+    def transitions(self, agent_id):
+        """Index tensors ``(t, b, t_prev)`` of the transitions recorded for ``agent_id``, in the reference's order
+        inside every environment (time-major)."""
+        sel = (self.agent[1:] == int(agent_id)) & (self.link[1:] >= 0)
+        t, b = torch.nonzero(sel, as_tuple=True)
+        t = t + 1
+        return t, b, self.link[t, b]
+
+    def batch(self, agent_id):
+        """The lists ``roll_out`` builds for one agent, as tensors (``:148-153``)."""
+        t, b, tp = self.transitions(agent_id)
+        out = dict(actions=self.act[tp, b], log_probs=self.logp[tp, b], rewards=self.reward[t, b].to(torch.float32),
+                   terminals=torch.zeros(t.shape, dtype=torch.float32, device=t.device), t=t, b=b,
+                   prev_time=self.now[tp, b], time=self.now[t, b])
+        if self.obs is not None:
+            out.update(states=self.obs[tp, b], next_states=self.obs[t, b])
+        return out
+
+    def cal_rt_adv(self, agent_id, value_fn, gamma, gae_lambda, gae=True, chunk=4096, values=None, next_values=None):
+        """``IPPO.cal_rt_adv`` (``:71-94``) for every (environment, episode) sequence of ``agent_id`` at once.
+
+        The reference evaluates the critic on an episode's states / next states and runs the recursion backwards over
+        that episode's list with the recorded ``terminals`` as the continuation factor — which are all False
+        (``:143-153``), so ``advantages = rewards - values`` and ``returns = rewards``; the recursion is kept general
+        (``terminals`` may be overridden through ``self.terminal_factor``) and runs backwards over the T steps with
+        one carry per environment, cleared where an episode begins.  ``values`` / ``next_values`` (one per transition of
+        ``batch(agent_id)``) replace the critic calls when given.
+        """
+        bt = self.batch(agent_id)
+        n = bt["rewards"].shape[0]
+        with torch.no_grad():
+            if values is None:
+                values = torch.cat([value_fn(bt["states"][i:i + chunk]) for i in range(0, n, chunk)]) if n else bt["rewards"]
+                next_values = torch.cat([value_fn(bt["next_states"][i:i + chunk]) for i in range(0, n, chunk)]) if n else bt["rewards"]
+            term = bt["terminals"] if self.terminal_factor is None else torch.full_like(bt["terminals"], self.terminal_factor)
+            B, dev = self.env.B, values.device
+            grid = lambda v: torch.zeros((self.T + 1, B), dtype=torch.float32, device=dev).index_put_((bt["t"], bt["b"]), v)
+            has = torch.zeros((self.T + 1, B), dtype=torch.bool, device=dev).index_put_((bt["t"], bt["b"]), torch.ones(n, dtype=torch.bool, device=dev))
+            r, v, nv, tm = grid(bt["rewards"]), grid(values), grid(next_values), grid(term)
+            out = torch.zeros_like(r)
+            carry = torch.zeros(B, dtype=torch.float32, device=dev)
+            for t in range(self.T, 0, -1):
+                if gae:                                                   # :77-82
+                    cur = r[t] + gamma * nv[t] * tm[t] - v[t] + gamma * gae_lambda * tm[t] * carry
+                else:                                                     # :84-91 (t == len(rewards) never holds)
+                    cur = r[t] + gamma * tm[t] * carry
+                out[t] = torch.where(has[t], cur, out[t])
+                carry = torch.where(has[t], cur, carry)
+                carry = torch.where(self.new_episode[t], torch.zeros_like(carry), carry)
+            seq = out[bt["t"], bt["b"]]
+            if gae:
+                advantages, returns = seq, seq + values
+            else:
+                returns, advantages = seq, seq - values
+        return returns, advantages, values, bt
+
+
+def select_batch(rewards, batch_size, generator=None):
+    """The reward-outlier batch selection of ``IPPO.roll_out`` (``:193-200``): the ``batch_size // 2`` transitions whose
+    reward is farthest from the mean, plus ``batch_size - batch_size // 2`` drawn without replacement from the first
+    ``len - batch_size // 2`` indices (of the *unsorted* list, as the reference does).  Index tensor on the rewards' device;
+    the draw uses torch's generator, not numpy's global one."""
+    n = rewards.shape[0]
+    selected = int(batch_size / 2.0)
+    random_num = int(batch_size) - selected
+    if n - selected < random_num:
+        raise ValueError("Cannot take a larger sample than population when 'replace=False'")   # np.random.choice's error
+    order = torch.argsort((rewards - rewards.mean()).abs(), stable=True)
+    draw = torch.randperm(n - selected, generator=generator, device=rewards.device)[:random_num]
+    return torch.cat((order[n - selected:], draw))

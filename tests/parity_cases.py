@@ -296,3 +296,118 @@ def check_pure_network_batches(scenario, device, horizon, every):
         assert not diff, (t, diff)
         t += every
     return a.counters()
+
+
+def _toy_policy(salt, clock, use_obs):
+    """Deterministic stand-in for IPPO.get_action: a 3-vector action and a 'log-probability' that depend on the agent, a
+    per-environment salt, the simulation time of the request and (``use_obs``) the observation only."""
+    def policy(agent_id, obs):
+        now = clock().to(torch.float64)
+        s = torch.as_tensor(salt, dtype=torch.float64, device=now.device)
+        a = agent_id.to(torch.float64)
+        m0 = m1 = torch.zeros_like(now)
+        if use_obs:
+            m = obs.to(torch.float64).mean(dim=(2, 3))                              # [B, 4]
+            m0, m1 = 1e3 * m[:, 0], 7e2 * m[:, 1]
+        u = torch.stack((torch.frac(m0 + 0.37 * s + 0.11 * a + 0.013 * now), torch.frac(m1 + 0.53 * s + 0.29 * a + 0.007 * now),
+                         0.25 * torch.frac(0.71 * s + 0.0031 * now)), dim=1)
+        return u.to(torch.float32), (torch.sin(now) + 0.01 * a).to(torch.float32)
+    return policy
+
+
+def check_ippo_rollout(scenarios, device, num_envs, steps, gamma=0.99, lam=0.95, with_obs=True):
+    """IPPORollout (batched, linked record) == the reference's roll_out loop (IPPO.py:128-155) written against the
+    single-environment façade, environment by environment: the same transitions in the same order for every agent,
+    and cal_rt_adv == the reference's recursion over every (episode, agent) list.  ``with_obs=False``: no observations
+    (the host emulation has no raster); the critic is then a function of the requests' simulation times."""
+    from multi_agent_rl_wrsn_b200 import WRSN
+    from multi_agent_rl_wrsn_b200.controllers import IPPORollout
+
+    class _NoObsWRSN(WRSN):
+        def get_state(self, agent_id):
+            return None
+    M = 3
+    env = BatchedWRSN(scenarios, num_agent=M, num_envs=num_envs, device=device)
+    env.reset()
+    ro = IPPORollout(env, steps, action_shape=(3,), obs_dtype=torch.float64, with_obs=with_obs)
+    salt = np.arange(num_envs)
+    ro.collect(_toy_policy(salt, lambda: env.req.now, with_obs))
+    value_fn = lambda s: (s[:, 0].mean(dim=(1, 2)) * 50.0 + s[:, 1].mean(dim=(1, 2))).to(torch.float32)
+    value_t = lambda t: torch.cos(0.01 * torch.as_tensor(t, dtype=torch.float64)).to(torch.float32)
+    n_tr = episodes = 0
+    for tf in (None, 1.0):                                    # the reference's all-False terminals, and a live recursion
+        ro.terminal_factor = tf
+        per_agent = []
+        for i in range(M):
+            bt = ro.batch(i)
+            kw = {} if with_obs else dict(values=value_t(bt["prev_time"]), next_values=value_t(bt["time"]))
+            per_agent.append(ro.cal_rt_adv(i, value_fn, gamma, lam, **kw))
+        for b in range(num_envs):
+            single = (WRSN if with_obs else _NoObsWRSN)(scenarios[b % len(scenarios)], None, M, device=device)
+            pol = _toy_policy(salt[b:b + 1], lambda: single._b.req.now, with_obs)
+            keys = ("states", "actions", "log_probs", "rewards", "next_states", "prev_time", "time")
+            rec = [dict({k: [] for k in keys}, adv=[], ret=[]) for _ in range(M)]
+            done = 0
+            first = True
+            while done < steps:
+                if not first:
+                    episodes += 1
+                first = False
+                request = single.reset()
+                lists = [{k: [] for k in keys} for _ in range(M)]
+                pre, asked = [None] * M, [None] * M
+                while done < steps:
+                    aid = request["agent_id"]
+                    x, lp = pol(torch.tensor([aid], dtype=torch.int32, device=device),
+                                torch.as_tensor(request["state"], device=device)[None] if with_obs else None)
+                    pre[aid], asked[aid] = float(lp[0]), single.env.now
+                    request = single.step(aid, x[0].cpu().numpy().astype(np.float64))
+                    done += 1
+                    if request["terminal"]:
+                        break
+                    aid = request["agent_id"]
+                    if pre[aid] is None:
+                        continue
+                    L = lists[aid]
+                    L["states"].append(request["prev_state"]); L["actions"].append(request["input_action"])
+                    L["next_states"].append(request["state"]); L["rewards"].append(request["reward"]); L["log_probs"].append(pre[aid])
+                    L["prev_time"].append(asked[aid]); L["time"].append(single.env.now)
+                for i in range(M):                             # IPPO.cal_rt_adv :71-83 on this episode's list
+                    L = lists[i]
+                    if not L["rewards"]:
+                        continue
+                    if with_obs:
+                        v = value_fn(torch.as_tensor(np.array(L["states"])))
+                        nv = value_fn(torch.as_tensor(np.array(L["next_states"])))
+                    else:
+                        v, nv = value_t(L["prev_time"]), value_t(L["time"])
+                    r = torch.tensor(L["rewards"], dtype=torch.float32)
+                    term = 0.0 if tf is None else tf
+                    adv = torch.zeros_like(r)
+                    last = 0.0
+                    for t in reversed(range(len(r))):
+                        delta = r[t] + gamma * nv[t] * term - v[t]
+                        last = delta + gamma * lam * term * last
+                        adv[t] = last
+                    for k in keys:
+                        rec[i][k].extend(L[k])
+                    rec[i]["adv"].extend(adv.tolist()); rec[i]["ret"].extend((adv + v).tolist())
+            for i in range(M):
+                returns, advantages, values, bt = per_agent[i]
+                sel = (bt["b"] == b).nonzero()[:, 0]
+                assert len(sel) == len(rec[i]["rewards"]), (b, i, len(sel), len(rec[i]["rewards"]))
+                if not len(sel):
+                    continue
+                n_tr += len(sel)
+                g = lambda k: bt[k][sel].cpu().numpy()
+                if with_obs:
+                    assert np.allclose(g("states"), np.array(rec[i]["states"]), rtol=1e-9, atol=1e-12), (b, i)
+                    assert np.allclose(g("next_states"), np.array(rec[i]["next_states"]), rtol=1e-9, atol=1e-12), (b, i)
+                assert np.array_equal(g("prev_time"), np.array(rec[i]["prev_time"])), (b, i)
+                assert np.array_equal(g("time"), np.array(rec[i]["time"])), (b, i)
+                assert np.allclose(g("actions"), np.array(rec[i]["actions"]), rtol=0, atol=1e-7), (b, i)
+                assert np.allclose(g("log_probs"), np.array(rec[i]["log_probs"]), rtol=1e-6), (b, i)
+                assert np.allclose(g("rewards"), np.array(rec[i]["rewards"], np.float32), rtol=1e-6, atol=1e-9), (b, i)
+                assert np.allclose(advantages[sel].cpu().numpy(), np.array(rec[i]["adv"]), rtol=1e-4, atol=1e-6), (b, i)
+                assert np.allclose(returns[sel].cpu().numpy(), np.array(rec[i]["ret"]), rtol=1e-4, atol=1e-6), (b, i)
+    return n_tr, episodes
