@@ -7,6 +7,8 @@ environments at once and nothing leaves HBM: the map is formed by torch from the
 loops do: ``controller/ippo/IPPO.py:137-143``).  Trainers (PPO / IPPO) plug in at the same place: anything with a
 ``make_action(agent_id, state)`` that returns either [B, S, S] maps or [B, 3] actions.
 """
+import math
+
 import torch
 
 from .sharding import reduce_stats
@@ -206,3 +208,41 @@ def select_batch(rewards, batch_size, generator=None):
     order = torch.argsort((rewards - rewards.mean()).abs(), stable=True)
     draw = torch.randperm(n - selected, generator=generator, device=rewards.device)[:random_num]
     return torch.cat((order[n - selected:], draw))
+
+
+class PerAgentPolicy:
+    """``IPPO.get_action`` (``controller/ippo/IPPO.py:96-106``) for a batch of requests: IPPO keeps one actor per
+    charger, so the requests are grouped by agent id and ``actors[i]`` runs once on its slice of the observation tensor
+    (in HBM, no host copy); the action is a sample of ``Normal(mean, exp(log_std))`` and the log-probability its sum over
+    the map, exactly what ``IPPO.evaluate`` (``:108-115``) recomputes during the update.  ``PPO`` (one shared network,
+    ``controller/ppo/PPO.py``) is ``PerAgentPolicy([actor] * num_agent)``.  One host synchronisation per call: the sizes
+    of the groups."""
+
+    def __init__(self, actors, generator=None):
+        self.actors, self.generator = list(actors), generator
+
+    @torch.no_grad()
+    def __call__(self, agent_id, obs):
+        B, S = obs.shape[0], obs.shape[-1]
+        M = len(self.actors)
+        ids = agent_id.to(torch.int64)
+        order = torch.argsort(ids, stable=True)
+        counts = torch.bincount(ids, minlength=M).tolist()
+        if len(counts) > M:
+            raise ValueError("request for agent %d but only %d actors" % (len(counts) - 1, M))
+        x = torch.empty((B, S, S), dtype=torch.float32, device=obs.device)
+        lp = torch.empty((B,), dtype=torch.float32, device=obs.device)
+        lo = 0
+        for i, n in enumerate(counts):
+            if n == 0:
+                continue
+            idx = order[lo:lo + n]
+            lo += n
+            mean, log_std = self.actors[i](obs[idx].to(torch.float32))
+            mean, log_std = mean.reshape(n, S, S), log_std.reshape(n, S, S)   # UNet.forward squeezes a batch of one away
+            std = log_std.exp()
+            a = mean + std * torch.randn(mean.shape, generator=self.generator, device=mean.device, dtype=mean.dtype)
+            logp = (-((a - mean) ** 2) / (2.0 * std * std) - log_std - 0.5 * math.log(2.0 * math.pi)).sum((1, 2))   # Normal.log_prob
+            x[idx] = a
+            lp[idx] = logp
+        return x, lp

@@ -78,3 +78,42 @@ def test_select_batch():
     assert len(set(rest.tolist())) == 32 and rest.max() < 300 - 32 and rest.min() >= 0
     with pytest.raises(ValueError):
         select_batch(torch.zeros(40), 64)
+
+
+class _TinyActor(torch.nn.Module):
+    """Same interface as the reference's UNet actor (controller/ppo/actor/UnetActor.py:73-80): (mean, log_std) maps, squeezed."""
+
+    def __init__(self, seed, size):
+        super().__init__()
+        torch.manual_seed(seed)
+        self.conv = torch.nn.Conv2d(4, 1, kernel_size=3, padding=1)
+        self.log_std = torch.nn.Parameter(torch.full((1, 1, size, size), -1.0 - 0.1 * seed))
+
+    def forward(self, x):
+        mean = self.conv(x)
+        return mean.squeeze(), self.log_std.expand_as(mean).squeeze()
+
+
+def test_per_agent_policy_matches_ippo_evaluate():
+    """The stored log-probability is what IPPO.evaluate (IPPO.py:108-115) recomputes with the same actor for the stored
+    action, request by request, and every request went to its own agent's actor (also for a group of one)."""
+    from torch.distributions.normal import Normal
+    from multi_agent_rl_wrsn_b200.controllers import PerAgentPolicy
+    S, B = 12, 9
+    actors = [_TinyActor(s, S) for s in range(3)]
+    g = torch.Generator().manual_seed(5)
+    obs = torch.rand((B, 4, S, S), generator=g)
+    agent = torch.tensor([0, 2, 2, 0, 0, 2, 0, 1, 2], dtype=torch.int32)           # agent 1: a group of one
+    x, lp = PerAgentPolicy(actors, generator=g)(agent, obs)
+    assert x.shape == (B, S, S) and lp.shape == (B,)
+    for b in range(B):
+        with torch.no_grad():
+            mean, log_std = actors[int(agent[b])](obs[b:b + 1])
+        ref = Normal(mean, log_std.exp()).log_prob(x[b]).sum().detach()
+        assert abs(float(ref) - float(lp[b])) <= 1e-4 * max(1.0, abs(float(ref))), b
+        with torch.no_grad():
+            m2, ls2 = actors[(int(agent[b]) + 1) % 3](obs[b:b + 1])
+        other = Normal(m2, ls2.exp()).log_prob(x[b]).sum()
+        assert abs(float(other) - float(lp[b])) > 1e-3
+    with pytest.raises(ValueError):
+        PerAgentPolicy(actors[:2])(agent, obs)
