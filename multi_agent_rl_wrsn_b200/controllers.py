@@ -246,3 +246,76 @@ class PerAgentPolicy:
             x[idx] = a
             lp[idx] = logp
         return x, lp
+
+
+def allreduce_gradients(parameters, group=None):
+    """Average the gradients of ``parameters`` over the ranks of ``group`` with ONE all-reduce of a flat bucket (the
+    reference's actor + critic pair is 8.3 MB: a single NCCL launch over NVLink / NVSwitch per minibatch; gloo in the CPU
+    tests).  The only collective a trainer adds to the path — the simulation itself has none."""
+    dist = torch.distributed
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    grads = [p.grad for p in parameters if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat.div_(dist.get_world_size(group))
+    off = 0
+    for g in grads:
+        g.copy_(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()
+
+
+def ppo_update(actor, critic, optimizer, batch, args, group=None, generator=None):
+    """The update of one agent in ``IPPO.train`` (``controller/ippo/IPPO.py:222-268``; ``PPO.train`` is the same code):
+    ``n_updates_per_iteration`` passes over ``batch`` (tensors of ``batch_size`` rows: states, actions, log_probs,
+    advantages, returns, values) in shuffled minibatches, clipped surrogate + (clipped) value loss - entropy bonus,
+    gradient-norm clipping of actor and critic separately, one optimizer step per minibatch.  ``args`` is the
+    ``alg_args`` mapping of ``alg_args/ippo.yaml`` / ``ppo.yaml``.  With several ranks every rank passes its own shard's
+    batch and the gradients are averaged before the clipping (``allreduce_gradients``), so all replicas stay identical.
+    Returns the statistics the reference writes to TensorBoard (``:270-279``) for the last minibatch."""
+    n = batch["states"].shape[0]
+    mbs, clip = int(args["minibatch_size"]), float(args["clip"])
+    params = list(actor.parameters()) + list(critic.parameters())
+    clipfracs, stats = [], {}
+    for _ in range(int(args["n_updates_per_iteration"])):
+        b_inds = torch.randperm(n, generator=generator).to(batch["states"].device)      # np.random.shuffle(b_inds), :229
+        for start in range(0, n, mbs):
+            mb = b_inds[start:start + mbs]
+            m = mb.numel()
+            states, actions = batch["states"][mb].to(torch.float32), batch["actions"][mb]
+            mean, log_std = actor(states)                                               # IPPO.evaluate, :108-115
+            mean, log_std = mean.reshape(actions.shape), log_std.reshape(actions.shape)
+            dist_ = torch.distributions.Normal(mean, torch.exp(log_std))
+            red = tuple(range(1, actions.dim()))
+            newlogprob, entropy = dist_.log_prob(actions).sum(red), dist_.entropy().sum(red)
+            newvalue = critic(states).sum(1).view(-1)                                   # IPPO.get_value, :117-119
+            logratio = newlogprob - batch["log_probs"][mb]
+            ratio = logratio.exp()
+            with torch.no_grad():
+                old_approx_kl = (-logratio).mean()
+                approx_kl = ((ratio - 1) - logratio).mean()
+                clipfracs.append(((ratio - 1.0).abs() > clip).float().mean())
+            adv = batch["advantages"][mb]
+            if args["norm_adv"]:
+                adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+            pg_loss = torch.max(-adv * ratio, -adv * torch.clamp(ratio, 1 - clip, 1 + clip)).mean()
+            ret, val = batch["returns"][mb], batch["values"][mb]
+            if args["clip_vloss"]:
+                v_clipped = val + torch.clamp(newvalue - val, -clip, clip)
+                v_loss = 0.5 * torch.max((newvalue - ret) ** 2, (v_clipped - ret) ** 2).mean()
+            else:
+                v_loss = 0.5 * ((newvalue - ret) ** 2).mean()
+            entropy_loss = entropy.mean()
+            loss = pg_loss - float(args["ent_coef"]) * entropy_loss + v_loss * float(args["vf_coef"])
+            optimizer.zero_grad()
+            loss.backward()
+            allreduce_gradients(params, group)
+            torch.nn.utils.clip_grad_norm_(actor.parameters(), float(args["max_grad_norm"]))
+            torch.nn.utils.clip_grad_norm_(critic.parameters(), float(args["max_grad_norm"]))
+            optimizer.step()
+            stats = dict(loss=loss.detach(), value_loss=v_loss.detach(), policy_loss=pg_loss.detach(),
+                         entropy=entropy_loss.detach(), old_approx_kl=old_approx_kl, approx_kl=approx_kl, minibatch=m)
+    stats["clipfrac"] = torch.stack(clipfracs).mean() if clipfracs else None
+    return stats
