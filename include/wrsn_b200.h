@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define WRSN_ABI_VERSION 12
+#define WRSN_ABI_VERSION 13
 #define WRSN_MAX_MC 16          /* chargers per environment */
 #define WRSN_RING 10            /* Node.operate keeps the last 10 per-second consumptions (Node.py:70-77) */
 
@@ -215,6 +215,17 @@ int wrsn_observe(const wrsn_dims *d, const void *scen, const int32_t *scen_id, c
  * comment for what is reproduced exactly and what within tolerance). */
 int wrsn_decode_density_map(const wrsn_dims *d, const void *scen, const int32_t *scen_id, const void *state,
                             const int32_t *agent_id, const void *dmap, int dmap_f64, double *action_out, void *stream);
+/* The bookkeeping of the trainers' roll_out loop (controller/ippo/IPPO.py:138-155, controller/ppo/PPO.py likewise) for
+ * every environment after rollout step t, one thread per environment:
+ *   last[b][agent_prev[b]] = t                      log_probs_pre[agent] = log_prob            (:140)
+ *   episode ended (req->stats[b][2] != resets_seen[b], then resets_seen[b] = it):  last[b][:] = -1   (:137-138, :143-144)
+ *   agent_next[b] = max(req->agent_id[b], 0)        the request handed out for step t + 1
+ *   link_next[b]  = last[b][agent_next[b]]          step at which that agent last acted in this episode, -1: none (:145-146)
+ *   new_episode_next[b], reward_next[b] (NaN -> 0), now_next[b]
+ * `last` is int64 [B][M], the *_next pointers are row t + 1 of the caller's time-major record. */
+int wrsn_record_transitions(const wrsn_dims *d, const wrsn_request *req, int64_t t, const int64_t *agent_prev,
+                            int64_t *last, double *resets_seen, int64_t *agent_next, int64_t *link_next,
+                            uint8_t *new_episode_next, double *reward_next, double *now_next, void *stream);
 /* WRSN.get_network_fitness (:188-220): per-target values fitness[B][T] (may be NULL) and their minimum fit_min[B]. */
 int wrsn_fitness(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state,
                  double *fitness, double *fit_min, void *stream);

@@ -7,10 +7,12 @@ environments at once and nothing leaves HBM: the map is formed by torch from the
 loops do: ``controller/ippo/IPPO.py:137-143``).  Trainers (PPO / IPPO) plug in at the same place: anything with a
 ``make_action(agent_id, state)`` that returns either [B, S, S] maps or [B, 3] actions.
 """
+import ctypes as C
 import math
 
 import torch
 
+from . import _lib
 from .sharding import reduce_stats
 
 
@@ -88,6 +90,7 @@ class IPPORollout:
         self.action = torch.zeros((B, 3), dtype=torch.float64, device=dev)
         self.terminal_factor = None
         self._collected = False
+        self._resets = None
         if bool((env.req.agent_id == -3).all()):                          # never reset: start the first episodes
             env.reset()
         if bool((env.req.agent_id < 0).any()):
@@ -96,31 +99,28 @@ class IPPORollout:
             env.get_state(out=self.obs[0])
         self.agent[0] = env.req.agent_id.to(torch.int64)
         self.now[0] = env.req.now
+        self._resets = env.req.stats[:, 2].clone()                       # episodes begun so far, per environment
 
     def collect(self, policy):
         """T rollout steps.  Row t of the record is the request answered at step t; row T is the request left open
         (its observation starts the next ``collect`` after ``carry_over``)."""
-        env = self.env
+        env, L = self.env, self.env.L
         for t in range(self.T):
             a = self.agent[t]
             x, lp = policy(a.to(torch.int32), None if self.obs is None else self.obs[t])
             self.act[t].copy_(x)
             self.logp[t].copy_(lp)
-            self.last.scatter_(1, a[:, None], t)                          # log_probs_pre[agent] = log_prob (:140)
             if x.dim() == 3:                                              # WRSN.step :293-297 on the device
                 env.density_map_to_action(self.act[t], out=self.action)
             else:
                 self.action.copy_(x)
-            resets = env.req.stats[:, 2].clone()
             env.rollout_step(self.action, None if self.obs is None else self.obs[t + 1])
-            ended = env.req.stats[:, 2] != resets                         # terminal -> env.reset() (:137, :143)
-            self.last.masked_fill_(ended[:, None], -1)                    # log_probs_pre = [None] * num_agent (:138)
-            nxt = env.req.agent_id.to(torch.int64).clamp_min(0)           # < 0 only with flags bit0 (every charger dead)
-            self.agent[t + 1] = nxt
-            self.new_episode[t + 1] = ended
-            self.link[t + 1] = self.last.gather(1, nxt[:, None])[:, 0]    # -1: `continue` (:145-146)
-            self.reward[t + 1] = torch.nan_to_num(env.req.reward, nan=0.0)
-            self.now[t + 1] = env.req.now
+            # one launch for the loop's bookkeeping (:138-155): last[b, a] = t, cleared where the episode ended and was
+            # reset; row t + 1 = the next request's agent, its link (-1: `continue`), reward and time
+            _lib.check(L.wrsn_record_transitions(C.byref(env.dims), C.byref(env.req.c), t, a.data_ptr(), self.last.data_ptr(),
+                                                 self._resets.data_ptr(), self.agent[t + 1].data_ptr(),
+                                                 self.link[t + 1].data_ptr(), self.new_episode[t + 1].data_ptr(),
+                                                 self.reward[t + 1].data_ptr(), self.now[t + 1].data_ptr(), env._stream()), L)
         self._collected = True
         return self
 

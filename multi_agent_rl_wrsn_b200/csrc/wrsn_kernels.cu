@@ -634,6 +634,33 @@ static KParams base_params(const wrsn_dims *d, const void *scen, const int32_t *
     return P;
 }
 
+/* roll_out bookkeeping (IPPO.py:138-155): one thread per environment, see include/wrsn_b200.h */
+__global__ void k_record_transitions(int B, int M, wrsn_request req, long long t, const long long *__restrict__ agent_prev,
+                                     long long *__restrict__ last, double *__restrict__ resets_seen,
+                                     long long *__restrict__ agent_next, long long *__restrict__ link_next,
+                                     uint8_t *__restrict__ new_episode_next, double *__restrict__ reward_next,
+                                     double *__restrict__ now_next) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    long long *row = last + (size_t)b * M;
+    const long long ap = agent_prev[b];
+    if (ap >= 0 && ap < M) row[ap] = t;
+    const double resets = req.stats[(size_t)b * 3 + 2];
+    const bool ended = resets != resets_seen[b];
+    resets_seen[b] = resets;
+    if (ended)
+        for (int a = 0; a < M; a++) row[a] = -1;
+    int an = req.agent_id[b];
+    if (an < 0) an = 0;
+    if (an >= M) an = M - 1;
+    agent_next[b] = an;
+    link_next[b] = row[an];
+    new_episode_next[b] = ended ? 1 : 0;
+    const double r = req.reward[b];
+    reward_next[b] = (r == r) ? r : 0.0;
+    now_next[b] = req.now[b];
+}
+
 extern "C" {
 
 int wrsn_build_obs_tables(const wrsn_dims *d, void *scen, void *stream) {
@@ -696,6 +723,20 @@ int wrsn_rollout_step(const wrsn_dims *d, const void *scen, const int32_t *scen_
     R.req = *req; R.snap = (const char *)snap; R.mask_mode = 2;
     if (launch_env<MODE_RESTORE_RESET>(R, stream)) return -1;
     if (obs) return wrsn_observe(d, scen, scen_id, state, req->agent_id, obs, obs_f64, stream);
+    return 0;
+}
+
+int wrsn_record_transitions(const wrsn_dims *d, const wrsn_request *req, int64_t t, const int64_t *agent_prev,
+                            int64_t *last, double *resets_seen, int64_t *agent_next, int64_t *link_next,
+                            uint8_t *new_episode_next, double *reward_next, double *now_next, void *stream) {
+    if (!d || !req || !req->agent_id || !req->reward || !req->now || !req->stats) WRSN_FAIL("req / its agent_id, reward, now or stats is NULL");
+    if (!agent_prev || !last || !resets_seen || !agent_next || !link_next || !new_episode_next || !reward_next || !now_next)
+        WRSN_FAIL("a record pointer is NULL");
+    if (d->B <= 0 || d->M <= 0) WRSN_FAIL("bad dims");
+    k_record_transitions<<<(d->B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        d->B, d->M, *req, (long long)t, (const long long *)agent_prev, (long long *)last, resets_seen,
+        (long long *)agent_next, (long long *)link_next, new_episode_next, reward_next, now_next);
+    WRSN_CUDA(cudaGetLastError());
     return 0;
 }
 

@@ -133,6 +133,27 @@ int wrsn_rollout_step(const wrsn_dims *d, const void *scen, const int32_t *scen_
     Args R = {d, (const char *)scen, scen_id, (char *)state, (const char *)snap, nullptr, nullptr, nullptr, nullptr, req, nullptr, nullptr, 0, 2};
     return run_mode(MODE_RESTORE_RESET, R);
 }
+int wrsn_record_transitions(const wrsn_dims *d, const wrsn_request *req, int64_t t, const int64_t *agent_prev, int64_t *last,
+                            double *resets_seen, int64_t *agent_next, int64_t *link_next, uint8_t *new_episode_next,
+                            double *reward_next, double *now_next, void *) {
+    if (!d || !req || !agent_prev || !last || !resets_seen || !agent_next || !link_next || !new_episode_next || !reward_next || !now_next)
+        WRSN_FAIL("a record pointer is NULL");
+    const int M = d->M;
+    for (int b = 0; b < d->B; b++) {                    /* host restatement of k_record_transitions, row by row */
+        int64_t *row = last + (size_t)b * M;
+        if (agent_prev[b] >= 0 && agent_prev[b] < M) row[agent_prev[b]] = t;
+        const double resets = req->stats[(size_t)b * 3 + 2];
+        const bool ended = resets != resets_seen[b];
+        resets_seen[b] = resets;
+        if (ended) for (int a = 0; a < M; a++) row[a] = -1;
+        int an = req->agent_id[b] < 0 ? 0 : req->agent_id[b];
+        if (an >= M) an = M - 1;
+        agent_next[b] = an; link_next[b] = row[an]; new_episode_next[b] = ended ? 1 : 0;
+        reward_next[b] = req->reward[b] == req->reward[b] ? req->reward[b] : 0.0;
+        now_next[b] = req->now[b];
+    }
+    return 0;
+}
 int wrsn_fitness(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state, double *fit, double *fmin_, void *) {
     Args A = {d, (const char *)scen, scen_id, (char *)state, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, fit, fmin_, 0};
     return run_mode(MODE_FITNESS, A);

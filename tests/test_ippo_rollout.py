@@ -113,7 +113,7 @@ def test_per_agent_policy_matches_ippo_evaluate():
         assert abs(float(ref) - float(lp[b])) <= 1e-4 * max(1.0, abs(float(ref))), b
         with torch.no_grad():
             m2, ls2 = actors[(int(agent[b]) + 1) % 3](obs[b:b + 1])
-        other = Normal(m2, ls2.exp()).log_prob(x[b]).sum()
+        other = Normal(m2, ls2.exp()).log_prob(x[b]).sum().detach()
         assert abs(float(other) - float(lp[b])) > 1e-3
     with pytest.raises(ValueError):
         PerAgentPolicy(actors[:2])(agent, obs)
