@@ -38,6 +38,9 @@ def parse():
     p.add_argument("--targets", type=int, default=None)
     p.add_argument("--chargers", type=int, default=3)
     p.add_argument("--topologies", type=int, default=64, help="distinct synthetic scenarios per GPU")
+    p.add_argument("--scenario", default=None,
+                   help="a shipped scenario of the reference, replicated in every environment: name of a committed fixture "
+                        "that carries it (e.g. net_hanoi1000n100; the reference's YAML files do not travel to the GPU box)")
     p.add_argument("--threads", type=int, default=0)
     p.add_argument("--preroll", type=int, default=160, help="untimed steps before warm-up that desynchronise the episodes")
     p.add_argument("--groups", type=int, default=8, help="asynchronous environment groups (CUDA streams) per GPU")
@@ -49,11 +52,21 @@ def parse():
 
 
 def workload_name(a):
+    if a.scenario:
+        return "%s of the reference replicated, %d chargers, %d envs per GPU, uniform 3-vector actions" % (
+            a.scenario.replace("net_", ""), a.chargers, a.envs)
     return "%d-node/%d-charger synthetic WRSN, %d envs per GPU, uniform 3-vector actions" % (a.nodes, a.chargers, a.envs)
 
 
 def scenarios_for(a, rank):
-    from multi_agent_rl_wrsn_b200 import synthetic
+    from multi_agent_rl_wrsn_b200 import Scenario, synthetic
+    if a.scenario:                                   # the arrays of the reference's YAML as stored in the golden fixture
+        g = np.load(os.path.join(REPO, "tests", "golden", a.scenario + ".npz"), allow_pickle=False)
+        q = g["sc_par"]
+        spe = dict(capacity=q[0], threshold=q[1], com_range=q[2], sen_range=q[3], prob_gp=q[4], package_size=q[5],
+                   er=q[6], et=q[7], efs=q[8], emp=q[9])
+        return [Scenario(nodes=g["sc_nodes"].reshape(-1, 2), targets=g["sc_targets"].reshape(-1, 2),
+                         base_station=g["sc_bs"], node_phy_spe=spe, max_time=float(q[10]), name=a.scenario)]
     T = a.nodes if a.targets is None else a.targets
     return [synthetic(num_nodes=a.nodes, num_targets=T, seed=1000 + rank * a.topologies + k) for k in range(a.topologies)]
 
