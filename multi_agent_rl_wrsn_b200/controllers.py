@@ -182,7 +182,8 @@ class IPPORollout:
             for t in range(self.T, 0, -1):
                 if gae:                                                   # :77-82
                     cur = r[t] + gamma * nv[t] * tm[t] - v[t] + gamma * gae_lambda * tm[t] * carry
-                else:                                                     # :84-91 (t == len(rewards) never holds)
+                else:                                                     # :84-91; the reference indexes returns[len] at the last
+                                                                          # step of a list (IndexError): here the tail value is 0
                     cur = r[t] + gamma * tm[t] * carry
                 out[t] = torch.where(has[t], cur, out[t])
                 carry = torch.where(has[t], cur, carry)
