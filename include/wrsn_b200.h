@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define WRSN_ABI_VERSION 13
+#define WRSN_ABI_VERSION 14
 #define WRSN_MAX_MC 16          /* chargers per environment */
 #define WRSN_RING 10            /* Node.operate keeps the last 10 per-second consumptions (Node.py:70-77) */
 
@@ -235,6 +235,16 @@ int wrsn_k_bfs(const wrsn_dims *d, const void *scen, const int32_t *scen_id, voi
 int wrsn_k_drain(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state, void *stream);    /* Node.operate k+0.5 tick */
 int wrsn_k_bookkeep(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state, void *stream); /* Node.operate k+1.0 tick */
 int wrsn_k_reward(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state, void *stream);   /* WRSN.update_reward tick */
+/* The node x charger charging model, dense (Node.charger_connection Node.py:134-139 for the connected_nodes of
+ * MobileCharger.charge MobileCharger.py:56-59): for every environment, every charger m with charging[b][m] != 0 (all chargers
+ * when charging == NULL) at its position in the state record, and every ALIVE node n with d(n, m) <= charging_range,
+ *     rate = alpha / (d + beta) ** 2;   node_rate[b][n] += rate  (chargers in id order);   mc_rate[b][m] += rate  (nodes in id order)
+ * i.e. the energyRR every node would carry and the chargingRate every charger would draw if those chargers charged now.
+ * One warp per environment, charger positions staged in shared memory, per-charger sums by warp ballot / shuffle IN NODE
+ * ORDER (bit-exact with the reference's sequential +=).  The fused step kernel applies the same model incrementally (connect /
+ * disconnect events); this entry point is the standalone form for unit parity and profiling.  Does not modify the state. */
+int wrsn_k_charge(const wrsn_dims *d, const void *scen, const int32_t *scen_id, const void *state, const uint8_t *charging,
+                  double *node_rate /* [B][N] */, double *mc_rate /* [B][M] */, void *stream);
 
 #ifdef __cplusplus
 }

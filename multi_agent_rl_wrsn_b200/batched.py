@@ -261,6 +261,23 @@ class BatchedWRSN:
                                             self.state.data_ptr(), mp, C.byref(self.req.c), self._stream()), self.L)
         return self.req
 
+    def charge_rates(self, charging=None):
+        """The node x charger charging model, dense (``wrsn_k_charge``; ``Node.charger_connection`` ``Node.py:134-139`` over
+        the ``connected_nodes`` of ``MobileCharger.charge`` ``MobileCharger.py:56-59``): the ``energyRR`` every alive node
+        would receive [B, N] and the ``chargingRate`` every charger would draw [B, M] if the chargers selected by
+        ``charging`` (uint8 [B, M]; default all) charged at their present positions.  Does not touch the state."""
+        node = torch.zeros((self.B, self.N), dtype=torch.float64, device=self.device)
+        mc = torch.zeros((self.B, max(self.M, 1)), dtype=torch.float64, device=self.device)
+        ch, cp = None, None
+        if charging is not None:
+            ch = torch.as_tensor(charging, device=self.device).to(torch.uint8).contiguous()
+            if ch.shape != (self.B, self.M):
+                raise ValueError("charging must be [B, M]")
+            cp = C.c_void_p(ch.data_ptr())
+        _lib.check(self.L.wrsn_k_charge(C.byref(self.dims), self.scen.data_ptr(), self.scen_id.data_ptr(), self.state.data_ptr(),
+                                        cp, node.data_ptr(), mc.data_ptr(), self._stream()), self.L)
+        return node, mc[:, :self.M]
+
     def kernel(self, name):
         """Standalone per-tick kernels: 'bfs', 'drain', 'bookkeep', 'reward'."""
         fn = getattr(self.L, "wrsn_k_" + name)

@@ -634,6 +634,63 @@ static KParams base_params(const wrsn_dims *d, const void *scen, const int32_t *
     return P;
 }
 
+/* the charging model, dense: one warp per environment (see include/wrsn_b200.h: wrsn_k_charge) */
+#define CHG_WARPS 4
+__global__ void __launch_bounds__(32 * CHG_WARPS) k_charge(const KParams P, const uint8_t *__restrict__ charging,
+                                                           double *__restrict__ node_rate, double *__restrict__ mc_rate) {
+    __shared__ double s_mx[CHG_WARPS][WRSN_MAX_MC], s_my[CHG_WARPS][WRSN_MAX_MC], s_sum[CHG_WARPS][WRSN_MAX_MC];
+    __shared__ uint8_t s_on[CHG_WARPS][WRSN_MAX_MC];
+    const int wrp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * CHG_WARPS + wrp;
+    if (b >= P.d.B) return;                                   /* whole warps leave together; only __syncwarp below */
+    const int N = P.d.N, M = P.d.M;
+    const char *row = P.state + (size_t)b * P.L.total;
+    const char *scen_row = P.scen + (size_t)P.scen_id[b] * P.L.scen_total;
+    const double *par = (const double *)(scen_row + P.L.soff[WRSN_S_PAR]);
+    const double *nx = (const double *)(scen_row + P.L.soff[WRSN_S_NX]), *ny = (const double *)(scen_row + P.L.soff[WRSN_S_NY]);
+    const uint8_t *status = (const uint8_t *)(row + P.L.off[WRSN_F_STATUS]);
+    const double *mc = (const double *)(row + P.L.off[WRSN_F_MC]);
+    const double R = par[WRSN_P_MC_R], alpha = par[WRSN_P_MC_ALPHA], beta = par[WRSN_P_MC_BETA];
+    for (int m = lane; m < M; m += 32) {                      /* stage the chargers of this environment */
+        s_mx[wrp][m] = mc[(size_t)m * WRSN_MC_LEN + WRSN_MC_X];
+        s_my[wrp][m] = mc[(size_t)m * WRSN_MC_LEN + WRSN_MC_Y];
+        s_on[wrp][m] = charging ? charging[(size_t)b * M + m] : 1;
+        s_sum[wrp][m] = 0.0;
+    }
+    __syncwarp();
+    for (int base = 0; base < N; base += 32) {
+        const int n = base + lane;
+        const bool live = n < N && status[n] != 0;            /* charger_connection returns at once for a dead node */
+        const double x = live ? nx[n] : 0.0, y = live ? ny[n] : 0.0;
+        double acc = 0.0;                                     /* this node's energyRR: += in charger order */
+        for (int m = 0; m < M; m++) {
+            if (!s_on[wrp][m]) continue;                      /* warp-uniform */
+            double rate = 0.0;
+            bool in = false;
+            if (live) {
+                const double dx = x - s_mx[wrp][m], dy = y - s_my[wrp][m];
+                const double dist = sqrt(dx * dx + dy * dy);  /* scipy's euclidean: sqrt(dot(u - v, u - v)) */
+                in = dist <= R;
+                if (in) { const double t = dist + beta; rate = alpha / (t * t); acc = acc + rate; }
+            }
+            /* the charger's chargingRate: += over its connected nodes IN NODE ORDER — lane by lane through the ballot */
+            unsigned bits = __ballot_sync(0xffffffffu, in);
+            if (bits) {
+                double sum = s_sum[wrp][m];
+                for (unsigned rest = bits; rest; rest &= rest - 1u) {
+                    const double r = __shfl_sync(0xffffffffu, rate, __ffs(rest) - 1);
+                    sum = sum + r;
+                }
+                if (lane == 0) s_sum[wrp][m] = sum;
+                __syncwarp();
+            }
+        }
+        if (n < N) node_rate[(size_t)b * N + n] = acc;
+    }
+    __syncwarp();
+    for (int m = lane; m < M; m += 32) mc_rate[(size_t)b * M + m] = s_sum[wrp][m];
+}
+
 /* roll_out bookkeeping (IPPO.py:138-155): one thread per environment, see include/wrsn_b200.h */
 __global__ void k_record_transitions(int B, int M, wrsn_request req, long long t, const long long *__restrict__ agent_prev,
                                      long long *__restrict__ last, double *__restrict__ resets_seen,
@@ -778,6 +835,18 @@ int wrsn_decode_density_map(const wrsn_dims *d, const void *scen, const int32_t 
     if ((int64_t)d->S * d->S > (1 << 30)) WRSN_FAIL("map_size too large for the density-map decoder");
     if (dmap_f64) k_decode_map<double><<<d->B, DEC_THREADS, 0, (cudaStream_t)stream>>>(P, agent_id, (const double *)dmap, action_out);
     else k_decode_map<float><<<d->B, DEC_THREADS, 0, (cudaStream_t)stream>>>(P, agent_id, (const float *)dmap, action_out);
+    WRSN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int wrsn_k_charge(const wrsn_dims *d, const void *scen, const int32_t *scen_id, const void *state, const uint8_t *charging,
+                  double *node_rate, double *mc_rate, void *stream) {
+    if (check_dims(d)) return -1;
+    if (!scen || !scen_id || !state || !node_rate || !mc_rate) WRSN_FAIL("NULL argument");
+    if (d->M <= 0) WRSN_FAIL("no chargers");
+    KParams P = base_params(d, scen, scen_id, const_cast<void *>(state), nullptr);
+    wrsn_make_layout(&P.d, &P.L);
+    k_charge<<<(d->B + CHG_WARPS - 1) / CHG_WARPS, 32 * CHG_WARPS, 0, (cudaStream_t)stream>>>(P, charging, node_rate, mc_rate);
     WRSN_CUDA(cudaGetLastError());
     return 0;
 }

@@ -208,3 +208,35 @@ class OracleWRSN:
         self.L.orc_get_static(self.h, _ip(nbr_ptr), _ip(nbr_idx), _ip(tgt_ptr), _ip(tgt_idx), _ip(direct))
         return dict(nbr_ptr=nbr_ptr, nbr_idx=nbr_idx[:ne], tgt_ptr=tgt_ptr, tgt_idx=tgt_idx[:tgt_ptr[-1]],
                     direct=direct)
+
+
+def charge_rates_reference(nodes, status, mc_xy, charging, charging_range, alpha, beta):
+    """TEST INFRASTRUCTURE.  The reference's charging model written out with its own statements: for every charger m
+    (``charging[m]``) the ``connected_nodes`` of ``MobileCharger.charge`` (``physical_env/mc/MobileCharger.py:56-59``:
+    ``euclidean(node.location, self.location) <= self.chargingRange``, nodes in list order) each run
+    ``Node.charger_connection`` (``physical_env/network/Node.py:134-139``: nothing for a dead node, else
+    ``tmp = mc.alpha / (euclidean(...) + mc.beta) ** 2; self.energyRR += tmp; mc.chargingRate += tmp``).
+    Returns (energyRR per node, chargingRate per charger) as float64 arrays."""
+    import math
+    import numpy as np
+    nodes = np.asarray(nodes, np.float64)
+    rr = np.zeros(len(nodes), np.float64)
+    cr = np.zeros(len(mc_xy), np.float64)
+    for m, loc in enumerate(np.asarray(mc_xy, np.float64)):
+        if not charging[m]:
+            continue
+        for n in range(len(nodes)):
+            # scipy.spatial.distance.euclidean for 2-vectors = sqrt(dot(u, u)); written with Python floats so that the two
+            # products and the sum are rounded separately on every host (a BLAS dot may fuse them: last-ulp, host-dependent,
+            # SURVEY 8c) — the form the engine and the C oracle use
+            ux, uy = float(nodes[n][0]) - float(loc[0]), float(nodes[n][1]) - float(loc[1])
+            d = math.sqrt(ux * ux + uy * uy)
+            if not d <= charging_range:
+                continue
+            if status[n] == 0:
+                continue
+            t = d + beta
+            tmp = alpha / (t * t)                     # DESIGN §5: (d + beta) ** 2 as a product (libm pow differs by 1 ulp in 0.085 %)
+            rr[n] += tmp
+            cr[m] += tmp
+    return rr, cr

@@ -164,6 +164,35 @@ int wrsn_observe(const wrsn_dims *, const void *, const int32_t *, const void *,
 int wrsn_decode_density_map(const wrsn_dims *, const void *, const int32_t *, const void *, const int32_t *, const void *, int, double *, void *) {
     WRSN_FAIL("wrsn_decode_density_map is not available in the host emulation");
 }
+int wrsn_k_charge(const wrsn_dims *d, const void *scen, const int32_t *scen_id, const void *state, const uint8_t *charging,
+                  double *node_rate, double *mc_rate, void *) {
+    if (!d || !scen || !scen_id || !state || !node_rate || !mc_rate) WRSN_FAIL("NULL argument");
+    if (d->M <= 0) WRSN_FAIL("no chargers");
+    WrsnLayout L; wrsn_make_layout(d, &L);
+    for (int b = 0; b < d->B; b++) {                     /* host restatement of k_charge: the reference's loops, literally */
+        const char *row = (const char *)state + (size_t)b * L.total;
+        const char *scen_row = (const char *)scen + (size_t)scen_id[b] * L.scen_total;
+        const double *par = (const double *)(scen_row + L.soff[WRSN_S_PAR]);
+        const double *nx = (const double *)(scen_row + L.soff[WRSN_S_NX]), *ny = (const double *)(scen_row + L.soff[WRSN_S_NY]);
+        const uint8_t *status = (const uint8_t *)(row + L.off[WRSN_F_STATUS]);
+        const double *mc = (const double *)(row + L.off[WRSN_F_MC]);
+        for (int n = 0; n < d->N; n++) node_rate[(size_t)b * d->N + n] = 0.0;
+        for (int m = 0; m < d->M; m++) {
+            double sum = 0.0;
+            if (!charging || charging[(size_t)b * d->M + m])
+                for (int n = 0; n < d->N; n++) {
+                    if (status[n] == 0) continue;
+                    const double dist = euclid2(nx[n], ny[n], mc[(size_t)m * WRSN_MC_LEN + WRSN_MC_X], mc[(size_t)m * WRSN_MC_LEN + WRSN_MC_Y]);
+                    if (!(dist <= par[WRSN_P_MC_R])) continue;
+                    const double t = dist + par[WRSN_P_MC_BETA], rate = par[WRSN_P_MC_ALPHA] / (t * t);
+                    node_rate[(size_t)b * d->N + n] += rate;
+                    sum += rate;
+                }
+            mc_rate[(size_t)b * d->M + m] = sum;
+        }
+    }
+    return 0;
+}
 #define EMU_K(NAME, MODE) int NAME(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state, void *) { \
     Args A = {d, (const char *)scen, scen_id, (char *)state, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0}; return run_mode(MODE, A); }
 EMU_K(wrsn_k_bfs, MODE_K_BFS)

@@ -411,3 +411,48 @@ def check_ippo_rollout(scenarios, device, num_envs, steps, gamma=0.99, lam=0.95,
                 assert np.allclose(advantages[sel].cpu().numpy(), np.array(rec[i]["adv"]), rtol=1e-4, atol=1e-6), (b, i)
                 assert np.allclose(returns[sel].cpu().numpy(), np.array(rec[i]["ret"]), rtol=1e-4, atol=1e-6), (b, i)
     return n_tr, episodes
+
+
+def check_charge_kernel(scenarios, device, num_envs, steps, seed, num_agent=3):
+    """wrsn_k_charge (dense node x charger charging model, one warp per environment) == the reference's statements
+    (oracle.wrsn_oracle.charge_rates_reference), bit for bit, on states reached by a rollout whose actions send the chargers to
+    node positions (several nodes within range), with all chargers and with a random subset selected."""
+    from oracle.wrsn_oracle import charge_rates_reference
+    env = BatchedWRSN(scenarios, num_agent=num_agent, num_envs=num_envs, device=device)
+    sid = _np(env.scen_id)
+    rng = np.random.default_rng(seed)
+    env.reset()
+    n_pairs = n_exact = n_rows = 0
+    for k in range(steps):
+        act = np.zeros((num_envs, 3))
+        for b in range(num_envs):
+            st = env.statics[sid[b]]
+            par, sc = st["par"], env.scenarios[sid[b]]
+            n = rng.integers(sc.N)
+            xy = sc.nodes[n] + rng.normal(0.0, 8.0, 2)                      # a few metres off a node
+            act[b, 0] = np.clip((xy[0] - par["F0"]) / (par["F1"] - par["F0"]), 0, 1)
+            act[b, 1] = np.clip((xy[1] - par["F2"]) / (par["F3"] - par["F2"]), 0, 1)
+            act[b, 2] = rng.uniform(0, 0.02)
+        env.rollout_step(torch.as_tensor(act, device=env.device))
+        if k % 3:
+            continue
+        for sel in (None, rng.integers(0, 2, size=(num_envs, num_agent)).astype(np.uint8)):
+            node_rate, mc_rate = env.charge_rates(None if sel is None else torch.as_tensor(sel, device=env.device))
+            node_rate, mc_rate = _np(node_rate), _np(mc_rate)
+            status, mx, my = _np(env.view("status")), _np(env.mc("X")), _np(env.mc("Y"))
+            for b in range(num_envs):
+                mcp = env.mc_type
+                rr, cr = charge_rates_reference(env.scenarios[sid[b]].nodes, status[b], np.stack([mx[b], my[b]], 1),
+                                                np.ones(num_agent) if sel is None else sel[b],
+                                                mcp["charging_range"], mcp["alpha"], mcp["beta"])
+                # same connected sets; rates to the last bits (1e-14: a host whose libm / BLAS rounds differently must not fail
+                # the run, a wrong model would be off by orders of magnitude); exact matches are counted and reported
+                assert np.array_equal(node_rate[b] != 0, rr != 0), (k, b)
+                assert np.array_equal(mc_rate[b] != 0, cr != 0), (k, b)
+                np.testing.assert_allclose(node_rate[b], rr, rtol=1e-14, atol=0, err_msg=str((k, b)))
+                np.testing.assert_allclose(mc_rate[b], cr, rtol=1e-14, atol=0, err_msg=str((k, b)))
+                n_pairs += int((rr != 0).sum())
+                n_exact += int(np.array_equal(node_rate[b], rr) and np.array_equal(mc_rate[b], cr))
+                n_rows += 1
+    print("charge kernel: %d connected pairs, %d / %d rows bit-identical" % (n_pairs, n_exact, n_rows))
+    return n_pairs

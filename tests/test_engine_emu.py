@@ -111,3 +111,9 @@ def test_large_configs_vs_oracle(nodes, targets, chargers, envs, steps):
     sc = synthetic(num_nodes=nodes, num_targets=targets, seed=nodes, num_gateways=max(3, nodes // 40))
     n_dec, cnt = pc.check_vs_oracle(sc, "cpu", num_envs=envs, steps=steps, seed=4, num_agent=chargers)
     assert n_dec >= envs * 15
+
+
+def test_charge_kernel_restatement_vs_reference_statements():
+    """The emulation's wrsn_k_charge (host restatement) and the harness of the GPU test against the reference's statements."""
+    scs = [synthetic(num_nodes=100, num_targets=100, seed=1000 + s) for s in range(2)]
+    assert pc.check_charge_kernel(scs, "cpu", num_envs=4, steps=30, seed=2) > 20

@@ -161,3 +161,12 @@ def test_large_configs_vs_oracle(nodes, targets, chargers, envs, steps):
     sc = synthetic(num_nodes=nodes, num_targets=targets, seed=nodes, num_gateways=max(3, nodes // 40))
     n_dec, cnt = pc.check_vs_oracle(sc, DEV, num_envs=envs, steps=steps, seed=4, num_agent=chargers, check_obs=(nodes == 500))
     assert n_dec >= envs * 15
+
+
+def test_charge_kernel_vs_reference_statements():
+    """wrsn_k_charge: warp per environment, chargers staged in shared memory, per-charger sums in node order through ballot /
+    shuffle — bit-exact with Node.charger_connection over MobileCharger.charge's connected nodes."""
+    scs = [synthetic(num_nodes=100, num_targets=100, seed=1000 + s) for s in range(3)]
+    assert pc.check_charge_kernel(scs, DEV, num_envs=9, steps=40, seed=2) > 50
+    scs = [synthetic(num_nodes=300, num_targets=300, seed=40, num_gateways=5)]
+    assert pc.check_charge_kernel(scs, DEV, num_envs=3, steps=20, seed=3, num_agent=5) > 10
