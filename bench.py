@@ -355,6 +355,39 @@ def run_b200(a):
     dec_bytes = Bg * (S * S * 4 + 24)
     del maps
 
+    # ---- the dense charging kernel (wrsn_k_charge): not launched by the rollout (the step kernel applies the same
+    # model incrementally), timed alone like the decoder; a failure here only drops the figure
+    chg = None
+    try:
+        import ctypes as C
+        from multi_agent_rl_wrsn_b200 import _lib
+        node_rate = torch.zeros((Bg, N), dtype=torch.float64, device=dev)
+        mc_rate = torch.zeros((Bg, M), dtype=torch.float64, device=dev)
+
+        def charge_launch(env):
+            _lib.check(env.L.wrsn_k_charge(C.byref(env.dims), env.scen.data_ptr(), env.scen_id.data_ptr(), env.state.data_ptr(),
+                                           None, node_rate.data_ptr(), mc_rate.data_ptr(), env._stream()), env.L)
+
+        for g in range(G):
+            charge_launch(groups[g])
+        n_chg = 6 * G
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        torch.cuda._sleep(int(2e7))
+        c0.record()
+        for k in range(n_chg):
+            charge_launch(groups[k % G])
+        c1.record()
+        sync_all()
+        chg_ms = c0.elapsed_time(c1) / n_chg
+        chg_bytes = Bg * (17 * N + 8 * N + 8 * M)
+        chg = dict(ms_per_launch=chg_ms, algorithmic_bytes=chg_bytes, gbs=chg_bytes / (chg_ms * 1e-3) / 1e9, share=0.0,
+                   note="dense node x charger charging model, standalone (unit parity / profiling); not launched by the "
+                        "rollout, which applies the model incrementally inside the step kernel")
+        del node_rate, mc_rate
+    except Exception as ex:                              # noqa: BLE001 - diagnostic figure only
+        chg = dict(error=str(ex)[:200])
+
     # ---- the reference's RandomController (controller/random/RandomController.py:12: map = s0 + s1 - 10 s2 + s3) as the
     # action source: torch forms the map from the observation in HBM, the decoder turns it into the action, rollout_step
     # consumes it.  A short device-timed run, reported beside the headline (which feeds 3-vector actions).
@@ -509,7 +542,8 @@ def run_b200(a):
                                                            gbs=dec_bytes / (dec_ms * 1e-3) / 1e9,
                                                            frac=dec_bytes / (dec_ms * 1e-3) / 1e9 / peak,
                                                            share=0.0, note="not launched by the headline workload (3-vector actions); "
-                                                                           "timed alone on maps larger than L2")}),
+                                                                           "timed alone on maps larger than L2"),
+                               "k_charge": chg}),
     )
     if world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = {k: v for k, v in cpu_baseline(a, 1, a.cpu_seconds).items() if k != "wall_s"}
