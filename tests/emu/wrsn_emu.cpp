@@ -5,7 +5,8 @@
  * `-m "not gpu"` tests can check the engine's event ordering and arithmetic against the oracle on a box
  * without a GPU.  It is built only by tests/ (tests/emu/Makefile), exports the C ABI of
  * include/wrsn_b200.h, and is never loaded by the product package, which has no CPU path.
- * wrsn_observe is not emulated (the raster kernel is checked on the GPU).
+ * wrsn_observe is a plain host restatement of the fp64 parity raster (the raster kernels themselves are checked on the GPU);
+ * wrsn_decode_density_map is not emulated.
  */
 #define WRSN_HOST_EMU 1
 #include <stdio.h>
@@ -126,12 +127,12 @@ int wrsn_step(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void
     return run_mode(MODE_STEP, A);
 }
 int wrsn_rollout_step(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state, const void *snap,
-                      const double *act, wrsn_request *req, void *obs, int, void *) {
-    if (obs) WRSN_FAIL("wrsn_observe is not available in the host emulation");
+                      const double *act, wrsn_request *req, void *obs, int obs_f64, void *) {
     Args A = {d, (const char *)scen, scen_id, (char *)state, nullptr, nullptr, nullptr, req->agent_id, act, req, nullptr, nullptr, 0, 1};
     if (run_mode(MODE_STEP, A)) return -1;
     Args R = {d, (const char *)scen, scen_id, (char *)state, (const char *)snap, nullptr, nullptr, nullptr, nullptr, req, nullptr, nullptr, 0, 2};
-    return run_mode(MODE_RESTORE_RESET, R);
+    if (run_mode(MODE_RESTORE_RESET, R)) return -1;
+    return obs ? wrsn_observe(d, scen, scen_id, state, req->agent_id, obs, obs_f64, nullptr) : 0;
 }
 int wrsn_record_transitions(const wrsn_dims *d, const wrsn_request *req, int64_t t, const int64_t *agent_prev, int64_t *last,
                             double *resets_seen, int64_t *agent_next, int64_t *link_next, uint8_t *new_episode_next,
@@ -158,8 +159,78 @@ int wrsn_fitness(const wrsn_dims *d, const void *scen, const int32_t *scen_id, v
     Args A = {d, (const char *)scen, scen_id, (char *)state, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, fit, fmin_, 0};
     return run_mode(MODE_FITNESS, A);
 }
-int wrsn_observe(const wrsn_dims *, const void *, const int32_t *, const void *, const int32_t *, void *, int, void *) {
-    WRSN_FAIL("wrsn_observe is not available in the host emulation");
+/* WRSN.get_state (rl_env/WRSN.py:130-186), host restatement of the fp64 parity raster k_observe<double> (same source order,
+ * same rounding: (w * gx) * gy added term by term; channel 4 as ((gx * gy) * w) / moving_time_max).  float output = the fp64
+ * map rounded once (the GPU's fp32 raster accumulates in fp32: equal to ~1e-6 of the channel maximum, not bit for bit). */
+static void emu_add_source(std::vector<double> &out, int S, double x0, double y0, double hx, double hy, double w, int mode, double mtm) {
+    const double unit = 1.0 / (double)S, start = unit / 2.0, delta = (start + unit) - start;
+    const double dnx = -2.0 * (hx * hx), dny = -2.0 * (hy * hy);
+    std::vector<double> gx(S), gy(S);
+    for (int i = 0; i < S; i++) {
+        const double cc = start + (double)i * delta, ux = cc - x0, uy = cc - y0;
+        const double ax = ux * ux / dnx, ay = uy * uy / dny;
+        gx[i] = ax > -745.2 ? exp(ax) : 0.0;
+        gy[i] = ay > -745.2 ? exp(ay) : 0.0;
+    }
+    for (int i = 0; i < S; i++)
+        for (int j = 0; j < S; j++) {
+            double &o = out[(size_t)i * S + j];
+            if (mode == 0) { const double a = w * gx[i]; o = o + a * gy[j]; }
+            else o = o + gx[i] * gy[j] * w / mtm;
+        }
+}
+int wrsn_observe(const wrsn_dims *d, const void *scen, const int32_t *scen_id, const void *state, const int32_t *agent_id,
+                 void *obs, int obs_f64, void *) {
+    if (!d || !scen || !scen_id || !state || !agent_id || !obs) WRSN_FAIL("NULL argument");
+    WrsnLayout L; wrsn_make_layout(d, &L);
+    const int S = d->S, N = d->N, M = d->M;
+    const size_t SS = (size_t)S * S;
+    for (int b = 0; b < d->B; b++) {
+        const int ag = agent_id[b];
+        if (ag < 0) continue;
+        const char *row = (const char *)state + (size_t)b * L.total;
+        const char *scen_row = (const char *)scen + (size_t)scen_id[b] * L.scen_total;
+        const double *par = (const double *)(scen_row + L.soff[WRSN_S_PAR]);
+        const double *nx = (const double *)(scen_row + L.soff[WRSN_S_NX]), *ny = (const double *)(scen_row + L.soff[WRSN_S_NY]);
+        const double *energy = (const double *)(row + L.off[WRSN_F_ENERGY]), *cs = (const double *)(row + L.off[WRSN_F_CS]);
+        const uint8_t *status = (const uint8_t *)(row + L.off[WRSN_F_STATUS]);
+        const double *mc = (const double *)(row + L.off[WRSN_F_MC]);
+        const double f0 = par[WRSN_P_F0], f1 = par[WRSN_P_F1], f2 = par[WRSN_P_F2], f3 = par[WRSN_P_F3];
+        const double Wd = f1 - f0, Hd = f3 - f2, R = par[WRSN_P_MC_R], mtm = par[WRSN_P_MTM];
+        const double *me = mc + (size_t)ag * WRSN_MC_LEN;
+        for (int ch = 0; ch < 4; ch++) {
+            std::vector<double> out(SS, 0.0);
+            if (ch == 0) {
+                for (int s = 0; s < N; s++) {
+                    if (status[s] == 0) continue;
+                    const double w = (cs[s] / par[WRSN_P_MC_AB2]) / ((energy[s] - par[WRSN_P_THR]) / par[WRSN_P_CAPMTHR]);
+                    if (w == 0.0) continue;
+                    emu_add_source(out, S, (nx[s] - f0) / Wd, (ny[s] - f2) / Hd, R / Wd, R / Hd, w, 0, mtm);
+                }
+            } else if (ch == 1) {
+                const double tmp = fmin(Hd, Wd);
+                emu_add_source(out, S, (me[WRSN_MC_X] - f0) / Wd, (me[WRSN_MC_Y] - f2) / Hd, 0.5 * tmp / Wd, 0.5 * tmp / Hd,
+                               me[WRSN_MC_ENERGY] / par[WRSN_P_MC_CAP], 0, mtm);
+            } else {
+                for (int s = 0; s < M; s++) {
+                    const double *an = mc + (size_t)s * WRSN_MC_LEN;
+                    const bool charging = an[WRSN_MC_TYPE] != 0.0;
+                    if (s == ag || (ch == 2 ? !charging : charging)) continue;
+                    const double x0 = (an[WRSN_MC_CPA0] - f0) / Wd, y0 = (an[WRSN_MC_CPA1] - f2) / Hd;
+                    if (ch == 2) emu_add_source(out, S, x0, y0, R / Wd, R / Hd, an[WRSN_MC_CPA2] / par[WRSN_P_CTM], 0, mtm);
+                    else {                               /* the observer's destination y */
+                        const double dx = an[WRSN_MC_X] - an[WRSN_MC_CPA0], dy = an[WRSN_MC_Y] - me[WRSN_MC_CPA1];
+                        emu_add_source(out, S, x0, y0, R / Wd, R / Hd, sqrt(dx * dx + dy * dy) / par[WRSN_P_MC_V], 1, mtm);
+                    }
+                }
+            }
+            for (size_t k = 0; k < SS; k++) {
+                if (obs_f64) ((double *)obs)[((size_t)b * 4 + ch) * SS + k] = out[k];
+                else ((float *)obs)[((size_t)b * 4 + ch) * SS + k] = (float)out[k];
+            }
+        }
+    }
+    return 0;
 }
 int wrsn_decode_density_map(const wrsn_dims *, const void *, const int32_t *, const void *, const int32_t *, const void *, int, double *, void *) {
     WRSN_FAIL("wrsn_decode_density_map is not available in the host emulation");

@@ -117,3 +117,10 @@ def test_charge_kernel_restatement_vs_reference_statements():
     """The emulation's wrsn_k_charge (host restatement) and the harness of the GPU test against the reference's statements."""
     scs = [synthetic(num_nodes=100, num_targets=100, seed=1000 + s) for s in range(2)]
     assert pc.check_charge_kernel(scs, "cpu", num_envs=4, steps=30, seed=2) > 20
+
+
+@pytest.mark.parametrize("name", ["ep_basic_n50", "ep_map32_n50", "ep_two_mc_sonla"])
+def test_emulated_raster_vs_reference_observations(name):
+    """The emulation's host raster (what lets the CPU tests of the trainers' loop see observations) against the reference's
+    golden get_state maps; the CUDA rasters are checked against the same fixtures in tests/test_gpu_parity.py."""
+    pc.check_episode(name, "cpu", check_obs=True)

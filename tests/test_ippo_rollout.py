@@ -34,6 +34,12 @@ def test_ippo_rollout_equals_reference_loop_emu(emu_library):
     assert n_tr > 200 and episodes >= 2
 
 
+def test_ippo_rollout_with_observations_emu(emu_library):
+    """The same with the observation record (prev_state / state of every transition) and a critic that looks at the maps."""
+    n_tr, episodes = pc.check_ippo_rollout(_scenarios(), "cpu", num_envs=3, steps=40, with_obs=True)
+    assert n_tr > 80
+
+
 def test_windows_carry_over(emu_library):
     """A record is reused window after window: carry_over on a fresh record changes nothing; after a window it starts from
     the open requests and drops the links into the finished window."""
