@@ -146,17 +146,21 @@ class IPPORollout:
         t = t + 1
         return t, b, self.link[t, b]
 
-    def batch(self, agent_id):
-        """The lists ``roll_out`` builds for one agent, as tensors (``:148-153``)."""
+    def batch(self, agent_id, states=True, next_states=True):
+        """The lists ``roll_out`` builds for one agent, as tensors (``:148-153``).  ``states`` / ``next_states`` = False leaves
+        the (large) observation gathers out; ``tp`` / ``t`` / ``b`` index them in ``self.obs`` (``obs[tp, b]``, ``obs[t, b]``)."""
         t, b, tp = self.transitions(agent_id)
         out = dict(actions=self.act[tp, b], log_probs=self.logp[tp, b], rewards=self.reward[t, b].to(torch.float32),
-                   terminals=torch.zeros(t.shape, dtype=torch.float32, device=t.device), t=t, b=b,
+                   terminals=torch.zeros(t.shape, dtype=torch.float32, device=t.device), t=t, b=b, tp=tp,
                    prev_time=self.now[tp, b], time=self.now[t, b])
-        if self.obs is not None:
-            out.update(states=self.obs[tp, b], next_states=self.obs[t, b])
+        if self.obs is not None and states:
+            out["states"] = self.obs[tp, b]
+        if self.obs is not None and next_states:
+            out["next_states"] = self.obs[t, b]
         return out
 
-    def cal_rt_adv(self, agent_id, value_fn, gamma, gae_lambda, gae=True, chunk=4096, values=None, next_values=None):
+    def cal_rt_adv(self, agent_id, value_fn, gamma, gae_lambda, gae=True, chunk=4096, values=None, next_values=None,
+                   keep_states=True):
         """``IPPO.cal_rt_adv`` (``:71-94``) for every (environment, episode) sequence of ``agent_id`` at once.
 
         The reference evaluates the critic on an episode's states / next states and runs the recursion backwards over
@@ -166,12 +170,13 @@ class IPPORollout:
         one carry per environment, cleared where an episode begins.  ``values`` / ``next_values`` (one per transition of
         ``batch(agent_id)``) replace the critic calls when given.
         """
-        bt = self.batch(agent_id)
+        bt = self.batch(agent_id, states=keep_states, next_states=False)
         n = bt["rewards"].shape[0]
         with torch.no_grad():
-            if values is None:
-                values = torch.cat([value_fn(bt["states"][i:i + chunk]) for i in range(0, n, chunk)]) if n else bt["rewards"]
-                next_values = torch.cat([value_fn(bt["next_states"][i:i + chunk]) for i in range(0, n, chunk)]) if n else bt["rewards"]
+            if values is None:                       # the critic on states / next states, gathered chunk by chunk from the record
+                ev = lambda tt: (torch.cat([value_fn(self.obs[tt[i:i + chunk], bt["b"][i:i + chunk]]) for i in range(0, n, chunk)])
+                                 if n else bt["rewards"])
+                values, next_values = ev(bt["tp"]), ev(bt["t"])
             term = bt["terminals"] if self.terminal_factor is None else torch.full_like(bt["terminals"], self.terminal_factor)
             B, dev = self.env.B, values.device
             grid = lambda v: torch.zeros((self.T + 1, B), dtype=torch.float32, device=dev).index_put_((bt["t"], bt["b"]), v)
@@ -219,8 +224,11 @@ class PerAgentPolicy:
     ``controller/ppo/PPO.py``) is ``PerAgentPolicy([actor] * num_agent)``.  One host synchronisation per call: the sizes
     of the groups."""
 
-    def __init__(self, actors, generator=None):
+    def __init__(self, actors, generator=None, action_shape=None):
+        """``action_shape``: shape of one action — default the S x S density map of the reference's actors; ``(3,)`` for
+        actors that emit the 3-vector action directly (``density_map=False``)."""
         self.actors, self.generator = list(actors), generator
+        self.action_shape = None if action_shape is None else tuple(action_shape)
 
     @torch.no_grad()
     def __call__(self, agent_id, obs):
@@ -231,7 +239,9 @@ class PerAgentPolicy:
         counts = torch.bincount(ids, minlength=M).tolist()
         if len(counts) > M:
             raise ValueError("request for agent %d but only %d actors" % (len(counts) - 1, M))
-        x = torch.empty((B, S, S), dtype=torch.float32, device=obs.device)
+        shape = (S, S) if self.action_shape is None else self.action_shape
+        red = tuple(range(1, 1 + len(shape)))
+        x = torch.empty((B,) + shape, dtype=torch.float32, device=obs.device)
         lp = torch.empty((B,), dtype=torch.float32, device=obs.device)
         lo = 0
         for i, n in enumerate(counts):
@@ -240,10 +250,10 @@ class PerAgentPolicy:
             idx = order[lo:lo + n]
             lo += n
             mean, log_std = self.actors[i](obs[idx].to(torch.float32))
-            mean, log_std = mean.reshape(n, S, S), log_std.reshape(n, S, S)   # UNet.forward squeezes a batch of one away
+            mean, log_std = mean.reshape((n,) + shape), log_std.reshape((n,) + shape)   # UNet.forward squeezes a batch of one away
             std = log_std.exp()
             a = mean + std * torch.randn(mean.shape, generator=self.generator, device=mean.device, dtype=mean.dtype)
-            logp = (-((a - mean) ** 2) / (2.0 * std * std) - log_std - 0.5 * math.log(2.0 * math.pi)).sum((1, 2))   # Normal.log_prob
+            logp = (-((a - mean) ** 2) / (2.0 * std * std) - log_std - 0.5 * math.log(2.0 * math.pi)).sum(red)   # Normal.log_prob
             x[idx] = a
             lp[idx] = logp
         return x, lp

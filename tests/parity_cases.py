@@ -402,7 +402,8 @@ def check_ippo_rollout(scenarios, device, num_envs, steps, gamma=0.99, lam=0.95,
                 g = lambda k: bt[k][sel].cpu().numpy()
                 if with_obs:
                     assert np.allclose(g("states"), np.array(rec[i]["states"]), rtol=1e-9, atol=1e-12), (b, i)
-                    assert np.allclose(g("next_states"), np.array(rec[i]["next_states"]), rtol=1e-9, atol=1e-12), (b, i)
+                    nxt = ro.obs[bt["t"][sel], bt["b"][sel]].cpu().numpy()           # cal_rt_adv's batch leaves the next states in the record
+                    assert np.allclose(nxt, np.array(rec[i]["next_states"]), rtol=1e-9, atol=1e-12), (b, i)
                 assert np.array_equal(g("prev_time"), np.array(rec[i]["prev_time"])), (b, i)
                 assert np.array_equal(g("time"), np.array(rec[i]["time"])), (b, i)
                 assert np.allclose(g("actions"), np.array(rec[i]["actions"]), rtol=0, atol=1e-7), (b, i)

@@ -1,0 +1,88 @@
+"""BatchedIPPO (the reference's IPPO trainer on a BatchedWRSN) on CPU through the host emulation:
+an iteration runs end to end, the checkpoint files have the reference's layout (controller/ippo/IPPO.py:296-309) and a
+trainer restarted from them (IPPO.py:50-64) continues its counters.  Actors emit 3-vector actions here (the emulation has
+no density-map decoder); the map path is the same code with action_shape=None and is exercised on the GPU."""
+import csv
+import os
+import subprocess
+
+import pytest
+import torch
+
+from multi_agent_rl_wrsn_b200 import BatchedIPPO, BatchedWRSN, _lib, synthetic
+from tests.helpers import REPO
+
+EMU_DIR = os.path.join(REPO, "tests", "emu")
+S = 16
+ARGS = dict(seed=0, lr=3.0e-4, gamma=0.99, clip=0.2, batch_size=24, n_updates_per_iteration=2, save_freq=1, gae=True,
+            norm_adv=True, minibatch_size=8, ent_coef=0.0, vf_coef=0.5, gae_lambda=0.95, max_grad_norm=0.5, clip_vloss=True)
+
+
+@pytest.fixture()
+def emu_library():
+    subprocess.check_call(["make", "-C", EMU_DIR, "libwrsn_emu.so"], stdout=subprocess.DEVNULL)
+    prev = _lib._lib
+    _lib.use_library(os.path.join(EMU_DIR, "libwrsn_emu.so"))
+    yield
+    _lib._lib = prev
+
+
+class Actor(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.fc = torch.nn.Linear(4 * S * S, 3)
+        self.log_std = torch.nn.Parameter(torch.full((1, 3), -2.0))
+
+    def forward(self, x):
+        mean = torch.sigmoid(self.fc(x.flatten(1))) * torch.tensor([1.0, 1.0, 0.05])
+        return mean, self.log_std.expand_as(mean)
+
+
+class Critic(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.fc = torch.nn.Linear(4 * S * S, 1)
+
+    def forward(self, x):
+        return self.fc(x.flatten(1))
+
+
+def _params(nets):
+    return torch.cat([p.detach().reshape(-1) for n in nets for p in n.parameters()])
+
+
+def test_train_iteration_checkpoint_and_resume(emu_library, tmp_path):
+    torch.manual_seed(0)
+    scs = [synthetic(num_nodes=40, num_targets=120, seed=s, num_gateways=2) for s in (3, 4)]
+    env = BatchedWRSN(scs, num_agent=3, num_envs=6, device="cpu", map_size=S)
+    gen = torch.Generator().manual_seed(1)
+    trainer = BatchedIPPO(ARGS, env, model_path=None, actor_factory=Actor, critic_factory=Critic, window=6,
+                          action_shape=(3,), generator=gen)
+    before = _params(trainer.actors + trainer.critics)
+    hist = trainer.train(0, str(tmp_path / "save"))                      # the reference's loop runs iterations + 1 times
+    assert len(hist) == 3 and all(h["iteration"] == 1 for h in hist)
+    assert not torch.equal(before, _params(trainer.actors + trainer.critics))
+    assert min(trainer.last_rollout["transitions"]) >= ARGS["batch_size"]
+    for i in range(3):
+        folder = tmp_path / "save" / "1" / str(i)
+        assert sorted(os.listdir(folder)) == ["actor.pth", "critic.pth", "log.csv"]
+        rows = list(csv.reader(open(folder / "log.csv")))
+        assert len(rows) == 1 and rows[0][0] == "1" and rows[0][1] == str(ARGS["batch_size"]) and len(rows[0]) == 7
+        sd = torch.load(folder / "actor.pth")
+        assert all(torch.equal(sd[k], v) for k, v in trainer.actors[i].state_dict().items())
+
+    env2 = BatchedWRSN(scs, num_agent=3, num_envs=6, device="cpu", map_size=S)
+    resumed = BatchedIPPO(ARGS, env2, model_path=str(tmp_path / "save" / "1"), actor_factory=Actor, critic_factory=Critic,
+                          window=6, action_shape=(3,), generator=gen)
+    assert torch.equal(_params(resumed.actors + resumed.critics), _params(trainer.actors + trainer.critics))
+    assert all(lg["i_so_far"] == 1 and lg["t_so_far"] == ARGS["batch_size"] for lg in resumed.loggers)
+    resumed.train(0, str(tmp_path / "save"))
+    rows = list(csv.reader(open(tmp_path / "save" / "2" / "0" / "log.csv")))
+    assert [r[0] for r in rows] == ["1", "2"]                           # the old log travels with the new checkpoint
+
+
+def test_shared_network_is_ppo(emu_library):
+    scs = [synthetic(num_nodes=40, num_targets=120, seed=3, num_gateways=2)]
+    env = BatchedWRSN(scs, num_agent=2, num_envs=4, device="cpu", map_size=S)
+    t = BatchedIPPO(ARGS, env, actor_factory=Actor, critic_factory=Critic, window=4, action_shape=(3,), shared=True)
+    assert t.actors[0] is t.actors[1] and t.critics[0] is t.critics[1] and t.optimizers[0] is t.optimizers[1]
