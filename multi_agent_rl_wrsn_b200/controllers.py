@@ -212,7 +212,8 @@ def select_batch(rewards, batch_size, generator=None):
     if n - selected < random_num:
         raise ValueError("Cannot take a larger sample than population when 'replace=False'")   # np.random.choice's error
     order = torch.argsort((rewards - rewards.mean()).abs(), stable=True)
-    draw = torch.randperm(n - selected, generator=generator, device=rewards.device)[:random_num]
+    gdev = rewards.device if generator is None else generator.device        # a generator draws on its own device
+    draw = torch.randperm(n - selected, generator=generator, device=gdev)[:random_num].to(rewards.device)
     return torch.cat((order[n - selected:], draw))
 
 
@@ -252,7 +253,8 @@ class PerAgentPolicy:
             mean, log_std = self.actors[i](obs[idx].to(torch.float32))
             mean, log_std = mean.reshape((n,) + shape), log_std.reshape((n,) + shape)   # UNet.forward squeezes a batch of one away
             std = log_std.exp()
-            a = mean + std * torch.randn(mean.shape, generator=self.generator, device=mean.device, dtype=mean.dtype)
+            gdev = mean.device if self.generator is None else self.generator.device
+            a = mean + std * torch.randn(mean.shape, generator=self.generator, device=gdev, dtype=mean.dtype).to(mean.device)
             logp = (-((a - mean) ** 2) / (2.0 * std * std) - log_std - 0.5 * math.log(2.0 * math.pi)).sum(red)   # Normal.log_prob
             x[idx] = a
             lp[idx] = logp
@@ -291,7 +293,8 @@ def ppo_update(actor, critic, optimizer, batch, args, group=None, generator=None
     params = list(actor.parameters()) + list(critic.parameters())
     clipfracs, stats = [], {}
     for _ in range(int(args["n_updates_per_iteration"])):
-        b_inds = torch.randperm(n, generator=generator).to(batch["states"].device)      # np.random.shuffle(b_inds), :229
+        gdev = "cpu" if generator is None else generator.device
+        b_inds = torch.randperm(n, generator=generator, device=gdev).to(batch["states"].device)      # np.random.shuffle(b_inds), :229
         for start in range(0, n, mbs):
             mb = b_inds[start:start + mbs]
             m = mb.numel()
