@@ -86,3 +86,41 @@ def test_shared_network_is_ppo(emu_library):
     env = BatchedWRSN(scs, num_agent=2, num_envs=4, device="cpu", map_size=S)
     t = BatchedIPPO(ARGS, env, actor_factory=Actor, critic_factory=Critic, window=4, action_shape=(3,), shared=True)
     assert t.actors[0] is t.actors[1] and t.critics[0] is t.critics[1] and t.optimizers[0] is t.optimizers[1]
+
+
+def _ddp_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    from multi_agent_rl_wrsn_b200.sharding import shard_range, shard_scenario_index
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    _lib.use_library(os.path.join(EMU_DIR, "libwrsn_emu.so"))
+    torch.manual_seed(0)                                                 # identical initial replicas
+    scs = [synthetic(num_nodes=40, num_targets=120, seed=s, num_gateways=2) for s in (3, 4)]
+    lo, hi = shard_range(8, rank, world)
+    env = BatchedWRSN(scs, num_agent=2, num_envs=hi - lo, device="cpu", map_size=S,
+                      scenario_index=shard_scenario_index(8, len(scs), rank, world))
+    a = dict(ARGS, batch_size=16, minibatch_size=8)
+    t = BatchedIPPO(a, env, actor_factory=Actor, critic_factory=Critic, window=6, action_shape=(3,),
+                    generator=torch.Generator().manual_seed(100 + rank))   # different samples, different shards
+    t.train(0, os.path.join(out_dir, "save"))
+    torch.save(dict(p=_params(t.actors + t.critics), dec=t.last_rollout["decisions"]), os.path.join(out_dir, "r%d.pt" % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_keep_identical_replicas(tmp_path):
+    """N > 1: every rank rolls out its own shard of environments; the gradient all-reduce keeps the replicas identical and
+    only rank 0 writes checkpoints."""
+    import socket
+    import torch.multiprocessing as mp
+    subprocess.check_call(["make", "-C", EMU_DIR, "libwrsn_emu.so"], stdout=subprocess.DEVNULL)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_ddp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = (torch.load(os.path.join(str(tmp_path), "r%d.pt" % r)) for r in range(2))
+    assert torch.equal(r0["p"], r1["p"])
+    torch.manual_seed(0)
+    fresh = _params([Actor(), Actor(), Critic(), Critic()])
+    assert r0["p"].shape == fresh.shape and not torch.equal(r0["p"], fresh)
+    assert sorted(os.listdir(tmp_path / "save" / "1")) == ["0", "1"]
