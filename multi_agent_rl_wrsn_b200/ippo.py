@@ -12,7 +12,9 @@ single all-reduce per minibatch (``controllers.ppo_update``).
 The networks are the caller's: ``actor_factory`` / ``critic_factory`` build one actor / critic per agent — the
 reference's own ``UNet`` and ``CNNCritic`` (``controller/ppo/actor/UnetActor.py``, ``controller/ppo/critic/CNNCritic.py``)
 or anything with the same interface (actor: obs -> (mean, log_std) maps; critic: obs -> [n, k] summed over k).
-``PPO`` (one shared pair, ``controller/ppo/PPO.py``) is ``shared=True``.
+``shared=True`` is the reference's ``PPO`` (``controller/ppo/PPO.py``): ONE actor / critic pair for all chargers, the
+transitions of all agents pooled into one batch of ``batch_size`` (``PPO.py:125-197``), one update per iteration and the flat
+checkpoint folder ``<save_folder>/<iteration>/actor.pth | critic.pth | log.csv`` (``PPO.py:281-294``, ``:48-55``).
 """
 import csv
 import os
@@ -41,10 +43,10 @@ class BatchedIPPO:
         self.shared = bool(shared)
         self.log_file = [None] * self.num_agent
         self.loggers = [dict(i_so_far=0, t_so_far=0, losses=[], delta_t=time.time_ns()) for _ in range(self.num_agent)]
-        if model_path is not None:                                        # IPPO.py:50-64
-            for agent_folder in sorted(os.listdir(model_path)):
-                i = int(agent_folder)
-                path = os.path.join(model_path, agent_folder)
+        if model_path is not None:                                        # IPPO.py:50-64 / PPO.py:48-55
+            for agent_folder in ([None] if shared else sorted(os.listdir(model_path))):
+                i = 0 if shared else int(agent_folder)
+                path = model_path if shared else os.path.join(model_path, agent_folder)
                 self.critics[i].load_state_dict(torch.load(os.path.join(path, "critic.pth"), map_location=self.device))
                 self.actors[i].load_state_dict(torch.load(os.path.join(path, "actor.pth"), map_location=self.device))
                 self.log_file[i] = os.path.join(path, "log.csv")
@@ -74,7 +76,7 @@ class BatchedIPPO:
         acc = [dict(states=[], actions=[], log_probs=[], rewards=[], advantages=[], returns=[], values=[]) for _ in range(self.num_agent)]
         counts = [0] * self.num_agent
         st0 = self.env.req.stats.sum(0).clone()
-        while min(counts) < self.batch_size:
+        while (sum(counts) if self.shared else min(counts)) < self.batch_size:        # PPO.py:126 / IPPO.py:183-189
             ro.carry_over()
             ro.collect(self.policy)
             for i in range(self.num_agent):
@@ -91,8 +93,10 @@ class BatchedIPPO:
         episodes = float(st1[2] - st0[2])
         self.last_rollout = dict(decisions=float(st1[0] - st0[0]), simulated_seconds=float(st1[1] - st0[1]), episodes=episodes,
                                  transitions=list(counts))
+        if self.shared:                                                  # one pooled batch, agents in id order (PPO.py:164-175)
+            acc = [{k: [x for i in range(self.num_agent) for x in acc[i][k]] for k in acc[0]}]
         out = []
-        for i in range(self.num_agent):
+        for i in range(len(acc)):
             full = {k: torch.cat(v) for k, v in acc[i].items()}
             idx = select_batch(full["rewards"], self.batch_size, generator=self.generator)     # :193-200
             sel = {k: v[idx.to(v.device)] for k, v in full.items()}
@@ -111,7 +115,7 @@ class BatchedIPPO:
         while i_so_far <= trained_iterations:                                                  # sic: one more than asked (:220)
             batches = self.roll_out()
             i_so_far += 1
-            for i in range(self.num_agent):
+            for i in range(1 if self.shared else self.num_agent):
                 lg = self.loggers[i]
                 lg["t_so_far"] += self.batch_size
                 lg["i_so_far"] += 1
@@ -122,7 +126,8 @@ class BatchedIPPO:
                 history.append(dict(agent=i, iteration=lg["i_so_far"], **{k: (float(v) if v is not None else None)
                                                                           for k, v in stats.items()}))
                 if lg["i_so_far"] % self.save_freq == 0 and rank0:                               # :296-309
-                    folder = os.path.join(save_folder, str(lg["i_so_far"]), str(i))
+                    folder = os.path.join(save_folder, str(lg["i_so_far"])) if self.shared else \
+                        os.path.join(save_folder, str(lg["i_so_far"]), str(i))
                     os.makedirs(folder, exist_ok=True)
                     torch.save(self.actors[i].state_dict(), os.path.join(folder, "actor.pth"))
                     torch.save(self.critics[i].state_dict(), os.path.join(folder, "critic.pth"))

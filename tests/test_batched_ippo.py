@@ -81,11 +81,21 @@ def test_train_iteration_checkpoint_and_resume(emu_library, tmp_path):
     assert [r[0] for r in rows] == ["1", "2"]                           # the old log travels with the new checkpoint
 
 
-def test_shared_network_is_ppo(emu_library):
+def test_shared_network_is_ppo(emu_library, tmp_path):
+    """shared=True = controller/ppo/PPO.py: one network pair, one pooled batch and one update per iteration, flat checkpoint folder."""
     scs = [synthetic(num_nodes=40, num_targets=120, seed=3, num_gateways=2)]
     env = BatchedWRSN(scs, num_agent=2, num_envs=4, device="cpu", map_size=S)
     t = BatchedIPPO(ARGS, env, actor_factory=Actor, critic_factory=Critic, window=4, action_shape=(3,), shared=True)
     assert t.actors[0] is t.actors[1] and t.critics[0] is t.critics[1] and t.optimizers[0] is t.optimizers[1]
+    hist = t.train(0, str(tmp_path / "ppo"))
+    assert len(hist) == 1                                                # one update per iteration, not one per agent
+    assert sum(t.last_rollout["transitions"]) >= ARGS["batch_size"]
+    assert sorted(os.listdir(tmp_path / "ppo" / "1")) == ["actor.pth", "critic.pth", "log.csv"]
+    env2 = BatchedWRSN(scs, num_agent=2, num_envs=4, device="cpu", map_size=S)
+    r = BatchedIPPO(ARGS, env2, model_path=str(tmp_path / "ppo" / "1"), actor_factory=Actor, critic_factory=Critic, window=4,
+                    action_shape=(3,), shared=True)
+    assert torch.equal(_params([r.actors[0], r.critics[0]]), _params([t.actors[0], t.critics[0]]))
+    assert r.loggers[0]["i_so_far"] == 1
 
 
 def _ddp_worker(rank, world, port, out_dir):
