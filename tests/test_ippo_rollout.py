@@ -123,3 +123,50 @@ def test_per_agent_policy_matches_ippo_evaluate():
         assert abs(float(other) - float(lp[b])) > 1e-3
     with pytest.raises(ValueError):
         PerAgentPolicy(actors[:2])(agent, obs)
+
+
+REFERENCE = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isfile(os.path.join(REFERENCE, "controller", "ppo", "actor", "UnetActor.py")),
+                    reason="needs a checkout of the reference (build container only)")
+def test_reference_networks_fit_the_batched_interfaces():
+    """The reference's own UNet actor and CNNCritic (imported unmodified, CPU) behind PerAgentPolicy and ppo_update: shapes,
+    the squeezed batch of one, and log-probabilities that IPPO.evaluate reproduces."""
+    import sys
+    from torch.distributions.normal import Normal
+    from multi_agent_rl_wrsn_b200.controllers import PerAgentPolicy, ppo_update
+    shims = os.path.join(REPO, "oracle", "shims")                          # matplotlib / gym stand-ins (the image has neither)
+    sys.path[:0] = [REFERENCE, shims]
+    loaded = set(sys.modules)
+    try:
+        from controller.ppo.actor.UnetActor import UNet
+        from controller.ppo.critic.CNNCritic import CNNCritic
+    finally:
+        sys.path.remove(REFERENCE)
+        sys.path.remove(shims)
+        for name in set(sys.modules) - loaded:                             # leave no reference / shim modules behind
+            if name.split(".")[0] in ("controller", "utils", "matplotlib", "gym", "seaborn", "simpy"):
+                del sys.modules[name]
+    torch.manual_seed(0)
+    actors, critics = [UNet(), UNet()], [CNNCritic(), CNNCritic()]
+    obs = torch.rand((5, 4, 100, 100))
+    agent = torch.tensor([0, 0, 1, 0, 0], dtype=torch.int32)              # agent 1: a batch of one (UNet squeezes it away)
+    x, lp = PerAgentPolicy(actors)(agent, obs)
+    assert x.shape == (5, 100, 100) and lp.shape == (5,)
+    with torch.no_grad():
+        mean, log_std = actors[0](obs[[0, 1, 3, 4]])
+        ref = Normal(mean, log_std.exp()).log_prob(x[[0, 1, 3, 4]]).sum((1, 2))          # IPPO.evaluate :108-115
+    assert torch.allclose(ref, lp[[0, 1, 3, 4]], rtol=1e-4)
+    values = critics[0](obs).sum(1)                                         # IPPO.get_value :117-119
+    assert values.shape == (5,)
+    idx = torch.tensor([0, 1, 3, 4])
+    batch = dict(states=obs[idx], actions=x[idx], log_probs=lp[idx], advantages=torch.randn(4), returns=torch.randn(4),
+                 values=values[idx].detach())
+    args = dict(clip=0.2, n_updates_per_iteration=1, norm_adv=True, minibatch_size=4, ent_coef=0.0, vf_coef=0.5,
+                max_grad_norm=0.5, clip_vloss=True)
+    opt = torch.optim.Adam(list(actors[0].parameters()) + list(critics[0].parameters()), lr=3e-4)
+    before = actors[0].out_mean.conv.weight.detach().clone()
+    st = ppo_update(actors[0], critics[0], opt, batch, args)
+    assert torch.isfinite(st["loss"]) and abs(float(st["approx_kl"])) < 1e-3    # same parameters: ratio = 1 at the first minibatch
+    assert not torch.equal(before, actors[0].out_mean.conv.weight.detach())
