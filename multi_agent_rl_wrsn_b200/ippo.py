@@ -27,10 +27,13 @@ from .controllers import IPPORollout, PerAgentPolicy, ppo_update, select_batch
 
 
 class BatchedIPPO:
-    def __init__(self, args, env, device=None, model_path=None, actor_factory=None, critic_factory=None, window=4,
+    def __init__(self, args, env, device=None, model_path=None, actor_factory=None, critic_factory=None, window=8,
                  shared=False, group=None, generator=None, action_shape=None):
         if actor_factory is None or critic_factory is None:
             raise ValueError("actor_factory and critic_factory are required (e.g. the reference's UNet and CNNCritic)")
+        # window: rollout steps per collection window.  A transition is recorded when its decision and its closing request fall
+        # into the same window (an agent decides about every num_agent-th step), so short windows drop more of them; the record
+        # holds (window + 1) x B observations (160 KB each at map size 100).
         self.env, self.args, self.group, self.generator = env, dict(args), group, generator
         self.num_agent = env.num_agent
         self.device = torch.device(device) if device is not None else env.device

@@ -30,7 +30,7 @@ def main():
     p.add_argument("--alg-args", default="alg_args/ippo.yaml")
     p.add_argument("--num-agent", type=int, default=3)
     p.add_argument("--envs", type=int, default=2048, help="environments of the whole job")
-    p.add_argument("--window", type=int, default=4, help="rollout steps per collection window")
+    p.add_argument("--window", type=int, default=8, help="rollout steps per collection window")
     p.add_argument("--iterations", type=int, default=1000)
     p.add_argument("--save-folder", default="save_model/ippo")
     p.add_argument("--model-path", default=None)
