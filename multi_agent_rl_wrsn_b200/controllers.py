@@ -72,8 +72,11 @@ class IPPORollout:
     ``input_action`` is a [B, S, S] density map (``density_map=True``, the runners' setting) or a [B, 3] action.
     """
 
-    def __init__(self, env, steps, action_shape=None, obs_dtype=torch.float32, with_obs=True):
-        """``with_obs=False`` keeps no observations (``policy`` is handed None; ``batch`` has no states): for policies that
+    def __init__(self, env, steps, action_shape=None, obs_dtype=torch.float32, with_obs=True, keep_open=False):
+        """``keep_open=True``: ``carry_over`` saves the decisions that are still open at the end of a window (observation, action,
+        log-probability per environment and agent: B x M x 160 KB at map size 100), so that transitions whose request arrives in
+        the next window are recorded too instead of being dropped at the window boundary.
+        ``with_obs=False`` keeps no observations (``policy`` is handed None; ``batch`` has no states): for policies that
         do not look at the map, and for the CPU tests of the record, whose host emulation has no raster."""
         B, S, M, dev = env.B, env.S, env.M, env.device
         self.env, self.T = env, int(steps)
@@ -91,6 +94,12 @@ class IPPORollout:
         self.terminal_factor = None
         self._collected = False
         self._resets = None
+        self.keep_open = bool(keep_open)
+        if self.keep_open:                                                # link == -2: the decision lives in these buffers
+            self.open_obs = torch.zeros((B, M, 4, S, S), dtype=obs_dtype, device=dev) if with_obs else None
+            self.open_act = torch.zeros((B, M) + action_shape, dtype=torch.float32, device=dev)
+            self.open_logp = torch.zeros((B, M), dtype=torch.float32, device=dev)
+            self.open_now = torch.zeros((B, M), dtype=torch.float64, device=dev)
         if bool((env.req.agent_id == -3).all()):                          # never reset: start the first episodes
             env.reset()
         if bool((env.req.agent_id < 0).any()):
@@ -125,23 +134,34 @@ class IPPORollout:
         return self
 
     def carry_over(self):
-        """Start the next window from the open requests: links into the finished window are dropped (the reference
-        starts every ``roll_out`` with ``env.reset()``; a continuing batch keeps its episodes instead).  No-op on a fresh record."""
+        """Start the next window from the open requests (the reference starts every ``roll_out`` with ``env.reset()``; a
+        continuing batch keeps its episodes instead).  Decisions still open are saved and stay linkable with ``keep_open``,
+        otherwise links into the finished window are dropped.  No-op on a fresh record."""
         if not self._collected:
             return
         self._collected = False
+        if self.keep_open:                                                # save what the open decisions will be linked to
+            fresh = self.last >= 0                                        # decided in the window that just ended
+            at = self.last.clamp_min(0)                                   # [B, M] step of the decision
+            rows = torch.arange(self.env.B, device=at.device)[:, None].expand_as(at)
+            pick = lambda rec, buf: torch.where(fresh.reshape(fresh.shape + (1,) * (buf.dim() - 2)), rec[at, rows].to(buf.dtype), buf)
+            if self.obs is not None:
+                self.open_obs = pick(self.obs, self.open_obs)
+            self.open_act, self.open_logp, self.open_now = pick(self.act, self.open_act), pick(self.logp, self.open_logp), pick(self.now, self.open_now)
+            self.last = torch.where(fresh, torch.full_like(self.last, -2), self.last)   # -2 stays -2, -1 stays -1
+        else:
+            self.last.fill_(-1)
         if self.obs is not None:
             self.obs[0].copy_(self.obs[self.T])
         self.agent[0] = self.agent[self.T]
         self.now[0] = self.now[self.T]
-        self.last.fill_(-1)
         self.link.fill_(-1)
         self.new_episode.zero_()
 
     def transitions(self, agent_id):
         """Index tensors ``(t, b, t_prev)`` of the transitions recorded for ``agent_id``, in the reference's order
         inside every environment (time-major)."""
-        sel = (self.agent[1:] == int(agent_id)) & (self.link[1:] >= 0)
+        sel = (self.agent[1:] == int(agent_id)) & (self.link[1:] != -1)        # -2: decided before this window (keep_open)
         t, b = torch.nonzero(sel, as_tuple=True)
         t = t + 1
         return t, b, self.link[t, b]
@@ -150,14 +170,24 @@ class IPPORollout:
         """The lists ``roll_out`` builds for one agent, as tensors (``:148-153``).  ``states`` / ``next_states`` = False leaves
         the (large) observation gathers out; ``tp`` / ``t`` / ``b`` index them in ``self.obs`` (``obs[tp, b]``, ``obs[t, b]``)."""
         t, b, tp = self.transitions(agent_id)
-        out = dict(actions=self.act[tp, b], log_probs=self.logp[tp, b], rewards=self.reward[t, b].to(torch.float32),
+        a = int(agent_id)
+        out = dict(actions=self._prev(self.act, "open_act", tp, b, a), log_probs=self._prev(self.logp, "open_logp", tp, b, a),
+                   rewards=self.reward[t, b].to(torch.float32),
                    terminals=torch.zeros(t.shape, dtype=torch.float32, device=t.device), t=t, b=b, tp=tp,
-                   prev_time=self.now[tp, b], time=self.now[t, b])
+                   prev_time=self._prev(self.now, "open_now", tp, b, a), time=self.now[t, b])
         if self.obs is not None and states:
-            out["states"] = self.obs[tp, b]
+            out["states"] = self._prev(self.obs, "open_obs", tp, b, a)
         if self.obs is not None and next_states:
             out["next_states"] = self.obs[t, b]
         return out
+
+    def _prev(self, rec, open_name, tp, b, agent_id):
+        """``rec[tp, b]``, or the saved open decision of ``agent_id`` where ``tp == -2`` (decided before this window)."""
+        got = rec[tp.clamp_min(0), b]
+        if not self.keep_open:
+            return got
+        saved = getattr(self, open_name)[b, agent_id].to(got.dtype)
+        return torch.where((tp < -1).reshape((-1,) + (1,) * (got.dim() - 1)), saved, got)
 
     def cal_rt_adv(self, agent_id, value_fn, gamma, gae_lambda, gae=True, chunk=4096, values=None, next_values=None,
                    keep_states=True):
@@ -174,9 +204,10 @@ class IPPORollout:
         n = bt["rewards"].shape[0]
         with torch.no_grad():
             if values is None:                       # the critic on states / next states, gathered chunk by chunk from the record
-                ev = lambda tt: (torch.cat([value_fn(self.obs[tt[i:i + chunk], bt["b"][i:i + chunk]]) for i in range(0, n, chunk)])
-                                 if n else bt["rewards"])
-                values, next_values = ev(bt["tp"]), ev(bt["t"])
+                cut = lambda x, i: x[i:i + chunk]
+                ev = lambda get: torch.cat([value_fn(get(i)) for i in range(0, n, chunk)]) if n else bt["rewards"]
+                values = ev(lambda i: self._prev(self.obs, "open_obs", cut(bt["tp"], i), cut(bt["b"], i), int(agent_id)))
+                next_values = ev(lambda i: self.obs[cut(bt["t"], i), cut(bt["b"], i)])
             term = bt["terminals"] if self.terminal_factor is None else torch.full_like(bt["terminals"], self.terminal_factor)
             B, dev = self.env.B, values.device
             grid = lambda v: torch.zeros((self.T + 1, B), dtype=torch.float32, device=dev).index_put_((bt["t"], bt["b"]), v)

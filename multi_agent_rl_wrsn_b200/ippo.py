@@ -31,9 +31,8 @@ class BatchedIPPO:
                  shared=False, group=None, generator=None, action_shape=None):
         if actor_factory is None or critic_factory is None:
             raise ValueError("actor_factory and critic_factory are required (e.g. the reference's UNet and CNNCritic)")
-        # window: rollout steps per collection window.  A transition is recorded when its decision and its closing request fall
-        # into the same window (an agent decides about every num_agent-th step), so short windows drop more of them; the record
-        # holds (window + 1) x B observations (160 KB each at map size 100).
+        # window: rollout steps per collection window; the record holds (window + 1) x B observations (160 KB each at map size
+        # 100) plus, for the decisions still open at a window end, B x num_agent more (keep_open: nothing is lost at the boundary).
         self.env, self.args, self.group, self.generator = env, dict(args), group, generator
         self.num_agent = env.num_agent
         self.device = torch.device(device) if device is not None else env.device
@@ -65,7 +64,7 @@ class BatchedIPPO:
             params = list(self.actors[i].parameters()) + list(self.critics[i].parameters())
             self.optimizers.append(torch.optim.Adam(params, lr=float(args["lr"])))
         # action_shape: None = S x S density maps decoded on the device (the runners' density_map=True); (3,) = direct actions
-        self.rollout = IPPORollout(env, int(window), action_shape=action_shape)
+        self.rollout = IPPORollout(env, int(window), action_shape=action_shape, keep_open=True)
         self.policy = PerAgentPolicy(self.actors, generator=generator, action_shape=action_shape)
         self.last_rollout = {}
 

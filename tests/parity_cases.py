@@ -315,11 +315,12 @@ def _toy_policy(salt, clock, use_obs):
     return policy
 
 
-def check_ippo_rollout(scenarios, device, num_envs, steps, gamma=0.99, lam=0.95, with_obs=True):
+def check_ippo_rollout(scenarios, device, num_envs, steps, gamma=0.99, lam=0.95, with_obs=True, windows=1):
     """IPPORollout (batched, linked record) == the reference's roll_out loop (IPPO.py:128-155) written against the
     single-environment façade, environment by environment: the same transitions in the same order for every agent,
     and cal_rt_adv == the reference's recursion over every (episode, agent) list.  ``with_obs=False``: no observations
-    (the host emulation has no raster); the critic is then a function of the requests' simulation times."""
+    (the host emulation has no raster); the critic is then a function of the requests' simulation times.  ``windows`` > 1: the same
+    steps collected in several windows with ``keep_open`` — no transition may be lost at a window boundary."""
     from multi_agent_rl_wrsn_b200 import WRSN
     from multi_agent_rl_wrsn_b200.controllers import IPPORollout
 
@@ -329,19 +330,39 @@ def check_ippo_rollout(scenarios, device, num_envs, steps, gamma=0.99, lam=0.95,
     M = 3
     env = BatchedWRSN(scenarios, num_agent=M, num_envs=num_envs, device=device)
     env.reset()
-    ro = IPPORollout(env, steps, action_shape=(3,), obs_dtype=torch.float64, with_obs=with_obs)
+    ro = IPPORollout(env, steps // windows, action_shape=(3,), obs_dtype=torch.float64, with_obs=with_obs, keep_open=windows > 1)
     salt = np.arange(num_envs)
-    ro.collect(_toy_policy(salt, lambda: env.req.now, with_obs))
     value_fn = lambda s: (s[:, 0].mean(dim=(1, 2)) * 50.0 + s[:, 1].mean(dim=(1, 2))).to(torch.float32)
     value_t = lambda t: torch.cos(0.01 * torch.as_tensor(t, dtype=torch.float64)).to(torch.float32)
-    n_tr = episodes = 0
-    for tf in (None, 1.0):                                    # the reference's all-False terminals, and a live recursion
-        ro.terminal_factor = tf
-        per_agent = []
+
+    def per_agent_of_window():
+        res = []
         for i in range(M):
-            bt = ro.batch(i)
+            bt = ro.batch(i, states=False, next_states=False)
             kw = {} if with_obs else dict(values=value_t(bt["prev_time"]), next_values=value_t(bt["time"]))
-            per_agent.append(ro.cal_rt_adv(i, value_fn, gamma, lam, **kw))
+            returns, advantages, values, bt = ro.cal_rt_adv(i, value_fn, gamma, lam, **kw)
+            if with_obs:
+                bt["next_states"] = ro.obs[bt["t"], bt["b"]]
+            res.append((returns, advantages, values, bt))
+        return res
+
+    n_tr = episodes = 0
+    if windows > 1:                                           # window by window; rows of one environment stay in time order
+        parts = []
+        for w in range(windows):
+            ro.carry_over()
+            ro.collect(_toy_policy(salt, lambda: env.req.now, with_obs))
+            parts.append(per_agent_of_window())
+        keys_cat = ("actions", "log_probs", "rewards", "prev_time", "time", "b") + (("states", "next_states") if with_obs else ())
+        merged = []
+        for i in range(M):
+            bt = {k: torch.cat([p[i][3][k] for p in parts]) for k in keys_cat}
+            merged.append(tuple(torch.cat([p[i][j] for p in parts]) for j in range(3)) + (bt,))
+    else:
+        ro.collect(_toy_policy(salt, lambda: env.req.now, with_obs))
+    for tf in ((None,) if windows > 1 else (None, 1.0)):      # the reference's all-False terminals, and a live recursion
+        ro.terminal_factor = tf
+        per_agent = merged if windows > 1 else per_agent_of_window()
         for b in range(num_envs):
             single = (WRSN if with_obs else _NoObsWRSN)(scenarios[b % len(scenarios)], None, M, device=device)
             pol = _toy_policy(salt[b:b + 1], lambda: single._b.req.now, with_obs)
@@ -394,7 +415,7 @@ def check_ippo_rollout(scenarios, device, num_envs, steps, gamma=0.99, lam=0.95,
                     rec[i]["adv"].extend(adv.tolist()); rec[i]["ret"].extend((adv + v).tolist())
             for i in range(M):
                 returns, advantages, values, bt = per_agent[i]
-                sel = (bt["b"] == b).nonzero()[:, 0]
+                sel = torch.sort((bt["b"] == b).nonzero()[:, 0]).values        # (several windows: already window-major = time order)
                 assert len(sel) == len(rec[i]["rewards"]), (b, i, len(sel), len(rec[i]["rewards"]))
                 if not len(sel):
                     continue
@@ -402,8 +423,7 @@ def check_ippo_rollout(scenarios, device, num_envs, steps, gamma=0.99, lam=0.95,
                 g = lambda k: bt[k][sel].cpu().numpy()
                 if with_obs:
                     assert np.allclose(g("states"), np.array(rec[i]["states"]), rtol=1e-9, atol=1e-12), (b, i)
-                    nxt = ro.obs[bt["t"][sel], bt["b"][sel]].cpu().numpy()           # cal_rt_adv's batch leaves the next states in the record
-                    assert np.allclose(nxt, np.array(rec[i]["next_states"]), rtol=1e-9, atol=1e-12), (b, i)
+                    assert np.allclose(g("next_states"), np.array(rec[i]["next_states"]), rtol=1e-9, atol=1e-12), (b, i)
                 assert np.array_equal(g("prev_time"), np.array(rec[i]["prev_time"])), (b, i)
                 assert np.array_equal(g("time"), np.array(rec[i]["time"])), (b, i)
                 assert np.allclose(g("actions"), np.array(rec[i]["actions"]), rtol=0, atol=1e-7), (b, i)

@@ -40,6 +40,14 @@ def test_ippo_rollout_with_observations_emu(emu_library):
     assert n_tr > 80
 
 
+@pytest.mark.parametrize("with_obs", [False, True])
+def test_windows_with_open_decisions_lose_nothing(emu_library, with_obs):
+    """keep_open: the same 60 steps collected in 5 windows of 12 give the transitions of the reference's loop, all of them, in order
+    (decisions still open at a window end are saved and linked from the next window; episode ends clear them)."""
+    n_tr, episodes = pc.check_ippo_rollout(_scenarios(), "cpu", num_envs=3, steps=60, with_obs=with_obs, windows=5)
+    assert n_tr > 100 and episodes >= 1
+
+
 def test_windows_carry_over(emu_library):
     """A record is reused window after window: carry_over on a fresh record changes nothing; after a window it starts from
     the open requests and drops the links into the finished window."""
