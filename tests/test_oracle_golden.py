@@ -4,6 +4,8 @@ The fixtures under tests/golden/ were produced by running the UNMODIFIED referen
 oracle shims (oracle/gen_golden.py).  Integer / set / time quantities must match exactly, node and
 charger energies to 1e-12 relative (observed: bit-exact), observations to 1e-9 absolute.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -101,3 +103,16 @@ def test_episode(name):
     _close(o.consts()["moving_time_max"], float(g["moving_time_max"]), rtol=0)
     _close(o.consts()["charging_time_max"], float(g["charging_time_max"]), rtol=0)
     _close(o.consts()["avg_nodes_agent"], float(g["avg_nodes_agent"]), rtol=1e-15)
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/rl_env/WRSN.py"), reason="needs the reference checkout (build container only)")
+def test_oracle_vs_live_reference_on_random_scenarios():
+    """Beyond the frozen fixtures: the C restatement against the unmodified reference run here under the shims, two random
+    synthetic scenarios with random actions (tests/fuzz_oracle_vs_reference.py is the long form: 44 configurations clean)."""
+    import subprocess
+    import sys
+    from tests.helpers import REPO
+    out = subprocess.run([sys.executable, os.path.join(REPO, "tests", "fuzz_oracle_vs_reference.py"), "--first-seed", "100",
+                          "--count", "2", "--decisions", "6"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "0 failing configurations" in out.stdout
