@@ -254,6 +254,48 @@ WRSN_D double red_min(const Ctx &c, double v) {
     return s;
 #endif
 }
+/* sums of TWO values over the environment's threads with ONE barrier: the per-warp partial sums are exchanged through
+ * alternating halves of c.red (`buf` flips at every call), so the writes of call r+1 cannot meet the reads of call r; the
+ * reads of call r-1 are over because every thread has passed call r's barrier since.  The caller puts one barrier before
+ * the first call of a sequence (other users of c.red) and keeps `buf` in a register. */
+WRSN_DI void red_sum2(const Ctx &c, double &a, double &b, int &buf) {
+#if defined(WRSN_HOST_EMU)
+    (void)c; (void)a; (void)b; (void)buf;
+#else
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+#if WRSN_GFIX != 32
+    double *x = c.red + 16 * buf;
+    buf ^= 1;
+    const int nw = c.G >> 5;
+    if ((c.tid & 31) == 0) { x[2 * (c.tid >> 5)] = a; x[2 * (c.tid >> 5) + 1] = b; }
+    __syncthreads();
+    a = x[0]; b = x[1];
+    for (int k = 1; k < nw; k++) { a += x[2 * k]; b += x[2 * k + 1]; }
+#else
+    (void)c; (void)buf;
+#endif
+#endif
+}
+WRSN_DI void red_sum1(const Ctx &c, double &a, int &buf) {
+#if defined(WRSN_HOST_EMU)
+    (void)c; (void)a; (void)buf;
+#else
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+#if WRSN_GFIX != 32
+    double *x = c.red + 16 * buf;
+    buf ^= 1;
+    const int nw = c.G >> 5;
+    if ((c.tid & 31) == 0) x[c.tid >> 5] = a;
+    __syncthreads();
+    a = x[0];
+    for (int k = 1; k < nw; k++) a += x[k];
+#else
+    (void)c; (void)buf;
+#endif
+#endif
+}
 WRSN_D int red_or(const Ctx &c, int v) {
 #if defined(WRSN_HOST_EMU)
     (void)c; return v ? 1 : 0;
@@ -303,6 +345,51 @@ WRSN_D int wrsn_popc(uint32_t v) {
 /* num / den for den > 0 and num >= 0.  A zero numerator (a node without traffic: energyCS == 0) would send CUDA's fp64
  * division down its special-case subroutine for the whole warp; the quotient is the (signed) zero itself. */
 WRSN_D double div_pos(double num, double den) { return num == 0.0 ? num : num / den; }
+
+/* ------------------------------------------------------------------ bounded-error fp64 helpers of the REWARD path
+ * WRSN.update_reward (WRSN.py:100-127) only feeds `reward` (tolerance 1e-6 relative): it is never read
+ * back by the simulation.  Its N divisions, N exponentials, one square root per simulated second therefore do not need
+ * IEEE rounding, they need few instructions: hardware seed (MUFU.RCP64H / RSQ64H) + Newton steps, and a table-driven
+ * exponential.  All three are within a few 1e-14 relative of the exact result (the tests hold the reward at 1e-9).  Nothing
+ * that is part of the simulated state (energies, energyCS, charger records) goes through these. */
+#if !defined(WRSN_HOST_EMU)
+WRSN_D double wrsn_fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+WRSN_D double wrsn_rcp(double d) {                  /* 1 / d, d > 0 normal: <= 2 ulp */
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = __fma_rn(-d, r, 1.0);
+    r = __fma_rn(r, e, r);
+    e = __fma_rn(-d, r, 1.0);
+    return __fma_rn(r, e, r);
+}
+WRSN_D double wrsn_rsqrt(double v) {                /* 1 / sqrt(v), v > 0 normal: <= 2 ulp */
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(v));
+    double e = __fma_rn(-v, r * r, 1.0);
+    r = __fma_rn(r * 0.5, e, r);
+    e = __fma_rn(-v, r * r, 1.0);
+    return __fma_rn(r * 0.5, e, r);
+}
+/* exp(z) for |z| <= 600 (clamped), relative error <= 1e-13: z = (64 n + j) ln2/64 + r, |r| <= ln2/128;
+ * exp(z) = 2^n * 2^(j/64) * (1 + r + r^2/2 + r^3/6 + r^4/24) — table of 64 doubles (wrsn_exp2_tab, one LDG), four FMAs. */
+WRSN_D double wrsn_exp_b(double z) {
+    z = fmin(fmax(z, -600.0), 600.0);
+    const double t = __fma_rn(z, 92.33248261689366, 6755399441055744.0);          /* 64 / ln2; 1.5 * 2^52: the integer lands in the low word */
+    const int k = __double2loint(t);
+    const double r = __fma_rn(t - 6755399441055744.0, -0.010830424696249145, z); /* ln2 / 64 */
+    double p = __fma_rn(r, 1.0 / 24.0, 1.0 / 6.0);
+    p = __fma_rn(p, r, 0.5);
+    p = __fma_rn(p, r, 1.0);
+    p = __fma_rn(p, r, 1.0);
+    const double y = p * __ldg(&wrsn_exp2_tab[k & 63]);
+    return __hiloint2double(__double2hiint(y) + ((k >> 6) << 20), __double2loint(y));
+}
+#else
+WRSN_D double wrsn_fma(double a, double b, double c) { return a * b + c; }
+WRSN_D double wrsn_rcp(double d) { return 1.0 / d; }
+WRSN_D double wrsn_rsqrt(double v) { return 1.0 / sqrt(v); }
+WRSN_D double wrsn_exp_b(double z) { return exp(fmin(fmax(z, -600.0), 600.0)); }
+#endif
 
 WRSN_NOINLINE double euclid2(double ax, double ay, double bx, double by) {
     /* scipy.spatial.distance.euclidean == sqrt(dot(u - v, u - v)) for 2-vectors */
@@ -910,7 +997,7 @@ WRSN_D double charge_rate_to(Ctx &c, const double *m, int node) {   /* alpha / (
 }
 
 /* the softmax priority + incentive sums; only reached when some incentive sum is non-empty */
-WRSN_NOINLINE void update_reward_body(Ctx &c, const double *dec);
+WRSN_NOINLINE void reward_cycles(Ctx &c, const double *dec, int n_cycles, double t_reward, int watched);
 WRSN_NOINLINE double drain_node(double e, double rr, double es, double er, int nb, int ow, int na, double cap);
 
 WRSN_D bool reward_pairs(Ctx &c) {                 /* is there any (charging charger, connected alive node) pair? */
@@ -926,26 +1013,52 @@ WRSN_D bool reward_pairs(Ctx &c) {                 /* is there any (charging cha
     return any;
 }
 
+WRSN_D void catch_up_for_reward(Ctx &c, double t_reward);
+
 WRSN_D void ev_update_reward(Ctx &c) {
-    if (reward_pairs(c)) update_reward_body(c, (const double *)0);   /* otherwise every incentive sum is empty: excl += 0 */
+    if (reward_pairs(c)) reward_cycles(c, (const double *)0, 1, 0.0, 0);   /* otherwise every incentive sum is empty: excl += 0 */
 }
 
-/* `dec` != NULL (whole-cycle batches): this second's k+0.5 drain is applied on the way — the per-second decrement of an
- * uncharged node, or the node's literal tick where dec[i] is NaN — so the batch needs no separate pass over the nodes */
-WRSN_NOINLINE void update_reward_body(Ctx &c, const double *dec) {
+/* `n_cycles` consecutive update_reward ticks (WRSN.py:100-127).
+ * dec == NULL (event path): one tick on the node rows as they are.
+ * dec != NULL (whole-cycle batches, nodes_batch): the grid events around every tick are applied on the way, node by node
+ * in registers — the k+1.0 bookkeeping of the PREVIOUS second (second top-up, energyCS towards its fixed point), then
+ * this second's k+0.5 drain (the per-second decrement of an uncharged node, or the node's literal tick where dec[i] is
+ * NaN), then the tick itself; the caller applies the bookkeeping of the last second.  Three barriers per second.
+ * Arithmetic: x_n = energyCS / (energy - threshold + eps) by reciprocal (wrsn_rcp), mean and variance from one pass
+ * (sum and sum of squares; two-pass when the variance is small against mean^2), 1 / std by wrsn_rsqrt, the softmax
+ * numerators by wrsn_exp_b — see the note at those helpers; the event path and the batches share this code, so they
+ * produce the same bits (tests: batches == event path). */
+WRSN_NOINLINE void reward_cycles(Ctx &c, const double *dec, int n_cycles, double t_reward, int watched) {
     const int N = c.N, G = WRSN_GSZ(c);
     const double thr = c.par[WRSN_P_THR], cap = c.par[WRSN_P_CAP], eps = c.par[WRSN_P_EPSENV];
-    double tot;
-    {   /* rolled on purpose: the step kernel is bound by instruction fetch, one compact loop body beats four unrolled
-           division / exp expansions */
-        double s = 0.0;
+    const double inv_n = c.par[WRSN_P_INVN];         /* 1 / N from the host */
+    const double L = (double)WRSN_RING;
+    uint32_t fixed = 0u;                             /* node slots of this thread whose energyCS has reached its fixed point */
+    int buf = 0;
+    gsync(c);
+    _Pragma("unroll 1")
+    for (int j = 0; j < n_cycles; j++) {
+        if (watched) { catch_up_for_reward(c, t_reward + (double)j); gsync(c); }
+        double s1 = 0.0, s2 = 0.0;
+        int sl = 0;
         _Pragma("unroll 1")
-        for (int i = c.tid; i < N; i += G) {
-            double p = 0.0;
+        for (int i = c.tid; i < N; i += G, sl++) {
+            double x = 0.0;
             if (c.status[i] != 0) {
-                double e = c.energy[i];
+                double e = c.energy[i], cs = c.cs[i];
                 if (dec) {
-                    const double d = dec[i];
+                    if (j > 0) {                     /* Node.operate k+1.0 of the previous second (Node.py:65-77) */
+                        const double rr = c.rr[i];
+                        if (rr != 0.0) e = fmin(e + rr * 0.5, cap);
+                        if (!(sl < 32 && ((fixed >> sl) & 1u))) {
+                            const double lg = c.logc[i];
+                            const double nx = div_pos(cs * L - lg + lg, L);
+                            if (nx == cs) { if (sl < 32) fixed |= 1u << sl; }
+                            else { cs = nx; c.cs[i] = nx; }
+                        }
+                    }
+                    const double d = dec[i];         /* k+0.5 drain */
                     if (d == d) e = e - d;
                     else {
                         const int ow = c.parent[i] != -1 ? (int)c.own[i] : 0;
@@ -953,45 +1066,50 @@ WRSN_NOINLINE void update_reward_body(Ctx &c, const double *dec) {
                     }
                     c.energy[i] = e;
                 }
-                p = div_pos(c.cs[i], e - thr + eps);
+                x = cs * wrsn_rcp(e - thr + eps);
             }
-            c.scr0[i] = p; s += p;
+            c.scr0[i] = x; s1 += x; s2 = wrsn_fma(x, x, s2);
         }
-        const double inv_n = c.par[WRSN_P_INVN];     /* 1 / N from the host: mean and variance by multiplication (1 ulp) */
-        const double mean = red_sum(c, s) * inv_n;
-        s = 0.0;
+        red_sum2(c, s1, s2, buf);
+        const double mean = s1 * inv_n;
+        double var = wrsn_fma(s2, inv_n, -(mean * mean));
+        if (!(var > 1e-3 * (mean * mean))) {         /* cancellation: the textbook two passes (np.std) */
+            double s = 0.0;
+            _Pragma("unroll 1")
+            for (int i = c.tid; i < N; i += G) { const double u = c.scr0[i] - mean; s = wrsn_fma(u, u, s); }
+            red_sum1(c, s, buf);
+            var = s * inv_n;
+        }
+        const double a = var > 0.0 ? wrsn_rsqrt(var) : 1.0 / eps;       /* std == 0 -> std = epsilon (:104-105) */
+        double tot = 0.0;
         _Pragma("unroll 1")
-        for (int i = c.tid; i < N; i += G) { double x = c.scr0[i] - mean; s += x * x; }
-        double sd = sqrt(red_sum(c, s) * inv_n);
-        if (sd == 0.0) sd = eps;
-        const double inv_sd = 1.0 / sd;              /* one division instead of N: (x - mean) * (1 / sd) is within 2 ulp of the
-                                                        reference's (x - mean) / sd, i.e. ~1e-15 relative on the softmax weight */
-        s = 0.0;
-        _Pragma("unroll 1")
-        for (int i = c.tid; i < N; i += G) { double q = exp((c.scr0[i] - mean) * inv_sd); c.scr0[i] = q; s += q; }
-        tot = red_sum(c, s);
-    }
-    if (tot == 0.0) tot = eps;
-    gsync(c);
-    for (int a = c.tid; a < c.M; a += G) {           /* one thread per charger: the incentive sums run side by side */
-        double *m = c.mc + (size_t)a * WRSN_MC_LEN;
-        if (m[WRSN_MC_STATUS] != 0.0 && m[WRSN_MC_TYPE] != 0.0) {
-            double incentive = 0.0;
-            const uint32_t *cm = c.conn + (size_t)a * c.W;
-            for (int w = 0; w < c.W; w++) {
-                for (uint32_t bits = cm[w]; bits; bits &= bits - 1u) {
-                    int i = 32 * w + wrsn_ctz(bits);
-                    if (c.status[i] != 1) continue;
-                    double rate = charge_rate_to(c, m, i);
-                    double e_no = fmin(c.energy[i] - c.cs[i], thr);
-                    double e_with = fmax(c.energy[i] - c.cs[i] + rate, cap);
-                    incentive += (c.scr0[i] / tot) * (e_with - e_no) / c.par[WRSN_P_MC_AB2];
+        for (int i = c.tid; i < N; i += G) { const double q = wrsn_exp_b((c.scr0[i] - mean) * a); c.scr0[i] = q; tot += q; }
+        red_sum1(c, tot, buf);
+        if (tot == 0.0) tot = eps;
+        const double inv_tot = wrsn_rcp(tot), inv_ab2 = wrsn_rcp(c.par[WRSN_P_MC_AB2]);
+        for (int a2 = c.tid; a2 < c.M; a2 += G) {    /* one thread per charger: the incentive sums run side by side */
+            double *m = c.mc + (size_t)a2 * WRSN_MC_LEN;
+            if (m[WRSN_MC_STATUS] != 0.0 && m[WRSN_MC_TYPE] != 0.0) {
+                double incentive = 0.0;
+                const double mx = m[WRSN_MC_X], my = m[WRSN_MC_Y], beta = c.par[WRSN_P_MC_BETA], alpha = c.par[WRSN_P_MC_ALPHA];
+                const uint32_t *cm = c.conn + (size_t)a2 * c.W;
+                for (int w = 0; w < c.W; w++) {
+                    for (uint32_t bits = cm[w]; bits; bits &= bits - 1u) {
+                        const int i = 32 * w + wrsn_ctz(bits);
+                        if (c.status[i] != 1) continue;
+                        const double dx = c.nx[i] - mx, dy = c.ny[i] - my, d2 = wrsn_fma(dx, dx, dy * dy);
+                        const double t = (d2 > 0.0 ? d2 * wrsn_rsqrt(d2) : 0.0) + beta;
+                        const double rate = alpha * wrsn_rcp(t * t);
+                        const double ec = c.energy[i] - c.cs[i];
+                        const double e_no = fmin(ec, thr), e_with = fmax(ec + rate, cap);
+                        incentive += (c.scr0[i] * inv_tot) * (e_with - e_no) * inv_ab2;
+                    }
                 }
+                m[WRSN_MC_EXCL] += incentive;
             }
-            m[WRSN_MC_EXCL] += incentive;
         }
+        gsync(c);
     }
-    gsync(c);
 }
 
 /* ------------------------------------------------------------------ WRSN.get_network_fitness (WRSN.py:188-220) -> min */
@@ -1242,8 +1360,41 @@ WRSN_NOINLINE int slot_ff(Ctx &c, int s, double limit, int mode, double *t_end) 
     } else {                                         /* PC_CS_FIRE: a charge whose disconnect / reconnect pairs change nothing */
         double en = m[WRSN_MC_ENERGY], cpa2 = m[WRSN_MC_CPA2], tmp = p[WRSN_PR_CHTMP], span = p[WRSN_PR_CHSPAN];
         const double rate = m[WRSN_MC_RATE];
+        const bool jumps = c.hdr[WRSN_H_OPT_NOBATCH] != 1.0;                      /* (test switch: every span literally) */
         while (tf < limit) {
             if (on_grid(tf)) { *t_end = tf; break; }
+            /* m one-second spans at once.  While the span stays 1.0 every step subtracts the same `rate` from the energy (the
+               same integer number of ulps inside a binade: sub_chain), 1.0 from the two countdowns (exact below 2^53) and adds
+               1.0 to the event time (exact inside the time's binade, where on_grid() cannot change either: the fraction of
+               tf is preserved).  m is cut so that all of that holds and none of the loop's exits can fire inside the jump;
+               whatever is left runs through the literal step below. */
+            if (span == 1.0 && tmp > 2.0 && tmp < 1073741824.0 && cpa2 < 4503599627370496.0 && jumps) {
+                const double fl = floor(tmp);
+                double m = fl == tmp ? tmp - 1.0 : fl;                             /* spans of 1.0 before the last, shorter one */
+                m = fmin(m, floor(limit - tf));                                    /* (inf - tf = inf) */
+                const int ext = wrsn_biased_exp(tf);
+                if (tf > 0.0 && ext > 60 && ext < 1100) m = fmin(m, floor(wrsn_pow2_biased(ext + 1) - tf)); else m = 0.0;
+                double en_m = en;
+                if (rate != 0.0) {
+                    const int ex = wrsn_biased_exp(en);
+                    if (en > 0.0 && ex > 60 && ex < 1900) {
+                        const double lo = wrsn_pow2_biased(ex), inv_u = wrsn_pow2_biased(2098 - ex), u = wrsn_pow2_biased(ex - 52);
+                        const double q = rate * inv_u, rq = rint(q);
+                        const double room = en - fmax(lo, thr);
+                        if (fabs(q - rq) == 0.5 || !(rq > 0.0) || !(room > 0.0)) m = 0.0;
+                        else {
+                            m = fmin(m, floor(room / (rq * u)) - 1.0);
+                            if (m >= 2.0 && rq * m < 4503599627370496.0) en_m = en - (rq * m) * u; else m = 0.0;
+                        }
+                    } else m = 0.0;
+                }
+                if (m >= 2.0) {
+                    en = en_m; cpa2 = cpa2 >= m ? cpa2 - m : 0.0; tmp = tmp - m;
+                    span = fmin(tmp, 1.0);
+                    tf = (tf + (m - 1.0)) + span; n += (int)m;
+                    continue;
+                }
+            }
             const double en1 = en - rate * span;                                   /* charge_step :45 */
             const double cpa21 = fmax(0.0, cpa2 - span);                           /* :46 */
             const double tmp1 = tmp - span;                                        /* charge :69 */
@@ -1685,28 +1836,21 @@ WRSN_NOINLINE int nodes_batch(Ctx &c, int n_max, int ur_on, double t_reward) {
         gsync(c);
         WRSN_PROFC_END(c, WRSN_H_PROF2, pc2);
     } else {
-        /* pass 2: cycle by cycle, because update_reward reads every node at every k+1.0 (before the bookkeeping) */
-        uint32_t fixed = 0u;                         /* node slots of this thread whose energyCS has reached its fixed point */
-        bool watched = false;                        /* is there a lazy move whose position update_reward reads (Q2)? */
-        for (int q = 0; q < c.n_slot; q++) watched = watched || slot_i(slot_of(c, q))[WRSN_PRI_LAZY] == 2;
+        /* pass 2: cycle by cycle, because update_reward reads every node at every k+1.0 (before the bookkeeping): the
+           drain, the tick and the previous second's bookkeeping in one pass over the nodes per second (reward_cycles) */
+        int watched = 0;                             /* is there a lazy move whose position update_reward reads (Q2)? */
+        for (int q = 0; q < c.n_slot; q++) watched |= slot_i(slot_of(c, q))[WRSN_PRI_LAZY] == 2 ? 1 : 0;
+        reward_cycles(c, c.scr1.ptr(), n_safe, t_reward, watched);
         _Pragma("unroll 1")
-        for (int j = 0; j < n_safe; j++) {
-            if (watched) catch_up_for_reward(c, t_reward + (double)j);
-            { WRSN_PROFC_BEGIN(pc4); update_reward_body(c, c.scr1.ptr()); WRSN_PROFC_END(c, WRSN_H_PROF4, pc4); }   /* drain + update_reward */
-            int sl = 0;
-            _Pragma("unroll 1")
-            for (int i = c.tid; i < N; i += WRSN_GSZ(c), sl++) {
-                if (c.status[i] != 1) continue;
-                const double rr = c.rr[i];
-                if (rr != 0.0) c.energy[i] = fmin(c.energy[i] + rr * 0.5, cap);
-                if (sl < 32 && ((fixed >> sl) & 1u)) continue;
-                const double lg = c.logc[i], cs = c.cs[i];
-                const double nx = div_pos(cs * L - lg + lg, L);
-                if (nx == cs) { if (sl < 32) fixed |= 1u << sl; }
-                else c.cs[i] = nx;
-            }
-            gsync(c);
+        for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {   /* bookkeeping of the last second */
+            if (c.status[i] != 1) continue;
+            const double rr = c.rr[i];
+            if (rr != 0.0) c.energy[i] = fmin(c.energy[i] + rr * 0.5, cap);
+            const double lg = c.logc[i], cs = c.cs[i];
+            const double nx = div_pos(cs * L - lg + lg, L);
+            if (nx != cs) c.cs[i] = nx;
         }
+        gsync(c);
         WRSN_PROFC_END(c, WRSN_H_PROF3, pc2);
     }
     if (c.tid == 0) {

@@ -12,8 +12,13 @@ env = BatchedWRSN(scs, num_agent=3, num_envs=B, device=dev)
 obs = torch.zeros((B, 4, 100, 100), dtype=torch.float32, device=dev)
 env.reset()
 g = torch.Generator(device=dev); g.manual_seed(0)
+RC = os.environ.get("WRSN_ACTIONS", "uniform") == "rc"      # the reference's RandomController map, decoded on the device
+env.get_state(out=obs)
 for k in range(pre + n):
-    a = torch.rand((B, 3), dtype=torch.float64, device=dev, generator=g); a[:, 2] *= 0.05
+    if RC:
+        a = env.density_map_to_action(obs[:, 0] + obs[:, 1] - 10.0 * obs[:, 2] + obs[:, 3])
+    else:
+        a = torch.rand((B, 3), dtype=torch.float64, device=dev, generator=g); a[:, 2] *= 0.05
     env.rollout_step(a, obs)
 torch.cuda.synchronize()
 print("ok", env.counters())

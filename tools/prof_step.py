@@ -23,9 +23,15 @@ names = ["total", "serial", "batch", "bfs", "fitness"] if VARIANT == 1 else (
     ["total", "batch_pass1", "batch_all_at_once", "batch_cycle_loop", "update_reward_in_loop"])
 idx = [env.E["WRSN_H_PROF%d" % k] for k in range(5)]
 acc = []
+RC = os.environ.get("WRSN_ACTIONS", "uniform") == "rc"      # the reference's RandomController map, decoded on the device
+obs = torch.zeros((B, 4, 100, 100), dtype=torch.float32, device="cuda:0")
+env.get_state(out=obs)
 for k in range(steps):
-    a = torch.rand((B, 3), dtype=torch.float64, device="cuda:0", generator=g); a[:, 2] *= 0.05
-    env.rollout_step(a)
+    if RC:
+        a = env.density_map_to_action(obs[:, 0] + obs[:, 1] - 10.0 * obs[:, 2] + obs[:, 3])
+    else:
+        a = torch.rand((B, 3), dtype=torch.float64, device="cuda:0", generator=g); a[:, 2] *= 0.05
+    env.rollout_step(a, obs if RC else None)
     if k >= steps - 50:
         h = env.view("hdr")[:, idx].cpu().numpy()
         acc.append(h)
