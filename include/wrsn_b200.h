@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define WRSN_ABI_VERSION 14
+#define WRSN_ABI_VERSION 15
 #define WRSN_MAX_MC 16          /* chargers per environment */
 #define WRSN_RING 10            /* Node.operate keeps the last 10 per-second consumptions (Node.py:70-77) */
 
@@ -68,6 +68,8 @@ enum {
     WRSN_H_PROF0, WRSN_H_PROF1, WRSN_H_PROF2, WRSN_H_PROF3, WRSN_H_PROF4, /* SM cycles of the last launch (builds with -DWRSN_PROF only):
                                                                        total, serial ticks, batches, BFS + tree, fitness */
     WRSN_H_NSPLIT,                                                  /* death ticks handled in pieces (drain_pieces: closed form around the death packet) */
+    WRSN_H_INFLIGHT,                                                /* 1: WRSN.step ran out of its launch budget (wrsn_dims.step_budget) and continues at the next call */
+    WRSN_H_NRESUME,                                                 /* how often that happened */
     WRSN_H_CHAIN_SLOT = 48,                                         /* [WRSN_MAX_MC] process slot watched by member j */
     WRSN_H_COND_TRIG = WRSN_H_CHAIN_SLOT + WRSN_MAX_MC,
     WRSN_H_COND_T = WRSN_H_COND_TRIG + WRSN_MAX_MC,                 /* time of the pending condition event, +inf when none */
@@ -151,11 +153,18 @@ typedef struct wrsn_dims {
     int32_t n_slot;   /* charger process slots per environment */
     int32_t state_bytes, state_resident_bytes, scen_bytes, smem_bytes;
     int32_t obs_pitch;  /* row pitch of the observation tables */
+    /* set by the caller at any time (not touched by wrsn_dims_finalize) */
+    int32_t step_budget;  /* 0: WRSN.step returns when the environment's next request is due, as the reference does.
+                             > 0: work units per launch and environment (about one per simulated second in which a charger
+                             charges a node, one per other event); a step that needs more returns agent_id = -4 ("in
+                             flight") and continues at the next wrsn_step / wrsn_rollout_step call, so that a launch over many
+                             environments lasts as long as the budget, not as long as its slowest environment */
 } wrsn_dims;
 
 /* request record written by reset / step, device pointers, one row per environment */
 typedef struct wrsn_request {
-    int32_t *agent_id;                  /* [B]  -1 = None (terminal), -2 = implicit None, -3 = untouched (masked out) */
+    int32_t *agent_id;                  /* [B]  -1 = None (terminal), -2 = implicit None, -3 = untouched (masked out),
+                                           -4 = the step is still in flight (wrsn_dims.step_budget): call again */
     uint8_t *terminal;                  /* [B] */
     double *reward;                     /* [B] */
     double *now;                        /* [B]  env.now */
@@ -219,7 +228,8 @@ int wrsn_decode_density_map(const wrsn_dims *d, const void *scen, const int32_t 
  * every environment after rollout step t, one thread per environment:
  *   last[b][agent_prev[b]] = t                      log_probs_pre[agent] = log_prob            (:140)
  *   episode ended (req->stats[b][2] != resets_seen[b], then resets_seen[b] = it):  last[b][:] = -1   (:137-138, :143-144)
- *   agent_next[b] = max(req->agent_id[b], 0)        the request handed out for step t + 1
+ *   agent_next[b] = req->agent_id[b]                the request handed out for step t + 1; -1 when the row has none (its step
+ *                                                   is still in flight, wrsn_dims.step_budget)
  *   link_next[b]  = last[b][agent_next[b]]          step at which that agent last acted in this episode, -1: none (:145-146)
  *   new_episode_next[b], reward_next[b] (NaN -> 0), now_next[b]
  * `last` is int64 [B][M], the *_next pointers are row t + 1 of the caller's time-major record. */

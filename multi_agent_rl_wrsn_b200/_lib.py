@@ -21,7 +21,8 @@ _enums = None
 class Dims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "B", "N", "T", "M", "S", "Emax", "TEmax", "n_scen", "threads",
-        "Npad", "W", "Tw", "n_slot", "state_bytes", "state_resident_bytes", "scen_bytes", "smem_bytes", "obs_pitch")]
+        "Npad", "W", "Tw", "n_slot", "state_bytes", "state_resident_bytes", "scen_bytes", "smem_bytes", "obs_pitch",
+        "step_budget")]
 
 
 class Request(C.Structure):

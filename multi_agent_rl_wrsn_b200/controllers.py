@@ -102,11 +102,11 @@ class IPPORollout:
             self.open_now = torch.zeros((B, M), dtype=torch.float64, device=dev)
         if bool((env.req.agent_id == -3).all()):                          # never reset: start the first episodes
             env.reset()
-        if bool((env.req.agent_id < 0).any()):
-            raise RuntimeError("IPPORollout needs an open request (a deciding charger) in every environment")
+        if bool(((env.req.agent_id < 0) & (env.req.agent_id != -4)).any()):
+            raise RuntimeError("IPPORollout needs an open request (a deciding charger) or a step in flight in every environment")
         if with_obs:
             env.get_state(out=self.obs[0])
-        self.agent[0] = env.req.agent_id.to(torch.int64)
+        self.agent[0] = env.req.agent_id.to(torch.int64).clamp_min(-1)
         self.now[0] = env.req.now
         self._resets = env.req.stats[:, 2].clone()                       # episodes begun so far, per environment
 
@@ -267,14 +267,16 @@ class PerAgentPolicy:
         B, S = obs.shape[0], obs.shape[-1]
         M = len(self.actors)
         ids = agent_id.to(torch.int64)
+        ids = torch.where(ids < 0, torch.full_like(ids, M), ids)         # rows without a request (step in flight): skipped
         order = torch.argsort(ids, stable=True)
-        counts = torch.bincount(ids, minlength=M).tolist()
-        if len(counts) > M:
+        counts = torch.bincount(ids, minlength=M + 1).tolist()
+        if len(counts) > M + 1:
             raise ValueError("request for agent %d but only %d actors" % (len(counts) - 1, M))
+        counts = counts[:M]
         shape = (S, S) if self.action_shape is None else self.action_shape
         red = tuple(range(1, 1 + len(shape)))
-        x = torch.empty((B,) + shape, dtype=torch.float32, device=obs.device)
-        lp = torch.empty((B,), dtype=torch.float32, device=obs.device)
+        x = torch.zeros((B,) + shape, dtype=torch.float32, device=obs.device)
+        lp = torch.zeros((B,), dtype=torch.float32, device=obs.device)
         lo = 0
         for i, n in enumerate(counts):
             if n == 0:

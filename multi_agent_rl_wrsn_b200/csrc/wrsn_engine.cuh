@@ -68,6 +68,13 @@
 #define WRSN_LEAD(c) ((c).tid == 0)
 #endif
 
+#undef WRSN_NPT_MAX                                 /* node slots per thread the register-resident loops are built for */
+#if WRSN_GFIX == 32
+#define WRSN_NPT_MAX 4                              /* one warp: N <= 128 */
+#else
+#define WRSN_NPT_MAX 9                              /* 256 threads: N <= 2304 (shared memory ends before that) */
+#endif
+
 #undef WRSN_LDG                                     /* read-only scenario data (CSR graph, flags): the non-coherent L1 path */
 #if defined(WRSN_HOST_EMU)
 #define WRSN_LDG(p) (*(p))
@@ -151,6 +158,8 @@ struct Ctx {
     SArr<int> bcast;
     SArr<double> red;
     SArr<double> par;                                /* scenario constants, copied next to the state */
+    SArr<double> exptab;                             /* 2^(j/64), j = 0..63 (wrsn_exp_b) */
+    SArr<double> spec;                               /* [WRSN_SPEC_MAX][WRSN_SPEC_LEN] irregular nodes of the current batch */
     /* global, per environment */
     double *logtick, *ring;
     char *gscratch;
@@ -180,13 +189,16 @@ WRSN_D void ctx_bind(Ctx &c, const wrsn_dims &d, const WrsnLayout &L, const char
     c.level.off = (uint32_t)L.off[WRSN_F_LEVEL]; c.parent.off = (uint32_t)L.off[WRSN_F_PARENT];
     c.status.off = (uint32_t)L.off[WRSN_F_STATUS]; c.tact.off = (uint32_t)L.off[WRSN_F_TACT]; c.conn.off = (uint32_t)L.off[WRSN_F_CONN];
     c.own.off = (uint32_t)L.s_own; c.scr0.off = (uint32_t)L.s_scr0; c.scr1.off = (uint32_t)L.s_scr1;
-    c.bcast.off = (uint32_t)L.s_bcast; c.red.off = (uint32_t)L.s_red; c.par.off = (uint32_t)L.s_par;
+    c.bcast.off = (uint32_t)L.s_bcast; c.red.off = (uint32_t)L.s_red; c.par.off = (uint32_t)L.s_par; c.spec.off = (uint32_t)L.s_spec; c.exptab.off = (uint32_t)L.s_exptab;
     c.logtick = (double *)(state_row + L.off[WRSN_F_LOGTICK]);
     c.ring = (double *)(state_row + L.off[WRSN_F_RING]);
     c.gscratch = state_row + L.off[WRSN_F_SCRATCH];
     {
         const double *gpar = (const double *)(scen_row + L.soff[WRSN_S_PAR]);
         for (int k = tid; k < WRSN_P_LEN; k += G) c.par[k] = gpar[k];   /* visible after the caller's first barrier */
+#if !defined(WRSN_HOST_EMU)
+        for (int k = tid; k < 64; k += G) c.exptab[k] = wrsn_exp2_tab[k];
+#endif
     }
     c.nx = (const double *)(scen_row + L.soff[WRSN_S_NX]);
     c.ny = (const double *)(scen_row + L.soff[WRSN_S_NY]);
@@ -296,6 +308,13 @@ WRSN_DI void red_sum1(const Ctx &c, double &a, int &buf) {
 #endif
 #endif
 }
+WRSN_D bool red_or_warp(int v) {                    /* over the calling warp only (no barrier) */
+#if defined(WRSN_HOST_EMU)
+    return v != 0;
+#else
+    return __any_sync(0xffffffffu, v != 0);
+#endif
+}
 WRSN_D int red_or(const Ctx &c, int v) {
 #if defined(WRSN_HOST_EMU)
     (void)c; return v ? 1 : 0;
@@ -317,6 +336,13 @@ WRSN_D void atomic_add_i32(int *p, int v) {
     atomicAdd(p, v);
 #else
     *p += v;
+#endif
+}
+WRSN_D int atomic_add_ret_i32(int *p, int v) {
+#if !defined(WRSN_HOST_EMU)
+    return atomicAdd(p, v);
+#else
+    const int o = *p; *p += v; return o;
 #endif
 }
 WRSN_D void atomic_max_nonneg(double *p, double v) {      /* v >= 0: order of the bit patterns == order of the values */
@@ -370,10 +396,10 @@ WRSN_D double wrsn_rsqrt(double v) {                /* 1 / sqrt(v), v > 0 normal
     e = __fma_rn(-v, r * r, 1.0);
     return __fma_rn(r * 0.5, e, r);
 }
-/* exp(z) for |z| <= 600 (clamped), relative error <= 1e-13: z = (64 n + j) ln2/64 + r, |r| <= ln2/128;
- * exp(z) = 2^n * 2^(j/64) * (1 + r + r^2/2 + r^3/6 + r^4/24) — table of 64 doubles (wrsn_exp2_tab, one LDG), four FMAs. */
-WRSN_D double wrsn_exp_b(double z) {
-    z = fmin(fmax(z, -600.0), 600.0);
+/* exp(z) for |z| < 700, relative error <= 1e-13: z = (64 n + j) ln2/64 + r, |r| <= ln2/128;
+ * exp(z) = 2^n * 2^(j/64) * (1 + r + r^2/2 + r^3/6 + r^4/24) — table of 64 doubles in shared memory (c.exptab, copied from
+ * wrsn_exp2_tab at kernel start), four FMAs.  The caller's z is a z-score of N values: |z| <= sqrt(N - 1). */
+WRSN_DI double wrsn_exp_tab(const double *tab, double z) {
     const double t = __fma_rn(z, 92.33248261689366, 6755399441055744.0);          /* 64 / ln2; 1.5 * 2^52: the integer lands in the low word */
     const int k = __double2loint(t);
     const double r = __fma_rn(t - 6755399441055744.0, -0.010830424696249145, z); /* ln2 / 64 */
@@ -381,15 +407,22 @@ WRSN_D double wrsn_exp_b(double z) {
     p = __fma_rn(p, r, 0.5);
     p = __fma_rn(p, r, 1.0);
     p = __fma_rn(p, r, 1.0);
-    const double y = p * __ldg(&wrsn_exp2_tab[k & 63]);
+    const double y = p * tab[k & 63];
     return __hiloint2double(__double2hiint(y) + ((k >> 6) << 20), __double2loint(y));
 }
 #else
 WRSN_D double wrsn_fma(double a, double b, double c) { return a * b + c; }
 WRSN_D double wrsn_rcp(double d) { return 1.0 / d; }
 WRSN_D double wrsn_rsqrt(double v) { return 1.0 / sqrt(v); }
-WRSN_D double wrsn_exp_b(double z) { return exp(fmin(fmax(z, -600.0), 600.0)); }
 #endif
+WRSN_DI double wrsn_exp_b(const Ctx &c, double z) {
+#if defined(WRSN_HOST_EMU)
+    (void)c; return exp(z);
+#else
+    return wrsn_exp_tab(c.exptab.ptr(), z);
+#endif
+}
+
 
 WRSN_NOINLINE double euclid2(double ax, double ay, double bx, double by) {
     /* scipy.spatial.distance.euclidean == sqrt(dot(u - v, u - v)) for 2-vectors */
@@ -474,6 +507,7 @@ struct Clk {
     double now, seq, nev;
     double net_t, net_key, ur_t, ur_key, nodes_t, nodes_key, until_t, until_key;
     int net_state, nodes_phase, stop;
+    int work;                                        /* work units of this launch (see run_loop: the step budget) */
     int mc_idx;                                      /* earliest pending charger-slot (< n_slot) / condition (>= n_slot) event */
     double mc_t, mc_key, mc_other_t;                 /* its position; earliest time among the OTHER slot / condition events */
 };
@@ -493,7 +527,7 @@ WRSN_DI void clk_load(Ctx &c, Clk &k) {
     k.ur_t = h[WRSN_H_UR_ON] != 0.0 ? h[WRSN_H_UR_T] : INFINITY; k.ur_key = WRSN_KEY_NORMAL + h[WRSN_H_UR_SEQ];
     k.nodes_t = h[WRSN_H_NODES_T]; k.nodes_key = WRSN_KEY_NORMAL + h[WRSN_H_NODES_SEQ]; k.nodes_phase = (int)h[WRSN_H_NODES_PHASE];
     k.until_t = h[WRSN_H_UNTIL_ON] != 0.0 ? h[WRSN_H_UNTIL_T] : INFINITY; k.until_key = h[WRSN_H_UNTIL_SEQ];   /* URGENT */
-    k.stop = 0; k.mc_idx = -1; k.mc_t = INFINITY; k.mc_key = 0.0; k.mc_other_t = INFINITY;
+    k.stop = 0; k.work = 0; k.mc_idx = -1; k.mc_t = INFINITY; k.mc_key = 0.0; k.mc_other_t = INFINITY;
 }
 WRSN_DI void clk_store(Ctx &c, const Clk &k) {
     gsync(c);
@@ -997,8 +1031,8 @@ WRSN_D double charge_rate_to(Ctx &c, const double *m, int node) {   /* alpha / (
 }
 
 /* the softmax priority + incentive sums; only reached when some incentive sum is non-empty */
-WRSN_NOINLINE void reward_cycles(Ctx &c, const double *dec, int n_cycles, double t_reward, int watched);
 WRSN_NOINLINE double drain_node(double e, double rr, double es, double er, int nb, int ow, int na, double cap);
+WRSN_D void catch_up_for_reward(Ctx &c, double t_reward);
 
 WRSN_D bool reward_pairs(Ctx &c) {                 /* is there any (charging charger, connected alive node) pair? */
     bool any = false;
@@ -1013,103 +1047,242 @@ WRSN_D bool reward_pairs(Ctx &c) {                 /* is there any (charging cha
     return any;
 }
 
-WRSN_D void catch_up_for_reward(Ctx &c, double t_reward);
+/* ------------------------------------------------------------------ the hot loop: update_reward second by second
+ * `n_cycles` consecutive update_reward ticks (WRSN.py:100-127) with the node rows of this thread IN REGISTERS.
+ * dec == NULL (event path): one tick on the node rows as they are.
+ * dec != NULL (whole-cycle batches, nodes_batch): the grid events around every tick are applied on the way — the k+1.0
+ *   bookkeeping of the PREVIOUS second (second top-up; energyCS towards its fixed point), then this second's k+0.5
+ *   drain, then the tick; the bookkeeping of the last second follows the loop.  A regular node (energyRR == 0, inside
+ *   its binade: dec[i] is its per-second decrement) costs one subtraction per second.  The few irregular ones — charged
+ *   nodes above all — are listed in a table (c.spec, built by nodes_batch: dec[i] = NaN carrying the table slot) and
+ *   handled once per second by as many threads as there are entries, on the shared-memory copy of their energy:
+ *   inside a binade the relay / own-packet chains and the two top-ups  min(e + energyRR * 0.5, capacity)  each move the
+ *   energy by a fixed whole number of ulps (sub_chain's argument; D1, D2, H of the table), so the second is four exact
+ *   additions and two minima while the energy stays between the table's guards, and the literal tick (drain_node)
+ *   otherwise.
+ * Arithmetic of the tick itself: x_n = energyCS / (energy - threshold + eps) by reciprocal (wrsn_rcp), mean and variance
+ * from one pass (sum and sum of squares; two passes when the variance is small against mean^2), 1 / std by wrsn_rsqrt,
+ * the softmax numerators by wrsn_exp_b — see the note at those helpers.  The event path and the batches share this code
+ * and the order of every sum, so they produce the same bits (tests: batches == event path).
+ * NPT = node slots per thread (compile time on the device: everything below unrolls into registers). */
+#undef WRSN_EMU_MAXN
+#undef WRSN_SLOT_ARR
+#undef WRSN_FOR_SLOTS
+#if defined(WRSN_HOST_EMU)
+#define WRSN_EMU_MAXN 32768
+#define WRSN_SLOT_ARR(T, name) static thread_local T name[WRSN_EMU_MAXN]
+#define WRSN_FOR_SLOTS(s) for (int s = 0; s < NPT; s++)
+#else
+#define WRSN_SLOT_ARR(T, name) T name[NPT_T > 0 ? NPT_T : WRSN_NPT_MAX]
+#define WRSN_FOR_SLOTS(s) _Pragma("unroll") for (int s = 0; s < (NPT_T > 0 ? NPT_T : NPT); s++)
+#endif
+/* per-slot flags of a thread: one bit mask per flag on the device (registers), byte arrays in the host emulation (one
+ * "thread" owns all N nodes there) */
+#undef WRSN_FLAGS_DECL
+#undef WRSN_FL_GET
+#undef WRSN_FL_SET
+#undef WRSN_FL_CLR
+#if defined(WRSN_HOST_EMU)
+#define WRSN_FLAGS_DECL(name) static thread_local uint8_t name[WRSN_EMU_MAXN]; memset(name, 0, (size_t)NPT)
+#define WRSN_FL_GET(name, s) (name[s] != 0)
+#define WRSN_FL_SET(name, s) (name[s] = 1)
+#define WRSN_FL_CLR(name, s) (name[s] = 0)
+#else
+#define WRSN_FLAGS_DECL(name) uint32_t name = 0u
+#define WRSN_FL_GET(name, s) (((name) >> (s)) & 1u)
+#define WRSN_FL_SET(name, s) ((name) |= 1u << (s))
+#define WRSN_FL_CLR(name, s) ((name) &= ~(1u << (s)))
+#endif
 
-WRSN_D void ev_update_reward(Ctx &c) {
-    if (reward_pairs(c)) reward_cycles(c, (const double *)0, 1, 0.0, 0);   /* otherwise every incentive sum is empty: excl += 0 */
+WRSN_D int nan_payload(double d) {
+#if !defined(WRSN_HOST_EMU)
+    return __double2loint(d);
+#else
+    uint64_t b; memcpy(&b, &d, 8); return (int)(uint32_t)b;
+#endif
+}
+WRSN_D double nan_with_payload(int slot) {
+    const uint64_t b = 0x7ff8000000000000ull | (uint64_t)(uint32_t)slot;
+#if !defined(WRSN_HOST_EMU)
+    return __longlong_as_double((long long)b);
+#else
+    double r; memcpy(&r, &b, 8); return r;
+#endif
 }
 
-/* `n_cycles` consecutive update_reward ticks (WRSN.py:100-127).
- * dec == NULL (event path): one tick on the node rows as they are.
- * dec != NULL (whole-cycle batches, nodes_batch): the grid events around every tick are applied on the way, node by node
- * in registers — the k+1.0 bookkeeping of the PREVIOUS second (second top-up, energyCS towards its fixed point), then
- * this second's k+0.5 drain (the per-second decrement of an uncharged node, or the node's literal tick where dec[i] is
- * NaN), then the tick itself; the caller applies the bookkeeping of the last second.  Three barriers per second.
- * Arithmetic: x_n = energyCS / (energy - threshold + eps) by reciprocal (wrsn_rcp), mean and variance from one pass
- * (sum and sum of squares; two-pass when the variance is small against mean^2), 1 / std by wrsn_rsqrt, the softmax
- * numerators by wrsn_exp_b — see the note at those helpers; the event path and the batches share this code, so they
- * produce the same bits (tests: batches == event path). */
-WRSN_NOINLINE void reward_cycles(Ctx &c, const double *dec, int n_cycles, double t_reward, int watched) {
-    const int N = c.N, G = WRSN_GSZ(c);
+/* one table node, one second: [the previous second's k+1.0 top-up,] [this second's k+0.5 tick] on c.energy[i] */
+WRSN_NOINLINE void spec_second(Ctx &c, int t, int book, int drain) {
+    const double *sp = c.spec + t * WRSN_SPEC_LEN;
+    const int i = (int)sp[5];
+    const double cap = c.par[WRSN_P_CAP];
+    double e = c.energy[i];
+    if (e >= sp[3] && e <= sp[4]) {                  /* inside the guards: whole ulps */
+        const double H = sp[2];
+        if (book) e = fmin(e + H, cap);
+        if (drain) e = fmin((e - sp[0]) + H, cap) - sp[1];
+    } else {
+        const double rr = c.rr[i];
+        if (book) e = fmin(e + rr * 0.5, cap);
+        if (drain) {
+            const int ow = c.parent[i] != -1 ? (int)c.own[i] : 0;
+            e = drain_node(e, rr, c.esend[i], c.par[WRSN_P_ERECV], c.nbef[i], ow, c.naft[i], cap);
+        }
+    }
+    c.energy[i] = e;
+}
+
+/* Node.py:75 with log[0] == log_energy, for the slots whose energyCS has not reached its fixed point yet (cold: a node gets
+ * there after one or two applications) */
+WRSN_NOINLINE double cs_step(double cs, double lg) { return div_pos(cs * (double)WRSN_RING - lg + lg, (double)WRSN_RING); }
+
+/* the incentive sums of one tick (WRSN.py:113-126), one thread per charger; q_n / tot are the softmax weights */
+WRSN_NOINLINE void reward_incentives(Ctx &c, double tot) {
+    const double thr = c.par[WRSN_P_THR], cap = c.par[WRSN_P_CAP];
+    const double inv_tot = wrsn_rcp(tot), ab2 = c.par[WRSN_P_MC_AB2], inv_ab2 = wrsn_rcp(ab2);
+    for (int a2 = c.tid; a2 < c.M; a2 += WRSN_GSZ(c)) {
+        double *m = c.mc + (size_t)a2 * WRSN_MC_LEN;
+        if (m[WRSN_MC_STATUS] != 0.0 && m[WRSN_MC_TYPE] != 0.0) {
+            double incentive = 0.0;
+            const uint32_t *cm = c.conn + (size_t)a2 * c.W;
+            for (int w = 0; w < c.W; w++) {
+                for (uint32_t bits = cm[w]; bits; bits &= bits - 1u) {
+                    const int i = 32 * w + wrsn_ctz(bits);
+                    if (c.status[i] != 1) continue;
+                    const double ec = c.energy[i] - c.cs[i];
+                    double e_with = cap;             /* max(ec + rate, capacity) with rate <= alpha / beta^2 */
+                    if (ec + ab2 > cap) {
+                        const double dx = c.nx[i] - m[WRSN_MC_X], dy = c.ny[i] - m[WRSN_MC_Y], d2 = wrsn_fma(dx, dx, dy * dy);
+                        const double t = (d2 > 0.0 ? d2 * wrsn_rsqrt(d2) : 0.0) + c.par[WRSN_P_MC_BETA];
+                        e_with = fmax(ec + c.par[WRSN_P_MC_ALPHA] * wrsn_rcp(t * t), cap);
+                    }
+                    incentive += (c.scr0[i] * inv_tot) * (e_with - fmin(ec, thr)) * inv_ab2;
+                }
+            }
+            m[WRSN_MC_EXCL] += incentive;
+        }
+    }
+}
+
+WRSN_NOINLINE bool node_in_incentive(Ctx &c, int i) {   /* does an incentive sum read node i? */
+    bool in = false;
+    for (int a = 0; a < c.M; a++) {
+        const double *m = c.mc + a * WRSN_MC_LEN;
+        if (m[WRSN_MC_STATUS] != 0.0 && m[WRSN_MC_TYPE] != 0.0 && ((c.conn[a * c.W + (i >> 5)] >> (i & 31)) & 1u)) in = true;
+    }
+    return in;
+}
+
+template <int NPT_T, bool BATCH>
+WRSN_NOINLINE void reward_cycles(Ctx &c, int n_cycles, double t_reward, int watched, int n_spec) {
+    const int N = c.N, G = WRSN_GSZ(c), tid = c.tid;
+#if defined(WRSN_HOST_EMU)
+    const int NPT = N;
+#else
+    const int NPT = NPT_T > 0 ? NPT_T : (N + G - 1) / G;   /* NPT_T == 0: any N, the slot arrays in local memory (rolled loops) */
+#endif
     const double thr = c.par[WRSN_P_THR], cap = c.par[WRSN_P_CAP], eps = c.par[WRSN_P_EPSENV];
     const double inv_n = c.par[WRSN_P_INVN];         /* 1 / N from the host */
-    const double L = (double)WRSN_RING;
-    uint32_t fixed = 0u;                             /* node slots of this thread whose energyCS has reached its fixed point */
-    int buf = 0;
+    const double *dec = c.scr1.ptr();
+    WRSN_SLOT_ARR(double, e); WRSN_SLOT_ARR(double, cs); WRSN_SLOT_ARR(double, d); WRSN_SLOT_ARR(double, x);
+    WRSN_FLAGS_DECL(f_in); WRSN_FLAGS_DECL(f_inc); WRSN_FLAGS_DECL(f_unfixed); WRSN_FLAGS_DECL(f_special);
+    int any_inc = 0, any_unfixed = 0, buf = 0;
     gsync(c);
+    WRSN_FOR_SLOTS(s) {
+        const int i = tid + s * G;
+        const bool ok = i < N && c.status[i] != 0;
+        e[s] = ok ? c.energy[i] : cap; cs[s] = ok ? c.cs[i] : 0.0; d[s] = (ok && BATCH) ? dec[i] : 0.0;
+        if (i < N) WRSN_FL_SET(f_in, s);
+        if (ok) {
+            if (node_in_incentive(c, i)) { WRSN_FL_SET(f_inc, s); any_inc = 1; }
+            if (BATCH) { WRSN_FL_SET(f_unfixed, s); any_unfixed = 1; }
+            if (d[s] != d[s]) WRSN_FL_SET(f_special, s);
+        }
+    }
+    any_inc = red_or(c, any_inc);                    /* (uniform over the environment: it decides about barriers) */
     _Pragma("unroll 1")
     for (int j = 0; j < n_cycles; j++) {
         if (watched) { catch_up_for_reward(c, t_reward + (double)j); gsync(c); }
-        double s1 = 0.0, s2 = 0.0;
-        int sl = 0;
-        _Pragma("unroll 1")
-        for (int i = c.tid; i < N; i += G, sl++) {
-            double x = 0.0;
-            if (c.status[i] != 0) {
-                double e = c.energy[i], cs = c.cs[i];
-                if (dec) {
-                    if (j > 0) {                     /* Node.operate k+1.0 of the previous second (Node.py:65-77) */
-                        const double rr = c.rr[i];
-                        if (rr != 0.0) e = fmin(e + rr * 0.5, cap);
-                        if (!(sl < 32 && ((fixed >> sl) & 1u))) {
-                            const double lg = c.logc[i];
-                            const double nx = div_pos(cs * L - lg + lg, L);
-                            if (nx == cs) { if (sl < 32) fixed |= 1u << sl; }
-                            else { cs = nx; c.cs[i] = nx; }
-                        }
-                    }
-                    const double d = dec[i];         /* k+0.5 drain */
-                    if (d == d) e = e - d;
-                    else {
-                        const int ow = c.parent[i] != -1 ? (int)c.own[i] : 0;
-                        e = drain_node(e, c.rr[i], c.esend[i], c.par[WRSN_P_ERECV], c.nbef[i], ow, c.naft[i], cap);
-                    }
-                    c.energy[i] = e;
+        if (BATCH && n_spec > 0) {                   /* the table nodes: previous bookkeeping + this second's drain */
+            for (int t = tid; t < n_spec; t += G) spec_second(c, t, j > 0, 1);
+            gsync(c);
+        }
+        if (BATCH && j > 0 && red_or_warp(any_unfixed)) {   /* energyCS towards its fixed point (bookkeeping of the previous second) */
+            any_unfixed = 0;
+            WRSN_FOR_SLOTS(s) {
+                if (WRSN_FL_GET(f_unfixed, s)) {
+                    const double nx = cs_step(cs[s], c.logc[tid + s * G]);
+                    if (nx == cs[s]) WRSN_FL_CLR(f_unfixed, s); else { cs[s] = nx; any_unfixed = 1; }
                 }
-                x = cs * wrsn_rcp(e - thr + eps);
             }
-            c.scr0[i] = x; s1 += x; s2 = wrsn_fma(x, x, s2);
+        }
+        double s1 = 0.0, s2 = 0.0;
+        WRSN_FOR_SLOTS(s) {
+            if (BATCH) {
+                if (WRSN_FL_GET(f_special, s)) e[s] = c.energy[tid + s * G];
+                else e[s] = e[s] - d[s];
+            }
+            x[s] = cs[s] * wrsn_rcp(e[s] - thr + eps);
+            s1 += x[s]; s2 = wrsn_fma(x[s], x[s], s2);
         }
         red_sum2(c, s1, s2, buf);
         const double mean = s1 * inv_n;
         double var = wrsn_fma(s2, inv_n, -(mean * mean));
         if (!(var > 1e-3 * (mean * mean))) {         /* cancellation: the textbook two passes (np.std) */
-            double s = 0.0;
-            _Pragma("unroll 1")
-            for (int i = c.tid; i < N; i += G) { const double u = c.scr0[i] - mean; s = wrsn_fma(u, u, s); }
-            red_sum1(c, s, buf);
-            var = s * inv_n;
+            double q = 0.0;
+            WRSN_FOR_SLOTS(s) { const double u = WRSN_FL_GET(f_in, s) ? x[s] - mean : 0.0; q = wrsn_fma(u, u, q); }
+            red_sum1(c, q, buf);
+            var = q * inv_n;
         }
         const double a = var > 0.0 ? wrsn_rsqrt(var) : 1.0 / eps;       /* std == 0 -> std = epsilon (:104-105) */
         double tot = 0.0;
-        _Pragma("unroll 1")
-        for (int i = c.tid; i < N; i += G) { const double q = wrsn_exp_b((c.scr0[i] - mean) * a); c.scr0[i] = q; tot += q; }
-        red_sum1(c, tot, buf);
-        if (tot == 0.0) tot = eps;
-        const double inv_tot = wrsn_rcp(tot), inv_ab2 = wrsn_rcp(c.par[WRSN_P_MC_AB2]);
-        for (int a2 = c.tid; a2 < c.M; a2 += G) {    /* one thread per charger: the incentive sums run side by side */
-            double *m = c.mc + (size_t)a2 * WRSN_MC_LEN;
-            if (m[WRSN_MC_STATUS] != 0.0 && m[WRSN_MC_TYPE] != 0.0) {
-                double incentive = 0.0;
-                const double mx = m[WRSN_MC_X], my = m[WRSN_MC_Y], beta = c.par[WRSN_P_MC_BETA], alpha = c.par[WRSN_P_MC_ALPHA];
-                const uint32_t *cm = c.conn + (size_t)a2 * c.W;
-                for (int w = 0; w < c.W; w++) {
-                    for (uint32_t bits = cm[w]; bits; bits &= bits - 1u) {
-                        const int i = 32 * w + wrsn_ctz(bits);
-                        if (c.status[i] != 1) continue;
-                        const double dx = c.nx[i] - mx, dy = c.ny[i] - my, d2 = wrsn_fma(dx, dx, dy * dy);
-                        const double t = (d2 > 0.0 ? d2 * wrsn_rsqrt(d2) : 0.0) + beta;
-                        const double rate = alpha * wrsn_rcp(t * t);
-                        const double ec = c.energy[i] - c.cs[i];
-                        const double e_no = fmin(ec, thr), e_with = fmax(ec + rate, cap);
-                        incentive += (c.scr0[i] * inv_tot) * (e_with - e_no) * inv_ab2;
-                    }
-                }
-                m[WRSN_MC_EXCL] += incentive;
+        WRSN_FOR_SLOTS(s) {
+            const double q = wrsn_exp_b(c, (x[s] - mean) * a);
+            tot += WRSN_FL_GET(f_in, s) ? q : 0.0;
+            if (WRSN_FL_GET(f_inc, s)) {             /* what the incentive sums read */
+                const int i = tid + s * G;
+                c.scr0[i] = q;
+                if (BATCH) { c.cs[i] = cs[s]; if (!WRSN_FL_GET(f_special, s)) c.energy[i] = e[s]; }
             }
+        }
+        red_sum1(c, tot, buf);                       /* (its barrier also publishes the stores above) */
+        if (WRSN_GFIX == 32) gsync(c);
+        if (tot == 0.0) tot = eps;
+        if (tid < c.M) reward_incentives(c, tot);
+        if (any_inc || n_spec > 0 || watched || WRSN_GFIX != 32) gsync(c);
+    }
+    if (BATCH) {                                     /* bookkeeping of the last second; rows back to shared memory */
+        if (n_spec > 0) {
+            for (int t = tid; t < n_spec; t += G) spec_second(c, t, 1, 0);
+        }
+        WRSN_FOR_SLOTS(s) {
+            const int i = tid + s * G;
+            if (!(i < N && c.status[i] != 0)) continue;
+            if (WRSN_FL_GET(f_unfixed, s)) cs[s] = cs_step(cs[s], c.logc[i]);
+            c.cs[i] = cs[s];
+            if (!WRSN_FL_GET(f_special, s)) c.energy[i] = e[s];
         }
         gsync(c);
     }
+}
+
+WRSN_NOINLINE void reward_cycles_any(Ctx &c, int batch, int n_cycles, double t_reward, int watched, int n_spec) {
+#if defined(WRSN_HOST_EMU)
+    if (batch) reward_cycles<0, true>(c, n_cycles, t_reward, watched, n_spec);
+    else reward_cycles<0, false>(c, 1, 0.0, 0, 0);
+#else
+    const int npt = (c.N + WRSN_GSZ(c) - 1) / WRSN_GSZ(c);
+    if (!batch) {                                    /* event path: one tick (cold) */
+        if (npt <= 4) reward_cycles<4, false>(c, 1, 0.0, 0, 0); else reward_cycles<0, false>(c, 1, 0.0, 0, 0);
+    }
+    else if (npt <= 1) reward_cycles<1, true>(c, n_cycles, t_reward, watched, n_spec);
+    else if (npt <= 2) reward_cycles<2, true>(c, n_cycles, t_reward, watched, n_spec);
+    else if (npt <= 4) reward_cycles<4, true>(c, n_cycles, t_reward, watched, n_spec);
+    else reward_cycles<0, true>(c, n_cycles, t_reward, watched, n_spec);
+#endif
+}
+
+WRSN_D void ev_update_reward(Ctx &c) {
+    if (reward_pairs(c)) reward_cycles_any(c, 0, 1, 0.0, 0, 0);   /* otherwise every incentive sum is empty: excl += 0 */
 }
 
 /* ------------------------------------------------------------------ WRSN.get_network_fitness (WRSN.py:188-220) -> min */
@@ -1750,7 +1923,9 @@ WRSN_NOINLINE double drain_node(double e, double rr, double es, double er, int n
     return sub_chain(e2, es, ow, er, na);
 }
 
-WRSN_NOINLINE int nodes_batch(Ctx &c, int n_max, int ur_on, double t_reward) {
+/* `n_active_max`: cap on the cycles of a batch in which update_reward is active (the step budget's granularity);
+ * returns the cycles applied, + 2^30 when they were of the active kind */
+WRSN_NOINLINE int nodes_batch(Ctx &c, int n_max, int ur_on, double t_reward, int n_active_max) {
     const int N = c.N;
     const double thr = c.par[WRSN_P_THR], cap = c.par[WRSN_P_CAP], er = c.par[WRSN_P_ERECV];
     const double slack = 1e-6;
@@ -1759,6 +1934,9 @@ WRSN_NOINLINE int nodes_batch(Ctx &c, int n_max, int ur_on, double t_reward) {
     if (h[WRSN_H_OPT_NOBATCH] == 1.0 || h[WRSN_H_BFS_DIRTY] != 0.0 || h[WRSN_H_LOG_LITERAL] != 0.0 ||
         h[WRSN_H_LOG_LEN] < (double)WRSN_RING || h[WRSN_H_LOG_UNIFORM] < 10.0) return 0;
     const bool active = ur_on && reward_pairs(c);    /* update_reward looks at every node every second */
+    if (active && n_max > n_active_max) n_max = n_active_max;
+    int *bc = c.bcast;                               /* [0]: entries of the table of irregular nodes (active batches) */
+    if (active) { gsync(c); if (c.tid == 0) bc[0] = 0; gsync(c); }
     /* pass 1: per node, the per-cycle decrement (scr1; NaN = replay cycle by cycle) and the number of safe cycles */
     WRSN_PROFC_BEGIN(pc1);
     int n_safe = n_max;
@@ -1801,6 +1979,30 @@ WRSN_NOINLINE int nodes_batch(Ctx &c, int n_max, int ur_on, double t_reward) {
             if (e - thr - 1.0 > cons * (double)n_safe) m = n_safe;
             else { double e_end; m = replay_cycles(e, rr, es, er, nb, ow, na, thr, cap, n_safe, &e_end); }
         }
+        if (active && dec != dec) {
+            /* table entry (reward_cycles / spec_second): inside e's binade the chain of relayed packets of lower ids, the
+               own packets + relays of higher ids and the top-up  min(e + energyRR * 0.5, cap)  move e by D1, D2 and H — whole
+               numbers of ulps — as long as e stays between the guards for the whole second (both top-ups, both chains) */
+            const int slot = atomic_add_ret_i32(&bc[0], 1);
+            if (slot < WRSN_SPEC_MAX) {
+                double *sp = c.spec + slot * WRSN_SPEC_LEN;
+                double D1 = 0.0, D2 = 0.0, H = 0.0, glo = INFINITY, ghi = -INFINITY;
+                const int ex = wrsn_biased_exp(e);
+                if (e > 0.0 && ex > 60 && ex < 1900) {
+                    const double lo = wrsn_pow2_biased(ex), inv_u = wrsn_pow2_biased(2098 - ex), u = wrsn_pow2_biased(ex - 52);
+                    const double qa = es * inv_u, qb = er * inv_u, qh = (rr * 0.5) * inv_u;
+                    const double ra = rint(qa), rb = rint(qb), rh = rint(qh);
+                    const bool tie = (n_a > 0 && fabs(qa - ra) == 0.5) || (n_b > 0 && fabs(qb - rb) == 0.5) || fabs(qh - rh) == 0.5;
+                    const double K1 = (ra + rb) * (double)nb, K2 = ra * (double)(ow + na) + rb * (double)na;
+                    if (!tie && K1 + K2 < 1125899906842624.0 && rh < 1125899906842624.0 && rr >= 0.0) {
+                        D1 = K1 * u; D2 = K2 * u; H = rh * u;
+                        glo = lo + (D1 + D2); ghi = (lo + lo) - (H + H) - (u + u);
+                    }
+                }
+                sp[0] = D1; sp[1] = D2; sp[2] = H; sp[3] = glo; sp[4] = ghi; sp[5] = (double)i;
+                dec = nan_with_payload(slot);
+            }
+        }
         c.scr1[i] = dec;
         if (m < n_safe) n_safe = m;
     }
@@ -1808,6 +2010,8 @@ WRSN_NOINLINE int nodes_batch(Ctx &c, int n_max, int ur_on, double t_reward) {
     n_safe = (int)red_min(c, (double)n_safe);
     WRSN_PROFC_END(c, WRSN_H_PROF1, pc1);
     if (n_safe <= 0) return 0;
+    const int n_spec = active ? bc[0] : 0;
+    if (n_spec > WRSN_SPEC_MAX) return 0;            /* more irregular nodes than the table holds: this second event by event */
     const double L = (double)WRSN_RING;
     WRSN_PROFC_BEGIN(pc2);
     if (!active) {
@@ -1840,17 +2044,7 @@ WRSN_NOINLINE int nodes_batch(Ctx &c, int n_max, int ur_on, double t_reward) {
            drain, the tick and the previous second's bookkeeping in one pass over the nodes per second (reward_cycles) */
         int watched = 0;                             /* is there a lazy move whose position update_reward reads (Q2)? */
         for (int q = 0; q < c.n_slot; q++) watched |= slot_i(slot_of(c, q))[WRSN_PRI_LAZY] == 2 ? 1 : 0;
-        reward_cycles(c, c.scr1.ptr(), n_safe, t_reward, watched);
-        _Pragma("unroll 1")
-        for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {   /* bookkeeping of the last second */
-            if (c.status[i] != 1) continue;
-            const double rr = c.rr[i];
-            if (rr != 0.0) c.energy[i] = fmin(c.energy[i] + rr * 0.5, cap);
-            const double lg = c.logc[i], cs = c.cs[i];
-            const double nx = div_pos(cs * L - lg + lg, L);
-            if (nx != cs) c.cs[i] = nx;
-        }
-        gsync(c);
+        reward_cycles_any(c, 1, n_safe, t_reward, watched, n_spec);
         WRSN_PROFC_END(c, WRSN_H_PROF3, pc2);
     }
     if (c.tid == 0) {
@@ -1862,16 +2056,23 @@ WRSN_NOINLINE int nodes_batch(Ctx &c, int n_max, int ur_on, double t_reward) {
     }
     gsync(c);
     WRSN_PROF_END(c, WRSN_H_PROF2);
-    return n_safe;
+    return n_safe + (active ? (1 << 30) : 0);
 }
 
 /* ------------------------------------------------------------------ the event loop: env.run(...) */
-WRSN_DI void run_loop(Ctx &c) {
+/* `budget` > 0: stop at an event boundary once the launch has done that many work units (one per event handled, plus
+ * one per simulated second in which update_reward is active — the expensive kind) and return 1: the clock is stored
+ * as it is, the pending run(until) / AnyOf chain stay pending, and the next launch continues where this one stopped.
+ * A launch then lasts as long as the budget allows, not as long as its slowest environment's whole step. */
+WRSN_DI int run_loop(Ctx &c, int budget) {
     Clk k;
     clk_load(c, k);
     const double maxtime = c.par[WRSN_P_MAXTIME];
     bool rescan = true;
+    int interrupted = 0;
     for (long guard = 0; guard < 400000000L; guard++) {
+        if (budget > 0 && k.work >= budget) { interrupted = 1; break; }
+        k.work++;
         if (rescan) { WRSN_PROFB_BEGIN(); mc_scan(c, k); rescan = false; WRSN_PROFB_END(c, WRSN_H_PROF4); }
         /* earliest of the grid items (Network.operate, update_reward, the node block, run(until=t)) */
         int gk = K_NODES;
@@ -1908,7 +2109,11 @@ WRSN_DI void run_loop(Ctx &c) {
                         const double span = fmin(H - gt, 1048576.0);
                         int n = (int)span;
                         while (n > 0 && !(gt + (double)n <= H)) n--;
-                        if (n > 0) batched = nodes_batch(c, n, ur_on ? 1 : 0, gt + 0.5);
+                        if (n > 0) {
+                            const int cap_active = budget > 0 ? (budget - k.work > 8 ? budget - k.work : 8) : n;
+                            batched = nodes_batch(c, n, ur_on ? 1 : 0, gt + 0.5, cap_active);
+                            if (batched >= (1 << 30)) { batched -= 1 << 30; k.work += batched; }
+                        }
                         if (batched > 0) {
                             /* the clock after `batched` cycles: every cycle drew its insertion counters in the order drain,
                                [update_reward,] [exit check,] bookkeeping, [connectivity] (Network.operate may have ended, Q1) */
@@ -1957,6 +2162,7 @@ WRSN_DI void run_loop(Ctx &c) {
     catch_up_many(c, k.now, 1);
     WRSN_PROFB_END(c, WRSN_H_PROF2); }
     clk_store(c, k);
+    return interrupted;
 }
 
 /* ------------------------------------------------------------------ entry points (one environment) */
@@ -2003,7 +2209,7 @@ WRSN_D void entry_run_until(Ctx &c, double at) {
         c.hdr[WRSN_H_UNTIL_ON] = 1.0; c.hdr[WRSN_H_UNTIL_T] = at; c.hdr[WRSN_H_UNTIL_SEQ] = take_seq_h(c);
     }
     gsync(c);
-    run_loop(c);
+    run_loop(c, 0);
 }
 
 WRSN_D int scan_decider(Ctx &c) {                  /* WRSN.py:321-322 */
@@ -2071,8 +2277,12 @@ WRSN_D void entry_reset_finish(Ctx &c, ReqOut *r) {
 }
 
 /* WRSN.step (WRSN.py:289-330) */
-WRSN_D void entry_step(Ctx &c, int agent_id, const double *input_action, ReqOut *r) {
-    if (c.tid == 0) {
+/* `budget`: see run_loop.  A step that ran out of budget returns agent = -4 ("in flight") and hdr[INFLIGHT] = 1; the
+ * next call for this environment ignores agent_id / input_action and continues the same env.run(until=general_process). */
+WRSN_D void entry_step(Ctx &c, int agent_id, const double *input_action, ReqOut *r, int budget) {
+    const bool resume = c.hdr[WRSN_H_INFLIGHT] != 0.0;
+    gsync(c);
+    if (c.tid == 0 && !resume) {
         double *h = c.hdr;
         if (agent_id >= 0 && agent_id < c.M) {       /* :290-305 */
             double *m = mc_of(c, agent_id);
@@ -2110,13 +2320,25 @@ WRSN_D void entry_step(Ctx &c, int agent_id, const double *input_action, ReqOut 
     }
     gsync(c);
     const int watched = (int)c.hdr[WRSN_H_CHAIN_N];
-    if (watched > 0) run_loop(c);
+    int interrupted = 0;
+    if (watched > 0) interrupted = run_loop(c, budget);
     gsync(c);
+    if (interrupted) {
+        if (c.tid == 0) {
+            c.hdr[WRSN_H_INFLIGHT] = 1.0; c.hdr[WRSN_H_NRESUME] += 1.0;
+            r->now = c.hdr[WRSN_H_NOW]; r->flags = c.hdr[WRSN_H_ERR] != 0.0 ? 2 : 0; r->agent = -4; r->terminal = 0;
+            r->reward = NAN; r->detail[0] = r->detail[1] = NAN;
+            for (int k = 0; k < 3; k++) r->act[k] = NAN;
+        }
+        gsync(c);
+        return;
+    }
     int id = -1;
     if (!(watched == 0 || c.hdr[WRSN_H_ALIVE] == 0.0)) { id = scan_decider(c); if (id < 0) id = -2; }   /* all threads */
     double fit = 0.0;
     if (id >= 0) fit = do_fitness(c, (double *)0);   /* get_reward :222-227 */
     if (c.tid == 0) {
+        c.hdr[WRSN_H_INFLIGHT] = 0.0;
         r->now = c.hdr[WRSN_H_NOW];
         r->flags = (watched == 0 ? 1 : 0) | (c.hdr[WRSN_H_ERR] != 0.0 ? 2 : 0);
         r->agent = id;

@@ -1,12 +1,12 @@
 /* wrsn_env_kernel.cuh — the one-CTA-per-environment kernel; included once per group-size specialisation (see
  * wrsn_engine.cuh), inside the same namespace. */
 template <int MODE>
-__global__ void __launch_bounds__(WRSN_GFIX ? WRSN_GFIX : 256, WRSN_GFIX ? 20 : 1) k_env(const KParams P) {
+__global__ void __launch_bounds__(WRSN_GFIX ? WRSN_GFIX : 256, WRSN_GFIX ? 16 : 1) k_env(const KParams P) {
     char *smem = reinterpret_cast<char *>(wrsn_smem_u4);
     const int b = blockIdx.x, tid = threadIdx.x, G = blockDim.x;
     if (P.mask && !P.mask[b]) return;
-    if (P.mask_mode == 1 && P.req.agent_id[b] < 0) return;
-    if (P.mask_mode == 2 && P.req.agent_id[b] >= 0) return;
+    if (P.mask_mode == 1 && P.req.agent_id[b] < 0 && P.req.agent_id[b] != -4) return;     /* (-4: a step in flight continues) */
+    if (P.mask_mode == 2 && (P.req.agent_id[b] >= 0 || P.req.agent_id[b] == -4)) return;
     char *row = P.state + (size_t)b * P.L.total;
     const char *scen_row = P.scen + (size_t)P.scen_id[b] * P.L.scen_total;
     Ctx c;
@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(WRSN_GFIX ? WRSN_GFIX : 256, WRSN_GFIX ? 20 : 
     case MODE_RUN_UNTIL: entry_run_until(c, P.t_until[b]); break;
     case MODE_RESET_FINISH:
     case MODE_RESTORE_RESET: entry_reset_finish(c, &r); break;
-    case MODE_STEP: entry_step(c, P.agent_in ? P.agent_in[b] : -1, P.action_in ? P.action_in + 3 * (size_t)b : nullptr, &r); break;
+    case MODE_STEP: entry_step(c, P.agent_in ? P.agent_in[b] : -1, P.action_in ? P.action_in + 3 * (size_t)b : nullptr, &r, P.d.step_budget); break;
     case MODE_FITNESS: {
         double mn = do_fitness(c, P.fitness ? P.fitness + (size_t)b * P.d.T : nullptr);
         if (tid == 0 && P.fit_min) P.fit_min[b] = mn;

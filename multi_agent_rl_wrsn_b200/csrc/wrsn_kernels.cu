@@ -727,11 +727,10 @@ __global__ void k_record_transitions(int B, int M, wrsn_request req, long long t
     resets_seen[b] = resets;
     if (ended)
         for (int a = 0; a < M; a++) row[a] = -1;
-    int an = req.agent_id[b];
-    if (an < 0) an = 0;
+    int an = req.agent_id[b];                        /* < 0: no request for this row (-4: its step is still in flight) */
     if (an >= M) an = M - 1;
-    agent_next[b] = an;
-    link_next[b] = row[an];
+    agent_next[b] = an < 0 ? -1 : an;
+    link_next[b] = an < 0 ? -1 : row[an];
     new_episode_next[b] = ended ? 1 : 0;
     const double r = req.reward[b];
     reward_next[b] = (r == r) ? r : 0.0;

@@ -15,11 +15,14 @@
 #define WRSN_HD __host__ __device__ static inline
 #endif
 
+#define WRSN_SPEC_MAX 32                            /* charged (or otherwise irregular) nodes a whole-cycle batch handles by table */
+#define WRSN_SPEC_LEN 6                             /* D1, D2, H, lo guard, hi guard, node id */
+
 /* ------------------------------------------------------------------ layouts */
 struct WrsnLayout {
     int64_t off[WRSN_F_COUNT];
     int64_t resident, total;                        /* bytes mirrored in shared memory / bytes per record */
-    int64_t s_own, s_scr0, s_scr1, s_bcast, s_red, s_par, smem_total;
+    int64_t s_own, s_scr0, s_scr1, s_bcast, s_red, s_par, s_spec, s_exptab, smem_total;
     int64_t soff[WRSN_S_COUNT];
     int64_t scen_total;
     int32_t scr_len;                                /* doubles per scratch row */
@@ -60,6 +63,8 @@ WRSN_HD void wrsn_make_layout(const wrsn_dims *d, WrsnLayout *L) {
     L->s_bcast = s; s += 64;
     L->s_red = s; s += 8 * 32;
     L->s_par = s; s += 8 * WRSN_P_LEN;             /* scenario constants: copied next to the state, never re-read from HBM */
+    L->s_spec = s; s += 8 * WRSN_SPEC_LEN * WRSN_SPEC_MAX;   /* per-batch table of the charged nodes (wrsn_engine.cuh: reward_cycles) */
+    L->s_exptab = s; s += 8 * 64;                  /* 2^(j/64): table of the reward path's exponential */
     L->smem_total = s;
     /* scenario record */
     o = 0;

@@ -37,8 +37,8 @@ static int run_mode(int mode, const Args &A) {
     std::vector<char> smem((size_t)L.smem_total + 64);
     for (int b = 0; b < d.B; b++) {
         if (A.mask && !A.mask[b]) continue;
-        if (A.mask_mode == 1 && A.req->agent_id[b] < 0) continue;
-        if (A.mask_mode == 2 && A.req->agent_id[b] >= 0) continue;
+        if (A.mask_mode == 1 && A.req->agent_id[b] < 0 && A.req->agent_id[b] != -4) continue;
+        if (A.mask_mode == 2 && (A.req->agent_id[b] >= 0 || A.req->agent_id[b] == -4)) continue;
         char *row = A.state + (size_t)b * L.total;
         const char *scen_row = A.scen + (size_t)A.scen_id[b] * L.scen_total;
         Ctx c;
@@ -57,7 +57,7 @@ static int run_mode(int mode, const Args &A) {
         case MODE_INIT: entry_init_network(c, A.with_reward); break;
         case MODE_RUN_UNTIL: entry_run_until(c, A.t_until[b]); break;
         case MODE_RESET_FINISH: case MODE_RESTORE_RESET: entry_reset_finish(c, &r); break;
-        case MODE_STEP: entry_step(c, A.agent_in ? A.agent_in[b] : -1, A.action_in ? A.action_in + 3 * (size_t)b : nullptr, &r); break;
+        case MODE_STEP: entry_step(c, A.agent_in ? A.agent_in[b] : -1, A.action_in ? A.action_in + 3 * (size_t)b : nullptr, &r, d.step_budget); break;
         case MODE_FITNESS: { double mn = do_fitness(c, A.fitness ? A.fitness + (size_t)b * d.T : nullptr); if (A.fit_min) A.fit_min[b] = mn; break; }
         case MODE_K_BFS: do_bfs(c); break;
         case MODE_K_DRAIN: ev_nodes_drain(c); break;
@@ -147,9 +147,9 @@ int wrsn_record_transitions(const wrsn_dims *d, const wrsn_request *req, int64_t
         const bool ended = resets != resets_seen[b];
         resets_seen[b] = resets;
         if (ended) for (int a = 0; a < M; a++) row[a] = -1;
-        int an = req->agent_id[b] < 0 ? 0 : req->agent_id[b];
+        int an = req->agent_id[b];
         if (an >= M) an = M - 1;
-        agent_next[b] = an; link_next[b] = row[an]; new_episode_next[b] = ended ? 1 : 0;
+        agent_next[b] = an < 0 ? -1 : an; link_next[b] = an < 0 ? -1 : row[an]; new_episode_next[b] = ended ? 1 : 0;
         reward_next[b] = req->reward[b] == req->reward[b] ? req->reward[b] : 0.0;
         now_next[b] = req->now[b];
     }
