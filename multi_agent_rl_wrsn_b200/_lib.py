@@ -1,9 +1,7 @@
 """ctypes binding of ``libwrsn_b200.so`` (C ABI: ``include/wrsn_b200.h``).
 
 There is no CPU path: if the CUDA library has not been built (``python -c "import __graft_entry__ as g;
-g.build()"``) or no sm_100 device is visible, importing a simulator raises.  ``use_library()`` exists so the
-test-suite can point the host layer at the single-lane host build of the kernel source
-(``tests/emu``) — product code never calls it.
+g.build()"``) or no sm_100 device is visible, constructing a simulator raises.
 """
 import ctypes as C
 import os
@@ -90,13 +88,6 @@ def _bind(L):
     return L
 
 
-def use_library(path):
-    """TEST HOOK: bind an explicit shared object (the tests' host emulation).  Never called by product code."""
-    global _lib
-    _lib = _bind(C.CDLL(path))
-    return _lib
-
-
 def lib():
     global _lib
     if _lib is None:
@@ -105,10 +96,6 @@ def lib():
                                "g.build()').  This package has no CPU fallback." % LIB_PATH)
         _lib = _bind(C.CDLL(LIB_PATH))
     return _lib
-
-
-def is_emulation(L):
-    return hasattr(L, "wrsn_is_emulation")
 
 
 def check(rc, L):

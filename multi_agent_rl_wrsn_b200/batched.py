@@ -25,8 +25,9 @@ class Requests:
     """The request record of ``WRSN.reset`` / ``WRSN.step`` (``WRSN.py:68-83,313-330``) for every environment.
 
     ``agent_id``: >= 0 deciding charger, -1 ``None`` (terminal), -2 implicit ``None``, -3 row not
-    touched by the call (masked out).  ``flags`` bit0: every charger is dead (the reference would never
-    return, Q1); bit1: engine error.
+    touched by the call (masked out), -4 the step is still in flight (``step_budget`` exhausted: the next ``step`` /
+    ``rollout_step`` continues it, whatever agent / action it is handed for that row).  ``flags`` bit0: every charger is
+    dead (the reference would never return, Q1); bit1: engine error.
     """
 
     def __init__(self, B, device):
@@ -45,23 +46,15 @@ class Requests:
 
 class BatchedWRSN:
     def __init__(self, scenarios, num_agent=3, mc_type=None, num_envs=None, scenario_index=None, map_size=100,
-                 warm_up_time=100, device=None, threads=0):
+                 warm_up_time=100, device=None, threads=0, step_budget=0):
         """``scenarios``: one or several ``Scenario`` / YAML paths (all with the same N and T);
-        ``scenario_index[b]`` picks the scenario of environment b (default: round robin)."""
+        ``scenario_index[b]`` picks the scenario of environment b (default: round robin).
+        ``step_budget`` (``wrsn_dims.step_budget``, may be changed later through ``self.dims``): 0 = every ``step`` returns
+        the environment's next request, as the reference does; > 0 = work units per launch and environment — a step that
+        needs more comes back with ``agent_id == -4`` and continues at the next call, so one launch over thousands of
+        environments lasts as long as the budget instead of as long as its slowest environment."""
         self.L = _lib.lib()
-        emu = _lib.is_emulation(self.L)
-        if device is None:
-            device = "cpu" if emu else "cuda"
-        self.device = torch.device(device)
-        if emu:
-            if self.device.type != "cpu":
-                raise RuntimeError("the host emulation only works on CPU tensors")
-        else:
-            if self.device.type != "cuda" or not torch.cuda.is_available():
-                raise RuntimeError("BatchedWRSN needs a CUDA device (sm_100a); there is no CPU path")
-            with torch.cuda.device(self.device):
-                if not self.L.wrsn_device_ok():
-                    raise RuntimeError("wrsn_b200: " + self.L.wrsn_last_error().decode())
+        self.device = self._require_device(device)
         if isinstance(scenarios, (str, Scenario)):
             scenarios = [scenarios]
         self.scenarios = [s if isinstance(s, Scenario) else Scenario.load_yaml(s) for s in scenarios]
@@ -83,15 +76,16 @@ class BatchedWRSN:
         d.Emax = max(len(st["nbr_idx"]) for st in statics)
         d.TEmax = max(len(st["tgt_idx"]) for st in statics)
         d.n_scen, d.threads = n_scen, int(threads)
-        _lib.check(self.L.wrsn_dims_finalize(C.byref(d)), self.L)
+        self._call(self.L.wrsn_dims_finalize, C.byref(d))
+        d.step_budget = int(step_budget)
         self.dims = d
         self._foff = (C.c_int64 * self.E["WRSN_F_COUNT"])()
         self._soff = (C.c_int64 * self.E["WRSN_S_COUNT"])()
-        _lib.check(self.L.wrsn_state_layout(C.byref(d), self._foff), self.L)
-        _lib.check(self.L.wrsn_scen_layout(C.byref(d), self._soff), self.L)
+        self._call(self.L.wrsn_state_layout, C.byref(d), self._foff)
+        self._call(self.L.wrsn_scen_layout, C.byref(d), self._soff)
 
         self.scen = torch.from_numpy(self._pack_scenarios(statics)).to(self.device)
-        _lib.check(self.L.wrsn_build_obs_tables(C.byref(d), self.scen.data_ptr(), self._stream()), self.L)
+        self._call(self.L.wrsn_build_obs_tables, C.byref(d), self.scen.data_ptr(), self._stream())
         if scenario_index is None:
             scenario_index = np.arange(B) % n_scen
         self.scen_id = torch.as_tensor(np.asarray(scenario_index, np.int32), device=self.device)
@@ -103,8 +97,33 @@ class BatchedWRSN:
         self._make_snapshot()
 
     # ------------------------------------------------------------------ plumbing
+    def _require_device(self, device):
+        """The sm_100 device this simulator lives on.  There is no CPU path: anything else raises."""
+        dev = torch.device("cuda" if device is None else device)
+        if dev.type != "cuda" or not torch.cuda.is_available():
+            raise RuntimeError("BatchedWRSN needs a CUDA device (sm_100a); there is no CPU path")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        with torch.cuda.device(dev):
+            if not self.L.wrsn_device_ok():
+                raise RuntimeError("wrsn_b200: " + self.L.wrsn_last_error().decode())
+        return dev
+
     def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream) if self.device.type == "cuda" else None
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _sync(self):
+        torch.cuda.synchronize(self.device)
+
+    def _call(self, fn, *args):
+        """Every launch runs with THIS simulator's device current (the C ABI launches on the CUDA runtime's current device;
+        the stream handle alone does not select it)."""
+        if torch.cuda.current_device() != self.device.index:
+            with torch.cuda.device(self.device):
+                rc = fn(*args)
+        else:
+            rc = fn(*args)
+        _lib.check(rc, self.L)
 
     def _pack_scenarios(self, statics):
         d, E = self.dims, self.E
@@ -150,11 +169,10 @@ class BatchedWRSN:
         ids = torch.arange(d.n_scen, dtype=torch.int32, device=self.device)
         until = torch.full((d.n_scen,), self.warm_up_time, dtype=torch.float64, device=self.device)
         L, st = self.L, self._stream()
-        _lib.check(L.wrsn_init_network(C.byref(ds), self.scen.data_ptr(), ids.data_ptr(), snap.data_ptr(), None, 1, st), L)
-        _lib.check(L.wrsn_run_until(C.byref(ds), self.scen.data_ptr(), ids.data_ptr(), snap.data_ptr(), None,
-                                    until.data_ptr(), st), L)
-        if self.device.type == "cuda":
-            torch.cuda.synchronize(self.device)
+        self._call(L.wrsn_init_network, C.byref(ds), self.scen.data_ptr(), ids.data_ptr(), snap.data_ptr(), None, 1, st)
+        self._call(L.wrsn_run_until, C.byref(ds), self.scen.data_ptr(), ids.data_ptr(), snap.data_ptr(), None,
+                                    until.data_ptr(), st)
+        self._sync()
         self._snap = snap
 
     # ------------------------------------------------------------------ the WRSN interface, batched
@@ -162,9 +180,9 @@ class BatchedWRSN:
         """``WRSN.reset`` (:41-83) for the selected environments (all when ``mask`` is None)."""
         m, mp = self._mask_ptr(mask)
         L = self.L
-        _lib.check(L.wrsn_reset_from_snapshot(C.byref(self.dims), self.scen.data_ptr(), self.scen_id.data_ptr(),
+        self._call(L.wrsn_reset_from_snapshot, C.byref(self.dims), self.scen.data_ptr(), self.scen_id.data_ptr(),
                                               self.state.data_ptr(), self._snap.data_ptr(), mp, C.byref(self.req.c),
-                                              self._stream()), L)
+                                              self._stream())
         return self.req
 
     def step(self, agent_id, action, mask=None):
@@ -175,8 +193,8 @@ class BatchedWRSN:
         if a.shape != (self.B,) or x.shape != (self.B, 3):
             raise ValueError("agent_id must be [B], action [B, 3]")
         m, mp = self._mask_ptr(mask)
-        _lib.check(L.wrsn_step(C.byref(self.dims), self.scen.data_ptr(), self.scen_id.data_ptr(), self.state.data_ptr(),
-                               mp, a.data_ptr(), x.data_ptr(), C.byref(self.req.c), self._stream()), L)
+        self._call(L.wrsn_step, C.byref(self.dims), self.scen.data_ptr(), self.scen_id.data_ptr(), self.state.data_ptr(),
+                               mp, a.data_ptr(), x.data_ptr(), C.byref(self.req.c), self._stream())
         return self.req
 
     def rollout_step(self, action, obs=None):
@@ -191,9 +209,9 @@ class BatchedWRSN:
             if obs.dtype not in (torch.float32, torch.float64) or not obs.is_contiguous() or obs.shape != (self.B, 4, self.S, self.S):
                 raise ValueError("obs must be a contiguous float32/float64 tensor [B, 4, S, S]")
             op, f64 = obs.data_ptr(), 1 if obs.dtype == torch.float64 else 0
-        _lib.check(self.L.wrsn_rollout_step(C.byref(self.dims), self.scen.data_ptr(), self.scen_id.data_ptr(),
+        self._call(self.L.wrsn_rollout_step, C.byref(self.dims), self.scen.data_ptr(), self.scen_id.data_ptr(),
                                             self.state.data_ptr(), self._snap.data_ptr(), action.data_ptr(),
-                                            C.byref(self.req.c), op, f64, self._stream()), self.L)
+                                            C.byref(self.req.c), op, f64, self._stream())
         return self.req
 
     def get_state(self, agent_id=None, out=None, dtype=torch.float32):
@@ -206,9 +224,9 @@ class BatchedWRSN:
             out = torch.zeros((self.B, 4, self.S, self.S), dtype=dtype, device=self.device)
         if out.dtype not in (torch.float32, torch.float64) or not out.is_contiguous() or out.shape != (self.B, 4, self.S, self.S):
             raise ValueError("out must be a contiguous float32/float64 tensor [B, 4, S, S]")
-        _lib.check(self.L.wrsn_observe(C.byref(self.dims), self.scen.data_ptr(), self.scen_id.data_ptr(),
+        self._call(self.L.wrsn_observe, C.byref(self.dims), self.scen.data_ptr(), self.scen_id.data_ptr(),
                                        self.state.data_ptr(), a.data_ptr(), out.data_ptr(),
-                                       1 if out.dtype == torch.float64 else 0, self._stream()), self.L)
+                                       1 if out.dtype == torch.float64 else 0, self._stream())
         return out
 
     def density_map_to_action(self, dmap, agent_id=None, out=None):
@@ -226,25 +244,24 @@ class BatchedWRSN:
             out = torch.zeros((self.B, 3), dtype=torch.float64, device=self.device)
         if out.dtype != torch.float64 or not out.is_contiguous() or out.shape != (self.B, 3):
             raise ValueError("out must be a contiguous float64 tensor [B, 3]")
-        _lib.check(self.L.wrsn_decode_density_map(C.byref(self.dims), self.scen.data_ptr(), self.scen_id.data_ptr(),
+        self._call(self.L.wrsn_decode_density_map, C.byref(self.dims), self.scen.data_ptr(), self.scen_id.data_ptr(),
                                                   self.state.data_ptr(), a.data_ptr(), dmap.data_ptr(),
-                                                  1 if dmap.dtype == torch.float64 else 0, out.data_ptr(), self._stream()),
-                   self.L)
+                                                  1 if dmap.dtype == torch.float64 else 0, out.data_ptr(), self._stream())
         return out
 
     def get_network_fitness(self):
         """``WRSN.get_network_fitness`` (:188-220): per-target values [B, T] and their minimum [B]."""
         fit = torch.zeros((self.B, max(self.T, 1)), dtype=torch.float64, device=self.device)
         mn = torch.zeros((self.B,), dtype=torch.float64, device=self.device)
-        _lib.check(self.L.wrsn_fitness(C.byref(self.dims), self.scen.data_ptr(), self.scen_id.data_ptr(),
-                                       self.state.data_ptr(), fit.data_ptr(), mn.data_ptr(), self._stream()), self.L)
+        self._call(self.L.wrsn_fitness, C.byref(self.dims), self.scen.data_ptr(), self.scen_id.data_ptr(),
+                                       self.state.data_ptr(), fit.data_ptr(), mn.data_ptr(), self._stream())
         return fit[:, :self.T], mn
 
     # ------------------------------------------------------------------ lower-level entry points (tests / profiling)
     def init_network(self, with_reward_process=True, mask=None):
         m, mp = self._mask_ptr(mask)
-        _lib.check(self.L.wrsn_init_network(C.byref(self.dims), self.scen.data_ptr(), self.scen_id.data_ptr(),
-                                            self.state.data_ptr(), mp, 1 if with_reward_process else 0, self._stream()), self.L)
+        self._call(self.L.wrsn_init_network, C.byref(self.dims), self.scen.data_ptr(), self.scen_id.data_ptr(),
+                                            self.state.data_ptr(), mp, 1 if with_reward_process else 0, self._stream())
 
     def run_until(self, t, mask=None):
         m, mp = self._mask_ptr(mask)
@@ -252,37 +269,39 @@ class BatchedWRSN:
         if tt.ndim == 0:
             tt = tt.expand(self.B)
         tt = tt.contiguous()
-        _lib.check(self.L.wrsn_run_until(C.byref(self.dims), self.scen.data_ptr(), self.scen_id.data_ptr(),
-                                         self.state.data_ptr(), mp, tt.data_ptr(), self._stream()), self.L)
+        self._call(self.L.wrsn_run_until, C.byref(self.dims), self.scen.data_ptr(), self.scen_id.data_ptr(),
+                                         self.state.data_ptr(), mp, tt.data_ptr(), self._stream())
 
     def reset_finish(self, mask=None):
         m, mp = self._mask_ptr(mask)
-        _lib.check(self.L.wrsn_reset_finish(C.byref(self.dims), self.scen.data_ptr(), self.scen_id.data_ptr(),
-                                            self.state.data_ptr(), mp, C.byref(self.req.c), self._stream()), self.L)
+        self._call(self.L.wrsn_reset_finish, C.byref(self.dims), self.scen.data_ptr(), self.scen_id.data_ptr(),
+                                            self.state.data_ptr(), mp, C.byref(self.req.c), self._stream())
         return self.req
 
-    def charge_rates(self, charging=None):
+    def charge_rates(self, charging=None, out=None):
         """The node x charger charging model, dense (``wrsn_k_charge``; ``Node.charger_connection`` ``Node.py:134-139`` over
         the ``connected_nodes`` of ``MobileCharger.charge`` ``MobileCharger.py:56-59``): the ``energyRR`` every alive node
         would receive [B, N] and the ``chargingRate`` every charger would draw [B, M] if the chargers selected by
         ``charging`` (uint8 [B, M]; default all) charged at their present positions.  Does not touch the state."""
-        node = torch.zeros((self.B, self.N), dtype=torch.float64, device=self.device)
-        mc = torch.zeros((self.B, max(self.M, 1)), dtype=torch.float64, device=self.device)
+        if out is not None:                              # (node [B, N], mc [B, max(M, 1)]) of an earlier call, reused
+            node, mc = out[0], out[1] if out[1].shape[1] == max(self.M, 1) else None
+        else:
+            node = torch.zeros((self.B, self.N), dtype=torch.float64, device=self.device)
+            mc = torch.zeros((self.B, max(self.M, 1)), dtype=torch.float64, device=self.device)
         ch, cp = None, None
         if charging is not None:
             ch = torch.as_tensor(charging, device=self.device).to(torch.uint8).contiguous()
             if ch.shape != (self.B, self.M):
                 raise ValueError("charging must be [B, M]")
             cp = C.c_void_p(ch.data_ptr())
-        _lib.check(self.L.wrsn_k_charge(C.byref(self.dims), self.scen.data_ptr(), self.scen_id.data_ptr(), self.state.data_ptr(),
-                                        cp, node.data_ptr(), mc.data_ptr(), self._stream()), self.L)
+        self._call(self.L.wrsn_k_charge, C.byref(self.dims), self.scen.data_ptr(), self.scen_id.data_ptr(), self.state.data_ptr(),
+                                        cp, node.data_ptr(), mc.data_ptr(), self._stream())
         return node, mc[:, :self.M]
 
     def kernel(self, name):
         """Standalone per-tick kernels: 'bfs', 'drain', 'bookkeep', 'reward'."""
-        fn = getattr(self.L, "wrsn_k_" + name)
-        _lib.check(fn(C.byref(self.dims), self.scen.data_ptr(), self.scen_id.data_ptr(), self.state.data_ptr(),
-                      self._stream()), self.L)
+        self._call(getattr(self.L, "wrsn_k_" + name), C.byref(self.dims), self.scen.data_ptr(), self.scen_id.data_ptr(),
+                   self.state.data_ptr(), self._stream())
 
     # ------------------------------------------------------------------ typed views of the state records (no copies)
     def view(self, name, state=None):

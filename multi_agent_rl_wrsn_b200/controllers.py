@@ -266,18 +266,17 @@ class PerAgentPolicy:
     def __call__(self, agent_id, obs):
         B, S = obs.shape[0], obs.shape[-1]
         M = len(self.actors)
-        ids = agent_id.to(torch.int64)
-        ids = torch.where(ids < 0, torch.full_like(ids, M), ids)         # rows without a request (step in flight): skipped
+        ids = agent_id.to(torch.int64).clamp_min(-1) + 1                 # 0: row without a request (step in flight), skipped
         order = torch.argsort(ids, stable=True)
         counts = torch.bincount(ids, minlength=M + 1).tolist()
         if len(counts) > M + 1:
-            raise ValueError("request for agent %d but only %d actors" % (len(counts) - 1, M))
-        counts = counts[:M]
+            raise ValueError("request for agent %d but only %d actors" % (len(counts) - 2, M))
+        skipped, counts = counts[0], counts[1:]
         shape = (S, S) if self.action_shape is None else self.action_shape
         red = tuple(range(1, 1 + len(shape)))
         x = torch.zeros((B,) + shape, dtype=torch.float32, device=obs.device)
         lp = torch.zeros((B,), dtype=torch.float32, device=obs.device)
-        lo = 0
+        lo = skipped
         for i, n in enumerate(counts):
             if n == 0:
                 continue

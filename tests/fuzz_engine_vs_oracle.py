@@ -25,7 +25,8 @@ def main():
     p.add_argument("--seconds", type=float, default=400.0)
     a = p.parse_args()
     if a.device == "cpu":
-        _lib.use_library(os.path.join(REPO, "tests", "emu", "libwrsn_emu.so"))
+        from tests import helpers
+        helpers.use_host_build()
     from tests import parity_cases as pc
     t0, fails, n = time.time(), 0, 0
     for seed in range(a.first_seed, a.first_seed + a.count):

@@ -114,12 +114,16 @@ def check_episode(name, device, check_obs=False, replicas=1):
 
 
 def check_vs_oracle(scenarios, device, num_envs, steps, seed, num_agent=3, mc=None, check_obs=False, scale2=0.05,
-                    map_size=100, scenario_index=None):
-    """B environments with DIFFERENT action streams (and possibly different scenarios) vs B oracle runs (ladder L6)."""
+                    map_size=100, scenario_index=None, controller=False, obs32=False, threads=0):
+    """B environments with DIFFERENT action streams (and possibly different scenarios) vs B oracle runs (ladder L6).
+    ``controller``: the actions are those of the reference's RandomController — the density map s0 + s1 - 10 s2 + s3 of the
+    float32 observation, decoded ON THE DEVICE (wrsn_decode_density_map) — and the oracle is fed the decoded 3-vectors, so
+    the simulation is compared on the trajectory the device controller drives (the decoder itself: tests/test_decode.py).
+    ``obs32``: also the float32 raster against the oracle's state at 1e-5 of the channel maximum."""
     if isinstance(scenarios, Scenario):
         scenarios = [scenarios]
     env = BatchedWRSN(scenarios, num_agent=num_agent, mc_type=mc, num_envs=num_envs, device=device, map_size=map_size,
-                      scenario_index=scenario_index)
+                      scenario_index=scenario_index, threads=threads)
     sid = _np(env.scen_id)
     B = num_envs
     rng = np.random.default_rng(seed)
@@ -130,7 +134,7 @@ def check_vs_oracle(scenarios, device, num_envs, steps, seed, num_agent=3, mc=No
     for o in oracles:
         o.set_event_budget(3_000_000)
     req = env.reset()
-    oreq = [o.reset(want_state=check_obs) for o in oracles]
+    oreq = [o.reset(want_state=check_obs or obs32) for o in oracles]
     live = np.ones(B, bool)
     n_dec = 0
     for k in range(steps + 1):
@@ -160,16 +164,32 @@ def check_vs_oracle(scenarios, device, num_envs, steps, seed, num_agent=3, mc=No
             for b in range(B):
                 if live[b] and oreq[b]["raw_agent_id"] >= 0:
                     np.testing.assert_allclose(obs[b], oreq[b]["state"], rtol=1e-9, atol=1e-12)
+        if obs32 or controller:
+            o32 = env.get_state(dtype=torch.float32)
+        if obs32:
+            got = _np(o32).astype(np.float64)
+            for b in range(B):
+                if live[b] and oreq[b]["raw_agent_id"] >= 0:
+                    ref = oreq[b]["state"]
+                    for ch in range(4):
+                        tol = 1e-5 * max(float(np.abs(ref[ch]).max()), 1e-3)
+                        assert float(np.abs(got[b][ch] - ref[ch]).max()) <= tol, (b, k, ch)
         if k == steps:
             break
         live &= aid >= 0
         if not live.any():
             break
         mask = torch.as_tensor(live.astype(np.uint8))
-        req = env.step(np.where(live, aid, -1).astype(np.int32), acts[k], mask=mask)
+        if controller:
+            dm = o32[:, 0] + o32[:, 1] - 10.0 * o32[:, 2] + o32[:, 3]
+            act_k = _np(env.density_map_to_action(dm.contiguous()))
+            act_k[~live] = 0.0
+        else:
+            act_k = acts[k]
+        req = env.step(np.where(live, aid, -1).astype(np.int32), act_k, mask=mask)
         for b in range(B):
             if live[b]:
-                oreq[b] = oracles[b].step(int(aid[b]), acts[k, b], want_state=check_obs)
+                oreq[b] = oracles[b].step(int(aid[b]), act_k[b], want_state=check_obs or obs32)
     assert float(_np(env.hdr("ERR")).max()) == 0.0
     return n_dec, env.counters()
 
@@ -477,3 +497,180 @@ def check_charge_kernel(scenarios, device, num_envs, steps, seed, num_agent=3):
                 n_rows += 1
     print("charge kernel: %d connected pairs, %d / %d rows bit-identical" % (n_pairs, n_exact, n_rows))
     return n_pairs
+
+
+def check_budget_equals_unbudgeted(scenarios, device, num_envs, calls, seed, budget, num_agent=3, scale2=0.3, threads=0):
+    """A step budget (wrsn_dims.step_budget) only cuts a WRSN.step into several launches: every request an environment hands
+    out — agent, time, reward, termination, clipped action — and every byte of its record at that moment are those of the
+    unbudgeted run answered with the same actions.  Returns how many interrupted launches it took."""
+    rng = np.random.default_rng(seed)
+    acts = rng.uniform(0.0, 1.0, size=(calls, num_envs, 3))
+    acts[..., 2] *= scale2
+    a = BatchedWRSN(scenarios, num_agent=num_agent, num_envs=num_envs, device=device, threads=threads)
+    b = BatchedWRSN(scenarios, num_agent=num_agent, num_envs=num_envs, device=device, threads=threads, step_budget=budget)
+    end = int(a._foff[a.E["WRSN_F_SCRATCH"]])            # the engine's scratch field (last in the record) is not state
+    hdr0 = int(a._foff[a.E["WRSN_F_HDR"]])
+    skip = [hdr0 + 8 * a.E["WRSN_H_" + f] for f in ("NRESUME",)]
+
+    def rows(env):
+        st = env.state[:, :end].clone()
+        for o in skip:
+            st[:, o:o + 8] = 0
+        return st.cpu()
+
+    fields = ("agent_id", "terminal", "now", "action", "reward", "detail", "flags")
+    a.reset(); b.reset()
+    rec = []
+    for k in range(calls):
+        a.rollout_step(torch.as_tensor(acts[k], device=a.device))
+        rec.append(({f: _np(getattr(a.req, f)) for f in fields}, rows(a)))
+        assert not bool((a.req.agent_id == -4).any())
+    count = np.zeros(num_envs, np.int64)
+    interrupted = launches = 0
+    while int(count.min()) < calls and launches < 400 * calls:
+        cur = np.minimum(count, calls - 1)
+        act = torch.as_tensor(acts[cur, np.arange(num_envs)], device=b.device)
+        b.rollout_step(act)
+        launches += 1
+        aid = _np(b.req.agent_id)
+        st = rows(b)
+        got = {f: _np(getattr(b.req, f)) for f in fields}
+        for e in range(num_envs):
+            if aid[e] == -4:
+                interrupted += 1
+                continue
+            if count[e] >= calls:
+                continue
+            want, wst = rec[count[e]]
+            for f in fields:
+                assert np.array_equal(got[f][e], want[f][e], equal_nan=True), (e, int(count[e]), f, got[f][e], want[f][e])
+            assert torch.equal(st[e], wst[e]), (e, int(count[e]), "state record differs")
+            count[e] += 1
+    assert int(count.min()) >= calls, "budgeted run did not finish"
+    return interrupted
+
+
+def check_tick_kernels(name, device, t_from, t_to):
+    """Ladder L1 / L2: the standalone per-tick kernels (wrsn_k_drain k+0.5, wrsn_k_bookkeep k+1.0, wrsn_k_bfs k+1.1) applied by
+    hand, tick after tick, to a state dumped from a pure-network run of a shipped scenario — against the oracle advanced
+    through the same ticks, across the death tick.  Returns the number of deaths seen."""
+    g = golden(name)
+    sc = sc_from_golden(g)
+    env = BatchedWRSN(sc, num_agent=0, num_envs=1, device=device)
+    env.init_network(with_reward_process=False)
+    o = OracleWRSN(scenario_from_dict(sc.to_dict()), num_agent=0)
+    o.start_network_only()
+    env.run_until(t_from + 0.25)                     # second t_from: connectivity at +0.1 done, drain at +0.5 next
+    o.run_until(t_from + 0.25)
+    dead0 = int((o.nodes()["status"] == 0).sum())
+
+    def same(tag, with_levels):
+        nd = o.nodes()
+        assert np.array_equal(_np(env.view("status"))[0], nd["status"]), tag
+        np.testing.assert_allclose(_np(env.view("energy"))[0], nd["energy"], rtol=E_RTOL, err_msg=str(tag))
+        np.testing.assert_allclose(_np(env.view("cs"))[0], nd["cs"], rtol=E_RTOL, err_msg=str(tag))
+        if with_levels:
+            assert np.array_equal(_np(env.view("level"))[0].astype(np.int32), nd["level"]), tag
+            assert np.array_equal(_np(env.targets_active())[0], o.targets_active()), tag
+            assert int(_np(env.alive)[0]) == int(o.alive), tag
+
+    for k in range(int(t_from), int(t_to)):
+        env.kernel("drain"); o.run_until(k + 0.75); same((k, "drain"), False)
+        env.kernel("bookkeep"); o.run_until(k + 1.05); same((k, "bookkeep"), False)
+        if float(_np(env.hdr("BFS_DIRTY"))[0]) != 0.0:
+            env.kernel("bfs")
+        o.run_until(k + 1.25); same((k, "bfs"), True)
+    return int((o.nodes()["status"] == 0).sum()) - dead0
+
+
+def reward_tick_reference(energy, cs, status, thr, cap, eps, mc_xy, mc_charging, conn, xy, alpha, beta):
+    """WRSN.update_reward (rl_env/WRSN.py:100-127), one tick, restated with numpy on plain arrays: the increments of
+    agents_exclusive_reward."""
+    pr = np.where(status != 0, cs / (energy - thr + eps), 0.0)
+    mean, std = np.mean(pr), np.std(pr)
+    if std == 0:
+        std = eps
+    pr = np.exp((pr - mean) / std)
+    tot = np.sum(pr)
+    if tot == 0:
+        tot = eps
+    pr = pr / tot
+    out = np.zeros(len(mc_xy))
+    for a in range(len(mc_xy)):
+        if not mc_charging[a]:
+            continue
+        inc = 0.0
+        for n in conn[a]:
+            if status[n] == 1:
+                d = float(np.sqrt((xy[n, 0] - mc_xy[a, 0]) ** 2 + (xy[n, 1] - mc_xy[a, 1]) ** 2))
+                rate = alpha / (d + beta) ** 2
+                e_no = min(energy[n] - cs[n], thr)
+                e_with = max(energy[n] - cs[n] + rate, cap)
+                inc += pr[n] * (e_with - e_no) / (alpha / beta ** 2)
+        out[a] = inc
+    return out
+
+
+def check_reward_kernel(scenarios, device, num_envs, steps, seed, num_agent=3):
+    """wrsn_k_reward (one WRSN.update_reward tick: softmax of z-scored priorities + incentive sums, reciprocal / table-exp
+    arithmetic) against the numpy restatement of the reference's statements on states reached by a rollout that parks the
+    chargers next to nodes.  Returns the number of (charger, tick) increments compared that were non-zero."""
+    env = BatchedWRSN(scenarios, num_agent=num_agent, num_envs=num_envs, device=device)
+    sid = _np(env.scen_id)
+    rng = np.random.default_rng(seed)
+    env.reset()
+    n_nonzero = 0
+    for k in range(steps):
+        act = np.zeros((num_envs, 3))
+        for b in range(num_envs):
+            st = env.statics[sid[b]]
+            par, sc = st["par"], env.scenarios[sid[b]]
+            xy = sc.nodes[rng.integers(sc.N)] + rng.normal(0.0, 6.0, 2)
+            act[b, 0] = np.clip((xy[0] - par["F0"]) / (par["F1"] - par["F0"]), 0, 1)
+            act[b, 1] = np.clip((xy[1] - par["F2"]) / (par["F3"] - par["F2"]), 0, 1)
+            act[b, 2] = rng.uniform(0.02, 0.1)
+        env.rollout_step(torch.as_tensor(act, device=env.device))
+        before = _np(env.mc("EXCL"))
+        energy, cs, status = _np(env.view("energy")), _np(env.view("cs")), _np(env.view("status"))
+        mx, my, typ, mst = _np(env.mc("X")), _np(env.mc("Y")), _np(env.mc("TYPE")), _np(env.mc("STATUS"))
+        conn = _np(env.view("conn_words")).astype(np.int64) & 0xFFFFFFFF
+        env.kernel("reward")
+        after = _np(env.mc("EXCL"))
+        for b in range(num_envs):
+            par = env.statics[sid[b]]["par"]
+            sets = [[n for n in range(env.N) if (conn[b, a, n >> 5] >> (n & 31)) & 1] for a in range(num_agent)]
+            ref = reward_tick_reference(energy[b], cs[b], status[b], par["THR"], par["CAP"], par["EPSENV"],
+                                        np.stack([mx[b], my[b]], 1), (typ[b] != 0) & (mst[b] != 0), sets,
+                                        np.asarray(env.scenarios[sid[b]].nodes, np.float64), par["MC_ALPHA"], par["MC_BETA"])
+            np.testing.assert_allclose(after[b] - before[b], ref, rtol=1e-9, atol=1e-12 * max(1.0, float(np.abs(before[b]).max())),
+                                       err_msg=str((k, b)))
+            n_nonzero += int((ref != 0).sum())
+    return n_nonzero
+
+
+def check_sharded_equals_unsharded(scenarios, device, num_envs, steps, seed, world=2, num_agent=3, budget=0):
+    """Environments shard by index: the records of `world` simulators holding contiguous blocks of the environments are, byte
+    for byte, the blocks of ONE simulator holding all of them (same scenario assignment, same actions)."""
+    from multi_agent_rl_wrsn_b200.sharding import shard_range, shard_scenario_index
+    rng = np.random.default_rng(seed)
+    acts = rng.uniform(0.0, 1.0, size=(steps, num_envs, 3))
+    acts[..., 2] *= 0.1
+    whole = BatchedWRSN(scenarios, num_agent=num_agent, num_envs=num_envs, device=device, step_budget=budget,
+                        scenario_index=shard_scenario_index(num_envs, len(scenarios), 0, 1))
+    parts = []
+    for r in range(world):
+        lo, hi = shard_range(num_envs, r, world)
+        parts.append((lo, hi, BatchedWRSN(scenarios, num_agent=num_agent, num_envs=hi - lo, device=device, step_budget=budget,
+                                          scenario_index=shard_scenario_index(num_envs, len(scenarios), r, world))))
+    whole.reset()
+    for _, _, p in parts:
+        p.reset()
+    end = int(whole._foff[whole.E["WRSN_F_SCRATCH"]])
+    for k in range(steps):
+        whole.rollout_step(torch.as_tensor(acts[k], device=whole.device))
+        for lo, hi, p in parts:
+            p.rollout_step(torch.as_tensor(acts[k, lo:hi], device=p.device))
+            assert torch.equal(p.state[:, :end], whole.state[lo:hi, :end]), (k, lo)
+            for f in ("agent_id", "terminal", "now", "action", "reward"):
+                assert np.array_equal(_np(getattr(p.req, f)), _np(getattr(whole.req, f))[lo:hi], equal_nan=True), (k, lo, f)
+    return whole.counters()

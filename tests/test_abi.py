@@ -65,10 +65,9 @@ def test_no_cpu_path():
     if torch.cuda.is_available():
         pytest.skip("GPU present")
     from multi_agent_rl_wrsn_b200 import BatchedWRSN, synthetic
-    prev = _lib._lib
-    _lib._lib = None
-    try:
-        with pytest.raises(RuntimeError):
-            BatchedWRSN(synthetic(num_nodes=20, num_targets=20, seed=0), num_agent=1, num_envs=1)
-    finally:
-        _lib._lib = prev
+    from tests import helpers
+    helpers.use_cuda_build_lazy()
+    with pytest.raises(RuntimeError):
+        BatchedWRSN(synthetic(num_nodes=20, num_targets=20, seed=0), num_agent=1, num_envs=1)
+    with pytest.raises(RuntimeError):
+        BatchedWRSN(synthetic(num_nodes=20, num_targets=20, seed=0), num_agent=1, num_envs=1, device="cpu")

@@ -7,6 +7,8 @@ import os
 import subprocess
 
 import pytest
+
+from tests import helpers
 import torch
 
 from multi_agent_rl_wrsn_b200 import BatchedIPPO, BatchedWRSN, _lib, synthetic
@@ -21,10 +23,9 @@ ARGS = dict(seed=0, lr=3.0e-4, gamma=0.99, clip=0.2, batch_size=24, n_updates_pe
 @pytest.fixture()
 def emu_library():
     subprocess.check_call(["make", "-C", EMU_DIR, "libwrsn_emu.so"], stdout=subprocess.DEVNULL)
-    prev = _lib._lib
-    _lib.use_library(os.path.join(EMU_DIR, "libwrsn_emu.so"))
+    helpers.use_host_build()
     yield
-    _lib._lib = prev
+    helpers.use_cuda_build_lazy()
 
 
 class Actor(torch.nn.Module):
@@ -103,7 +104,7 @@ def _ddp_worker(rank, world, port, out_dir):
     from multi_agent_rl_wrsn_b200.sharding import shard_range, shard_scenario_index
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    _lib.use_library(os.path.join(EMU_DIR, "libwrsn_emu.so"))
+    helpers.use_host_build()
     torch.manual_seed(0)                                                 # identical initial replicas
     scs = [synthetic(num_nodes=40, num_targets=120, seed=s, num_gateways=2) for s in (3, 4)]
     lo, hi = shard_range(8, rank, world)

@@ -7,7 +7,7 @@ import torch
 from multi_agent_rl_wrsn_b200 import BatchedWRSN, _lib, synthetic
 from oracle import decode_oracle as do
 from oracle.wrsn_oracle import OracleWRSN, scenario_from_dict
-from tests import parity_cases as pc
+from tests import helpers, parity_cases as pc
 from tests.helpers import golden, mc_dict_of
 
 DEV = "cuda:0"
@@ -58,12 +58,9 @@ def test_percentile_and_argmax_conventions():
 
 @pytest.fixture()
 def cuda_library():
-    prev = _lib._lib
-    _lib._lib = None
-    L = _lib.lib()
-    assert not _lib.is_emulation(L) and torch.cuda.is_available()
+    L = helpers.use_cuda_build()
+    assert not helpers.is_host_build(L) and torch.cuda.is_available()
     yield
-    _lib._lib = prev
 
 
 def _rolled_env(B, steps, seed, scale2=0.05):

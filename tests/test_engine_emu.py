@@ -7,6 +7,8 @@ import subprocess
 import numpy as np
 import pytest
 
+from tests import helpers
+
 from multi_agent_rl_wrsn_b200 import _lib, synthetic
 from tests import parity_cases as pc
 from tests.helpers import REPO, golden_names
@@ -17,10 +19,9 @@ EMU_DIR = os.path.join(REPO, "tests", "emu")
 @pytest.fixture(scope="module", autouse=True)
 def emu_library():
     subprocess.check_call(["make", "-C", EMU_DIR, "libwrsn_emu.so"], stdout=subprocess.DEVNULL)
-    prev = _lib._lib
-    _lib.use_library(os.path.join(EMU_DIR, "libwrsn_emu.so"))
+    helpers.use_host_build()
     yield
-    _lib._lib = prev
+    helpers.use_cuda_build_lazy()
 
 
 @pytest.mark.parametrize("name", golden_names("net_"))
@@ -124,3 +125,28 @@ def test_emulated_raster_vs_reference_observations(name):
     """The emulation's host raster (what lets the CPU tests of the trainers' loop see observations) against the reference's
     golden get_state maps; the CUDA rasters are checked against the same fixtures in tests/test_gpu_parity.py."""
     pc.check_episode(name, "cpu", check_obs=True)
+
+
+@pytest.mark.parametrize("budget,scale2", [(12, 0.3), (40, 0.05), (3, 0.3)])
+def test_step_budget_only_cuts_steps_into_launches(budget, scale2):
+    """wrsn_dims.step_budget: interrupted steps continue where they stopped; requests and records are those of the
+    unbudgeted run (episodes end and restart on the way)."""
+    scs = [synthetic(num_nodes=40, num_targets=120, seed=s, num_gateways=2) for s in (3, 4)]
+    n = pc.check_budget_equals_unbudgeted(scs, "cpu", num_envs=4, calls=60, seed=5, budget=budget, scale2=scale2)
+    assert n > 20
+
+
+def test_tick_kernels_across_a_death_tick():
+    """Ladder L1 / L2 on the host build: the per-tick entry points, tick by tick, across hanoi1000n200's death tick (518.5)."""
+    assert pc.check_tick_kernels("net_hanoi1000n200", "cpu", 512, 524) >= 1
+
+
+def test_reward_tick_vs_reference_statements():
+    scs = [synthetic(num_nodes=60, num_targets=70, seed=s) for s in (11, 12)]
+    assert pc.check_reward_kernel(scs, "cpu", num_envs=4, steps=25, seed=3) > 10
+
+
+def test_sharded_equals_unsharded_records():
+    scs = [synthetic(num_nodes=40, num_targets=60, seed=s) for s in (31, 32, 33)]
+    pc.check_sharded_equals_unsharded(scs, "cpu", num_envs=7, steps=40, seed=2, world=2, num_agent=2)
+    pc.check_sharded_equals_unsharded(scs, "cpu", num_envs=7, steps=40, seed=2, world=3, num_agent=2, budget=10)

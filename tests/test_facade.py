@@ -12,11 +12,9 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module", autouse=True)
 def cuda_library():
-    prev = _lib._lib
-    _lib._lib = None
-    _lib.lib()
+    from tests import helpers
+    helpers.use_cuda_build()
     yield
-    _lib._lib = prev
 
 
 def test_request_dict_matches_reference_episode():

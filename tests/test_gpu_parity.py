@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from multi_agent_rl_wrsn_b200 import BatchedWRSN, _lib, synthetic
-from tests import parity_cases as pc
+from tests import helpers, parity_cases as pc
 from tests.helpers import golden_names
 
 pytestmark = pytest.mark.gpu
@@ -14,13 +14,10 @@ DEV = "cuda:0"
 
 @pytest.fixture(scope="module", autouse=True)
 def cuda_library():
-    prev = _lib._lib
-    _lib._lib = None
-    L = _lib.lib()                      # raises if the extension is missing: no fallback
-    assert not _lib.is_emulation(L)
+    L = helpers.use_cuda_build()        # raises if the extension is missing: no fallback
+    assert not helpers.is_host_build(L)
     assert torch.cuda.is_available()
     yield
-    _lib._lib = prev
 
 
 @pytest.mark.parametrize("name", golden_names("net_"))
@@ -170,3 +167,90 @@ def test_charge_kernel_vs_reference_statements():
     assert pc.check_charge_kernel(scs, DEV, num_envs=9, steps=40, seed=2) > 50
     scs = [synthetic(num_nodes=300, num_targets=300, seed=40, num_gateways=5)]
     assert pc.check_charge_kernel(scs, DEV, num_envs=3, steps=20, seed=3, num_agent=5) > 10
+
+
+# ------------------------------------------------------------------ round 2: the bench's own workload, budgets, shards, per-tick kernels
+BENCH_SCENARIOS = [1000, 1001, 1002, 1003]           # bench.py: synthetic(100, 100, seed=1000 + k), 3 chargers
+
+
+@pytest.mark.parametrize("threads", [32, 64])
+def test_bench_scenarios_vs_oracle_uniform_actions(threads):
+    """bench.py's exact scenarios (--actions uniform law), 64 environments x 60 steps against the oracle, float32 raster at
+    1e-5 of the channel maximum — on one warp per environment (the bench's build) and on two."""
+    scs = [synthetic(num_nodes=100, num_targets=100, seed=s) for s in BENCH_SCENARIOS]
+    n_dec, cnt = pc.check_vs_oracle(scs, DEV, num_envs=64, steps=60, seed=11, obs32=True, threads=threads)
+    assert n_dec > 64 * 50
+
+
+def test_bench_scenarios_vs_oracle_random_controller():
+    """The headline workload as bench.py drives it: RandomController density map of the float32 observation, decoded on the
+    device, 64 environments x 60 steps; the oracle is fed the decoded actions.  Agent ids, times, termination, status / level /
+    coverage sets exact, energies 1e-9, reward 1e-9 (spec 1e-6): update_reward is active almost every second here."""
+    scs = [synthetic(num_nodes=100, num_targets=100, seed=s) for s in BENCH_SCENARIOS]
+    n_dec, cnt = pc.check_vs_oracle(scs, DEV, num_envs=64, steps=60, seed=12, controller=True, obs32=True)
+    assert n_dec > 64 * 40 and cnt["batched_ticks"] > 0.5 * cnt["ticks"]
+
+
+@pytest.mark.parametrize("threads,budget", [(32, 25), (64, 60), (32, 160)])
+def test_step_budget_only_cuts_steps_into_launches(threads, budget):
+    scs = [synthetic(num_nodes=100, num_targets=100, seed=s) for s in BENCH_SCENARIOS]
+    n = pc.check_budget_equals_unbudgeted(scs, DEV, num_envs=32, calls=80, seed=5, budget=budget, scale2=0.1, threads=threads)
+    assert n > 10
+    scs = [synthetic(num_nodes=40, num_targets=120, seed=s, num_gateways=2) for s in (3, 4)]
+    pc.check_budget_equals_unbudgeted(scs, DEV, num_envs=8, calls=60, seed=6, budget=budget, scale2=0.3, threads=threads)
+
+
+def test_sharded_equals_unsharded_records():
+    """Two / three simulators holding contiguous blocks of the environments == one simulator holding all of them, byte for
+    byte (environments shard by index, nothing is exchanged) — also with a step budget."""
+    scs = [synthetic(num_nodes=100, num_targets=100, seed=s) for s in BENCH_SCENARIOS[:3]]
+    pc.check_sharded_equals_unsharded(scs, DEV, num_envs=50, steps=60, seed=2, world=2)
+    pc.check_sharded_equals_unsharded(scs, DEV, num_envs=50, steps=60, seed=3, world=3, budget=40)
+
+
+@pytest.mark.parametrize("name,t_from,t_to", [("net_hanoi1000n200", 512, 524), ("net_hanoi1000n100", 1598, 1608)])
+def test_tick_kernels_across_a_death_tick(name, t_from, t_to):
+    """Ladder L1 / L2: wrsn_k_drain / wrsn_k_bookkeep / wrsn_k_bfs launched by hand, tick by tick, across the death ticks of the
+    shipped scenarios (hanoi1000n200 518.5, hanoi1000n100 1602.5), against the oracle."""
+    assert pc.check_tick_kernels(name, DEV, t_from, t_to) >= 1
+
+
+def test_reward_kernel_vs_reference_statements():
+    scs = [synthetic(num_nodes=100, num_targets=100, seed=s) for s in BENCH_SCENARIOS[:2]]
+    assert pc.check_reward_kernel(scs, DEV, num_envs=8, steps=30, seed=3) > 20
+
+
+@pytest.mark.parametrize("chunk", range(5))
+def test_fuzz_engine_vs_oracle(chunk):
+    """Ladder L7 on the device: 10 random configurations per case (20-90 nodes, 10-150 targets, 1-4 chargers, charge fractions
+    up to 1, 30-160 steps, every fourth with observations) against the C restatement, decision by decision."""
+    n = 0
+    for seed in range(5000 + 10 * chunk, 5010 + 10 * chunk):
+        rng = np.random.default_rng(seed)
+        N, T, M = int(rng.integers(20, 90)), int(rng.integers(10, 150)), int(rng.integers(1, 5))
+        gw, scale2 = int(rng.integers(2, 5)), float(rng.choice([0.02, 0.1, 0.5, 1.0]))
+        steps = int(rng.integers(30, 160))
+        sc = synthetic(num_nodes=N, num_targets=T, seed=seed, num_gateways=gw)
+        n_dec, _ = pc.check_vs_oracle(sc, DEV, num_envs=3, steps=steps, seed=seed, num_agent=M, scale2=scale2,
+                                      check_obs=seed % 4 == 0)
+        n += n_dec
+    assert n > 300
+
+
+def test_simulator_on_a_device_that_is_not_current():
+    """The launches must follow the simulator's device, not the CUDA runtime's current one (needs two GPUs)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("one GPU")
+    sc = synthetic(num_nodes=60, num_targets=60, seed=3)
+    rng = np.random.default_rng(0)
+    acts = rng.uniform(0, 1, size=(10, 4, 3)); acts[..., 2] *= 0.05
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        with torch.cuda.device(0):                   # cuda:0 stays current
+            env = BatchedWRSN(sc, num_agent=3, num_envs=4, device=dev)
+            env.reset()
+            for k in range(10):
+                env.rollout_step(torch.as_tensor(acts[k], device=dev))
+            obs = env.get_state()
+            outs.append((env.state.cpu(), obs.cpu()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])

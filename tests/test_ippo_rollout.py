@@ -6,6 +6,8 @@ import subprocess
 
 import numpy as np
 import pytest
+
+from tests import helpers
 import torch
 
 from multi_agent_rl_wrsn_b200 import _lib, synthetic
@@ -19,10 +21,9 @@ EMU_DIR = os.path.join(REPO, "tests", "emu")
 @pytest.fixture()
 def emu_library():
     subprocess.check_call(["make", "-C", EMU_DIR, "libwrsn_emu.so"], stdout=subprocess.DEVNULL)
-    prev = _lib._lib
-    _lib.use_library(os.path.join(EMU_DIR, "libwrsn_emu.so"))
+    helpers.use_host_build()
     yield
-    _lib._lib = prev
+    helpers.use_cuda_build_lazy()
 
 
 def _scenarios():

@@ -21,7 +21,8 @@ NUM_ENVS, STEPS, SEEDS = 7, 25, (31, 32, 33)
 
 def _run(rank, world, lo_hi=None):
     from multi_agent_rl_wrsn_b200 import BatchedWRSN
-    _lib.use_library(EMU)
+    from tests import helpers
+    helpers.use_host_build(EMU)
     scs = [synthetic(num_nodes=40, num_targets=60, seed=s) for s in SEEDS]
     lo, hi = shard_range(NUM_ENVS, rank, world)
     env = BatchedWRSN(scs, num_agent=2, num_envs=hi - lo, device="cpu",

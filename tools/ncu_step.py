@@ -8,7 +8,8 @@ pre = int(sys.argv[2]) if len(sys.argv) > 2 else 60
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 dev = torch.device("cuda:0")
 scs = [synthetic(num_nodes=100, num_targets=100, seed=1000 + k) for k in range(64)]
-env = BatchedWRSN(scs, num_agent=3, num_envs=B, device=dev)
+env = BatchedWRSN(scs, num_agent=3, num_envs=B, device=dev, threads=int(os.environ.get("WRSN_THREADS", "0")))
+env.dims.step_budget = int(os.environ.get("WRSN_BUDGET", "0"))
 obs = torch.zeros((B, 4, 100, 100), dtype=torch.float32, device=dev)
 env.reset()
 g = torch.Generator(device=dev); g.manual_seed(0)

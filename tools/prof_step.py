@@ -8,7 +8,8 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 from multi_agent_rl_wrsn_b200 import _lib, BatchedWRSN, synthetic
 VARIANT = int(sys.argv[3]) if len(sys.argv) > 3 else 1
-_lib.use_library(os.path.join(REPO, "multi_agent_rl_wrsn_b200", "csrc", "libwrsn_b200_prof%d.so" % VARIANT))
+import ctypes
+_lib._lib = _lib._bind(ctypes.CDLL(os.path.join(REPO, "multi_agent_rl_wrsn_b200", "csrc", "libwrsn_b200_prof%d.so" % VARIANT)))
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 200
 NODES = int(sys.argv[4]) if len(sys.argv) > 4 else 100
