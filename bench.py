@@ -49,6 +49,7 @@ def parse(argv=None):
                         "uniform: 3-vector actions a ~ U[0,1]^3, a[2] *= 0.05")
     p.add_argument("--threads", type=int, default=0)
     p.add_argument("--budget", type=int, default=DEFAULT_BUDGET, help="work units per launch and environment (wrsn_dims.step_budget; 0 = unlimited)")
+    p.add_argument("--rounds", type=int, default=DEFAULT_ROUNDS, help="wrsn_dims.step_rounds: rounds of (events kernel, batch kernel) per step; 0 = one kernel")
     p.add_argument("--preroll", type=int, default=200, help="untimed steps before warm-up that desynchronise the episodes")
     p.add_argument("--groups", type=int, default=DEFAULT_GROUPS, help="asynchronous environment groups (CUDA streams) per GPU")
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -61,6 +62,7 @@ def parse(argv=None):
 
 DEFAULT_BUDGET = 100
 DEFAULT_GROUPS = 4
+DEFAULT_ROUNDS = 0
 
 
 def workload_name(a):
@@ -249,7 +251,7 @@ def run_b200(a):
     # G asynchronous groups of environments, one CUDA stream each: one group's kernels (decode | step | reset | observe) overlap
     # with the other groups'.  Inside a launch the step budget bounds what one environment can do, so a launch lasts about as
     # long as the budget, not as long as its slowest environment (environments are independent; no collective).
-    groups = [BatchedWRSN(scs, num_agent=M, num_envs=Bg, device=dev, threads=a.threads, map_size=S, step_budget=a.budget,
+    groups = [BatchedWRSN(scs, num_agent=M, num_envs=Bg, device=dev, threads=a.threads, map_size=S, step_budget=a.budget, step_rounds=a.rounds,
                           scenario_index=(np.arange(Bg) + g * Bg) % len(scs)) for g in range(G)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(G)]
     if a.engine_switch:
@@ -523,7 +525,7 @@ def run_b200(a):
         data="synthetic",
         config=config_common(
             a, groups="%d asynchronous groups of %d environments, one CUDA stream each" % (G, Bg),
-            step_budget=a.budget, topologies_per_gpu=a.topologies, threads_per_env=int(groups[0].dims.threads),
+            step_budget=a.budget, step_rounds=a.rounds, topologies_per_gpu=a.topologies, threads_per_env=int(groups[0].dims.threads),
             observation="float32 [B,4,100,100]",
             l2="working set (state %.0f MB + observations %.0f MB per GPU) exceeds the 126 MB L2; no explicit flush"
                % (B * groups[0].dims.state_bytes / 1e6, B * 4 * S * S * 4 / 1e6),

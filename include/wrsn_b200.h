@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define WRSN_ABI_VERSION 15
+#define WRSN_ABI_VERSION 16
 #define WRSN_MAX_MC 16          /* chargers per environment */
 #define WRSN_RING 10            /* Node.operate keeps the last 10 per-second consumptions (Node.py:70-77) */
 
@@ -68,8 +68,10 @@ enum {
     WRSN_H_PROF0, WRSN_H_PROF1, WRSN_H_PROF2, WRSN_H_PROF3, WRSN_H_PROF4, /* SM cycles of the last launch (builds with -DWRSN_PROF only):
                                                                        total, serial ticks, batches, BFS + tree, fitness */
     WRSN_H_NSPLIT,                                                  /* death ticks handled in pieces (drain_pieces: closed form around the death packet) */
-    WRSN_H_INFLIGHT,                                                /* 1: WRSN.step ran out of its launch budget (wrsn_dims.step_budget) and continues at the next call */
+    WRSN_H_INFLIGHT,                                                /* WRSN.step ran out of its launch budget (wrsn_dims.step_budget) and continues at the next call:
+                                                                       1 in the events kernel, 2 in the batch kernel (wrsn_dims.step_rounds) */
     WRSN_H_NRESUME,                                                 /* how often that happened */
+    WRSN_H_NOBATCH_ONCE,                                            /* split steps: the batch kernel handed the pending second back to the events kernel */
     WRSN_H_CHAIN_SLOT = 48,                                         /* [WRSN_MAX_MC] process slot watched by member j */
     WRSN_H_COND_TRIG = WRSN_H_CHAIN_SLOT + WRSN_MAX_MC,
     WRSN_H_COND_T = WRSN_H_COND_TRIG + WRSN_MAX_MC,                 /* time of the pending condition event, +inf when none */
@@ -159,6 +161,12 @@ typedef struct wrsn_dims {
                              charges a node, one per other event); a step that needs more returns agent_id = -4 ("in
                              flight") and continues at the next wrsn_step / wrsn_rollout_step call, so that a launch over many
                              environments lasts as long as the budget, not as long as its slowest environment */
+    int32_t step_rounds;  /* with step_budget > 0.  0: one launch of the whole engine per wrsn_step / wrsn_rollout_step.
+                             R > 0: a step is cut by KIND of work as well — R rounds of two launches, the events kernel (charger
+                             events, fitness, deaths, cheap batches: everything but ...) and the batch kernel (... the
+                             second-by-second loop of the seconds in which update_reward is active, at most step_budget of them
+                             per launch).  Same results; the hot loop runs in launches of its own, where nothing else
+                             competes for the instruction caches. */
 } wrsn_dims;
 
 /* request record written by reset / step, device pointers, one row per environment */

@@ -46,13 +46,16 @@ class Requests:
 
 class BatchedWRSN:
     def __init__(self, scenarios, num_agent=3, mc_type=None, num_envs=None, scenario_index=None, map_size=100,
-                 warm_up_time=100, device=None, threads=0, step_budget=0):
+                 warm_up_time=100, device=None, threads=0, step_budget=0, step_rounds=0):
         """``scenarios``: one or several ``Scenario`` / YAML paths (all with the same N and T);
         ``scenario_index[b]`` picks the scenario of environment b (default: round robin).
         ``step_budget`` (``wrsn_dims.step_budget``, may be changed later through ``self.dims``): 0 = every ``step`` returns
         the environment's next request, as the reference does; > 0 = work units per launch and environment — a step that
         needs more comes back with ``agent_id == -4`` and continues at the next call, so one launch over thousands of
-        environments lasts as long as the budget instead of as long as its slowest environment."""
+        environments lasts as long as the budget instead of as long as its slowest environment.
+        ``step_rounds`` (``wrsn_dims.step_rounds``, with a budget): R > 0 cuts a step by kind of work as well — R rounds of
+        two launches per call, the events kernel and the batch kernel that holds nothing but the hot second-by-second
+        loop (same results, better instruction-cache behaviour; see include/wrsn_b200.h)."""
         self.L = _lib.lib()
         self.device = self._require_device(device)
         if isinstance(scenarios, (str, Scenario)):
@@ -77,7 +80,7 @@ class BatchedWRSN:
         d.TEmax = max(len(st["tgt_idx"]) for st in statics)
         d.n_scen, d.threads = n_scen, int(threads)
         self._call(self.L.wrsn_dims_finalize, C.byref(d))
-        d.step_budget = int(step_budget)
+        d.step_budget, d.step_rounds = int(step_budget), int(step_rounds)
         self.dims = d
         self._foff = (C.c_int64 * self.E["WRSN_F_COUNT"])()
         self._soff = (C.c_int64 * self.E["WRSN_S_COUNT"])()

@@ -158,6 +158,7 @@ struct Ctx {
     SArr<int> bcast;
     SArr<double> red;
     SArr<double> par;                                /* scenario constants, copied next to the state */
+    SArr<double> pairs;                              /* see wrsn_layout.h: s_pairs */
     SArr<double> exptab;                             /* 2^(j/64), j = 0..63 (wrsn_exp_b) */
     SArr<double> spec;                               /* [WRSN_SPEC_MAX][WRSN_SPEC_LEN] irregular nodes of the current batch */
     /* global, per environment */
@@ -189,7 +190,7 @@ WRSN_D void ctx_bind(Ctx &c, const wrsn_dims &d, const WrsnLayout &L, const char
     c.level.off = (uint32_t)L.off[WRSN_F_LEVEL]; c.parent.off = (uint32_t)L.off[WRSN_F_PARENT];
     c.status.off = (uint32_t)L.off[WRSN_F_STATUS]; c.tact.off = (uint32_t)L.off[WRSN_F_TACT]; c.conn.off = (uint32_t)L.off[WRSN_F_CONN];
     c.own.off = (uint32_t)L.s_own; c.scr0.off = (uint32_t)L.s_scr0; c.scr1.off = (uint32_t)L.s_scr1;
-    c.bcast.off = (uint32_t)L.s_bcast; c.red.off = (uint32_t)L.s_red; c.par.off = (uint32_t)L.s_par; c.spec.off = (uint32_t)L.s_spec; c.exptab.off = (uint32_t)L.s_exptab;
+    c.bcast.off = (uint32_t)L.s_bcast; c.red.off = (uint32_t)L.s_red; c.par.off = (uint32_t)L.s_par; c.spec.off = (uint32_t)L.s_spec; c.exptab.off = (uint32_t)L.s_exptab; c.pairs.off = (uint32_t)L.s_pairs;
     c.logtick = (double *)(state_row + L.off[WRSN_F_LOGTICK]);
     c.ring = (double *)(state_row + L.off[WRSN_F_RING]);
     c.gscratch = state_row + L.off[WRSN_F_SCRATCH];
@@ -508,6 +509,7 @@ struct Clk {
     double net_t, net_key, ur_t, ur_key, nodes_t, nodes_key, until_t, until_key;
     int net_state, nodes_phase, stop;
     int work;                                        /* work units of this launch (see run_loop: the step budget) */
+    int nobatch_once;                                /* the batch kernel could not batch the pending second: event by event, once */
     int mc_idx;                                      /* earliest pending charger-slot (< n_slot) / condition (>= n_slot) event */
     double mc_t, mc_key, mc_other_t;                 /* its position; earliest time among the OTHER slot / condition events */
 };
@@ -527,7 +529,7 @@ WRSN_DI void clk_load(Ctx &c, Clk &k) {
     k.ur_t = h[WRSN_H_UR_ON] != 0.0 ? h[WRSN_H_UR_T] : INFINITY; k.ur_key = WRSN_KEY_NORMAL + h[WRSN_H_UR_SEQ];
     k.nodes_t = h[WRSN_H_NODES_T]; k.nodes_key = WRSN_KEY_NORMAL + h[WRSN_H_NODES_SEQ]; k.nodes_phase = (int)h[WRSN_H_NODES_PHASE];
     k.until_t = h[WRSN_H_UNTIL_ON] != 0.0 ? h[WRSN_H_UNTIL_T] : INFINITY; k.until_key = h[WRSN_H_UNTIL_SEQ];   /* URGENT */
-    k.stop = 0; k.work = 0; k.mc_idx = -1; k.mc_t = INFINITY; k.mc_key = 0.0; k.mc_other_t = INFINITY;
+    k.stop = 0; k.work = 0; k.nobatch_once = h[WRSN_H_NOBATCH_ONCE] != 0.0 ? 1 : 0; k.mc_idx = -1; k.mc_t = INFINITY; k.mc_key = 0.0; k.mc_other_t = INFINITY;
 }
 WRSN_DI void clk_store(Ctx &c, const Clk &k) {
     gsync(c);
@@ -541,6 +543,7 @@ WRSN_DI void clk_store(Ctx &c, const Clk &k) {
         h[WRSN_H_NODES_T] = k.nodes_t; h[WRSN_H_NODES_SEQ] = k.nodes_key - WRSN_KEY_NORMAL; h[WRSN_H_NODES_PHASE] = k.nodes_phase;
         h[WRSN_H_UNTIL_ON] = k.until_t < INFINITY ? 1.0 : 0.0; if (k.until_t < INFINITY) h[WRSN_H_UNTIL_T] = k.until_t;
         h[WRSN_H_UNTIL_SEQ] = k.until_key;
+        h[WRSN_H_NOBATCH_ONCE] = k.nobatch_once ? 1.0 : 0.0;
     }
     gsync(c);
 }
@@ -1135,7 +1138,14 @@ WRSN_NOINLINE void spec_second(Ctx &c, int t, int book, int drain) {
  * there after one or two applications) */
 WRSN_NOINLINE double cs_step(double cs, double lg) { return div_pos(cs * (double)WRSN_RING - lg + lg, (double)WRSN_RING); }
 
-/* the incentive sums of one tick (WRSN.py:113-126), one thread per charger; q_n / tot are the softmax weights */
+WRSN_NOINLINE double charge_rate_fast(Ctx &c, const double *m, int i) {   /* alpha / (d + beta)^2, reward path (few ulps) */
+    const double dx = c.nx[i] - m[WRSN_MC_X], dy = c.ny[i] - m[WRSN_MC_Y], d2 = wrsn_fma(dx, dx, dy * dy);
+    const double t = (d2 > 0.0 ? d2 * wrsn_rsqrt(d2) : 0.0) + c.par[WRSN_P_MC_BETA];
+    return c.par[WRSN_P_MC_ALPHA] * wrsn_rcp(t * t);
+}
+
+/* the incentive sums of one tick (WRSN.py:113-126), one thread per charger; q_n / tot are the softmax weights.  (General form:
+ * reward_cycles handles up to WRSN_PAIR_MAX pairs by list and comes here beyond that.) */
 WRSN_NOINLINE void reward_incentives(Ctx &c, double tot) {
     const double thr = c.par[WRSN_P_THR], cap = c.par[WRSN_P_CAP];
     const double inv_tot = wrsn_rcp(tot), ab2 = c.par[WRSN_P_MC_AB2], inv_ab2 = wrsn_rcp(ab2);
@@ -1150,12 +1160,8 @@ WRSN_NOINLINE void reward_incentives(Ctx &c, double tot) {
                     if (c.status[i] != 1) continue;
                     const double ec = c.energy[i] - c.cs[i];
                     double e_with = cap;             /* max(ec + rate, capacity) with rate <= alpha / beta^2 */
-                    if (ec + ab2 > cap) {
-                        const double dx = c.nx[i] - m[WRSN_MC_X], dy = c.ny[i] - m[WRSN_MC_Y], d2 = wrsn_fma(dx, dx, dy * dy);
-                        const double t = (d2 > 0.0 ? d2 * wrsn_rsqrt(d2) : 0.0) + c.par[WRSN_P_MC_BETA];
-                        e_with = fmax(ec + c.par[WRSN_P_MC_ALPHA] * wrsn_rcp(t * t), cap);
-                    }
-                    incentive += (c.scr0[i] * inv_tot) * (e_with - fmin(ec, thr)) * inv_ab2;
+                    if (ec + ab2 > cap) e_with = fmax(ec + charge_rate_fast(c, m, i), cap);
+                    incentive += (c.scr0[i] * inv_tot) * (e_with - (ec < thr ? ec : thr)) * inv_ab2;
                 }
             }
             m[WRSN_MC_EXCL] += incentive;
@@ -1199,11 +1205,47 @@ WRSN_NOINLINE void reward_cycles(Ctx &c, int n_cycles, double t_reward, int watc
         }
     }
     any_inc = red_or(c, any_inc);                    /* (uniform over the environment: it decides about barriers) */
+    /* the (charging charger, connected alive node) pairs of the incentive sums, charger by charger in node order */
+    double *pair_term = c.pairs.ptr();
+    int *pair_ids = (int *)(pair_term + WRSN_PAIR_MAX), *pair_seg = pair_ids + 2 * WRSN_PAIR_MAX;
+    if (tid == 0) {
+        int np = 0;
+        for (int a = 0; a < c.M; a++) {
+            const double *m = c.mc + a * WRSN_MC_LEN;
+            pair_seg[2 * a] = np;
+            if (m[WRSN_MC_STATUS] != 0.0 && m[WRSN_MC_TYPE] != 0.0) {
+                const uint32_t *cm = c.conn + a * c.W;
+                for (int w = 0; w < c.W; w++)
+                    for (uint32_t bits = cm[w]; bits; bits &= bits - 1u) {
+                        const int i = 32 * w + wrsn_ctz(bits);
+                        if (c.status[i] != 1) continue;
+                        if (np < WRSN_PAIR_MAX) { pair_ids[2 * np] = a; pair_ids[2 * np + 1] = i; }
+                        np++;
+                    }
+            }
+            pair_seg[2 * a + 1] = np;
+        }
+        c.bcast[8] = np;
+    }
+    gsync(c);
+    const int n_pairs = c.bcast[8];
+    const double ab2 = c.par[WRSN_P_MC_AB2], inv_ab2 = wrsn_rcp(ab2);
+    const double *spec = c.spec.ptr();
     _Pragma("unroll 1")
     for (int j = 0; j < n_cycles; j++) {
         if (watched) { catch_up_for_reward(c, t_reward + (double)j); gsync(c); }
         if (BATCH && n_spec > 0) {                   /* the table nodes: previous bookkeeping + this second's drain */
-            for (int t = tid; t < n_spec; t += G) spec_second(c, t, j > 0, 1);
+            for (int t = tid; t < n_spec; t += G) {
+                const double *sp = spec + t * WRSN_SPEC_LEN;
+                const int i = (int)sp[5];
+                double en = c.energy[i];
+                if (en >= sp[3] && en <= sp[4]) {    /* inside the guards: whole ulps (see spec_second) */
+                    const double H = sp[2];
+                    if (j > 0) { en = en + H; en = en < cap ? en : cap; }
+                    en = (en - sp[0]) + H;
+                    c.energy[i] = (en < cap ? en : cap) - sp[1];
+                } else spec_second(c, t, j > 0, 1);
+            }
             gsync(c);
         }
         if (BATCH && j > 0 && red_or_warp(any_unfixed)) {   /* energyCS towards its fixed point (bookkeeping of the previous second) */
@@ -1247,7 +1289,26 @@ WRSN_NOINLINE void reward_cycles(Ctx &c, int n_cycles, double t_reward, int watc
         red_sum1(c, tot, buf);                       /* (its barrier also publishes the stores above) */
         if (WRSN_GFIX == 32) gsync(c);
         if (tot == 0.0) tot = eps;
-        if (tid < c.M) reward_incentives(c, tot);
+        if (n_pairs > WRSN_PAIR_MAX) { if (tid < c.M) reward_incentives(c, tot); }
+        else if (n_pairs > 0) {
+            const double inv_tot = wrsn_rcp(tot);
+            for (int p = tid; p < n_pairs; p += G) {     /* one thread per pair: its term of the sum */
+                const int a2 = pair_ids[2 * p], i = pair_ids[2 * p + 1];
+                const double ec = c.energy[i] - c.cs[i];
+                double e_with = cap;                 /* max(ec + rate, capacity) with rate <= alpha / beta^2 */
+                if (ec + ab2 > cap) e_with = fmax(ec + charge_rate_fast(c, c.mc + a2 * WRSN_MC_LEN, i), cap);
+                pair_term[p] = (c.scr0[i] * inv_tot) * (e_with - (ec < thr ? ec : thr)) * inv_ab2;
+            }
+            gsync(c);
+            for (int a2 = tid; a2 < c.M; a2 += G) {      /* one thread per charger: its pairs in node order */
+                const int p0 = pair_seg[2 * a2], p1 = pair_seg[2 * a2 + 1];
+                if (p1 > p0) {
+                    double incentive = 0.0;
+                    for (int p = p0; p < p1; p++) incentive += pair_term[p];
+                    c.mc[a2 * WRSN_MC_LEN + WRSN_MC_EXCL] += incentive;
+                }
+            }
+        }
         if (any_inc || n_spec > 0 || watched || WRSN_GFIX != 32) gsync(c);
     }
     if (BATCH) {                                     /* bookkeeping of the last second; rows back to shared memory */
@@ -1925,6 +1986,8 @@ WRSN_NOINLINE double drain_node(double e, double rr, double es, double er, int n
 
 /* `n_active_max`: cap on the cycles of a batch in which update_reward is active (the step budget's granularity);
  * returns the cycles applied, + 2^30 when they were of the active kind */
+/* KIND 0: any batch; 2: only batches of the active kind (the batch kernel: the all-at-once branch is not even compiled in) */
+template <int KIND>
 WRSN_NOINLINE int nodes_batch(Ctx &c, int n_max, int ur_on, double t_reward, int n_active_max) {
     const int N = c.N;
     const double thr = c.par[WRSN_P_THR], cap = c.par[WRSN_P_CAP], er = c.par[WRSN_P_ERECV];
@@ -1933,7 +1996,7 @@ WRSN_NOINLINE int nodes_batch(Ctx &c, int n_max, int ur_on, double t_reward, int
     WRSN_PROF_BEGIN();
     if (h[WRSN_H_OPT_NOBATCH] == 1.0 || h[WRSN_H_BFS_DIRTY] != 0.0 || h[WRSN_H_LOG_LITERAL] != 0.0 ||
         h[WRSN_H_LOG_LEN] < (double)WRSN_RING || h[WRSN_H_LOG_UNIFORM] < 10.0) return 0;
-    const bool active = ur_on && reward_pairs(c);    /* update_reward looks at every node every second */
+    const bool active = KIND == 2 ? true : (ur_on && reward_pairs(c));    /* update_reward looks at every node every second */
     if (active && n_max > n_active_max) n_max = n_active_max;
     int *bc = c.bcast;                               /* [0]: entries of the table of irregular nodes (active batches) */
     if (active) { gsync(c); if (c.tid == 0) bc[0] = 0; gsync(c); }
@@ -2014,7 +2077,7 @@ WRSN_NOINLINE int nodes_batch(Ctx &c, int n_max, int ur_on, double t_reward, int
     if (n_spec > WRSN_SPEC_MAX) return 0;            /* more irregular nodes than the table holds: this second event by event */
     const double L = (double)WRSN_RING;
     WRSN_PROFC_BEGIN(pc2);
-    if (!active) {
+    if (KIND != 2 && !active) {
         /* pass 2: all cycles at once */
         _Pragma("unroll 1")
         for (int i = c.tid; i < N; i += WRSN_GSZ(c)) {
@@ -2060,11 +2123,54 @@ WRSN_NOINLINE int nodes_batch(Ctx &c, int n_max, int ur_on, double t_reward, int
 }
 
 /* ------------------------------------------------------------------ the event loop: env.run(...) */
+/* Whole cycles strictly before the next charger / condition / until event, seen from the k+0.5 drain of the node block at
+ * `gt`: the canonical pending set is {drain now, update_reward and the exit check of Network.operate at +0.5 (in that
+ * order)}.  Returns how many (0: this second runs event by event). */
+WRSN_DI int batch_window(Ctx &c, const Clk &k, double gt, double maxtime) {
+    const double H = fmin(fmin(k.mc_t, k.until_t), maxtime - 2.0);
+    const bool ur_on = k.ur_t < INFINITY, net_on = k.net_t < INFINITY;
+    if (!(gt + 1.0 <= H && (!net_on || (k.net_state == 2 && k.net_t == gt + 0.5 && c.hdr[WRSN_H_ALIVE] != 0.0)) &&
+          (!ur_on || (k.ur_t == gt + 0.5 && (!net_on || k.ur_key < k.net_key))))) return 0;
+    const double span = fmin(H - gt, 1048576.0);
+    int n = (int)span;
+    while (n > 0 && !(gt + (double)n <= H)) n--;
+    return n;
+}
+/* the clock after `batched` cycles: every cycle drew its insertion counters in the order drain, [update_reward,] [exit
+ * check,] bookkeeping, [connectivity] (Network.operate may have ended, Q1) */
+WRSN_DI void batch_commit(Clk &k, double gt, int batched) {
+    const bool ur_on = k.ur_t < INFINITY, net_on = k.net_t < INFINITY;
+    const double nb = (double)batched;
+    const double per = 2.0 + (ur_on ? 1.0 : 0.0) + (net_on ? 2.0 : 0.0);
+    double s0 = k.seq + per * (nb - 1.0);
+    if (ur_on) { s0 += 1.0; k.ur_key = WRSN_KEY_NORMAL + s0; k.ur_t += nb; }
+    if (net_on) { s0 += 1.0; k.net_key = WRSN_KEY_NORMAL + (s0 + 2.0); k.net_t += nb; }
+    k.nodes_key = WRSN_KEY_NORMAL + (s0 + 1.0);
+    k.seq += per * nb; k.nev += per * nb - 1.0;
+    k.nodes_t = gt + nb;
+    k.now = net_on ? (k.net_t - 1.0) + 0.1 : gt + (nb - 0.5);
+}
+WRSN_D bool batch_ready(Ctx &c) {                   /* the preconditions nodes_batch checks first (cheap: header fields) */
+    const double *h = c.hdr;
+    return !(h[WRSN_H_OPT_NOBATCH] == 1.0 || h[WRSN_H_BFS_DIRTY] != 0.0 || h[WRSN_H_LOG_LITERAL] != 0.0 ||
+             h[WRSN_H_LOG_LEN] < (double)WRSN_RING || h[WRSN_H_LOG_UNIFORM] < 10.0);
+}
+WRSN_D bool any_watched(Ctx &c) {                   /* a lazy move whose position update_reward reads (Q2)? */
+    bool w = false;
+    for (int q = 0; q < c.n_slot; q++) w = w || slot_i(slot_of(c, q))[WRSN_PRI_LAZY] == 2;
+    return w;
+}
+#define WRSN_SPLIT_MIN_CYCLES 4                     /* shorter active batches are not worth a launch of their own */
+
 /* `budget` > 0: stop at an event boundary once the launch has done that many work units (one per event handled, plus
  * one per simulated second in which update_reward is active — the expensive kind) and return 1: the clock is stored
  * as it is, the pending run(until) / AnyOf chain stay pending, and the next launch continues where this one stopped.
- * A launch then lasts as long as the budget allows, not as long as its slowest environment's whole step. */
-WRSN_DI int run_loop(Ctx &c, int budget) {
+ * A launch then lasts as long as the budget allows, not as long as its slowest environment's whole step.
+ * `split` != 0 (the events kernel of a split step, wrsn_dims.step_rounds): additionally stop — return 2 — in front of a
+ * batch of the active kind; the batch kernel (run_batches) takes it from there.  The hot second-by-second loop then runs in
+ * launches that contain nothing else: its code stays in the SMs' instruction caches instead of competing with the event
+ * machinery of the environments next door (profiles/r02*_icache.md). */
+WRSN_DI int run_loop(Ctx &c, int budget, int split) {
     Clk k;
     clk_load(c, k);
     const double maxtime = c.par[WRSN_P_MAXTIME];
@@ -2095,43 +2201,28 @@ WRSN_DI int run_loop(Ctx &c, int budget) {
             } else ev_cond(c, k, k.mc_idx - c.n_slot);
             rescan = true;
         } else {
-            k.now = gt;
-            k.nev += 1.0;
             if (gk == K_NODES) {
                 int batched = 0;
-                if (k.nodes_phase == 1) {
-                    /* whole cycles strictly before the next charger / condition / until event: the canonical pending set
-                       is {drain now, update_reward and the exit check of Network.operate at +0.5 (in that order)} */
-                    const double H = fmin(fmin(k.mc_t, k.until_t), maxtime - 2.0);
-                    const bool ur_on = k.ur_t < INFINITY, net_on = k.net_t < INFINITY;
-                    if (gt + 1.0 <= H && (!net_on || (k.net_state == 2 && k.net_t == gt + 0.5 && c.hdr[WRSN_H_ALIVE] != 0.0)) &&
-                        (!ur_on || (k.ur_t == gt + 0.5 && (!net_on || k.ur_key < k.net_key)))) {
-                        const double span = fmin(H - gt, 1048576.0);
-                        int n = (int)span;
-                        while (n > 0 && !(gt + (double)n <= H)) n--;
-                        if (n > 0) {
-                            const int cap_active = budget > 0 ? (budget - k.work > 8 ? budget - k.work : 8) : n;
-                            batched = nodes_batch(c, n, ur_on ? 1 : 0, gt + 0.5, cap_active);
-                            if (batched >= (1 << 30)) { batched -= 1 << 30; k.work += batched; }
+                if (k.nodes_phase == 1 && !k.nobatch_once) {
+                    const int n = batch_window(c, k, gt, maxtime);
+                    if (n > 0) {
+                        const bool ur_on = k.ur_t < INFINITY;
+                        if (split && n >= WRSN_SPLIT_MIN_CYCLES && ur_on && batch_ready(c) && reward_pairs(c) && !any_watched(c)) {
+                            interrupted = 2;             /* the batch kernel's: nothing of this event has happened yet */
+                            break;
                         }
-                        if (batched > 0) {
-                            /* the clock after `batched` cycles: every cycle drew its insertion counters in the order drain,
-                               [update_reward,] [exit check,] bookkeeping, [connectivity] (Network.operate may have ended, Q1) */
-                            const double nb = (double)batched;
-                            const double per = 2.0 + (ur_on ? 1.0 : 0.0) + (net_on ? 2.0 : 0.0);
-                            double s0 = k.seq + per * (nb - 1.0);
-                            if (ur_on) { s0 += 1.0; k.ur_key = WRSN_KEY_NORMAL + s0; k.ur_t += nb; }
-                            if (net_on) { s0 += 1.0; k.net_key = WRSN_KEY_NORMAL + (s0 + 2.0); k.net_t += nb; }
-                            k.nodes_key = WRSN_KEY_NORMAL + (s0 + 1.0);
-                            k.seq += per * nb; k.nev += per * nb - 1.0;
-                            k.nodes_t = gt + nb;
-                            k.now = net_on ? (k.net_t - 1.0) + 0.1 : gt + (nb - 0.5);
-                        }
+                        k.now = gt;
+                        const int cap_active = budget > 0 ? (budget - k.work > 8 ? budget - k.work : 8) : n;
+                        batched = nodes_batch<0>(c, n, ur_on ? 1 : 0, gt + 0.5, cap_active);
+                        if (batched >= (1 << 30)) { batched -= 1 << 30; k.work += batched; }
+                        if (batched > 0) { k.nev += 1.0; batch_commit(k, gt, batched); }
                     }
                 }
                 if (!batched) {
                     WRSN_PROFB_BEGIN();
+                    k.now = gt; k.nev += 1.0;
                     if (k.nodes_phase == 1) {
+                        k.nobatch_once = 0;
                         ev_nodes_drain(c); k.nodes_phase = 2;
                         if (c.hdr[WRSN_H_BFS_DIRTY] != 0.0) { wake_lazy_all(c, k); rescan = true; }
                     }
@@ -2140,18 +2231,21 @@ WRSN_DI int run_loop(Ctx &c, int budget) {
                     WRSN_PROFB_END(c, WRSN_H_PROF3);
                 }
             } else if (gk == K_NET) {                /* Network.operate :74-80 */
+                k.now = gt; k.nev += 1.0;
                 if (k.net_state == 1) {
                     if (c.hdr[WRSN_H_BFS_DIRTY] != 0.0) do_bfs(c);
                     k.net_t = gt + 0.9; k.net_key = WRSN_KEY_NORMAL + take_seq(k); k.net_state = 2;
                 } else if (c.hdr[WRSN_H_ALIVE] == 0.0 || gt >= maxtime) k.net_t = INFINITY;
                 else { k.net_t = gt + 0.1; k.net_key = WRSN_KEY_NORMAL + take_seq(k); k.net_state = 1; }
             } else if (gk == K_UR) {
+                k.now = gt; k.nev += 1.0;
                 WRSN_PROFB_BEGIN();
                 catch_up_for_reward(c, gt);
                 ev_update_reward(c);
                 WRSN_PROFB_END(c, WRSN_H_PROF3);
                 k.ur_t = gt + 1.0; k.ur_key = WRSN_KEY_NORMAL + take_seq(k);
             } else {                                 /* K_UNTIL */
+                k.now = gt; k.nev += 1.0;
                 k.until_t = INFINITY; k.stop = 1;
             }
         }
@@ -2163,6 +2257,38 @@ WRSN_DI int run_loop(Ctx &c, int budget) {
     WRSN_PROFB_END(c, WRSN_H_PROF2); }
     clk_store(c, k);
     return interrupted;
+}
+
+/* The batch kernel of a split step: as long as the environment's next event is the k+0.5 drain of the node block in
+ * front of a batch of the active kind, apply it (at most `budget` simulated seconds per launch).  Returns 2 when the
+ * budget ran out in front of another such batch, 1 when anything else is next (the events kernel's).  A second that
+ * cannot be batched (a possible death, more irregular nodes than the table holds) goes back with `nobatch_once` set. */
+WRSN_DI int run_batches(Ctx &c, int budget) {
+    Clk k;
+    clk_load(c, k);
+    mc_scan(c, k);                                   /* (nothing in here moves a charger event) */
+    const double maxtime = c.par[WRSN_P_MAXTIME];
+    int ret = 1;
+    for (int guard = 0; guard < 1000000; guard++) {
+        int gk = K_NODES;
+        double gt = k.nodes_t, gkey = k.nodes_key;
+        if (ev_before(k.net_t, k.net_key, gt, gkey)) gk = K_NET;
+        if (ev_before(k.ur_t, k.ur_key, gt, gkey)) gk = K_UR;
+        if (ev_before(k.until_t, k.until_key, gt, gkey)) gk = K_UNTIL;
+        if (gk != K_NODES || ev_before(k.mc_t, k.mc_key, gt, gkey) || k.nodes_phase != 1 || k.nobatch_once) break;
+        const int n = batch_window(c, k, gt, maxtime);
+        if (n < WRSN_SPLIT_MIN_CYCLES || !(k.ur_t < INFINITY) || !batch_ready(c) || !reward_pairs(c) || any_watched(c)) break;
+        if (k.work >= budget) { ret = 2; break; }
+        k.now = gt;
+        int batched = nodes_batch<2>(c, n, 1, gt + 0.5, budget - k.work > 8 ? budget - k.work : 8);
+        if (batched >= (1 << 30)) batched -= 1 << 30;
+        if (batched <= 0) { k.nobatch_once = 1; break; }
+        k.work += batched;
+        k.nev += 1.0;
+        batch_commit(k, gt, batched);
+    }
+    clk_store(c, k);
+    return ret;
 }
 
 /* ------------------------------------------------------------------ entry points (one environment) */
@@ -2209,7 +2335,7 @@ WRSN_D void entry_run_until(Ctx &c, double at) {
         c.hdr[WRSN_H_UNTIL_ON] = 1.0; c.hdr[WRSN_H_UNTIL_T] = at; c.hdr[WRSN_H_UNTIL_SEQ] = take_seq_h(c);
     }
     gsync(c);
-    run_loop(c, 0);
+    run_loop(c, 0, 0);
 }
 
 WRSN_D int scan_decider(Ctx &c) {                  /* WRSN.py:321-322 */
@@ -2279,7 +2405,24 @@ WRSN_D void entry_reset_finish(Ctx &c, ReqOut *r) {
 /* WRSN.step (WRSN.py:289-330) */
 /* `budget`: see run_loop.  A step that ran out of budget returns agent = -4 ("in flight") and hdr[INFLIGHT] = 1; the
  * next call for this environment ignores agent_id / input_action and continues the same env.run(until=general_process). */
-WRSN_D void entry_step(Ctx &c, int agent_id, const double *input_action, ReqOut *r, int budget) {
+WRSN_D void entry_in_flight(Ctx &c, ReqOut *r, int code) {       /* the request record of a step that continues later */
+    if (c.tid == 0) {
+        c.hdr[WRSN_H_INFLIGHT] = (double)code; c.hdr[WRSN_H_NRESUME] += 1.0;
+        r->now = c.hdr[WRSN_H_NOW]; r->flags = c.hdr[WRSN_H_ERR] != 0.0 ? 2 : 0; r->agent = -4; r->terminal = 0;
+        r->reward = NAN; r->detail[0] = r->detail[1] = NAN;
+        for (int k = 0; k < 3; k++) r->act[k] = NAN;
+    }
+    gsync(c);
+}
+
+/* the batch kernel of a split step (wrsn_dims.step_rounds): only for environments with hdr[INFLIGHT] == 2 */
+WRSN_D void entry_batches(Ctx &c, ReqOut *r, int budget) {
+    const int code = run_batches(c, budget > 0 ? budget : (1 << 30));
+    gsync(c);
+    entry_in_flight(c, r, code);
+}
+
+WRSN_D void entry_step(Ctx &c, int agent_id, const double *input_action, ReqOut *r, int budget, int split) {
     const bool resume = c.hdr[WRSN_H_INFLIGHT] != 0.0;
     gsync(c);
     if (c.tid == 0 && !resume) {
@@ -2321,18 +2464,9 @@ WRSN_D void entry_step(Ctx &c, int agent_id, const double *input_action, ReqOut 
     gsync(c);
     const int watched = (int)c.hdr[WRSN_H_CHAIN_N];
     int interrupted = 0;
-    if (watched > 0) interrupted = run_loop(c, budget);
+    if (watched > 0) interrupted = run_loop(c, budget, split);
     gsync(c);
-    if (interrupted) {
-        if (c.tid == 0) {
-            c.hdr[WRSN_H_INFLIGHT] = 1.0; c.hdr[WRSN_H_NRESUME] += 1.0;
-            r->now = c.hdr[WRSN_H_NOW]; r->flags = c.hdr[WRSN_H_ERR] != 0.0 ? 2 : 0; r->agent = -4; r->terminal = 0;
-            r->reward = NAN; r->detail[0] = r->detail[1] = NAN;
-            for (int k = 0; k < 3; k++) r->act[k] = NAN;
-        }
-        gsync(c);
-        return;
-    }
+    if (interrupted) { entry_in_flight(c, r, interrupted); return; }
     int id = -1;
     if (!(watched == 0 || c.hdr[WRSN_H_ALIVE] == 0.0)) { id = scan_decider(c); if (id < 0) id = -2; }   /* all threads */
     double fit = 0.0;

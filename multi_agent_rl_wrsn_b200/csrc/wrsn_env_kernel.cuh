@@ -7,7 +7,13 @@ __global__ void __launch_bounds__(WRSN_GFIX ? WRSN_GFIX : 256, WRSN_GFIX ? 16 : 
     if (P.mask && !P.mask[b]) return;
     if (P.mask_mode == 1 && P.req.agent_id[b] < 0 && P.req.agent_id[b] != -4) return;     /* (-4: a step in flight continues) */
     if (P.mask_mode == 2 && (P.req.agent_id[b] >= 0 || P.req.agent_id[b] == -4)) return;
+    if (P.resume_only && P.req.agent_id[b] != -4) return;
     char *row = P.state + (size_t)b * P.L.total;
+    const bool split = P.d.step_budget > 0 && P.d.step_rounds > 0;
+    if (MODE == MODE_STEP && split && P.req.agent_id && P.req.agent_id[b] == -4 &&
+        reinterpret_cast<const double *>(row + P.L.off[WRSN_F_HDR])[WRSN_H_INFLIGHT] == 2.0) return;   /* waits for the batch kernel */
+    if (MODE == MODE_STEP_BATCH && (P.req.agent_id[b] != -4 ||
+        reinterpret_cast<const double *>(row + P.L.off[WRSN_F_HDR])[WRSN_H_INFLIGHT] != 2.0)) return;
     const char *scen_row = P.scen + (size_t)P.scen_id[b] * P.L.scen_total;
     Ctx c;
     ctx_bind(c, P.d, P.L, scen_row, row, tid, G);
@@ -37,7 +43,8 @@ __global__ void __launch_bounds__(WRSN_GFIX ? WRSN_GFIX : 256, WRSN_GFIX ? 16 : 
     case MODE_RUN_UNTIL: entry_run_until(c, P.t_until[b]); break;
     case MODE_RESET_FINISH:
     case MODE_RESTORE_RESET: entry_reset_finish(c, &r); break;
-    case MODE_STEP: entry_step(c, P.agent_in ? P.agent_in[b] : -1, P.action_in ? P.action_in + 3 * (size_t)b : nullptr, &r, P.d.step_budget); break;
+    case MODE_STEP: entry_step(c, P.agent_in ? P.agent_in[b] : -1, P.action_in ? P.action_in + 3 * (size_t)b : nullptr, &r, P.d.step_budget, split ? 1 : 0); break;
+    case MODE_STEP_BATCH: entry_batches(c, &r, P.d.step_budget); break;
     case MODE_FITNESS: {
         double mn = do_fitness(c, P.fitness ? P.fitness + (size_t)b * P.d.T : nullptr);
         if (tid == 0 && P.fit_min) P.fit_min[b] = mn;
@@ -53,11 +60,11 @@ __global__ void __launch_bounds__(WRSN_GFIX ? WRSN_GFIX : 256, WRSN_GFIX ? 16 : 
     if (MODE == MODE_STEP) { if (tid == 0) c.hdr[WRSN_H_PROF0] = (double)(clock64() - prof_start); gsync(c); }
 #endif
     if (MODE != MODE_FITNESS) copy16(row, smem, P.L.resident, tid, G);
-    if ((MODE == MODE_RESET_FINISH || MODE == MODE_RESTORE_RESET || MODE == MODE_STEP) && tid == 0) {
+    if ((MODE == MODE_RESET_FINISH || MODE == MODE_RESTORE_RESET || MODE == MODE_STEP || MODE == MODE_STEP_BATCH) && tid == 0) {
         write_request(P.req, b, r);
         if (P.req.stats) {
             if (r.agent >= 0) P.req.stats[3 * b] += 1.0;
-            if (MODE == MODE_STEP) P.req.stats[3 * b + 1] += r.now - now_before;
+            if (MODE == MODE_STEP || MODE == MODE_STEP_BATCH) P.req.stats[3 * b + 1] += r.now - now_before;
             if (MODE == MODE_RESTORE_RESET || MODE == MODE_RESET_FINISH) P.req.stats[3 * b + 2] += 1.0;
         }
     }

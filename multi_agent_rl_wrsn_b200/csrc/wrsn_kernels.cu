@@ -17,7 +17,7 @@ static thread_local char g_err[512] = "";
 #define WRSN_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) WRSN_FAIL("%s: %s", #x, cudaGetErrorString(e_)); } while (0)
 
 enum { MODE_INIT = 0, MODE_RUN_UNTIL, MODE_RESET_FINISH, MODE_RESTORE_RESET, MODE_STEP, MODE_FITNESS, MODE_K_BFS,
-       MODE_K_DRAIN, MODE_K_BOOK, MODE_K_REWARD };
+       MODE_K_DRAIN, MODE_K_BOOK, MODE_K_REWARD, MODE_STEP_BATCH };
 
 struct KParams {
     wrsn_dims d;
@@ -34,6 +34,7 @@ struct KParams {
     wrsn_request req;
     double *fitness, *fit_min;
     int with_reward;
+    int resume_only;                                 /* later rounds of a split step: only rows whose step is in flight (agent_id == -4) */
 };
 
 __device__ __forceinline__ void copy16(char *dst, const char *src, int64_t bytes, int tid, int G) {
@@ -655,6 +656,22 @@ static int launch_env(KParams &P, void *stream) {
     return 0;
 }
 
+/* WRSN.step: one launch of the whole engine, or — wrsn_dims.step_rounds > 0 with a step budget — rounds of two launches, the
+ * events kernel and the batch kernel (see include/wrsn_b200.h).  In the later launches a row is selected by its own state
+ * (request record -4 + hdr[INFLIGHT]); rows that finished their step stay out. */
+static int launch_step(KParams &P, void *stream) {
+    if (!(P.d.step_budget > 0 && P.d.step_rounds > 0)) return launch_env<MODE_STEP>(P, stream);
+    if (!P.req.agent_id) WRSN_FAIL("split steps need req->agent_id");
+    for (int r = 0; r < P.d.step_rounds; r++) {
+        if (launch_env<MODE_STEP>(P, stream)) return -1;
+        KParams Q = P;
+        Q.agent_in = nullptr; Q.action_in = nullptr;
+        if (launch_env<MODE_STEP_BATCH>(Q, stream)) return -1;
+        P.resume_only = 1;                           /* later rounds: only rows still in flight (the others hold a fresh request) */
+    }
+    return 0;
+}
+
 static KParams base_params(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state, const uint8_t *mask) {
     KParams P;
     memset(&P, 0, sizeof(P));
@@ -795,7 +812,7 @@ int wrsn_step(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void
     if (agent_id_in && !action_in) WRSN_FAIL("action_in is NULL");
     KParams P = base_params(d, scen, scen_id, state, env_mask);
     P.agent_in = agent_id_in; P.action_in = action_in; P.req = *req;
-    return launch_env<MODE_STEP>(P, stream);
+    return launch_step(P, stream);
 }
 
 int wrsn_rollout_step(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state, const void *snap,
@@ -803,7 +820,7 @@ int wrsn_rollout_step(const wrsn_dims *d, const void *scen, const int32_t *scen_
     if (!req || !req->agent_id || !snap || !action_in) WRSN_FAIL("req / req->agent_id / snap / action_in is NULL");
     KParams P = base_params(d, scen, scen_id, state, nullptr);
     P.req = *req; P.agent_in = req->agent_id; P.action_in = action_in; P.mask_mode = 1;
-    if (launch_env<MODE_STEP>(P, stream)) return -1;
+    if (launch_step(P, stream)) return -1;
     KParams R = base_params(d, scen, scen_id, state, nullptr);
     R.req = *req; R.snap = (const char *)snap; R.mask_mode = 2;
     if (launch_env<MODE_RESTORE_RESET>(R, stream)) return -1;

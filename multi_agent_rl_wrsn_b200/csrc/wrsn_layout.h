@@ -16,13 +16,14 @@
 #endif
 
 #define WRSN_SPEC_MAX 32                            /* charged (or otherwise irregular) nodes a whole-cycle batch handles by table */
+#define WRSN_PAIR_MAX 32                            /* (charger, node) pairs the incentive sums of a batch handle by list */
 #define WRSN_SPEC_LEN 6                             /* D1, D2, H, lo guard, hi guard, node id */
 
 /* ------------------------------------------------------------------ layouts */
 struct WrsnLayout {
     int64_t off[WRSN_F_COUNT];
     int64_t resident, total;                        /* bytes mirrored in shared memory / bytes per record */
-    int64_t s_own, s_scr0, s_scr1, s_bcast, s_red, s_par, s_spec, s_exptab, smem_total;
+    int64_t s_own, s_scr0, s_scr1, s_bcast, s_red, s_par, s_spec, s_exptab, s_pairs, smem_total;
     int64_t soff[WRSN_S_COUNT];
     int64_t scen_total;
     int32_t scr_len;                                /* doubles per scratch row */
@@ -65,6 +66,8 @@ WRSN_HD void wrsn_make_layout(const wrsn_dims *d, WrsnLayout *L) {
     L->s_par = s; s += 8 * WRSN_P_LEN;             /* scenario constants: copied next to the state, never re-read from HBM */
     L->s_spec = s; s += 8 * WRSN_SPEC_LEN * WRSN_SPEC_MAX;   /* per-batch table of the charged nodes (wrsn_engine.cuh: reward_cycles) */
     L->s_exptab = s; s += 8 * 64;                  /* 2^(j/64): table of the reward path's exponential */
+    L->s_pairs = s; s += 8 * WRSN_PAIR_MAX + 4 * 2 * WRSN_PAIR_MAX + 4 * 2 * WRSN_MAX_MC;   /* (charging charger, connected alive node) pairs of the current batch:
+                                                      term double[PAIR_MAX]; {charger, node} int[PAIR_MAX][2]; per charger {first, end} int[MAX_MC][2] */
     L->smem_total = s;
     /* scenario record */
     o = 0;

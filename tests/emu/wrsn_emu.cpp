@@ -22,12 +22,12 @@ static thread_local char g_err[512] = "";
 #define WRSN_FAIL(...) do { snprintf(g_err, sizeof(g_err), __VA_ARGS__); return -1; } while (0)
 
 enum { MODE_INIT = 0, MODE_RUN_UNTIL, MODE_RESET_FINISH, MODE_RESTORE_RESET, MODE_STEP, MODE_FITNESS, MODE_K_BFS,
-       MODE_K_DRAIN, MODE_K_BOOK, MODE_K_REWARD };
+       MODE_K_DRAIN, MODE_K_BOOK, MODE_K_REWARD, MODE_STEP_BATCH };
 
 struct Args {
     const wrsn_dims *d; const char *scen; const int32_t *scen_id; char *state; const char *snap; const uint8_t *mask;
     const double *t_until; const int32_t *agent_in; const double *action_in; wrsn_request *req;
-    double *fitness, *fit_min; int with_reward; int mask_mode;
+    double *fitness, *fit_min; int with_reward; int mask_mode; int resume_only;
 };
 
 static int run_mode(int mode, const Args &A) {
@@ -39,7 +39,12 @@ static int run_mode(int mode, const Args &A) {
         if (A.mask && !A.mask[b]) continue;
         if (A.mask_mode == 1 && A.req->agent_id[b] < 0 && A.req->agent_id[b] != -4) continue;
         if (A.mask_mode == 2 && (A.req->agent_id[b] >= 0 || A.req->agent_id[b] == -4)) continue;
+        if (A.resume_only && A.req->agent_id[b] != -4) continue;
         char *row = A.state + (size_t)b * L.total;
+        const bool split = d.step_budget > 0 && d.step_rounds > 0;
+        const double infl = reinterpret_cast<const double *>(row + L.off[WRSN_F_HDR])[WRSN_H_INFLIGHT];
+        if (mode == MODE_STEP && split && A.req && A.req->agent_id && A.req->agent_id[b] == -4 && infl == 2.0) continue;
+        if (mode == MODE_STEP_BATCH && (A.req->agent_id[b] != -4 || infl != 2.0)) continue;
         const char *scen_row = A.scen + (size_t)A.scen_id[b] * L.scen_total;
         Ctx c;
         wrsn_smem_host = smem.data();
@@ -57,7 +62,8 @@ static int run_mode(int mode, const Args &A) {
         case MODE_INIT: entry_init_network(c, A.with_reward); break;
         case MODE_RUN_UNTIL: entry_run_until(c, A.t_until[b]); break;
         case MODE_RESET_FINISH: case MODE_RESTORE_RESET: entry_reset_finish(c, &r); break;
-        case MODE_STEP: entry_step(c, A.agent_in ? A.agent_in[b] : -1, A.action_in ? A.action_in + 3 * (size_t)b : nullptr, &r, d.step_budget); break;
+        case MODE_STEP: entry_step(c, A.agent_in ? A.agent_in[b] : -1, A.action_in ? A.action_in + 3 * (size_t)b : nullptr, &r, d.step_budget, split ? 1 : 0); break;
+        case MODE_STEP_BATCH: entry_batches(c, &r, d.step_budget); break;
         case MODE_FITNESS: { double mn = do_fitness(c, A.fitness ? A.fitness + (size_t)b * d.T : nullptr); if (A.fit_min) A.fit_min[b] = mn; break; }
         case MODE_K_BFS: do_bfs(c); break;
         case MODE_K_DRAIN: ev_nodes_drain(c); break;
@@ -65,7 +71,7 @@ static int run_mode(int mode, const Args &A) {
         case MODE_K_REWARD: ev_update_reward(c); break;
         }
         if (mode != MODE_FITNESS) memcpy(row, smem.data(), (size_t)L.resident);
-        if (mode == MODE_RESET_FINISH || mode == MODE_RESTORE_RESET || mode == MODE_STEP) {
+        if (mode == MODE_RESET_FINISH || mode == MODE_RESTORE_RESET || mode == MODE_STEP || mode == MODE_STEP_BATCH) {
             wrsn_request &q = *A.req;
             if (q.agent_id) q.agent_id[b] = r.agent;
             if (q.terminal) q.terminal[b] = (uint8_t)r.terminal;
@@ -74,9 +80,21 @@ static int run_mode(int mode, const Args &A) {
             if (q.action) for (int k = 0; k < 3; k++) q.action[3 * b + k] = r.act[k];
             if (q.detail) { q.detail[2 * b] = r.detail[0]; q.detail[2 * b + 1] = r.detail[1]; }
             if (q.flags) q.flags[b] = r.flags;
-            if (q.stats) { if (r.agent >= 0) q.stats[3 * b] += 1.0; if (mode == MODE_STEP) q.stats[3 * b + 1] += r.now - now_before;
+            if (q.stats) { if (r.agent >= 0) q.stats[3 * b] += 1.0; if (mode == MODE_STEP || mode == MODE_STEP_BATCH) q.stats[3 * b + 1] += r.now - now_before;
                            if (mode == MODE_RESTORE_RESET || mode == MODE_RESET_FINISH) q.stats[3 * b + 2] += 1.0; }
         }
+    }
+    return 0;
+}
+
+static int run_step(Args A) {                       /* launch_step of wrsn_kernels.cu */
+    const wrsn_dims &d = *A.d;
+    if (!(d.step_budget > 0 && d.step_rounds > 0)) return run_mode(MODE_STEP, A);
+    for (int r = 0; r < d.step_rounds; r++) {
+        if (run_mode(MODE_STEP, A)) return -1;
+        Args Q = A; Q.agent_in = nullptr; Q.action_in = nullptr;
+        if (run_mode(MODE_STEP_BATCH, Q)) return -1;
+        A.resume_only = 1;
     }
     return 0;
 }
@@ -124,12 +142,12 @@ int wrsn_reset_from_snapshot(const wrsn_dims *d, const void *scen, const int32_t
 }
 int wrsn_step(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state, const uint8_t *m, const int32_t *ag, const double *act, wrsn_request *req, void *) {
     Args A = {d, (const char *)scen, scen_id, (char *)state, nullptr, m, nullptr, ag, act, req, nullptr, nullptr, 0};
-    return run_mode(MODE_STEP, A);
+    return run_step(A);
 }
 int wrsn_rollout_step(const wrsn_dims *d, const void *scen, const int32_t *scen_id, void *state, const void *snap,
                       const double *act, wrsn_request *req, void *obs, int obs_f64, void *) {
     Args A = {d, (const char *)scen, scen_id, (char *)state, nullptr, nullptr, nullptr, req->agent_id, act, req, nullptr, nullptr, 0, 1};
-    if (run_mode(MODE_STEP, A)) return -1;
+    if (run_step(A)) return -1;
     Args R = {d, (const char *)scen, scen_id, (char *)state, (const char *)snap, nullptr, nullptr, nullptr, nullptr, req, nullptr, nullptr, 0, 2};
     if (run_mode(MODE_RESTORE_RESET, R)) return -1;
     return obs ? wrsn_observe(d, scen, scen_id, state, req->agent_id, obs, obs_f64, nullptr) : 0;

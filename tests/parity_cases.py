@@ -499,7 +499,7 @@ def check_charge_kernel(scenarios, device, num_envs, steps, seed, num_agent=3):
     return n_pairs
 
 
-def check_budget_equals_unbudgeted(scenarios, device, num_envs, calls, seed, budget, num_agent=3, scale2=0.3, threads=0):
+def check_budget_equals_unbudgeted(scenarios, device, num_envs, calls, seed, budget, num_agent=3, scale2=0.3, threads=0, rounds=0):
     """A step budget (wrsn_dims.step_budget) only cuts a WRSN.step into several launches: every request an environment hands
     out — agent, time, reward, termination, clipped action — and every byte of its record at that moment are those of the
     unbudgeted run answered with the same actions.  Returns how many interrupted launches it took."""
@@ -507,10 +507,11 @@ def check_budget_equals_unbudgeted(scenarios, device, num_envs, calls, seed, bud
     acts = rng.uniform(0.0, 1.0, size=(calls, num_envs, 3))
     acts[..., 2] *= scale2
     a = BatchedWRSN(scenarios, num_agent=num_agent, num_envs=num_envs, device=device, threads=threads)
-    b = BatchedWRSN(scenarios, num_agent=num_agent, num_envs=num_envs, device=device, threads=threads, step_budget=budget)
+    b = BatchedWRSN(scenarios, num_agent=num_agent, num_envs=num_envs, device=device, threads=threads, step_budget=budget,
+                    step_rounds=rounds)
     end = int(a._foff[a.E["WRSN_F_SCRATCH"]])            # the engine's scratch field (last in the record) is not state
     hdr0 = int(a._foff[a.E["WRSN_F_HDR"]])
-    skip = [hdr0 + 8 * a.E["WRSN_H_" + f] for f in ("NRESUME",)]
+    skip = [hdr0 + 8 * a.E["WRSN_H_" + f] for f in ("NRESUME", "NBATCH")]   # (a split step may run a short batch event by event)
 
     def rows(env):
         st = env.state[:, :end].clone()
@@ -648,20 +649,20 @@ def check_reward_kernel(scenarios, device, num_envs, steps, seed, num_agent=3):
     return n_nonzero
 
 
-def check_sharded_equals_unsharded(scenarios, device, num_envs, steps, seed, world=2, num_agent=3, budget=0):
+def check_sharded_equals_unsharded(scenarios, device, num_envs, steps, seed, world=2, num_agent=3, budget=0, rounds=0):
     """Environments shard by index: the records of `world` simulators holding contiguous blocks of the environments are, byte
     for byte, the blocks of ONE simulator holding all of them (same scenario assignment, same actions)."""
     from multi_agent_rl_wrsn_b200.sharding import shard_range, shard_scenario_index
     rng = np.random.default_rng(seed)
     acts = rng.uniform(0.0, 1.0, size=(steps, num_envs, 3))
     acts[..., 2] *= 0.1
-    whole = BatchedWRSN(scenarios, num_agent=num_agent, num_envs=num_envs, device=device, step_budget=budget,
+    whole = BatchedWRSN(scenarios, num_agent=num_agent, num_envs=num_envs, device=device, step_budget=budget, step_rounds=rounds,
                         scenario_index=shard_scenario_index(num_envs, len(scenarios), 0, 1))
     parts = []
     for r in range(world):
         lo, hi = shard_range(num_envs, r, world)
         parts.append((lo, hi, BatchedWRSN(scenarios, num_agent=num_agent, num_envs=hi - lo, device=device, step_budget=budget,
-                                          scenario_index=shard_scenario_index(num_envs, len(scenarios), r, world))))
+                                          step_rounds=rounds, scenario_index=shard_scenario_index(num_envs, len(scenarios), r, world))))
     whole.reset()
     for _, _, p in parts:
         p.reset()

@@ -127,12 +127,13 @@ def test_emulated_raster_vs_reference_observations(name):
     pc.check_episode(name, "cpu", check_obs=True)
 
 
-@pytest.mark.parametrize("budget,scale2", [(12, 0.3), (40, 0.05), (3, 0.3)])
-def test_step_budget_only_cuts_steps_into_launches(budget, scale2):
-    """wrsn_dims.step_budget: interrupted steps continue where they stopped; requests and records are those of the
+@pytest.mark.parametrize("budget,scale2,rounds", [(12, 0.3, 0), (40, 0.05, 0), (3, 0.3, 0), (12, 0.3, 1), (30, 0.1, 2), (5, 0.3, 3)])
+def test_step_budget_only_cuts_steps_into_launches(budget, scale2, rounds):
+    """wrsn_dims.step_budget / step_rounds: interrupted steps continue where they stopped — in the same kernel or, split by
+    kind of work, alternating between the events kernel and the batch kernel; requests and records are those of the
     unbudgeted run (episodes end and restart on the way)."""
     scs = [synthetic(num_nodes=40, num_targets=120, seed=s, num_gateways=2) for s in (3, 4)]
-    n = pc.check_budget_equals_unbudgeted(scs, "cpu", num_envs=4, calls=60, seed=5, budget=budget, scale2=scale2)
+    n = pc.check_budget_equals_unbudgeted(scs, "cpu", num_envs=4, calls=60, seed=5, budget=budget, scale2=scale2, rounds=rounds)
     assert n > 20
 
 
@@ -150,3 +151,4 @@ def test_sharded_equals_unsharded_records():
     scs = [synthetic(num_nodes=40, num_targets=60, seed=s) for s in (31, 32, 33)]
     pc.check_sharded_equals_unsharded(scs, "cpu", num_envs=7, steps=40, seed=2, world=2, num_agent=2)
     pc.check_sharded_equals_unsharded(scs, "cpu", num_envs=7, steps=40, seed=2, world=3, num_agent=2, budget=10)
+    pc.check_sharded_equals_unsharded(scs, "cpu", num_envs=7, steps=40, seed=2, world=2, num_agent=2, budget=20, rounds=2)

@@ -191,13 +191,15 @@ def test_bench_scenarios_vs_oracle_random_controller():
     assert n_dec > 64 * 40 and cnt["batched_ticks"] > 0.5 * cnt["ticks"]
 
 
-@pytest.mark.parametrize("threads,budget", [(32, 25), (64, 60), (32, 160)])
-def test_step_budget_only_cuts_steps_into_launches(threads, budget):
+@pytest.mark.parametrize("threads,budget,rounds", [(32, 25, 0), (64, 60, 0), (32, 160, 0), (32, 40, 1), (32, 100, 2), (64, 30, 3)])
+def test_step_budget_only_cuts_steps_into_launches(threads, budget, rounds):
+    """wrsn_dims.step_budget / step_rounds (events kernel + batch kernel): same requests, same records as the unbudgeted run."""
     scs = [synthetic(num_nodes=100, num_targets=100, seed=s) for s in BENCH_SCENARIOS]
-    n = pc.check_budget_equals_unbudgeted(scs, DEV, num_envs=32, calls=80, seed=5, budget=budget, scale2=0.1, threads=threads)
+    n = pc.check_budget_equals_unbudgeted(scs, DEV, num_envs=32, calls=80, seed=5, budget=budget, scale2=0.1, threads=threads,
+                                          rounds=rounds)
     assert n > 10
     scs = [synthetic(num_nodes=40, num_targets=120, seed=s, num_gateways=2) for s in (3, 4)]
-    pc.check_budget_equals_unbudgeted(scs, DEV, num_envs=8, calls=60, seed=6, budget=budget, scale2=0.3, threads=threads)
+    pc.check_budget_equals_unbudgeted(scs, DEV, num_envs=8, calls=60, seed=6, budget=budget, scale2=0.3, threads=threads, rounds=rounds)
 
 
 def test_sharded_equals_unsharded_records():
@@ -206,6 +208,7 @@ def test_sharded_equals_unsharded_records():
     scs = [synthetic(num_nodes=100, num_targets=100, seed=s) for s in BENCH_SCENARIOS[:3]]
     pc.check_sharded_equals_unsharded(scs, DEV, num_envs=50, steps=60, seed=2, world=2)
     pc.check_sharded_equals_unsharded(scs, DEV, num_envs=50, steps=60, seed=3, world=3, budget=40)
+    pc.check_sharded_equals_unsharded(scs, DEV, num_envs=50, steps=60, seed=4, world=2, budget=60, rounds=2)
 
 
 @pytest.mark.parametrize("name,t_from,t_to", [("net_hanoi1000n200", 512, 524), ("net_hanoi1000n100", 1598, 1608)])

@@ -10,6 +10,7 @@ p.add_argument("--groups", type=int, default=1); p.add_argument("--actions", def
 p.add_argument("--envs", type=int, default=4096); p.add_argument("--steps", type=int, default=60)
 p.add_argument("--pre", type=int, default=160); p.add_argument("--nodes", type=int, default=100)
 p.add_argument("--chargers", type=int, default=3); p.add_argument("--topologies", type=int, default=64)
+p.add_argument("--rounds", type=int, default=0)
 a = p.parse_args()
 dev = torch.device("cuda:0")
 kw = dict(num_gateways=max(3, a.nodes // 40)) if a.nodes > 100 else {}
@@ -18,7 +19,7 @@ G, Bg = a.groups, a.envs // a.groups
 envs = [BatchedWRSN(scs, num_agent=a.chargers, num_envs=Bg, device=dev, threads=a.threads,
                     scenario_index=(np.arange(Bg) + g * Bg) % len(scs)) for g in range(G)]
 for e in envs:
-    e.dims.step_budget = a.budget
+    e.dims.step_budget = a.budget; e.dims.step_rounds = a.rounds
 streams = [torch.cuda.Stream(device=dev) for _ in range(G)]
 obs = [torch.zeros((Bg, 4, 100, 100), dtype=torch.float32, device=dev) for _ in range(G)]
 act = [torch.zeros((Bg, 3), dtype=torch.float64, device=dev) for _ in range(G)]
@@ -49,5 +50,5 @@ for k in range(a.steps):
 for st in streams: torch.cuda.current_stream().wait_stream(st)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1); d1, s1 = totals()
-print("threads=%d budget=%d groups=%d actions=%s nodes=%d: %.3f M decisions/s, %.3f ms/step, %.1f sim-s/decision, %.2f decisions/env-step"
-      % (envs[0].dims.threads, a.budget, G, a.actions, a.nodes, (d1 - d0) / ms / 1e3, ms / a.steps, (s1 - s0) / max(d1 - d0, 1), (d1 - d0) / (a.steps * a.envs)), flush=True)
+print("threads=%d budget=%d rounds=%d groups=%d actions=%s nodes=%d: %.3f M decisions/s, %.3f ms/step, %.1f sim-s/decision, %.2f decisions/env-step"
+      % (envs[0].dims.threads, a.budget, a.rounds, G, a.actions, a.nodes, (d1 - d0) / ms / 1e3, ms / a.steps, (s1 - s0) / max(d1 - d0, 1), (d1 - d0) / (a.steps * a.envs)), flush=True)
