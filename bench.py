@@ -281,7 +281,7 @@ def run_b200(a):
         controller law, 3 for uniform actions (the map itself is three elementwise torch kernels: the controller's arithmetic)"""
         with torch.cuda.stream(streams[g]):
             if law == "controller":
-                groups[g].density_map_to_action(controller_map(obs[g]), out=act[g])
+                groups[g].linear_controller_action(obs[g], CONTROLLER_WEIGHTS, out=act[g])   # == density_map_to_action(controller_map(obs))
             else:
                 torch.mul(torch.rand((Bg, 3), generator=gen, dtype=torch.float64, device=dev), scale, out=act[g])
             groups[g].rollout_step(act[g], obs[g])

@@ -232,6 +232,15 @@ int wrsn_observe(const wrsn_dims *d, const void *scen, const int32_t *scen_id, c
  * comment for what is reproduced exactly and what within tolerance). */
 int wrsn_decode_density_map(const wrsn_dims *d, const void *scen, const int32_t *scen_id, const void *state,
                             const int32_t *agent_id, const void *dmap, int dmap_f64, double *action_out, void *stream);
+/* The same decode for a controller whose density map is a LINEAR COMBINATION of the observation's channels — the reference's
+ * RandomController (controller/random/RandomController.py:12-15: state[0] + state[1] - 10 * state[2] + state[3]) with
+ * weights = {1, 1, -10, 1}: obs[b][channels][S][S] (float, as wrsn_observe writes it), weights[channels] on the HOST.  The
+ * map is formed on the fly in float32, one rounding per multiply and add, channel by channel — the bits torch produces for
+ * that expression — so the result equals wrsn_decode_density_map on the materialised map, without the controller's
+ * elementwise passes over the observations. */
+int wrsn_decode_linear_controller(const wrsn_dims *d, const void *scen, const int32_t *scen_id, const void *state,
+                                  const int32_t *agent_id, const float *obs, int channels, const float *weights,
+                                  double *action_out, void *stream);
 /* The bookkeeping of the trainers' roll_out loop (controller/ippo/IPPO.py:138-155, controller/ppo/PPO.py likewise) for
  * every environment after rollout step t, one thread per environment:
  *   last[b][agent_prev[b]] = t                      log_probs_pre[agent] = log_prob            (:140)

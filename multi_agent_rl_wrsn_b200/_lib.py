@@ -77,6 +77,7 @@ def _bind(L):
     L.wrsn_fitness.argtypes = [dp, vp, vp, vp, vp, vp, vp]
     L.wrsn_k_charge.argtypes = [dp, vp, vp, vp, vp, vp, vp, vp]
     L.wrsn_decode_density_map.argtypes = [dp, vp, vp, vp, vp, vp, ip, vp, vp]
+    L.wrsn_decode_linear_controller.argtypes = [dp, vp, vp, vp, vp, vp, ip, C.POINTER(C.c_float), vp, vp]
     for k in ("wrsn_k_bfs", "wrsn_k_drain", "wrsn_k_bookkeep", "wrsn_k_reward"):
         getattr(L, k).argtypes = [dp, vp, vp, vp, vp]
     e = enums()

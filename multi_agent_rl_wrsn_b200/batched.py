@@ -252,6 +252,28 @@ class BatchedWRSN:
                                                   1 if dmap.dtype == torch.float64 else 0, out.data_ptr(), self._stream())
         return out
 
+    def linear_controller_action(self, obs, weights, agent_id=None, out=None):
+        """``density_map_to_action`` for a controller whose map is a linear combination of the observation's channels — the
+        reference's RandomController is ``weights = (1, 1, -10, 1)`` (``controller/random/RandomController.py:12-15``) —
+        without materialising the map: ``obs`` [B, C, S, S] float32 in HBM -> actions [B, 3] float64.  Equal, bit for bit, to
+        ``density_map_to_action(w0 * obs[:, 0] + w1 * obs[:, 1] + ...)`` evaluated by torch in float32."""
+        if agent_id is None:
+            agent_id = self.req.agent_id
+        a = torch.as_tensor(agent_id, device=self.device).to(torch.int32).contiguous()
+        if obs.dtype != torch.float32 or not obs.is_contiguous() or obs.dim() != 4 or obs.shape[0] != self.B \
+                or obs.shape[2:] != (self.S, self.S) or obs.device != self.state.device:
+            raise ValueError("obs must be a contiguous float32 tensor [B, C, S, S] on the simulator's device")
+        w = (C.c_float * obs.shape[1])(*[float(x) for x in weights])
+        if len(w) != obs.shape[1]:
+            raise ValueError("one weight per channel")
+        if out is None:
+            out = torch.zeros((self.B, 3), dtype=torch.float64, device=self.device)
+        if out.dtype != torch.float64 or not out.is_contiguous() or out.shape != (self.B, 3):
+            raise ValueError("out must be a contiguous float64 tensor [B, 3]")
+        self._call(self.L.wrsn_decode_linear_controller, C.byref(self.dims), self.scen.data_ptr(), self.scen_id.data_ptr(),
+                   self.state.data_ptr(), a.data_ptr(), obs.data_ptr(), int(obs.shape[1]), w, out.data_ptr(), self._stream())
+        return out
+
     def get_network_fitness(self):
         """``WRSN.get_network_fitness`` (:188-220): per-target values [B, T] and their minimum [B]."""
         fit = torch.zeros((self.B, max(self.T, 1)), dtype=torch.float64, device=self.device)

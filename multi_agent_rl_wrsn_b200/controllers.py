@@ -17,7 +17,10 @@ from .sharding import reduce_stats
 
 
 class BatchedRandomController:
-    """``RandomController.make_action`` for a batch: ``state`` is the [B, 4, S, S] observation tensor."""
+    """``RandomController.make_action`` for a batch: ``state`` is the [B, 4, S, S] observation tensor.  ``weights``: the map is
+    this linear combination of the channels, which lets ``rollout`` decode it without materialising it
+    (``BatchedWRSN.linear_controller_action``)."""
+    weights = (1.0, 1.0, -10.0, 1.0)
 
     def make_action(self, agent_id, state, info=None, wrsn=None):
         return state[:, 0] + state[:, 1] - 10.0 * state[:, 2] + state[:, 3]
@@ -37,7 +40,13 @@ def rollout(env, controller, steps, obs=None, group=None):
     local = torch.zeros(2, dtype=torch.float64, device=dev)               # episodes finished, sum of rewards
     resets0 = env.req.stats[:, 2].sum()
     dec0, sim0 = reduce_stats(env, group)
+    fused = getattr(controller, "weights", None) is not None and obs.dtype == torch.float32
     for _ in range(int(steps)):
+        if fused:                                                         # map formed inside the decoder, channel by channel
+            env.linear_controller_action(obs, controller.weights, out=action)
+            env.rollout_step(action, obs)
+            local[1] += torch.nan_to_num(env.req.reward, nan=0.0).sum()
+            continue
         a = controller.make_action(env.req.agent_id, obs)
         if a.dim() == 3:                                                  # density maps: WRSN.step :293-297 on the device
             env.density_map_to_action(a.contiguous(), out=action)

@@ -100,8 +100,16 @@ namespace gany {                                     /* 64 ... 256 threads per e
 #define OBS_TI 4
 #define OBS_TJ64 10                 /* fp64 parity raster: 4 x 10 tiles, 256 threads */
 #define OBS_THREADS64 256
+#ifndef OBS_TJ32
 #define OBS_TJ32 20                 /* fp32 raster: 4 x 20 tiles, 128 threads */
 #define OBS_THREADS32 128
+#endif
+#ifndef OBS_CH32
+#define OBS_CH32 32                 /* sources staged per pass (fp32 raster) */
+#endif
+#ifndef OBS_MINB32
+#define OBS_MINB32 4                /* CTAs per SM the fp32 raster is compiled for */
+#endif
 
 struct ObsSrc { double x0, y0, hx, hy, w; int mode; int node; };     /* mode 0: (w*gx)*gy ; 1: ((gx*gy)*w)/mtm ; node >= 0: table row */
 
@@ -128,8 +136,8 @@ __global__ void k_obs_tables(const wrsn_dims d, const WrsnLayout L, char *scen) 
 /* tile = OBS_TI rows x TJ columns of output cells per thread.  fp64 parity raster: 4 x 10 on 256 threads; fp32 raster: 4 x 20 on
  * 128 threads (125 tiles of a 100 x 100 map: 80 FFMA per source against one 16-byte and five 16-byte shared-memory loads) */
 template <typename AccT, int TJ, int THREADS>
-__global__ void __launch_bounds__(THREADS, sizeof(AccT) == 4 ? 3 : 1) k_observe(const KParams P, const int32_t *agent_id, AccT *obs) {
-    constexpr int CH = sizeof(AccT) == 4 ? 64 : 16;      /* sources staged per pass */
+__global__ void __launch_bounds__(THREADS, sizeof(AccT) == 4 ? OBS_MINB32 : 1) k_observe(const KParams P, const int32_t *agent_id, AccT *obs) {
+    constexpr int CH = sizeof(AccT) == 4 ? OBS_CH32 : 16;      /* sources staged per pass */
     extern __shared__ uint4 smem_u4[];
     const int S = P.d.S, N = P.d.N, M = P.d.M, TP = P.d.obs_pitch;
     const int tiles_i = (S + OBS_TI - 1) / OBS_TI, tiles_j = (S + TJ - 1) / TJ;
@@ -343,25 +351,49 @@ __global__ void __launch_bounds__(THREADS, sizeof(AccT) == 4 ? 3 : 1) k_observe(
 #define DEC_THREADS 256
 #define DEC_MAXR 34
 #define DEC_MAXC 64
-template <typename MapT>
-__global__ void __launch_bounds__(DEC_THREADS, 4) k_decode_map(const KParams P, const int32_t *agent_id, const MapT *dmap, double *action) {
+/* LIN = false: dmap[b][S][S] is the map.  LIN = true: the map is a linear combination of the channels of the observation
+ * tensor, dmap[b][C][S][S] (float), formed on the fly in float32 with one rounding per multiply and per add, channel by
+ * channel — (((w0 o0) + w1 o1) + w2 o2) + ... — which is, bit for bit, what torch computes for the reference's
+ * RandomController (controller/random/RandomController.py:12-15: s0 + s1 - 10 s2 + s3; multiplying by 1 and negating are
+ * exact): the controller's three elementwise passes over the observations and the map itself never touch HBM. */
+struct LinMap { int C; float w[8]; };
+/* LINC: 0 = plain map; 4 = four channels, unrolled (weights in registers); -1 = any number of channels (rolled).
+ * This kernel produces the statistics of the map — charge-time fraction -> action[b][2], flat index of the argmax cell ->
+ * action[b][0] (as a double) — with all 256 threads busy; the location search, a serial climb of ONE warp, runs in
+ * k_decode_locate (one warp per environment) so that no warp waits at a barrier for it. */
+template <typename MapT, int LINC>
+__global__ void __launch_bounds__(DEC_THREADS, 4) k_decode_map(const KParams P, const int32_t *agent_id, const MapT *dmap, double *action,
+                                                               const LinMap lin) {
+    constexpr bool LIN = LINC != 0;
     __shared__ double cand_v[(DEC_THREADS / 32) * DEC_MAXR];
     __shared__ int cand_i[(DEC_THREADS / 32) * DEC_MAXR];
     __shared__ double red_s[3][DEC_THREADS / 32];
     __shared__ double top_v[DEC_MAXR];
     __shared__ int top_i[DEC_MAXR];
     __shared__ double bc[4];
-    __shared__ double cn_x[DEC_MAXC], cn_y[DEC_MAXC], cn_w[DEC_MAXC];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (agent_id[b] < 0) return;
-    const int S = P.d.S, n = S * S, N = P.d.N;
-    const MapT *src = dmap + (size_t)b * n;
+    const int S = P.d.S, n = S * S;
+    const MapT *src0 = dmap + (size_t)b * n * (LIN ? lin.C : 1);
+    const float w0 = lin.w[0], w1 = lin.w[1], w2 = lin.w[2], w3 = lin.w[3];
+    auto at = [&](int k) -> MapT {
+        if (LINC == 0) return src0[k];
+        if (LINC == 4) {
+            float acc = __fmul_rn(w0, (float)src0[k]);
+            acc = __fadd_rn(acc, __fmul_rn(w1, (float)src0[n + k]));
+            acc = __fadd_rn(acc, __fmul_rn(w2, (float)src0[2 * n + k]));
+            return (MapT)__fadd_rn(acc, __fmul_rn(w3, (float)src0[3 * n + k]));
+        }
+        float acc = __fmul_rn(lin.w[0], (float)src0[k]);
+        for (int ch = 1; ch < lin.C; ch++) acc = __fadd_rn(acc, __fmul_rn(lin.w[ch], (float)src0[(size_t)ch * n + k]));
+        return (MapT)acc;
+    };
     /* pass 1: min / max / sum and this thread's two heads (value descending, index ascending; k only grows here) */
     MapT mn = (MapT)INFINITY, mx = (MapT)-INFINITY; double sm = 0.0;
     MapT h1v = (MapT)-INFINITY, h2v = (MapT)-INFINITY; int h1i = 0x7fffffff, h2i = 0x7fffffff;
 #pragma unroll 4
     for (int k = tid; k < n; k += DEC_THREADS) {
-        const MapT v = src[k];
+        const MapT v = at(k);
         mn = v < mn ? v : mn; mx = v > mx ? v : mx; sm += (double)v;
         if (v > h1v) { h2v = h1v; h2i = h1i; h1v = v; h1i = k; }
         else if (v > h2v) { h2v = v; h2i = k; }
@@ -386,7 +418,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 4) k_decode_map(const KParams P, 
             if (taken == 2) {                        /* both heads gone: the next two of this thread's share after (lastv, lasti) */
                 h1v = h2v = (MapT)-INFINITY; h1i = h2i = 0x7fffffff;
                 for (int k = tid; k < n; k += DEC_THREADS) {
-                    const MapT v = src[k];
+                    const MapT v = at(k);
                     if (!(v < lastv || (v == lastv && k > lasti))) continue;
                     if (v > h1v) { h2v = h1v; h2i = h1i; h1v = v; h1i = k; }
                     else if (v > h2v) { h2v = v; h2i = k; }
@@ -442,7 +474,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 4) k_decode_map(const KParams P, 
         }
     } else {                                         /* values equal to the percentile all over the map: sum them in a second pass */
         for (int k = tid; k < n; k += DEC_THREADS) {
-            const double x = (double)src[k];
+            const double x = (double)at(k);
             if (x >= a_x) { const double v = is_dist ? x : exp(x); if (v >= thr_q) keep += v; }
         }
         for (int o = 16; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
@@ -454,8 +486,23 @@ __global__ void __launch_bounds__(DEC_THREADS, 4) k_decode_map(const KParams P, 
             bc[0] = (is_dist ? top_v[0] : exp(top_v[0])) / tot;
         }
     }
-    /* ---- location (warp 0) */
-    if (wid == 0) {
+    __syncthreads();
+    if (tid == 0) { action[3 * (size_t)b] = (double)top_i[0]; action[3 * (size_t)b + 2] = bc[0]; }
+}
+
+/* the location search of WRSN.density_map_to_action (:240-262), one warp per environment: reads the argmax cell left in
+ * action[b][0] by k_decode_map, writes action[b][0..1] */
+#define LOC_WARPS 4
+__global__ void __launch_bounds__(32 * LOC_WARPS) k_decode_locate(const KParams P, const int32_t *agent_id, double *action) {
+    __shared__ double s_cn[LOC_WARPS][3][DEC_MAXC];
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int b = blockIdx.x * LOC_WARPS + wrp;
+    if (b >= P.d.B || agent_id[b] < 0) return;           /* whole warps leave together; only __syncwarp below */
+    double *cn_x = s_cn[wrp][0], *cn_y = s_cn[wrp][1], *cn_w = s_cn[wrp][2];
+    const int S = P.d.S, N = P.d.N;
+    const int flat0 = (int)action[3 * (size_t)b];
+    double out_x, out_y;
+    {
         const char *row = P.state + (size_t)b * P.L.total;
         const char *scen_row = P.scen + (size_t)P.scen_id[b] * P.L.scen_total;
         const double *par = (const double *)(scen_row + P.L.soff[WRSN_S_PAR]);
@@ -465,7 +512,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 4) k_decode_map(const KParams P, 
         const double f0 = par[WRSN_P_F0], f1 = par[WRSN_P_F1], f2 = par[WRSN_P_F2], f3 = par[WRSN_P_F3];
         const double R = par[WRSN_P_MC_R], alpha = par[WRSN_P_MC_ALPHA], beta = par[WRSN_P_MC_BETA], thr = par[WRSN_P_THR];
         const double unit = 1.0 / (double)S;
-        const int flat = top_i[0], m0 = flat / S, m1 = flat - m0 * S;
+        const int flat = flat0, m0 = flat / S, m1 = flat - m0 * S;
         const double cx = ((double)m0 + 0.5) * unit, cy = ((double)m1 + 0.5) * unit;
         const double rx = R / (f1 - f0), ry = R / (f3 - f2);
         const double lox = (cx - rx) * (f1 - f0) + f0, loy = (cy - ry) * (f3 - f2) + f2;      /* up_mapping :91-93 */
@@ -544,10 +591,9 @@ __global__ void __launch_bounds__(DEC_THREADS, 4) k_decode_map(const KParams P, 
             if (done) break;
             t = (s_y > 0.0 && y_y > 0.0) ? s_y / y_y : tt * 4.0;
         }
-        if (lane == 0) { bc[1] = (x - f0) / (f1 - f0); bc[2] = (y - f2) / (f3 - f2); }       /* down_mapping :86-88 */
-    }
-    __syncthreads();
-    if (tid < 3) action[3 * (size_t)b + tid] = tid == 0 ? bc[1] : (tid == 1 ? bc[2] : bc[0]);
+        out_x = (x - f0) / (f1 - f0); out_y = (y - f2) / (f3 - f2);                            /* down_mapping :86-88 */
+        }
+    if (lane == 0) { action[3 * (size_t)b] = out_x; action[3 * (size_t)b + 1] = out_y; }
 }
 
 /* ------------------------------------------------------------------ host side of the C ABI */
@@ -861,7 +907,7 @@ int wrsn_observe(const wrsn_dims *d, const void *scen, const int32_t *scen_id, c
         if (smem > 48 * 1024) WRSN_CUDA(cudaFuncSetAttribute(k_observe<double, OBS_TJ64, OBS_THREADS64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         k_observe<double, OBS_TJ64, OBS_THREADS64><<<d->B, OBS_THREADS64, smem, (cudaStream_t)stream>>>(P, agent_id, (double *)obs);
     } else {
-        size_t smem = sizeof(float) * 2 * 64 * (size_t)d->obs_pitch;
+        size_t smem = sizeof(float) * 2 * OBS_CH32 * (size_t)d->obs_pitch;
         if (smem > 200 * 1024) WRSN_FAIL("map_size too large");
         static bool attr[WRSN_MAX_DEVICES];            /* per device, see launch_env */
         int dev = 0;
@@ -881,8 +927,29 @@ int wrsn_decode_density_map(const wrsn_dims *d, const void *scen, const int32_t 
     KParams P = base_params(d, scen, scen_id, const_cast<void *>(state), nullptr);
     wrsn_make_layout(&P.d, &P.L);
     if ((int64_t)d->S * d->S > (1 << 30)) WRSN_FAIL("map_size too large for the density-map decoder");
-    if (dmap_f64) k_decode_map<double><<<d->B, DEC_THREADS, 0, (cudaStream_t)stream>>>(P, agent_id, (const double *)dmap, action_out);
-    else k_decode_map<float><<<d->B, DEC_THREADS, 0, (cudaStream_t)stream>>>(P, agent_id, (const float *)dmap, action_out);
+    LinMap lin; memset(&lin, 0, sizeof(lin));
+    if (dmap_f64) k_decode_map<double, 0><<<d->B, DEC_THREADS, 0, (cudaStream_t)stream>>>(P, agent_id, (const double *)dmap, action_out, lin);
+    else k_decode_map<float, 0><<<d->B, DEC_THREADS, 0, (cudaStream_t)stream>>>(P, agent_id, (const float *)dmap, action_out, lin);
+    k_decode_locate<<<(d->B + LOC_WARPS - 1) / LOC_WARPS, 32 * LOC_WARPS, 0, (cudaStream_t)stream>>>(P, agent_id, action_out);
+    WRSN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int wrsn_decode_linear_controller(const wrsn_dims *d, const void *scen, const int32_t *scen_id, const void *state,
+                                  const int32_t *agent_id, const float *obs, int channels, const float *weights,
+                                  double *action_out, void *stream) {
+    if (check_dims(d)) return -1;
+    if (!agent_id || !obs || !weights || !action_out || !scen || !scen_id || !state) WRSN_FAIL("NULL argument");
+    if (channels < 1 || channels > 8) WRSN_FAIL("1 to 8 channels");
+    KParams P = base_params(d, scen, scen_id, const_cast<void *>(state), nullptr);
+    wrsn_make_layout(&P.d, &P.L);
+    if ((int64_t)d->S * d->S > (1 << 30)) WRSN_FAIL("map_size too large for the density-map decoder");
+    LinMap lin; memset(&lin, 0, sizeof(lin));
+    lin.C = channels;
+    for (int k = 0; k < channels; k++) lin.w[k] = weights[k];
+    if (channels == 4) k_decode_map<float, 4><<<d->B, DEC_THREADS, 0, (cudaStream_t)stream>>>(P, agent_id, obs, action_out, lin);
+    else k_decode_map<float, -1><<<d->B, DEC_THREADS, 0, (cudaStream_t)stream>>>(P, agent_id, obs, action_out, lin);
+    k_decode_locate<<<(d->B + LOC_WARPS - 1) / LOC_WARPS, 32 * LOC_WARPS, 0, (cudaStream_t)stream>>>(P, agent_id, action_out);
     WRSN_CUDA(cudaGetLastError());
     return 0;
 }

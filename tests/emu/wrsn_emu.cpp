@@ -250,6 +250,10 @@ int wrsn_observe(const wrsn_dims *d, const void *scen, const int32_t *scen_id, c
     }
     return 0;
 }
+int wrsn_decode_linear_controller(const wrsn_dims *, const void *, const int32_t *, const void *, const int32_t *, const float *, int, const float *,
+                                  double *, void *) {
+    WRSN_FAIL("wrsn_decode_linear_controller is not available in the host emulation");
+}
 int wrsn_decode_density_map(const wrsn_dims *, const void *, const int32_t *, const void *, const int32_t *, const void *, int, double *, void *) {
     WRSN_FAIL("wrsn_decode_density_map is not available in the host emulation");
 }

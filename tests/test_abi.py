@@ -42,7 +42,7 @@ def test_layout_and_enums(cuda_so):
     d = _lib.Dims()
     d.B, d.N, d.T, d.M, d.S, d.Emax, d.TEmax, d.n_scen = 4096, 100, 100, 3, 100, 240, 130, 4
     assert L.wrsn_dims_finalize(ctypes.byref(d)) == 0
-    assert d.Npad == 112 and d.W == 4 and d.Tw == 4 and d.threads == 64
+    assert d.Npad == 112 and d.W == 4 and d.Tw == 4 and d.threads == 32
     off = (ctypes.c_int64 * e["WRSN_F_COUNT"])()
     assert L.wrsn_state_layout(ctypes.byref(d), off) == 0
     offs = list(off)

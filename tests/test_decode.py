@@ -196,3 +196,21 @@ def test_decode_full_size_properties(cuda_library):
     np.testing.assert_allclose(a[0].cpu().numpy(), [0.5 / S, 0.5 / S, 1.0 / (S * S)], rtol=1e-12)
     r = torch.rand((B, S, S), dtype=torch.float32, device=DEV, generator=g)
     assert torch.equal(env.density_map_to_action(r), env.density_map_to_action(r))
+
+
+@pytest.mark.gpu
+def test_linear_controller_decode_equals_materialised_map(cuda_library):
+    """wrsn_decode_linear_controller (the RandomController map formed inside the decoder, channel by channel) == the decoder
+    on the map torch materialises for the same expression, bit for bit, on 512 rolled-out environments."""
+    B = 512
+    env, scs = _rolled_env(B, 80, seed=7, scale2=0.1)
+    obs = env.get_state(dtype=torch.float32)
+    agents = torch.zeros(B, dtype=torch.int32, device=DEV)
+    dm = obs[:, 0] + obs[:, 1] - 10.0 * obs[:, 2] + obs[:, 3]
+    want = env.density_map_to_action(dm.contiguous(), agent_id=agents)
+    got = env.linear_controller_action(obs, (1.0, 1.0, -10.0, 1.0), agent_id=agents)
+    same = lambda x, y: bool(((x == y) | (torch.isnan(x) & torch.isnan(y))).all())   # (a map that overflows exp() decodes to a NaN
+    assert same(want, got)                                                            #  charge fraction on both paths alike)
+    w = (0.5, -2.0, 3.0, 0.25)                           # any weights: torch multiplies, then adds, left to right
+    dm = w[0] * obs[:, 0] + w[1] * obs[:, 1] + w[2] * obs[:, 2] + w[3] * obs[:, 3]
+    assert same(env.density_map_to_action(dm.contiguous(), agent_id=agents), env.linear_controller_action(obs, w, agent_id=agents))

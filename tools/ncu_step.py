@@ -10,6 +10,8 @@ dev = torch.device("cuda:0")
 scs = [synthetic(num_nodes=100, num_targets=100, seed=1000 + k) for k in range(64)]
 env = BatchedWRSN(scs, num_agent=3, num_envs=B, device=dev, threads=int(os.environ.get("WRSN_THREADS", "0")))
 env.dims.step_budget = int(os.environ.get("WRSN_BUDGET", "0"))
+env.dims.step_rounds = int(os.environ.get("WRSN_ROUNDS", "0"))
+FUSED = os.environ.get("WRSN_FUSED", "1") == "1"
 obs = torch.zeros((B, 4, 100, 100), dtype=torch.float32, device=dev)
 env.reset()
 g = torch.Generator(device=dev); g.manual_seed(0)
@@ -17,7 +19,7 @@ RC = os.environ.get("WRSN_ACTIONS", "uniform") == "rc"      # the reference's Ra
 env.get_state(out=obs)
 for k in range(pre + n):
     if RC:
-        a = env.density_map_to_action(obs[:, 0] + obs[:, 1] - 10.0 * obs[:, 2] + obs[:, 3])
+        a = env.linear_controller_action(obs, (1.0, 1.0, -10.0, 1.0)) if FUSED else env.density_map_to_action(obs[:, 0] + obs[:, 1] - 10.0 * obs[:, 2] + obs[:, 3])
     else:
         a = torch.rand((B, 3), dtype=torch.float64, device=dev, generator=g); a[:, 2] *= 0.05
     env.rollout_step(a, obs)
