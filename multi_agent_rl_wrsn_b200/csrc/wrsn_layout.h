@@ -15,7 +15,7 @@
 #define WRSN_HD __host__ __device__ static inline
 #endif
 
-#define WRSN_SPEC_MAX 32                            /* charged (or otherwise irregular) nodes a whole-cycle batch handles by table */
+#define WRSN_SPEC_MAX 16                            /* charged (or otherwise irregular) nodes a whole-cycle batch handles by table */
 #define WRSN_PAIR_MAX 32                            /* (charger, node) pairs the incentive sums of a batch handle by list */
 #define WRSN_SPEC_LEN 6                             /* D1, D2, H, lo guard, hi guard, node id */
 

@@ -3,7 +3,10 @@
 import argparse, os, sys, time
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from multi_agent_rl_wrsn_b200 import BatchedWRSN, synthetic
+from multi_agent_rl_wrsn_b200 import BatchedWRSN, synthetic, _lib
+if os.environ.get("WRSN_LIB"):                      # a tuning build of the library
+    import ctypes
+    _lib._lib = _lib._bind(ctypes.CDLL(os.path.abspath(os.environ["WRSN_LIB"])))
 p = argparse.ArgumentParser()
 p.add_argument("--threads", type=int, default=0); p.add_argument("--budget", type=int, default=0)
 p.add_argument("--groups", type=int, default=1); p.add_argument("--actions", default="rc")
