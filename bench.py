@@ -52,6 +52,12 @@ def parse(argv=None):
     p.add_argument("--rounds", type=int, default=DEFAULT_ROUNDS, help="wrsn_dims.step_rounds: rounds of (events kernel, batch kernel) per step; 0 = one kernel")
     p.add_argument("--preroll", type=int, default=200, help="untimed steps before warm-up that desynchronise the episodes")
     p.add_argument("--groups", type=int, default=DEFAULT_GROUPS, help="asynchronous environment groups (CUDA streams) per GPU")
+    p.add_argument("--workload", default="rollout", choices=["rollout", "ippo"],
+                   help="rollout: the simulator's hot path under the configured controller (the headline); ippo: BASELINE.json "
+                        "configs[2], the IPPO training loop (alg_args/ippo.yaml) on the batched simulator — roll_out + clipped-PPO "
+                        "update with the gradient all-reduce, U-Net actors / CNN critics per charger (SURVEY 8 f2)")
+    p.add_argument("--iterations", type=int, default=3, help="--workload ippo: timed training iterations")
+    p.add_argument("--window", type=int, default=4, help="--workload ippo: rollout steps per collection window")
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -573,9 +579,115 @@ def run_b200(a):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------- configs[2]: IPPO training
+IPPO_ARGS = dict(seed=0, lr=3.0e-4, gamma=0.99, clip=0.2, batch_size=512, n_updates_per_iteration=5, save_freq=10 ** 9, gae=True,
+                 norm_adv=True, minibatch_size=64, ent_coef=0.0, vf_coef=0.5, gae_lambda=0.95, max_grad_norm=0.5,
+                 clip_vloss=True)                                    # alg_args/ippo.yaml (save_freq: no checkpoints while timing)
+
+
+def run_ippo(a):
+    """One training iteration = IPPO.train's loop body (controller/ippo/IPPO.py:212-310): roll_out until every charger's
+    network has batch_size transitions (batched: every environment of the shard advances together, the record stays in HBM),
+    then n_updates_per_iteration x (batch_size / minibatch_size) clipped-PPO minibatch steps per charger with ONE gradient
+    all-reduce per minibatch (NCCL over NVLink: 8.3 MB per actor + critic pair).  Reports agent-decisions/s of the whole loop
+    and where the time goes: simulator kernels vs actor inference in roll_out, update compute vs all-reduce."""
+    import torch
+    import torch.distributed as dist
+    from multi_agent_rl_wrsn_b200 import BatchedWRSN
+    from multi_agent_rl_wrsn_b200 import controllers as ctl
+    from multi_agent_rl_wrsn_b200.ippo import BatchedIPPO
+    from multi_agent_rl_wrsn_b200.nets import CNNCritic, UNetActor, num_parameters
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(1234 + rank)                           # (different seeds on purpose: the constructor broadcasts rank 0's weights)
+    B, M, S = a.envs, a.chargers, 100
+    env = BatchedWRSN(scenarios_for(a, rank), num_agent=M, num_envs=B, device=dev, threads=a.threads, map_size=S,
+                      step_budget=a.budget, step_rounds=a.rounds)
+    env.reset()
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(99 + rank)
+    tr = BatchedIPPO(IPPO_ARGS, env, device=dev, window=a.window, generator=gen)
+    n_params = num_parameters(tr.actors[0]) + num_parameters(tr.critics[0])
+    timers = []
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def iteration(timed):
+        e = [ev() for _ in range(3)]
+        e[0].record()
+        batches = tr.roll_out()
+        e[1].record()
+        for i in range(M):
+            ctl.ppo_update(tr.actors[i], tr.critics[i], tr.optimizers[i], batches[i], IPPO_ARGS, group=None, generator=gen,
+                           timers=timers if timed else None)
+        e[2].record()
+        return e, dict(tr.last_rollout)
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(max(1, a.warmup // 3)):
+        iteration(False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    sync_all()
+    t0w = time.perf_counter()
+    g0, g1 = ev(), ev()
+    g0.record()
+    recs = [iteration(True) for _ in range(a.iterations)]
+    g1.record()
+    sync_all()
+    t1w = time.perf_counter()
+    clocks = sampler.stop(t0w, t1w) if rank == 0 else None
+    total_ms = g0.elapsed_time(g1)
+    roll_ms = sum(e[0].elapsed_time(e[1]) for e, _ in recs)
+    upd_ms = sum(e[1].elapsed_time(e[2]) for e, _ in recs)
+    ar_ms = sum(x.elapsed_time(y) for x, y in timers)
+    decisions = sum(r["decisions"] for _, r in recs)         # (already summed over ranks by roll_out)
+    sim_s = sum(r["simulated_seconds"] for _, r in recs)
+    # the simulator's own share of roll_out: the same number of rollout steps without any network (RandomController law)
+    t = torch.tensor([total_ms, roll_ms, upd_ms, ar_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, roll_ms, upd_ms, ar_ms = [float(x) for x in t.tolist()]
+    if rank == 0:
+        cfg = config_common(a, envs_per_gpu=B, step_budget=a.budget, window=a.window, alg_args="alg_args/ippo.yaml",
+                            networks="U-Net actor (%d parameters) + CNN critic per charger, cuDNN convolutions (TF32), written from "
+                                     "the reference's shapes (multi_agent_rl_wrsn_b200/nets.py); %d parameters = %.1f MB per all-reduce"
+                                     % (num_parameters(tr.actors[0]), n_params, n_params * 4 / 1e6),
+                            iterations=a.iterations, minibatch_steps_per_iteration=len(timers) // max(a.iterations, 1),
+                            sim_seconds_per_decision=sim_s / max(decisions, 1.0))
+        cfg["workload"] = "IPPO training loop (alg_args/ippo.yaml), %d-node/%d-charger synthetic WRSN, %d envs per GPU" % (a.nodes, M, B)
+        line = dict(metric=METRIC, value=decisions / (total_ms * 1e-3), unit=UNIT, n_gpus=world, steps=a.iterations, warmup=a.warmup,
+                    ms_per_step=total_ms / a.iterations, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64 simulator / tf32 networks",
+                    data="synthetic", config=cfg, clocks=clocks,
+                    breakdown=dict(roll_out_ms=roll_ms / a.iterations, update_ms=upd_ms / a.iterations, allreduce_ms=ar_ms / a.iterations,
+                                   allreduce_share_of_update=ar_ms / max(upd_ms, 1e-9),
+                                   limiter="update" if upd_ms > roll_ms else "roll_out",
+                                   note="roll_out = simulator kernels + actor inference (U-Net forward on every request) + critic "
+                                        "values for the advantages; update = forward / backward of actor + critic on %d minibatches "
+                                        "per charger; all-reduce = one flat %.1f MB bucket per minibatch" % (
+                                            IPPO_ARGS["n_updates_per_iteration"] * IPPO_ARGS["batch_size"] // IPPO_ARGS["minibatch_size"],
+                                            n_params * 4 / 1e6)))
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "ippo":
+        run_ippo(args)
     else:
         run_b200(args)

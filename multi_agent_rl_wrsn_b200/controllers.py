@@ -265,11 +265,12 @@ class PerAgentPolicy:
     ``controller/ppo/PPO.py``) is ``PerAgentPolicy([actor] * num_agent)``.  One host synchronisation per call: the sizes
     of the groups."""
 
-    def __init__(self, actors, generator=None, action_shape=None):
+    def __init__(self, actors, generator=None, action_shape=None, chunk=512):
         """``action_shape``: shape of one action — default the S x S density map of the reference's actors; ``(3,)`` for
         actors that emit the 3-vector action directly (``density_map=False``)."""
         self.actors, self.generator = list(actors), generator
         self.action_shape = None if action_shape is None else tuple(action_shape)
+        self.chunk = int(chunk)                       # rows per forward pass (bounds the activations of a 4096-row batch)
 
     @torch.no_grad()
     def __call__(self, agent_id, obs):
@@ -289,16 +290,18 @@ class PerAgentPolicy:
         for i, n in enumerate(counts):
             if n == 0:
                 continue
-            idx = order[lo:lo + n]
+            for c0 in range(0, n, self.chunk):
+                idx = order[lo + c0:lo + min(n, c0 + self.chunk)]
+                m = int(idx.numel())
+                mean, log_std = self.actors[i](obs[idx].to(torch.float32))
+                mean, log_std = mean.reshape((m,) + shape), log_std.reshape((m,) + shape)   # UNet.forward squeezes a batch of one away
+                std = log_std.exp()
+                gdev = mean.device if self.generator is None else self.generator.device
+                a = mean + std * torch.randn(mean.shape, generator=self.generator, device=gdev, dtype=mean.dtype).to(mean.device)
+                logp = (-((a - mean) ** 2) / (2.0 * std * std) - log_std - 0.5 * math.log(2.0 * math.pi)).sum(red)   # Normal.log_prob
+                x[idx] = a
+                lp[idx] = logp
             lo += n
-            mean, log_std = self.actors[i](obs[idx].to(torch.float32))
-            mean, log_std = mean.reshape((n,) + shape), log_std.reshape((n,) + shape)   # UNet.forward squeezes a batch of one away
-            std = log_std.exp()
-            gdev = mean.device if self.generator is None else self.generator.device
-            a = mean + std * torch.randn(mean.shape, generator=self.generator, device=gdev, dtype=mean.dtype).to(mean.device)
-            logp = (-((a - mean) ** 2) / (2.0 * std * std) - log_std - 0.5 * math.log(2.0 * math.pi)).sum(red)   # Normal.log_prob
-            x[idx] = a
-            lp[idx] = logp
         return x, lp
 
 
@@ -321,7 +324,7 @@ def allreduce_gradients(parameters, group=None):
         off += g.numel()
 
 
-def ppo_update(actor, critic, optimizer, batch, args, group=None, generator=None):
+def ppo_update(actor, critic, optimizer, batch, args, group=None, generator=None, timers=None):
     """The update of one agent in ``IPPO.train`` (``controller/ippo/IPPO.py:222-268``; ``PPO.train`` is the same code):
     ``n_updates_per_iteration`` passes over ``batch`` (tensors of ``batch_size`` rows: states, actions, log_probs,
     advantages, returns, values) in shuffled minibatches, clipped surrogate + (clipped) value loss - entropy bonus,
@@ -366,7 +369,13 @@ def ppo_update(actor, critic, optimizer, batch, args, group=None, generator=None
             loss = pg_loss - float(args["ent_coef"]) * entropy_loss + v_loss * float(args["vf_coef"])
             optimizer.zero_grad()
             loss.backward()
+            if timers is not None:                                                      # CUDA events around the collective
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
             allreduce_gradients(params, group)
+            if timers is not None:
+                ev[1].record()
+                timers.append(ev)
             torch.nn.utils.clip_grad_norm_(actor.parameters(), float(args["max_grad_norm"]))
             torch.nn.utils.clip_grad_norm_(critic.parameters(), float(args["max_grad_norm"]))
             optimizer.step()

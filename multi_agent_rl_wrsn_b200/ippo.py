@@ -9,9 +9,16 @@ transition record never leave HBM), the advantage recursion covers all (environm
 and with several ranks (one process per GPU, each with its own shard of environments) the gradients are averaged by a
 single all-reduce per minibatch (``controllers.ppo_update``).
 
-The networks are the caller's: ``actor_factory`` / ``critic_factory`` build one actor / critic per agent — the
-reference's own ``UNet`` and ``CNNCritic`` (``controller/ppo/actor/UnetActor.py``, ``controller/ppo/critic/CNNCritic.py``)
-or anything with the same interface (actor: obs -> (mean, log_std) maps; critic: obs -> [n, k] summed over k).
+``actor_factory`` / ``critic_factory`` build one actor / critic per agent: by default ``nets.UNetActor`` / ``nets.CNNCritic``,
+written from the shapes of the reference's ``UNet`` and ``CNNCritic`` (``controller/ppo/actor/UnetActor.py``,
+``controller/ppo/critic/CNNCritic.py``; same parameter names, so checkpoints are interchangeable) — or the reference's own
+classes, or anything with the same interface (actor: obs -> (mean, log_std) maps; critic: obs -> [n, k] summed over k).
+
+Several ranks (one process per GPU, ``torch.distributed`` initialised by the caller): every rank holds its own shard of
+environments and an identical replica of the networks — the constructor broadcasts rank 0's parameters, so replicas are
+identical whatever the caller seeded; every rank feeds ITS ``batch_size`` transitions per agent into an update, gradients are
+averaged (one all-reduce per minibatch), i.e. the effective batch is ``world_size * batch_size`` while ``t_so_far`` counts
+``batch_size`` per iteration as the reference's log does; the episode statistics of ``log.csv`` are summed over ranks.
 ``shared=True`` is the reference's ``PPO`` (``controller/ppo/PPO.py``): ONE actor / critic pair for all chargers, the
 transitions of all agents pooled into one batch of ``batch_size`` (``PPO.py:125-197``), one update per iteration and the flat
 checkpoint folder ``<save_folder>/<iteration>/actor.pth | critic.pth | log.csv`` (``PPO.py:281-294``, ``:48-55``).
@@ -30,7 +37,9 @@ class BatchedIPPO:
     def __init__(self, args, env, device=None, model_path=None, actor_factory=None, critic_factory=None, window=8,
                  shared=False, group=None, generator=None, action_shape=None):
         if actor_factory is None or critic_factory is None:
-            raise ValueError("actor_factory and critic_factory are required (e.g. the reference's UNet and CNNCritic)")
+            from .nets import CNNCritic, UNetActor
+            actor_factory = actor_factory or (lambda: UNetActor(map_size=env.S))
+            critic_factory = critic_factory or (lambda: CNNCritic(map_size=env.S))
         # window: rollout steps per collection window; the record holds (window + 1) x B observations (160 KB each at map size
         # 100) plus, for the decisions still open at a window end, B x num_agent more (keep_open: nothing is lost at the boundary).
         self.env, self.args, self.group, self.generator = env, dict(args), group, generator
@@ -56,6 +65,11 @@ class BatchedIPPO:
                     rows = list(csv.reader(f))
                 if rows:
                     self.loggers[i]["i_so_far"], self.loggers[i]["t_so_far"] = int(rows[-1][0]), int(rows[-1][1])
+        dist = torch.distributed
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            for net in nets_a + nets_c:                                   # identical replicas: rank 0's parameters and buffers
+                for t in list(net.parameters()) + list(net.buffers()):
+                    dist.broadcast(t.data, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
         self.optimizers = []
         for i in range(self.num_agent):                                   # one Adam over actor + critic, IPPO.py:65-69
             if shared and i > 0:
@@ -91,9 +105,11 @@ class BatchedIPPO:
                 for k, v in (("states", bt["states"]), ("actions", bt["actions"]), ("log_probs", bt["log_probs"]),
                              ("rewards", bt["rewards"]), ("advantages", advantages), ("returns", returns), ("values", values)):
                     acc[i][k].append(v)
-        st1 = self.env.req.stats.sum(0)
-        episodes = float(st1[2] - st0[2])
-        self.last_rollout = dict(decisions=float(st1[0] - st0[0]), simulated_seconds=float(st1[1] - st0[1]), episodes=episodes,
+        delta = (self.env.req.stats.sum(0) - st0).clone()
+        dist = torch.distributed
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(delta, group=self.group)                      # job-wide statistics for log.csv
+        self.last_rollout = dict(decisions=float(delta[0]), simulated_seconds=float(delta[1]), episodes=float(delta[2]),
                                  transitions=list(counts))
         if self.shared:                                                  # one pooled batch, agents in id order (PPO.py:164-175)
             acc = [{k: [x for i in range(self.num_agent) for x in acc[i][k]] for k in acc[0]}]

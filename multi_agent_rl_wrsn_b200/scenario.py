@@ -17,6 +17,7 @@ import yaml
 
 DEFAULT_NODE_PHY = dict(capacity=10800, com_range=80.1, efs=1.0e-08, emp=1.3e-12, er=0.0001, et=5.0e-05,
                         package_size=400, prob_gp=1, sen_range=40.1, threshold=540)   # hanoi1000n50.yaml:1-11
+SHIPPED_MAX_TIME = 604800.0                          # max_time of hanoi1000n*.yaml / sonla1000n50.yaml (line 13 of each)
 DEFAULT_MC = dict(capacity=108000, threshold=0, velocity=5, pm=1, charging_range=27, alpha=4500, beta=30,
                   epsilon=1e-10)                                                     # mc_types/default.yaml:2-9
 
@@ -41,10 +42,16 @@ class Scenario:
 
     # -- reference schema ------------------------------------------------------------------------
     @staticmethod
-    def from_dict(d, name=""):
+    def from_dict(d, name="", default_max_time=None):
+        """``default_max_time``: the fix-up switch for scenarios that ship without ``max_time`` (the reference's four
+        ``bacgiang_*.yaml``: ``NetworkIO.py:34`` raises ``KeyError`` on them).  ``None`` keeps the
+        reference's behaviour (``KeyError``); a number — e.g. ``SHIPPED_MAX_TIME``, what the five loadable scenarios
+        carry — is used where the key is missing."""
         if "max_time" not in d:
-            # bacgiang_*.yaml ship without it and fail in the reference with KeyError
-            raise KeyError("scenario has no 'max_time' (NetworkIO.py:34 would raise too); add one")
+            if default_max_time is None:
+                raise KeyError("scenario has no 'max_time' (NetworkIO.py:34 would raise too): pass default_max_time=... "
+                               "(e.g. scenario.SHIPPED_MAX_TIME) to load it")
+            d = dict(d, max_time=float(default_max_time))
         spe = dict(d["node_phy_spe"])
         if float(spe.get("prob_gp", 1)) < 1.0:
             raise ValueError("prob_gp < 1 needs the reference's MT19937 stream (SURVEY Q12); not supported")
@@ -54,9 +61,9 @@ class Scenario:
                         node_phy_spe=spe, seed=int(d.get("seed", 0)), max_time=float(d["max_time"]), name=name)
 
     @staticmethod
-    def load_yaml(path):
+    def load_yaml(path, default_max_time=None):
         with open(path) as f:
-            return Scenario.from_dict(yaml.safe_load(f), name=str(path))
+            return Scenario.from_dict(yaml.safe_load(f), name=str(path), default_max_time=default_max_time)
 
     def to_dict(self):
         """Reference-schema dict (``yaml.safe_dump`` of it loads in ``NetworkIO``)."""

@@ -6,6 +6,11 @@ Drop-in for ``rl_env.WRSN.WRSN`` (``rl_env/WRSN.py:21-330``) as the controllers 
 ``action_space``.  The simulation itself runs in the sm_100a kernels of ``BatchedWRSN`` with one environment;
 use ``BatchedWRSN`` directly for throughput.
 
+A density-map action (``density_map=True``, the runners' setting) is decoded ON THE DEVICE (``wrsn_decode_density_map``:
+see DESIGN §4.4 for what is reproduced exactly); there is no host-side decode in this package.  The views in ``info`` read
+from ONE host copy of the environment's record per request (a single device-to-host transfer), not from one transfer per
+attribute.
+
 Differences from the reference, on purpose:
   * the request carries ``detailed_rewards`` = [term_all, term_exclusive, reward]; the reference's controllers read that
     key (``IPPO.py:162-164``) although its environment never writes it (SURVEY Q10);
@@ -38,7 +43,7 @@ class _Clock:
 
     @property
     def now(self):
-        return float(self._o._b.now[0].item())
+        return float(self._o._host("hdr")[self._o._b.E["WRSN_H_NOW"]])
 
 
 class _NodeView:
@@ -51,23 +56,23 @@ class _NodeView:
 
     @property
     def energy(self):
-        return float(self._n._o._b.view("energy")[0, self.id].item())
+        return float(self._n._o._host("energy")[self.id])
 
     @property
     def energyCS(self):
-        return float(self._n._o._b.view("cs")[0, self.id].item())
+        return float(self._n._o._host("cs")[self.id])
 
     @property
     def energyRR(self):
-        return float(self._n._o._b.view("rr")[0, self.id].item())
+        return float(self._n._o._host("rr")[self.id])
 
     @property
     def status(self):
-        return int(self._n._o._b.view("status")[0, self.id].item())
+        return int(self._n._o._host("status")[self.id])
 
     @property
     def level(self):
-        return int(self._n._o._b.view("level")[0, self.id].item())
+        return int(self._n._o._host("level")[self.id])
 
 
 class _NetView:
@@ -86,11 +91,13 @@ class _NetView:
 
     @property
     def targets_active(self):
-        return [int(v) for v in self._o._b.targets_active()[0].cpu().numpy()]
+        w = self._o._host("tact_words").astype(np.int64) & 0xFFFFFFFF
+        bits = (w[:, None] >> np.arange(32)) & 1
+        return [int(v) for v in bits.reshape(-1)[:self._o._b.T]]
 
     @property
     def alive(self):
-        return int(self._o._b.alive[0].item())
+        return int(self._o._host("hdr")[self._o._b.E["WRSN_H_ALIVE"]])
 
 
 class _AgentView:
@@ -102,7 +109,7 @@ class _AgentView:
         self.chargingRange, self.epsilon = mc["charging_range"], mc["epsilon"]
 
     def _f(self, name):
-        return float(self._o._b.mc(name)[0, self.id].item())
+        return float(self._o._host("mc")[self.id, self._o._b.E["WRSN_MC_" + name]])
 
     @property
     def location(self):
@@ -127,13 +134,8 @@ class _AgentView:
 
 class WRSN:
     def __init__(self, scenario_path, agent_type_path, num_agent, map_size=100, warm_up_time=100, density_map=False,
-                 device=None, decode="host"):
-        """Same arguments as the reference's constructor (``rl_env/WRSN.py:22``).  ``decode``: where a density-map action
-        is turned into the 3-vector — ``"host"`` (scipy's L-BFGS-B, as the reference does it) or ``"device"``
-        (``wrsn_decode_density_map``: no host round trip; see DESIGN §4.4 for what is reproduced exactly)."""
-        if decode not in ("host", "device"):
-            raise ValueError("decode must be 'host' or 'device'")
-        self.decode = decode
+                 device=None):
+        """Same arguments as the reference's constructor (``rl_env/WRSN.py:22``), plus the CUDA device."""
         scenario = scenario_path if isinstance(scenario_path, Scenario) else Scenario.load_yaml(scenario_path)
         if isinstance(agent_type_path, dict) or agent_type_path is None:
             self.agent_phy_para = agent_type_path
@@ -155,6 +157,7 @@ class WRSN:
         self.agents = [_AgentView(self, i) for i in range(self.num_agent)]
         self.agents_input_action = [None] * self.num_agent
         self.agents_prev_state = [None] * self.num_agent
+        self._row = None
         self.reset()
 
     # ------------------------------------------------------------------ reference helpers (WRSN.py:86-98)
@@ -179,49 +182,29 @@ class WRSN:
 
     # ------------------------------------------------------------------ WRSN.density_map_to_action (:229-287)
     def density_map_to_action(self, dmap, id):
-        """Host-side decode of an S x S density map into a 3-vector action, as the reference does it (argmax cell,
-        L-BFGS-B inside the +-charging_range box around it, 99.9-percentile mass as charging time)."""
-        from scipy.optimize import minimize
-        dmap = np.asarray(dmap, np.float64)
-        unit = 1.0 / self.map_size
-        f = self.net.frame
-        R, alpha, beta = self.agent_phy_para["charging_range"], self.agent_phy_para["alpha"], self.agent_phy_para["beta"]
-        max_index = np.unravel_index(np.argmax(dmap), dmap.shape)
-        lo = self.up_mapping([(max_index[0] + 0.5) * unit - R / (f[1] - f[0]), (max_index[1] + 0.5) * unit - R / (f[3] - f[2])])
-        hi = self.up_mapping([(max_index[0] + 0.5) * unit + R / (f[1] - f[0]), (max_index[1] + 0.5) * unit + R / (f[3] - f[2])])
-        bounds = [(lo[0], hi[0]), (lo[1], hi[1])]
-        xy = self.net._xy
-        st = self._b.view("status")[0].cpu().numpy()
-        en = self._b.view("energy")[0].cpu().numpy()
-        cs = self._b.view("cs")[0].cpu().numpy()
-        thr = self._b.statics[0]["par"]["THR"]
-        alive = np.nonzero(st != 0)[0]
+        """An S x S density map (already a distribution, as ``WRSN.step`` hands it over, or raw: the device applies the same
+        normalisation rule, ``:293-296``) -> the 3-vector action, decoded by ``wrsn_decode_density_map`` on the device."""
+        dm = torch.as_tensor(np.ascontiguousarray(dmap, np.float64).reshape(1, self.map_size, self.map_size), device=self._b.device)
+        aid = torch.tensor([int(id)], dtype=torch.int32, device=self._b.device)
+        return self._b.density_map_to_action(dm, agent_id=aid)[0].cpu().numpy()
 
-        def objective(loc):
-            res = 0
-            for n in alive:
-                d = float(np.sqrt((loc[0] - xy[n, 0]) ** 2 + (loc[1] - xy[n, 1]) ** 2))
-                res += int(d <= R) * (cs[n] / (en[n] - thr)) * alpha / ((d + beta) ** 2)
-            return -res
-
-        result = minimize(objective, [(lo[0] + hi[0]) / 2, (lo[1] + hi[1]) / 2], bounds=bounds, method="L-BFGS-B")
-        flat = np.copy(dmap).flatten()
-        flat[flat < np.percentile(flat, 99.9)] = 0
-        prob = flat.reshape(dmap.shape)
-        prob = prob / np.sum(prob)
-        loc = self.down_mapping(np.array(result.x))
-        return np.array([loc[0], loc[1], prob[max_index[0]][max_index[1]]])
+    def _host(self, name):
+        """Typed view of ONE host copy of the environment's record, fetched once per request (invalidated by reset / step)."""
+        if self._row is None:
+            self._row = self._b.state.cpu()
+        return self._b.view(name, self._row)[0].numpy()
 
     # ------------------------------------------------------------------ reset / step
     def _request(self, req, agent_in=None):
-        aid = int(req.agent_id[0].item())
-        flags = int(req.flags[0].item())
+        self._row = None                                 # the views refetch the record when they are next read
+        pack = torch.cat([req.agent_id.to(torch.float64), req.flags.to(torch.float64), req.terminal.to(torch.float64),
+                          req.reward, req.detail.reshape(-1), req.action.reshape(-1)]).cpu().numpy()   # one transfer
+        aid, flags, terminal, reward, det, action = int(pack[0]), int(pack[1]), bool(pack[2]), float(pack[3]), pack[4:6], pack[6:9]
         if flags & 2:
-            raise RuntimeError("wrsn_b200 engine error %g" % float(self._b.hdr("ERR")[0].item()))
+            raise RuntimeError("wrsn_b200 engine error %g" % float(self._host("hdr")[self._b.E["WRSN_H_ERR"]]))
         if flags & 1:
             raise RuntimeError("every mobile charger is dead: the reference's WRSN.step would never return (SURVEY Q1)")
         info = [self.net, self.agents]
-        terminal = bool(req.terminal[0].item())
         if aid == -2:                                # the reference falls off the end of step() and returns None (Q7)
             return None
         if aid < 0:
@@ -229,10 +212,8 @@ class WRSN:
                     "state": None, "terminal": terminal, "info": info, "detailed_rewards": None}
         state = self.get_state(aid)
         prev = self.agents_prev_state[aid] if self.agents_prev_state[aid] is not None else state
-        reward = float(req.reward[0].item())
-        det = req.detail[0].cpu().numpy()
         return {"agent_id": aid, "prev_state": prev, "input_action": self.agents_input_action[aid],
-                "action": req.action[0].cpu().numpy().copy(), "reward": reward, "state": state, "terminal": terminal,
+                "action": action.copy(), "reward": reward, "state": state, "terminal": terminal,
                 "info": info, "detailed_rewards": [float(det[0]), float(det[1]), reward]}
 
     def reset(self):
@@ -249,14 +230,7 @@ class WRSN:
         if agent_id is not None:
             action = np.array(input_action)
             self.agents_input_action[agent_id] = action.copy()
-            if self.density_map and self.decode == "device":
-                dm = torch.as_tensor(np.ascontiguousarray(action, np.float64).reshape(1, self.map_size, self.map_size), device=dev)
-                aid = torch.tensor([agent_id], dtype=torch.int32, device=dev)
-                action = self._b.density_map_to_action(dm, agent_id=aid)[0].cpu().numpy()
-            elif self.density_map:
-                if not (np.all((action >= 0) & (action <= 1)) and np.isclose(np.sum(action), 1)):
-                    action = np.exp(action)
-                    action = action / (np.sum(action) + self.epsilon)
+            if self.density_map:                         # normalisation (:293-296) + decode (:229-287) on the device
                 action = self.density_map_to_action(action, agent_id)
             # prev_state = get_state(agent_id) before the simulation advances == the state last handed out for it
             last = getattr(self, "_last_state", None)

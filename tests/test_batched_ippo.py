@@ -6,6 +6,7 @@ import csv
 import os
 import subprocess
 
+import numpy as np
 import pytest
 
 from tests import helpers
@@ -135,3 +136,40 @@ def test_two_ranks_keep_identical_replicas(tmp_path):
     fresh = _params([Actor(), Actor(), Critic(), Critic()])
     assert r0["p"].shape == fresh.shape and not torch.equal(r0["p"], fresh)
     assert sorted(os.listdir(tmp_path / "save" / "1")) == ["0", "1"]
+
+
+# ------------------------------------------------------------------ on the device, with the real networks
+def test_in_tree_networks_have_the_reference_shapes():
+    from multi_agent_rl_wrsn_b200.nets import CNNCritic, UNetActor, num_parameters
+    a, c = UNetActor(), CNNCritic()
+    assert num_parameters(a) == 936401 and num_parameters(c) == 1147513
+    x = torch.rand(2, 4, 100, 100)
+    mean, log_std = a(x)
+    assert mean.shape == (2, 100, 100) and log_std.shape == (2, 100, 100) and c(x).shape == (2, 1)
+    keys = set(a.state_dict())
+    assert {"inc.conv.weight", "down1.conv_block.bn.running_mean", "up2.conv_block.conv.bias", "out_mean.conv.weight", "log_std"} <= keys
+    assert set(c.state_dict()) == {"conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias", "conv3.weight", "conv3.bias",
+                                   "fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias"}
+
+
+@pytest.mark.gpu
+def test_ippo_iteration_on_the_device_with_unet_and_cnn_critic(tmp_path):
+    """BatchedIPPO.roll_out + ppo_update (IPPO.py:119-310) on the B200 with the U-Net actors / CNN critics and density-map
+    actions decoded on the device, step budget on (rows whose step is in flight carry no request): every agent gets its
+    batch, the update changes the weights, losses are finite, the checkpoint loads back."""
+    helpers.use_cuda_build()
+    torch.manual_seed(0)
+    dev = "cuda:0"
+    args = dict(ARGS, batch_size=64, minibatch_size=32, n_updates_per_iteration=2, save_freq=1)
+    scs = [synthetic(num_nodes=100, num_targets=100, seed=1000 + k) for k in range(4)]
+    env = BatchedWRSN(scs, num_agent=3, num_envs=96, device=dev, step_budget=60)
+    gen = torch.Generator(device=dev).manual_seed(1)
+    t = BatchedIPPO(args, env, window=4, generator=gen)
+    before = _params(t.actors + t.critics).clone()
+    hist = t.train(0, str(tmp_path / "save"))
+    assert len(hist) == 3 and all(np.isfinite(h["loss"]) and np.isfinite(h["approx_kl"]) for h in hist)
+    assert min(t.last_rollout["transitions"]) >= 64 and not torch.equal(before, _params(t.actors + t.critics))
+    assert float(env.hdr("ERR").max()) == 0.0
+    env2 = BatchedWRSN(scs, num_agent=3, num_envs=8, device=dev)
+    r = BatchedIPPO(args, env2, model_path=str(tmp_path / "save" / "1"), window=2, generator=gen)
+    assert torch.equal(_params(r.actors + r.critics), _params(t.actors + t.critics))

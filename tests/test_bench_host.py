@@ -14,7 +14,7 @@ def _bench():
 
 
 def _args(**kw):
-    base = dict(nodes=100, targets=None, chargers=3, envs=4096, topologies=3, scenario=None)
+    base = dict(nodes=100, targets=None, chargers=3, envs=4096, topologies=3, scenario=None, actions="controller")
     base.update(kw)
     return argparse.Namespace(**base)
 
@@ -34,5 +34,9 @@ def test_workloads():
 def test_cpu_sample_of_the_reference_arm():
     """One short single-core sample of the C restatement, as `cpu_baseline` / `--impl reference` take it."""
     b = _bench()
-    out = b.cpu_baseline(_args(topologies=1), cores=1, budget_s=1.0)
+    out = b.cpu_baseline(_args(topologies=1, actions="uniform"), cores=1, budget_s=1.0)
     assert out["kind"] == "port" and out["cores"] == 1 and out["unit"] == b.UNIT and out["value"] > 10.0
+    # the headline law: the RandomController map decoded by the reference's own numpy / scipy statements (slow: L-BFGS-B)
+    out = b.cpu_baseline(_args(topologies=1), cores=1, budget_s=2.0)
+    assert out["value"] > 0.5 and "RandomController" in out["sample"]
+    assert "RandomController" in b.workload_name(_args()) and "uniform" in b.workload_name(_args(actions="uniform"))
