@@ -94,6 +94,9 @@ def scenarios_for(a, rank):
     return [synthetic(num_nodes=a.nodes, num_targets=T, seed=1000 + rank * a.topologies + k, **kw) for k in range(a.topologies)]
 
 
+CONTROLLER_WEIGHTS = (1.0, 1.0, -10.0, 1.0)          # RandomController: state[0] + state[1] - 10 * state[2] + state[3]
+
+
 def controller_map(obs):
     """``RandomController.make_action`` (controller/random/RandomController.py:12-15) for a batch of observations."""
     return obs[:, 0] + obs[:, 1] - 10.0 * obs[:, 2] + obs[:, 3]
