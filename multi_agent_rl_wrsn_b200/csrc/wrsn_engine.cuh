@@ -1113,6 +1113,31 @@ WRSN_D double nan_with_payload(int slot) {
 #endif
 }
 
+/* table entry of node i at energy e (reward_cycles / spec_second): inside e's binade the chain of relayed packets of lower
+ * ids, the own packets + relays of higher ids and the top-up  min(e + energyRR * 0.5, cap)  move e by D1, D2 and H — whole
+ * numbers of ulps — as long as e stays between the guards for the whole second (both top-ups, both chains) */
+WRSN_NOINLINE void spec_entry(Ctx &c, int i, int slot, double e) {
+    double *sp = c.spec + slot * WRSN_SPEC_LEN;
+    const double es = c.esend[i], er = c.par[WRSN_P_ERECV], rr = c.rr[i];
+    const int nb = c.nbef[i], na = c.naft[i];
+    const int ow = c.parent[i] != -1 ? (int)c.own[i] : 0;
+    const int n_a = nb + ow + na, n_b = nb + na;
+    double D1 = 0.0, D2 = 0.0, H = 0.0, glo = INFINITY, ghi = -INFINITY;
+    const int ex = wrsn_biased_exp(e);
+    if (e > 0.0 && ex > 60 && ex < 1900) {
+        const double lo = wrsn_pow2_biased(ex), inv_u = wrsn_pow2_biased(2098 - ex), u = wrsn_pow2_biased(ex - 52);
+        const double qa = es * inv_u, qb = er * inv_u, qh = (rr * 0.5) * inv_u;
+        const double ra = rint(qa), rb = rint(qb), rh = rint(qh);
+        const bool tie = (n_a > 0 && fabs(qa - ra) == 0.5) || (n_b > 0 && fabs(qb - rb) == 0.5) || fabs(qh - rh) == 0.5;
+        const double K1 = (ra + rb) * (double)nb, K2 = ra * (double)(ow + na) + rb * (double)na;
+        if (!tie && K1 + K2 < 1125899906842624.0 && rh < 1125899906842624.0 && rr >= 0.0) {
+            D1 = K1 * u; D2 = K2 * u; H = rh * u;
+            glo = lo + (D1 + D2); ghi = (lo + lo) - (H + H) - (u + u);
+        }
+    }
+    sp[0] = D1; sp[1] = D2; sp[2] = H; sp[3] = glo; sp[4] = ghi; sp[5] = (double)i;
+}
+
 /* one table node, one second: [the previous second's k+1.0 top-up,] [this second's k+0.5 tick] on c.energy[i] */
 WRSN_NOINLINE void spec_second(Ctx &c, int t, int book, int drain) {
     const double *sp = c.spec + t * WRSN_SPEC_LEN;
@@ -1130,6 +1155,7 @@ WRSN_NOINLINE void spec_second(Ctx &c, int t, int book, int drain) {
             const int ow = c.parent[i] != -1 ? (int)c.own[i] : 0;
             e = drain_node(e, rr, c.esend[i], c.par[WRSN_P_ERECV], c.nbef[i], ow, c.naft[i], cap);
         }
+        spec_entry(c, i, t, e);                      /* e.g. the node has left the binade its entry was made for: a new one */
     }
     c.energy[i] = e;
 }
@@ -1176,6 +1202,126 @@ WRSN_NOINLINE bool node_in_incentive(Ctx &c, int i) {   /* does an incentive sum
         if (m[WRSN_MC_STATUS] != 0.0 && m[WRSN_MC_TYPE] != 0.0 && ((c.conn[a * c.W + (i >> 5)] >> (i & 31)) & 1u)) in = true;
     }
     return in;
+}
+
+/* the table nodes of one second of a batch: the previous second's k+1.0 top-up (`book`) and this second's k+0.5 tick
+ * (`drain`), as many threads as there are entries */
+WRSN_NOINLINE void spec_phase(Ctx &c, int n_spec, int book, int drain) {
+    const double cap = c.par[WRSN_P_CAP];
+    const double *spec = c.spec.ptr();
+    for (int t = c.tid; t < n_spec; t += WRSN_GSZ(c)) {
+        const double *sp = spec + t * WRSN_SPEC_LEN;
+        const int i = (int)sp[5];
+        double en = c.energy[i];
+        if (en >= sp[3] && en <= sp[4]) {            /* inside the guards: whole ulps (see spec_second) */
+            const double H = sp[2];
+            if (book) { en = en + H; en = en < cap ? en : cap; }
+            if (drain) { en = (en - sp[0]) + H; en = (en < cap ? en : cap) - sp[1]; }
+            c.energy[i] = en;
+        } else spec_second(c, t, book, drain);
+    }
+}
+
+/* the incentive sums of one tick from the pair list (built by reward_cycles): one thread per pair computes its term, one
+ * thread per charger adds its terms in node order */
+WRSN_NOINLINE void pairs_phase(Ctx &c, double tot, int n_pairs) {
+    const int G = WRSN_GSZ(c), tid = c.tid;
+    if (n_pairs > WRSN_PAIR_MAX) { if (tid < c.M) reward_incentives(c, tot); return; }
+    const double thr = c.par[WRSN_P_THR], cap = c.par[WRSN_P_CAP], ab2 = c.par[WRSN_P_MC_AB2];
+    const double inv_tot = wrsn_rcp(tot), inv_ab2 = wrsn_rcp(ab2);
+    double *pair_term = c.pairs.ptr();
+    const int *pair_ids = (const int *)(pair_term + WRSN_PAIR_MAX), *pair_seg = pair_ids + 2 * WRSN_PAIR_MAX;
+    for (int p = tid; p < n_pairs; p += G) {
+        const int a2 = pair_ids[2 * p], i = pair_ids[2 * p + 1];
+        const double ec = c.energy[i] - c.cs[i];
+        double e_with = cap;                         /* max(ec + rate, capacity) with rate <= alpha / beta^2 */
+        if (ec + ab2 > cap) e_with = fmax(ec + charge_rate_fast(c, c.mc + a2 * WRSN_MC_LEN, i), cap);
+        pair_term[p] = (c.scr0[i] * inv_tot) * (e_with - (ec < thr ? ec : thr)) * inv_ab2;
+    }
+    gsync(c);
+    for (int a2 = tid; a2 < c.M; a2 += G) {
+        const int p0 = pair_seg[2 * a2], p1 = pair_seg[2 * a2 + 1];
+        if (p1 > p0) {
+            double incentive = 0.0;
+            for (int p = p0; p < p1; p++) incentive += pair_term[p];
+            c.mc[a2 * WRSN_MC_LEN + WRSN_MC_EXCL] += incentive;
+        }
+    }
+}
+
+/* The steady state of a batch: every energyCS has reached its fixed point, no charger position moves under update_reward
+ * (`watched`), the pair list stands.  Per second and node slot: one subtraction (or the table node's energy from shared
+ * memory), reciprocal, two sums; after the first reduction one exponential and a sum; nothing else.  Called by
+ * reward_cycles<.., true> once those conditions hold, with the node rows current in shared memory; applies the last
+ * second's bookkeeping before it returns, like its caller would.  Same arithmetic, same order of every sum as the
+ * general loop (tests: batches == event path, byte for byte). */
+template <int NPT_T>
+WRSN_NOINLINE void reward_hot(Ctx &c, int n_cycles, int n_spec) {
+    const int N = c.N, G = WRSN_GSZ(c), tid = c.tid;
+#if defined(WRSN_HOST_EMU)
+    const int NPT = N;
+#else
+    const int NPT = NPT_T > 0 ? NPT_T : (N + G - 1) / G;
+#endif
+    const double thr = c.par[WRSN_P_THR], eps = c.par[WRSN_P_EPSENV], inv_n = c.par[WRSN_P_INVN];
+    const double *dec = c.scr1.ptr();
+    WRSN_SLOT_ARR(double, e); WRSN_SLOT_ARR(double, cs); WRSN_SLOT_ARR(double, d); WRSN_SLOT_ARR(double, x);
+    WRSN_FLAGS_DECL(f_in); WRSN_FLAGS_DECL(f_inc); WRSN_FLAGS_DECL(f_special);
+    int any_inc = 0, buf = 0;
+    WRSN_FOR_SLOTS(s) {
+        const int i = tid + s * G;
+        const bool ok = i < N && c.status[i] != 0;
+        e[s] = ok ? c.energy[i] : c.par[WRSN_P_CAP]; cs[s] = ok ? c.cs[i] : 0.0; d[s] = ok ? dec[i] : 0.0;
+        if (i < N) WRSN_FL_SET(f_in, s);
+        if (ok) {
+            if (node_in_incentive(c, i)) { WRSN_FL_SET(f_inc, s); any_inc = 1; }
+            if (d[s] != d[s]) WRSN_FL_SET(f_special, s);
+        }
+    }
+    any_inc = red_or(c, any_inc);
+    const int n_pairs = c.bcast[8];
+    _Pragma("unroll 1")
+    for (int j = 0; j < n_cycles; j++) {
+        if (n_spec > 0) { spec_phase(c, n_spec, 1, 1); gsync(c); }
+        double s1 = 0.0, s2 = 0.0;
+        WRSN_FOR_SLOTS(s) {
+            const double e_next = e[s] - d[s];
+            e[s] = WRSN_FL_GET(f_special, s) ? c.energy[tid + s * G] : e_next;
+            x[s] = cs[s] * wrsn_rcp(e[s] - thr + eps);
+            s1 += x[s]; s2 = wrsn_fma(x[s], x[s], s2);
+        }
+        red_sum2(c, s1, s2, buf);
+        const double mean = s1 * inv_n;
+        double var = wrsn_fma(s2, inv_n, -(mean * mean));
+        if (!(var > 1e-3 * (mean * mean))) {         /* cancellation: the textbook two passes (np.std) */
+            double q = 0.0;
+            WRSN_FOR_SLOTS(s) { const double u = WRSN_FL_GET(f_in, s) ? x[s] - mean : 0.0; q = wrsn_fma(u, u, q); }
+            red_sum1(c, q, buf);
+            var = q * inv_n;
+        }
+        const double a = var > 0.0 ? wrsn_rsqrt(var) : 1.0 / eps;
+        double tot = 0.0;
+        WRSN_FOR_SLOTS(s) {
+            const double q = wrsn_exp_b(c, (x[s] - mean) * a);
+            tot += WRSN_FL_GET(f_in, s) ? q : 0.0;
+            if (WRSN_FL_GET(f_inc, s)) {
+                const int i = tid + s * G;
+                c.scr0[i] = q;
+                if (!WRSN_FL_GET(f_special, s)) c.energy[i] = e[s];
+            }
+        }
+        red_sum1(c, tot, buf);
+        if (WRSN_GFIX == 32) gsync(c);
+        if (tot == 0.0) tot = eps;
+        if (n_pairs > 0) pairs_phase(c, tot, n_pairs);
+        if (any_inc || n_spec > 0 || WRSN_GFIX != 32) gsync(c);
+    }
+    if (n_spec > 0) spec_phase(c, n_spec, 1, 0);     /* bookkeeping of the last second; rows back to shared memory */
+    WRSN_FOR_SLOTS(s) {
+        const int i = tid + s * G;
+        if (i < N && c.status[i] != 0 && !WRSN_FL_GET(f_special, s)) c.energy[i] = e[s];
+    }
+    gsync(c);
 }
 
 template <int NPT_T, bool BATCH>
@@ -1310,6 +1456,19 @@ WRSN_NOINLINE void reward_cycles(Ctx &c, int n_cycles, double t_reward, int watc
             }
         }
         if (any_inc || n_spec > 0 || watched || WRSN_GFIX != 32) gsync(c);
+        if (BATCH && !watched && j >= 1 && j + 1 < n_cycles && !red_or(c, any_unfixed)) {
+            /* steady state: hand the remaining seconds to the lean loop (rows back to shared memory first; the bookkeeping
+               of second j is the first thing it does) */
+            WRSN_FOR_SLOTS(s) {
+                const int i = tid + s * G;
+                if (!(i < N && c.status[i] != 0)) continue;
+                c.cs[i] = cs[s];
+                if (!WRSN_FL_GET(f_special, s)) c.energy[i] = e[s];
+            }
+            gsync(c);
+            reward_hot<NPT_T>(c, n_cycles - (j + 1), n_spec);
+            return;
+        }
     }
     if (BATCH) {                                     /* bookkeeping of the last second; rows back to shared memory */
         if (n_spec > 0) {
@@ -2047,24 +2206,7 @@ WRSN_NOINLINE int nodes_batch(Ctx &c, int n_max, int ur_on, double t_reward, int
                own packets + relays of higher ids and the top-up  min(e + energyRR * 0.5, cap)  move e by D1, D2 and H — whole
                numbers of ulps — as long as e stays between the guards for the whole second (both top-ups, both chains) */
             const int slot = atomic_add_ret_i32(&bc[0], 1);
-            if (slot < WRSN_SPEC_MAX) {
-                double *sp = c.spec + slot * WRSN_SPEC_LEN;
-                double D1 = 0.0, D2 = 0.0, H = 0.0, glo = INFINITY, ghi = -INFINITY;
-                const int ex = wrsn_biased_exp(e);
-                if (e > 0.0 && ex > 60 && ex < 1900) {
-                    const double lo = wrsn_pow2_biased(ex), inv_u = wrsn_pow2_biased(2098 - ex), u = wrsn_pow2_biased(ex - 52);
-                    const double qa = es * inv_u, qb = er * inv_u, qh = (rr * 0.5) * inv_u;
-                    const double ra = rint(qa), rb = rint(qb), rh = rint(qh);
-                    const bool tie = (n_a > 0 && fabs(qa - ra) == 0.5) || (n_b > 0 && fabs(qb - rb) == 0.5) || fabs(qh - rh) == 0.5;
-                    const double K1 = (ra + rb) * (double)nb, K2 = ra * (double)(ow + na) + rb * (double)na;
-                    if (!tie && K1 + K2 < 1125899906842624.0 && rh < 1125899906842624.0 && rr >= 0.0) {
-                        D1 = K1 * u; D2 = K2 * u; H = rh * u;
-                        glo = lo + (D1 + D2); ghi = (lo + lo) - (H + H) - (u + u);
-                    }
-                }
-                sp[0] = D1; sp[1] = D2; sp[2] = H; sp[3] = glo; sp[4] = ghi; sp[5] = (double)i;
-                dec = nan_with_payload(slot);
-            }
+            if (slot < WRSN_SPEC_MAX) { spec_entry(c, i, slot, e); dec = nan_with_payload(slot); }
         }
         c.scr1[i] = dec;
         if (m < n_safe) n_safe = m;

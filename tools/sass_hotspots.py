@@ -29,6 +29,9 @@ for ln in dis:
         name = lab
         if mm:
             n = int(mm.group(1)); name = mm.group(2)[:n]
+            t = re.match(r"I((?:L[ib]\d+E)+)E", mm.group(2)[n:])          # template arguments, e.g. ILi4ELb1EE -> <4,1>
+            if t:
+                name += "<" + ",".join(re.findall(r"L[ib](\d+)E", t.group(1))) + ">"
         elif "$__internal" in lab or "$__cuda" in lab:
             name = lab.split("$")[-1]
         func = name; continue
