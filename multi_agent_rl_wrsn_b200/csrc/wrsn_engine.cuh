@@ -1249,29 +1249,48 @@ WRSN_NOINLINE void pairs_phase(Ctx &c, double tot, int n_pairs) {
     }
 }
 
+/* 32-bit shared-memory addressing for the hot loop: on the device an address is the byte offset inside the CTA's shared
+ * window (ld.shared / st.shared with a register address: no generic pointers, nothing to re-derive inside the loop); in
+ * the host emulation it is the offset from the environment's image. */
+#if !defined(WRSN_HOST_EMU)
+typedef uint32_t saddr_t;
+WRSN_DI saddr_t saddr_of(const void *p) { return (saddr_t)__cvta_generic_to_shared(p); }
+WRSN_DI double lds64(saddr_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+WRSN_DI void sts64(saddr_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" :: "r"(a), "d"(v) : "memory"); }
+#else
+typedef size_t saddr_t;
+WRSN_DI saddr_t saddr_of(const void *p) { return (saddr_t)((const char *)p - WRSN_SMEM_BASE); }
+WRSN_DI double lds64(saddr_t a) { return *(const double *)(WRSN_SMEM_BASE + a); }
+WRSN_DI void sts64(saddr_t a, double v) { *(double *)(WRSN_SMEM_BASE + a) = v; }
+#endif
+
 /* The steady state of a batch: every energyCS has reached its fixed point, no charger position moves under update_reward
  * (`watched`), the pair list stands.  Per second and node slot: one subtraction (or the table node's energy from shared
- * memory), reciprocal, two sums; after the first reduction one exponential and a sum; nothing else.  Called by
- * reward_cycles<.., true> once those conditions hold, with the node rows current in shared memory; applies the last
- * second's bookkeeping before it returns, like its caller would.  Same arithmetic, same order of every sum as the
- * general loop (tests: batches == event path, byte for byte). */
+ * memory), reciprocal, two sums; after the first reduction one exponential and a sum.  The few-lane work of a second —
+ * the table nodes (thread t < n_spec owns entry t and keeps it in registers) and the incentive sums (thread p < n_pairs
+ * owns pair p) — is inline, on precomputed shared-memory addresses; nothing inside the loop goes through the context
+ * record.  Called by reward_cycles<.., true> once those conditions hold, with the node rows current in shared memory;
+ * applies the last second's bookkeeping before it returns, like its caller would.  Same arithmetic, same order of
+ * every sum as the general loop (tests: batches == event path, byte for byte). */
 template <int NPT_T>
 WRSN_NOINLINE void reward_hot(Ctx &c, int n_cycles, int n_spec) {
-    const int N = c.N, G = WRSN_GSZ(c), tid = c.tid;
+    const int N = c.N, G = WRSN_GSZ(c), tid = c.tid, M = c.M;
 #if defined(WRSN_HOST_EMU)
     const int NPT = N;
 #else
     const int NPT = NPT_T > 0 ? NPT_T : (N + G - 1) / G;
 #endif
-    const double thr = c.par[WRSN_P_THR], eps = c.par[WRSN_P_EPSENV], inv_n = c.par[WRSN_P_INVN];
+    const double thr = c.par[WRSN_P_THR], eps = c.par[WRSN_P_EPSENV], inv_n = c.par[WRSN_P_INVN], cap = c.par[WRSN_P_CAP];
+    const double ab2 = c.par[WRSN_P_MC_AB2], inv_ab2 = wrsn_rcp(ab2);
     const double *dec = c.scr1.ptr();
+    const saddr_t a_energy = saddr_of(c.energy.ptr()) + 8 * tid, a_q = saddr_of(c.scr0.ptr()) + 8 * tid;
     WRSN_SLOT_ARR(double, e); WRSN_SLOT_ARR(double, cs); WRSN_SLOT_ARR(double, d); WRSN_SLOT_ARR(double, x);
     WRSN_FLAGS_DECL(f_in); WRSN_FLAGS_DECL(f_inc); WRSN_FLAGS_DECL(f_special);
     int any_inc = 0, buf = 0;
     WRSN_FOR_SLOTS(s) {
         const int i = tid + s * G;
         const bool ok = i < N && c.status[i] != 0;
-        e[s] = ok ? c.energy[i] : c.par[WRSN_P_CAP]; cs[s] = ok ? c.cs[i] : 0.0; d[s] = ok ? dec[i] : 0.0;
+        e[s] = ok ? c.energy[i] : cap; cs[s] = ok ? c.cs[i] : 0.0; d[s] = ok ? dec[i] : 0.0;
         if (i < N) WRSN_FL_SET(f_in, s);
         if (ok) {
             if (node_in_incentive(c, i)) { WRSN_FL_SET(f_inc, s); any_inc = 1; }
@@ -1279,14 +1298,54 @@ WRSN_NOINLINE void reward_hot(Ctx &c, int n_cycles, int n_spec) {
         }
     }
     any_inc = red_or(c, any_inc);
+    /* this thread's table entry (t = tid; more entries than threads: the rest through spec_phase) and pair (p = tid) */
+    const bool own_spec = tid < n_spec, more_spec = n_spec > G;
+    double sD1 = 0.0, sD2 = 0.0, sH = 0.0, sLo = INFINITY, sHi = -INFINITY;
+    saddr_t a_spec_e = 0;
+    if (own_spec) {
+        const double *sp = c.spec + tid * WRSN_SPEC_LEN;
+        sD1 = sp[0]; sD2 = sp[1]; sH = sp[2]; sLo = sp[3]; sHi = sp[4];
+        a_spec_e = saddr_of(c.energy.ptr() + (int)sp[5]);
+    }
     const int n_pairs = c.bcast[8];
+    const bool listed = n_pairs <= WRSN_PAIR_MAX && n_pairs <= G && M <= G;   /* one thread per pair, one per charger */
+    double *pair_term = c.pairs.ptr();
+    const int *pair_ids = (const int *)(pair_term + WRSN_PAIR_MAX), *pair_seg = pair_ids + 2 * WRSN_PAIR_MAX;
+    const bool own_pair = listed && tid < n_pairs;
+    saddr_t a_pe = 0, a_pc = 0, a_pq = 0, a_pt = 0, a_excl = 0, a_seg = 0;
+    int p_node = 0, p_chg = 0, seg_n = 0;
+    if (own_pair) {
+        p_chg = pair_ids[2 * tid]; p_node = pair_ids[2 * tid + 1];
+        a_pe = saddr_of(c.energy.ptr() + p_node); a_pc = saddr_of(c.cs.ptr() + p_node); a_pq = saddr_of(c.scr0.ptr() + p_node);
+        a_pt = saddr_of(pair_term + tid);
+    }
+    if (listed && tid < M) {
+        seg_n = pair_seg[2 * tid + 1] - pair_seg[2 * tid];
+        a_seg = saddr_of(pair_term + pair_seg[2 * tid]);
+        a_excl = saddr_of(c.mc.ptr() + tid * WRSN_MC_LEN + WRSN_MC_EXCL);
+    }
     _Pragma("unroll 1")
     for (int j = 0; j < n_cycles; j++) {
-        if (n_spec > 0) { spec_phase(c, n_spec, 1, 1); gsync(c); }
+        if (n_spec > 0) {                            /* the table nodes: the previous second's top-up, this second's tick */
+            if (own_spec) {
+                double en = lds64(a_spec_e);
+                if (en >= sLo && en <= sHi) {
+                    en = en + sH; en = en < cap ? en : cap;
+                    en = (en - sD1) + sH;
+                    sts64(a_spec_e, (en < cap ? en : cap) - sD2);
+                } else {
+                    spec_second(c, tid, 1, 1);       /* literal second; the entry may have been rebuilt */
+                    const double *sp = c.spec + tid * WRSN_SPEC_LEN;
+                    sD1 = sp[0]; sD2 = sp[1]; sH = sp[2]; sLo = sp[3]; sHi = sp[4];
+                }
+            }
+            if (more_spec) { for (int t = tid + G; t < n_spec; t += G) spec_second(c, t, 1, 1); }
+            gsync(c);
+        }
         double s1 = 0.0, s2 = 0.0;
         WRSN_FOR_SLOTS(s) {
             const double e_next = e[s] - d[s];
-            e[s] = WRSN_FL_GET(f_special, s) ? c.energy[tid + s * G] : e_next;
+            e[s] = WRSN_FL_GET(f_special, s) ? lds64(a_energy + 8 * s * G) : e_next;
             x[s] = cs[s] * wrsn_rcp(e[s] - thr + eps);
             s1 += x[s]; s2 = wrsn_fma(x[s], x[s], s2);
         }
@@ -1304,16 +1363,30 @@ WRSN_NOINLINE void reward_hot(Ctx &c, int n_cycles, int n_spec) {
         WRSN_FOR_SLOTS(s) {
             const double q = wrsn_exp_b(c, (x[s] - mean) * a);
             tot += WRSN_FL_GET(f_in, s) ? q : 0.0;
-            if (WRSN_FL_GET(f_inc, s)) {
-                const int i = tid + s * G;
-                c.scr0[i] = q;
-                if (!WRSN_FL_GET(f_special, s)) c.energy[i] = e[s];
+            if (WRSN_FL_GET(f_inc, s)) {             /* what the incentive sums read */
+                sts64(a_q + 8 * s * G, q);
+                if (!WRSN_FL_GET(f_special, s)) sts64(a_energy + 8 * s * G, e[s]);
             }
         }
         red_sum1(c, tot, buf);
         if (WRSN_GFIX == 32) gsync(c);
         if (tot == 0.0) tot = eps;
-        if (n_pairs > 0) pairs_phase(c, tot, n_pairs);
+        if (n_pairs > 0) {
+            if (listed) {
+                if (own_pair) {
+                    const double ec = lds64(a_pe) - lds64(a_pc);
+                    double e_with = cap;             /* max(ec + rate, capacity) with rate <= alpha / beta^2 */
+                    if (ec + ab2 > cap) e_with = fmax(ec + charge_rate_fast(c, c.mc + p_chg * WRSN_MC_LEN, p_node), cap);
+                    sts64(a_pt, (lds64(a_pq) * wrsn_rcp(tot)) * (e_with - (ec < thr ? ec : thr)) * inv_ab2);
+                }
+                gsync(c);
+                if (seg_n > 0) {
+                    double incentive = 0.0;
+                    for (int p = 0; p < seg_n; p++) incentive += lds64(a_seg + 8 * p);
+                    sts64(a_excl, lds64(a_excl) + incentive);
+                }
+            } else pairs_phase(c, tot, n_pairs);
+        }
         if (any_inc || n_spec > 0 || WRSN_GFIX != 32) gsync(c);
     }
     if (n_spec > 0) spec_phase(c, n_spec, 1, 0);     /* bookkeeping of the last second; rows back to shared memory */
