@@ -1050,24 +1050,8 @@ WRSN_D bool reward_pairs(Ctx &c) {                 /* is there any (charging cha
     return any;
 }
 
-/* ------------------------------------------------------------------ the hot loop: update_reward second by second
- * `n_cycles` consecutive update_reward ticks (WRSN.py:100-127) with the node rows of this thread IN REGISTERS.
- * dec == NULL (event path): one tick on the node rows as they are.
- * dec != NULL (whole-cycle batches, nodes_batch): the grid events around every tick are applied on the way — the k+1.0
- *   bookkeeping of the PREVIOUS second (second top-up; energyCS towards its fixed point), then this second's k+0.5
- *   drain, then the tick; the bookkeeping of the last second follows the loop.  A regular node (energyRR == 0, inside
- *   its binade: dec[i] is its per-second decrement) costs one subtraction per second.  The few irregular ones — charged
- *   nodes above all — are listed in a table (c.spec, built by nodes_batch: dec[i] = NaN carrying the table slot) and
- *   handled once per second by as many threads as there are entries, on the shared-memory copy of their energy:
- *   inside a binade the relay / own-packet chains and the two top-ups  min(e + energyRR * 0.5, capacity)  each move the
- *   energy by a fixed whole number of ulps (sub_chain's argument; D1, D2, H of the table), so the second is four exact
- *   additions and two minima while the energy stays between the table's guards, and the literal tick (drain_node)
- *   otherwise.
- * Arithmetic of the tick itself: x_n = energyCS / (energy - threshold + eps) by reciprocal (wrsn_rcp), mean and variance
- * from one pass (sum and sum of squares; two passes when the variance is small against mean^2), 1 / std by wrsn_rsqrt,
- * the softmax numerators by wrsn_exp_b — see the note at those helpers.  The event path and the batches share this code
- * and the order of every sum, so they produce the same bits (tests: batches == event path).
- * NPT = node slots per thread (compile time on the device: everything below unrolls into registers). */
+/* per-thread node slots of the register-resident loops (reward_loop below): compile-time arrays on the device, the
+ * whole node range in the single-lane host build */
 #undef WRSN_EMU_MAXN
 #undef WRSN_SLOT_ARR
 #undef WRSN_FOR_SLOTS
@@ -1113,7 +1097,7 @@ WRSN_D double nan_with_payload(int slot) {
 #endif
 }
 
-/* table entry of node i at energy e (reward_cycles / spec_second): inside e's binade the chain of relayed packets of lower
+/* table entry of node i at energy e (reward_loop / spec_second): inside e's binade the chain of relayed packets of lower
  * ids, the own packets + relays of higher ids and the top-up  min(e + energyRR * 0.5, cap)  move e by D1, D2 and H — whole
  * numbers of ulps — as long as e stays between the guards for the whole second (both top-ups, both chains) */
 WRSN_NOINLINE void spec_entry(Ctx &c, int i, int slot, double e) {
@@ -1171,7 +1155,7 @@ WRSN_NOINLINE double charge_rate_fast(Ctx &c, const double *m, int i) {   /* alp
 }
 
 /* the incentive sums of one tick (WRSN.py:113-126), one thread per charger; q_n / tot are the softmax weights.  (General form:
- * reward_cycles handles up to WRSN_PAIR_MAX pairs by list and comes here beyond that.) */
+ * reward_loop handles up to WRSN_PAIR_MAX pairs by list and comes here beyond that.) */
 WRSN_NOINLINE void reward_incentives(Ctx &c, double tot) {
     const double thr = c.par[WRSN_P_THR], cap = c.par[WRSN_P_CAP];
     const double inv_tot = wrsn_rcp(tot), ab2 = c.par[WRSN_P_MC_AB2], inv_ab2 = wrsn_rcp(ab2);
@@ -1222,7 +1206,7 @@ WRSN_NOINLINE void spec_phase(Ctx &c, int n_spec, int book, int drain) {
     }
 }
 
-/* the incentive sums of one tick from the pair list (built by reward_cycles): one thread per pair computes its term, one
+/* the incentive sums of one tick from the pair list (built by reward_loop): one thread per pair computes its term, one
  * thread per charger adds its terms in node order */
 WRSN_NOINLINE void pairs_phase(Ctx &c, double tot, int n_pairs) {
     const int G = WRSN_GSZ(c), tid = c.tid;
@@ -1264,162 +1248,50 @@ WRSN_DI double lds64(saddr_t a) { return *(const double *)(WRSN_SMEM_BASE + a); 
 WRSN_DI void sts64(saddr_t a, double v) { *(double *)(WRSN_SMEM_BASE + a) = v; }
 #endif
 
-/* The steady state of a batch: every energyCS has reached its fixed point, no charger position moves under update_reward
- * (`watched`), the pair list stands.  Per second and node slot: one subtraction (or the table node's energy from shared
- * memory), reciprocal, two sums; after the first reduction one exponential and a sum.  The few-lane work of a second —
- * the table nodes (thread t < n_spec owns entry t and keeps it in registers) and the incentive sums (thread p < n_pairs
- * owns pair p) — is inline, on precomputed shared-memory addresses; nothing inside the loop goes through the context
- * record.  Called by reward_cycles<.., true> once those conditions hold, with the node rows current in shared memory;
- * applies the last second's bookkeeping before it returns, like its caller would.  Same arithmetic, same order of
- * every sum as the general loop (tests: batches == event path, byte for byte). */
+/* ------------------------------------------------------------------ the hot loop: update_reward second by second
+ * `n_cycles` consecutive update_reward ticks (WRSN.py:100-127) with the node rows of this thread IN REGISTERS.
+ * batch == 0 (event path): one tick on the node rows as they are.
+ * batch != 0 (whole-cycle batches, nodes_batch): the grid events around every tick are applied on the way — the k+1.0
+ *   bookkeeping of the PREVIOUS second (second top-up; energyCS towards its fixed point), then this second's k+0.5
+ *   drain, then the tick; the bookkeeping of the last second follows the loop.  A regular node (energyRR == 0, inside
+ *   its binade: dec[i] is its per-second decrement) costs one subtraction per second.  The few irregular ones — charged
+ *   nodes above all — are listed in a table (c.spec, built by nodes_batch: dec[i] = NaN carrying the table slot); thread
+ *   t < n_spec owns entry t, keeps it in registers and works on the shared-memory copy of the node's energy: inside a
+ *   binade the relay / own-packet chains and the two top-ups  min(e + energyRR * 0.5, capacity)  each move the energy by a
+ *   fixed whole number of ulps (sub_chain's argument; D1, D2, H of the table), so the second is four exact additions
+ *   and two minima while the energy stays between the table's guards, and the literal tick (spec_second) otherwise.
+ *   The incentive sums work the same way: thread p < n_pairs owns the p-th (charging charger, connected alive node)
+ *   pair.  Nothing in the steady-state path goes through the context record: 32-bit shared-memory addresses, computed
+ *   before the loop.
+ * Arithmetic of the tick itself: x_n = energyCS / (energy - threshold + eps) by reciprocal (wrsn_rcp), mean and variance
+ * from one pass (sum and sum of squares; two passes when the variance is small against mean^2), 1 / std by wrsn_rsqrt,
+ * the softmax numerators by wrsn_exp_b — see the note at those helpers.  The event path and the batches run this very
+ * code, so they produce the same bits (tests: batches == event path).
+ * NPT = node slots per thread (compile time on the device: everything below unrolls into registers). */
 template <int NPT_T>
-WRSN_NOINLINE void reward_hot(Ctx &c, int n_cycles, int n_spec) {
+WRSN_NOINLINE void reward_loop(Ctx &c, int batch, int n_cycles, double t_reward, int watched, int n_spec) {
     const int N = c.N, G = WRSN_GSZ(c), tid = c.tid, M = c.M;
 #if defined(WRSN_HOST_EMU)
     const int NPT = N;
 #else
-    const int NPT = NPT_T > 0 ? NPT_T : (N + G - 1) / G;
+    const int NPT = NPT_T > 0 ? NPT_T : (N + G - 1) / G;   /* NPT_T == 0: any N, the slot arrays in local memory (rolled loops) */
 #endif
     const double thr = c.par[WRSN_P_THR], eps = c.par[WRSN_P_EPSENV], inv_n = c.par[WRSN_P_INVN], cap = c.par[WRSN_P_CAP];
     const double ab2 = c.par[WRSN_P_MC_AB2], inv_ab2 = wrsn_rcp(ab2);
     const double *dec = c.scr1.ptr();
     const saddr_t a_energy = saddr_of(c.energy.ptr()) + 8 * tid, a_q = saddr_of(c.scr0.ptr()) + 8 * tid;
     WRSN_SLOT_ARR(double, e); WRSN_SLOT_ARR(double, cs); WRSN_SLOT_ARR(double, d); WRSN_SLOT_ARR(double, x);
-    WRSN_FLAGS_DECL(f_in); WRSN_FLAGS_DECL(f_inc); WRSN_FLAGS_DECL(f_special);
-    int any_inc = 0, buf = 0;
-    WRSN_FOR_SLOTS(s) {
-        const int i = tid + s * G;
-        const bool ok = i < N && c.status[i] != 0;
-        e[s] = ok ? c.energy[i] : cap; cs[s] = ok ? c.cs[i] : 0.0; d[s] = ok ? dec[i] : 0.0;
-        if (i < N) WRSN_FL_SET(f_in, s);
-        if (ok) {
-            if (node_in_incentive(c, i)) { WRSN_FL_SET(f_inc, s); any_inc = 1; }
-            if (d[s] != d[s]) WRSN_FL_SET(f_special, s);
-        }
-    }
-    any_inc = red_or(c, any_inc);
-    /* this thread's table entry (t = tid; more entries than threads: the rest through spec_phase) and pair (p = tid) */
-    const bool own_spec = tid < n_spec, more_spec = n_spec > G;
-    double sD1 = 0.0, sD2 = 0.0, sH = 0.0, sLo = INFINITY, sHi = -INFINITY;
-    saddr_t a_spec_e = 0;
-    if (own_spec) {
-        const double *sp = c.spec + tid * WRSN_SPEC_LEN;
-        sD1 = sp[0]; sD2 = sp[1]; sH = sp[2]; sLo = sp[3]; sHi = sp[4];
-        a_spec_e = saddr_of(c.energy.ptr() + (int)sp[5]);
-    }
-    const int n_pairs = c.bcast[8];
-    const bool listed = n_pairs <= WRSN_PAIR_MAX && n_pairs <= G && M <= G;   /* one thread per pair, one per charger */
-    double *pair_term = c.pairs.ptr();
-    const int *pair_ids = (const int *)(pair_term + WRSN_PAIR_MAX), *pair_seg = pair_ids + 2 * WRSN_PAIR_MAX;
-    const bool own_pair = listed && tid < n_pairs;
-    saddr_t a_pe = 0, a_pc = 0, a_pq = 0, a_pt = 0, a_excl = 0, a_seg = 0;
-    int p_node = 0, p_chg = 0, seg_n = 0;
-    if (own_pair) {
-        p_chg = pair_ids[2 * tid]; p_node = pair_ids[2 * tid + 1];
-        a_pe = saddr_of(c.energy.ptr() + p_node); a_pc = saddr_of(c.cs.ptr() + p_node); a_pq = saddr_of(c.scr0.ptr() + p_node);
-        a_pt = saddr_of(pair_term + tid);
-    }
-    if (listed && tid < M) {
-        seg_n = pair_seg[2 * tid + 1] - pair_seg[2 * tid];
-        a_seg = saddr_of(pair_term + pair_seg[2 * tid]);
-        a_excl = saddr_of(c.mc.ptr() + tid * WRSN_MC_LEN + WRSN_MC_EXCL);
-    }
-    _Pragma("unroll 1")
-    for (int j = 0; j < n_cycles; j++) {
-        if (n_spec > 0) {                            /* the table nodes: the previous second's top-up, this second's tick */
-            if (own_spec) {
-                double en = lds64(a_spec_e);
-                if (en >= sLo && en <= sHi) {
-                    en = en + sH; en = en < cap ? en : cap;
-                    en = (en - sD1) + sH;
-                    sts64(a_spec_e, (en < cap ? en : cap) - sD2);
-                } else {
-                    spec_second(c, tid, 1, 1);       /* literal second; the entry may have been rebuilt */
-                    const double *sp = c.spec + tid * WRSN_SPEC_LEN;
-                    sD1 = sp[0]; sD2 = sp[1]; sH = sp[2]; sLo = sp[3]; sHi = sp[4];
-                }
-            }
-            if (more_spec) { for (int t = tid + G; t < n_spec; t += G) spec_second(c, t, 1, 1); }
-            gsync(c);
-        }
-        double s1 = 0.0, s2 = 0.0;
-        WRSN_FOR_SLOTS(s) {
-            const double e_next = e[s] - d[s];
-            e[s] = WRSN_FL_GET(f_special, s) ? lds64(a_energy + 8 * s * G) : e_next;
-            x[s] = cs[s] * wrsn_rcp(e[s] - thr + eps);
-            s1 += x[s]; s2 = wrsn_fma(x[s], x[s], s2);
-        }
-        red_sum2(c, s1, s2, buf);
-        const double mean = s1 * inv_n;
-        double var = wrsn_fma(s2, inv_n, -(mean * mean));
-        if (!(var > 1e-3 * (mean * mean))) {         /* cancellation: the textbook two passes (np.std) */
-            double q = 0.0;
-            WRSN_FOR_SLOTS(s) { const double u = WRSN_FL_GET(f_in, s) ? x[s] - mean : 0.0; q = wrsn_fma(u, u, q); }
-            red_sum1(c, q, buf);
-            var = q * inv_n;
-        }
-        const double a = var > 0.0 ? wrsn_rsqrt(var) : 1.0 / eps;
-        double tot = 0.0;
-        WRSN_FOR_SLOTS(s) {
-            const double q = wrsn_exp_b(c, (x[s] - mean) * a);
-            tot += WRSN_FL_GET(f_in, s) ? q : 0.0;
-            if (WRSN_FL_GET(f_inc, s)) {             /* what the incentive sums read */
-                sts64(a_q + 8 * s * G, q);
-                if (!WRSN_FL_GET(f_special, s)) sts64(a_energy + 8 * s * G, e[s]);
-            }
-        }
-        red_sum1(c, tot, buf);
-        if (WRSN_GFIX == 32) gsync(c);
-        if (tot == 0.0) tot = eps;
-        if (n_pairs > 0) {
-            if (listed) {
-                if (own_pair) {
-                    const double ec = lds64(a_pe) - lds64(a_pc);
-                    double e_with = cap;             /* max(ec + rate, capacity) with rate <= alpha / beta^2 */
-                    if (ec + ab2 > cap) e_with = fmax(ec + charge_rate_fast(c, c.mc + p_chg * WRSN_MC_LEN, p_node), cap);
-                    sts64(a_pt, (lds64(a_pq) * wrsn_rcp(tot)) * (e_with - (ec < thr ? ec : thr)) * inv_ab2);
-                }
-                gsync(c);
-                if (seg_n > 0) {
-                    double incentive = 0.0;
-                    for (int p = 0; p < seg_n; p++) incentive += lds64(a_seg + 8 * p);
-                    sts64(a_excl, lds64(a_excl) + incentive);
-                }
-            } else pairs_phase(c, tot, n_pairs);
-        }
-        if (any_inc || n_spec > 0 || WRSN_GFIX != 32) gsync(c);
-    }
-    if (n_spec > 0) spec_phase(c, n_spec, 1, 0);     /* bookkeeping of the last second; rows back to shared memory */
-    WRSN_FOR_SLOTS(s) {
-        const int i = tid + s * G;
-        if (i < N && c.status[i] != 0 && !WRSN_FL_GET(f_special, s)) c.energy[i] = e[s];
-    }
-    gsync(c);
-}
-
-template <int NPT_T, bool BATCH>
-WRSN_NOINLINE void reward_cycles(Ctx &c, int n_cycles, double t_reward, int watched, int n_spec) {
-    const int N = c.N, G = WRSN_GSZ(c), tid = c.tid;
-#if defined(WRSN_HOST_EMU)
-    const int NPT = N;
-#else
-    const int NPT = NPT_T > 0 ? NPT_T : (N + G - 1) / G;   /* NPT_T == 0: any N, the slot arrays in local memory (rolled loops) */
-#endif
-    const double thr = c.par[WRSN_P_THR], cap = c.par[WRSN_P_CAP], eps = c.par[WRSN_P_EPSENV];
-    const double inv_n = c.par[WRSN_P_INVN];         /* 1 / N from the host */
-    const double *dec = c.scr1.ptr();
-    WRSN_SLOT_ARR(double, e); WRSN_SLOT_ARR(double, cs); WRSN_SLOT_ARR(double, d); WRSN_SLOT_ARR(double, x);
-    WRSN_FLAGS_DECL(f_in); WRSN_FLAGS_DECL(f_inc); WRSN_FLAGS_DECL(f_unfixed); WRSN_FLAGS_DECL(f_special);
+    WRSN_FLAGS_DECL(f_in); WRSN_FLAGS_DECL(f_inc); WRSN_FLAGS_DECL(f_special); WRSN_FLAGS_DECL(f_unfixed);
     int any_inc = 0, any_unfixed = 0, buf = 0;
     gsync(c);
     WRSN_FOR_SLOTS(s) {
         const int i = tid + s * G;
         const bool ok = i < N && c.status[i] != 0;
-        e[s] = ok ? c.energy[i] : cap; cs[s] = ok ? c.cs[i] : 0.0; d[s] = (ok && BATCH) ? dec[i] : 0.0;
+        e[s] = ok ? c.energy[i] : cap; cs[s] = ok ? c.cs[i] : 0.0; d[s] = (ok && batch) ? dec[i] : 0.0;
         if (i < N) WRSN_FL_SET(f_in, s);
         if (ok) {
             if (node_in_incentive(c, i)) { WRSN_FL_SET(f_inc, s); any_inc = 1; }
-            if (BATCH) { WRSN_FL_SET(f_unfixed, s); any_unfixed = 1; }
+            if (batch) { WRSN_FL_SET(f_unfixed, s); any_unfixed = 1; }
             if (d[s] != d[s]) WRSN_FL_SET(f_special, s);
         }
     }
@@ -1429,7 +1301,7 @@ WRSN_NOINLINE void reward_cycles(Ctx &c, int n_cycles, double t_reward, int watc
     int *pair_ids = (int *)(pair_term + WRSN_PAIR_MAX), *pair_seg = pair_ids + 2 * WRSN_PAIR_MAX;
     if (tid == 0) {
         int np = 0;
-        for (int a = 0; a < c.M; a++) {
+        for (int a = 0; a < M; a++) {
             const double *m = c.mc + a * WRSN_MC_LEN;
             pair_seg[2 * a] = np;
             if (m[WRSN_MC_STATUS] != 0.0 && m[WRSN_MC_TYPE] != 0.0) {
@@ -1448,40 +1320,64 @@ WRSN_NOINLINE void reward_cycles(Ctx &c, int n_cycles, double t_reward, int watc
     }
     gsync(c);
     const int n_pairs = c.bcast[8];
-    const double ab2 = c.par[WRSN_P_MC_AB2], inv_ab2 = wrsn_rcp(ab2);
-    const double *spec = c.spec.ptr();
+    const bool listed = n_pairs <= WRSN_PAIR_MAX && n_pairs <= G && M <= G;   /* one thread per pair, one per charger */
+    const bool own_pair = listed && tid < n_pairs;
+    saddr_t a_pe = 0, a_pc = 0, a_pq = 0, a_pt = 0, a_excl = 0, a_seg = 0;
+    int p_node = 0, p_chg = 0, seg_n = 0;
+    if (own_pair) {
+        p_chg = pair_ids[2 * tid]; p_node = pair_ids[2 * tid + 1];
+        a_pe = saddr_of(c.energy.ptr() + p_node); a_pc = saddr_of(c.cs.ptr() + p_node); a_pq = saddr_of(c.scr0.ptr() + p_node);
+        a_pt = saddr_of(pair_term + tid);
+    }
+    if (listed && tid < M) {
+        seg_n = pair_seg[2 * tid + 1] - pair_seg[2 * tid];
+        a_seg = saddr_of(pair_term + pair_seg[2 * tid]);
+        a_excl = saddr_of(c.mc.ptr() + tid * WRSN_MC_LEN + WRSN_MC_EXCL);
+    }
+    /* this thread's table entry (t = tid; more entries than threads: the rest through spec_second) */
+    const bool own_spec = tid < n_spec, more_spec = n_spec > G;
+    double sD1 = 0.0, sD2 = 0.0, sH = 0.0, sLo = INFINITY, sHi = -INFINITY;
+    saddr_t a_spec_e = 0;
+    if (own_spec) {
+        const double *sp = c.spec + tid * WRSN_SPEC_LEN;
+        sD1 = sp[0]; sD2 = sp[1]; sH = sp[2]; sLo = sp[3]; sHi = sp[4];
+        a_spec_e = saddr_of(c.energy.ptr() + (int)sp[5]);
+    }
     _Pragma("unroll 1")
     for (int j = 0; j < n_cycles; j++) {
         if (watched) { catch_up_for_reward(c, t_reward + (double)j); gsync(c); }
-        if (BATCH && n_spec > 0) {                   /* the table nodes: previous bookkeeping + this second's drain */
-            for (int t = tid; t < n_spec; t += G) {
-                const double *sp = spec + t * WRSN_SPEC_LEN;
-                const int i = (int)sp[5];
-                double en = c.energy[i];
-                if (en >= sp[3] && en <= sp[4]) {    /* inside the guards: whole ulps (see spec_second) */
-                    const double H = sp[2];
-                    if (j > 0) { en = en + H; en = en < cap ? en : cap; }
-                    en = (en - sp[0]) + H;
-                    c.energy[i] = (en < cap ? en : cap) - sp[1];
-                } else spec_second(c, t, j > 0, 1);
+        if (n_spec > 0) {                            /* the table nodes: the previous second's top-up, this second's tick */
+            if (own_spec) {
+                double en = lds64(a_spec_e);
+                if (en >= sLo && en <= sHi) {
+                    if (j > 0) { en = en + sH; en = en < cap ? en : cap; }
+                    en = (en - sD1) + sH;
+                    sts64(a_spec_e, (en < cap ? en : cap) - sD2);
+                } else {
+                    spec_second(c, tid, j > 0, 1);   /* literal second; the entry may have been rebuilt */
+                    const double *sp = c.spec + tid * WRSN_SPEC_LEN;
+                    sD1 = sp[0]; sD2 = sp[1]; sH = sp[2]; sLo = sp[3]; sHi = sp[4];
+                }
             }
+            if (more_spec) { for (int t = tid + G; t < n_spec; t += G) spec_second(c, t, j > 0, 1); }
             gsync(c);
         }
-        if (BATCH && j > 0 && red_or_warp(any_unfixed)) {   /* energyCS towards its fixed point (bookkeeping of the previous second) */
+        if (j > 0 && red_or_warp(any_unfixed)) {     /* energyCS towards its fixed point (bookkeeping of the previous second;
+                                                        cold: a node gets there after one or two applications) */
             any_unfixed = 0;
             WRSN_FOR_SLOTS(s) {
                 if (WRSN_FL_GET(f_unfixed, s)) {
-                    const double nx = cs_step(cs[s], c.logc[tid + s * G]);
-                    if (nx == cs[s]) WRSN_FL_CLR(f_unfixed, s); else { cs[s] = nx; any_unfixed = 1; }
+                    const int i = tid + s * G;
+                    const double nx = cs_step(cs[s], c.logc[i]);
+                    if (nx == cs[s]) WRSN_FL_CLR(f_unfixed, s);
+                    else { cs[s] = nx; any_unfixed = 1; if (WRSN_FL_GET(f_inc, s)) c.cs[i] = nx; }
                 }
             }
         }
         double s1 = 0.0, s2 = 0.0;
         WRSN_FOR_SLOTS(s) {
-            if (BATCH) {
-                if (WRSN_FL_GET(f_special, s)) e[s] = c.energy[tid + s * G];
-                else e[s] = e[s] - d[s];
-            }
+            const double e_next = e[s] - d[s];       /* (event path: d == 0) */
+            e[s] = WRSN_FL_GET(f_special, s) ? lds64(a_energy + 8 * s * G) : e_next;
             x[s] = cs[s] * wrsn_rcp(e[s] - thr + eps);
             s1 += x[s]; s2 = wrsn_fma(x[s], x[s], s2);
         }
@@ -1500,53 +1396,33 @@ WRSN_NOINLINE void reward_cycles(Ctx &c, int n_cycles, double t_reward, int watc
             const double q = wrsn_exp_b(c, (x[s] - mean) * a);
             tot += WRSN_FL_GET(f_in, s) ? q : 0.0;
             if (WRSN_FL_GET(f_inc, s)) {             /* what the incentive sums read */
-                const int i = tid + s * G;
-                c.scr0[i] = q;
-                if (BATCH) { c.cs[i] = cs[s]; if (!WRSN_FL_GET(f_special, s)) c.energy[i] = e[s]; }
+                sts64(a_q + 8 * s * G, q);
+                if (batch && !WRSN_FL_GET(f_special, s)) sts64(a_energy + 8 * s * G, e[s]);
             }
         }
         red_sum1(c, tot, buf);                       /* (its barrier also publishes the stores above) */
         if (WRSN_GFIX == 32) gsync(c);
         if (tot == 0.0) tot = eps;
-        if (n_pairs > WRSN_PAIR_MAX) { if (tid < c.M) reward_incentives(c, tot); }
-        else if (n_pairs > 0) {
-            const double inv_tot = wrsn_rcp(tot);
-            for (int p = tid; p < n_pairs; p += G) {     /* one thread per pair: its term of the sum */
-                const int a2 = pair_ids[2 * p], i = pair_ids[2 * p + 1];
-                const double ec = c.energy[i] - c.cs[i];
-                double e_with = cap;                 /* max(ec + rate, capacity) with rate <= alpha / beta^2 */
-                if (ec + ab2 > cap) e_with = fmax(ec + charge_rate_fast(c, c.mc + a2 * WRSN_MC_LEN, i), cap);
-                pair_term[p] = (c.scr0[i] * inv_tot) * (e_with - (ec < thr ? ec : thr)) * inv_ab2;
-            }
-            gsync(c);
-            for (int a2 = tid; a2 < c.M; a2 += G) {      /* one thread per charger: its pairs in node order */
-                const int p0 = pair_seg[2 * a2], p1 = pair_seg[2 * a2 + 1];
-                if (p1 > p0) {
-                    double incentive = 0.0;
-                    for (int p = p0; p < p1; p++) incentive += pair_term[p];
-                    c.mc[a2 * WRSN_MC_LEN + WRSN_MC_EXCL] += incentive;
+        if (n_pairs > 0) {
+            if (listed) {
+                if (own_pair) {
+                    const double ec = lds64(a_pe) - lds64(a_pc);
+                    double e_with = cap;             /* max(ec + rate, capacity) with rate <= alpha / beta^2 */
+                    if (ec + ab2 > cap) e_with = fmax(ec + charge_rate_fast(c, c.mc + p_chg * WRSN_MC_LEN, p_node), cap);
+                    sts64(a_pt, (lds64(a_pq) * wrsn_rcp(tot)) * (e_with - (ec < thr ? ec : thr)) * inv_ab2);
                 }
-            }
+                gsync(c);
+                if (seg_n > 0) {
+                    double incentive = 0.0;
+                    for (int p = 0; p < seg_n; p++) incentive += lds64(a_seg + 8 * p);
+                    sts64(a_excl, lds64(a_excl) + incentive);
+                }
+            } else pairs_phase(c, tot, n_pairs);
         }
         if (any_inc || n_spec > 0 || watched || WRSN_GFIX != 32) gsync(c);
-        if (BATCH && !watched && j >= 1 && j + 1 < n_cycles && !red_or(c, any_unfixed)) {
-            /* steady state: hand the remaining seconds to the lean loop (rows back to shared memory first; the bookkeeping
-               of second j is the first thing it does) */
-            WRSN_FOR_SLOTS(s) {
-                const int i = tid + s * G;
-                if (!(i < N && c.status[i] != 0)) continue;
-                c.cs[i] = cs[s];
-                if (!WRSN_FL_GET(f_special, s)) c.energy[i] = e[s];
-            }
-            gsync(c);
-            reward_hot<NPT_T>(c, n_cycles - (j + 1), n_spec);
-            return;
-        }
     }
-    if (BATCH) {                                     /* bookkeeping of the last second; rows back to shared memory */
-        if (n_spec > 0) {
-            for (int t = tid; t < n_spec; t += G) spec_second(c, t, 1, 0);
-        }
+    if (batch) {                                     /* bookkeeping of the last second; rows back to shared memory */
+        if (n_spec > 0) spec_phase(c, n_spec, 1, 0);
         WRSN_FOR_SLOTS(s) {
             const int i = tid + s * G;
             if (!(i < N && c.status[i] != 0)) continue;
@@ -1560,17 +1436,14 @@ WRSN_NOINLINE void reward_cycles(Ctx &c, int n_cycles, double t_reward, int watc
 
 WRSN_NOINLINE void reward_cycles_any(Ctx &c, int batch, int n_cycles, double t_reward, int watched, int n_spec) {
 #if defined(WRSN_HOST_EMU)
-    if (batch) reward_cycles<0, true>(c, n_cycles, t_reward, watched, n_spec);
-    else reward_cycles<0, false>(c, 1, 0.0, 0, 0);
+    reward_loop<0>(c, batch, batch ? n_cycles : 1, t_reward, batch ? watched : 0, batch ? n_spec : 0);
 #else
     const int npt = (c.N + WRSN_GSZ(c) - 1) / WRSN_GSZ(c);
-    if (!batch) {                                    /* event path: one tick (cold) */
-        if (npt <= 4) reward_cycles<4, false>(c, 1, 0.0, 0, 0); else reward_cycles<0, false>(c, 1, 0.0, 0, 0);
-    }
-    else if (npt <= 1) reward_cycles<1, true>(c, n_cycles, t_reward, watched, n_spec);
-    else if (npt <= 2) reward_cycles<2, true>(c, n_cycles, t_reward, watched, n_spec);
-    else if (npt <= 4) reward_cycles<4, true>(c, n_cycles, t_reward, watched, n_spec);
-    else reward_cycles<0, true>(c, n_cycles, t_reward, watched, n_spec);
+    if (!batch) { n_cycles = 1; watched = 0; n_spec = 0; }
+    if (npt <= 1) reward_loop<1>(c, batch, n_cycles, t_reward, watched, n_spec);
+    else if (npt <= 2) reward_loop<2>(c, batch, n_cycles, t_reward, watched, n_spec);
+    else if (npt <= 4) reward_loop<4>(c, batch, n_cycles, t_reward, watched, n_spec);
+    else reward_loop<0>(c, batch, n_cycles, t_reward, watched, n_spec);
 #endif
 }
 
@@ -2275,7 +2148,7 @@ WRSN_NOINLINE int nodes_batch(Ctx &c, int n_max, int ur_on, double t_reward, int
             else { double e_end; m = replay_cycles(e, rr, es, er, nb, ow, na, thr, cap, n_safe, &e_end); }
         }
         if (active && dec != dec) {
-            /* table entry (reward_cycles / spec_second): inside e's binade the chain of relayed packets of lower ids, the
+            /* table entry (reward_loop / spec_second): inside e's binade the chain of relayed packets of lower ids, the
                own packets + relays of higher ids and the top-up  min(e + energyRR * 0.5, cap)  move e by D1, D2 and H — whole
                numbers of ulps — as long as e stays between the guards for the whole second (both top-ups, both chains) */
             const int slot = atomic_add_ret_i32(&bc[0], 1);
@@ -2319,7 +2192,7 @@ WRSN_NOINLINE int nodes_batch(Ctx &c, int n_max, int ur_on, double t_reward, int
         WRSN_PROFC_END(c, WRSN_H_PROF2, pc2);
     } else {
         /* pass 2: cycle by cycle, because update_reward reads every node at every k+1.0 (before the bookkeeping): the
-           drain, the tick and the previous second's bookkeeping in one pass over the nodes per second (reward_cycles) */
+           drain, the tick and the previous second's bookkeeping in one pass over the nodes per second (reward_loop) */
         int watched = 0;                             /* is there a lazy move whose position update_reward reads (Q2)? */
         for (int q = 0; q < c.n_slot; q++) watched |= slot_i(slot_of(c, q))[WRSN_PRI_LAZY] == 2 ? 1 : 0;
         reward_cycles_any(c, 1, n_safe, t_reward, watched, n_spec);
