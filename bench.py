@@ -397,36 +397,39 @@ def run_b200(a):
     e2e_ms = f0.elapsed_time(f1)
     del host_obs, host_map, dev_map
 
-    # ---- roofline pass: the same hot path issued serially on ONE stream through the separate entry points, CUDA events
-    # around every launch (concurrent groups time-share the SMs and blur per-launch durations); the kernels' shares of this
-    # pass are what the in-situ fractions below are scaled by
+    # ---- roofline pass: the same hot path issued serially on ONE stream through the separate entry points, a pair of CUDA
+    # events around every launch (concurrent groups time-share the SMs and blur per-launch durations).  The row masks are
+    # computed before the events are recorded, so that an interval holds this library's launches and nothing else.
     R = min(a.steps, 16)
     names = ("decode", "step", "reset", "observe")
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(R * G)]
+    ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in names] for _ in range(R * G)]
+    u8 = lambda t: t.to(torch.uint8)
     sync_all()
     rd0 = totals()
     for k in range(R):
         for g in range(G):
             env = groups[g]
             e = ev[k * G + g]
-            e[0].record()
+            aid = env.req.agent_id
+            m_step = u8((aid >= 0) | (aid == -4))
+            e[0][0].record()
             if a.actions == "controller":
-                env.density_map_to_action(controller_map(obs[g]), out=act[g])
+                env.linear_controller_action(obs[g], CONTROLLER_WEIGHTS, out=act[g])     # k_decode_map + k_decode_locate
             else:
                 torch.mul(torch.rand((Bg, 3), generator=gen, dtype=torch.float64, device=dev), scale, out=act[g])
-            e[1].record()
-            aid = env.req.agent_id
-            env.step(aid, act[g], mask=(aid >= 0) | (aid == -4))
-            e[2].record()
-            done = (env.req.agent_id < 0) & (env.req.agent_id != -4)
-            keep = env.req.agent_id.clone()
-            env.reset(mask=done)
-            env.req.agent_id.copy_(torch.where(done, env.req.agent_id, keep))
-            e[3].record()
+            e[0][1].record()
+            e[1][0].record()
+            env.step(aid, act[g], mask=m_step)
+            e[1][1].record()
+            m_done = u8((env.req.agent_id < 0) & (env.req.agent_id != -4))
+            e[2][0].record()
+            env.reset(mask=m_done)
+            e[2][1].record()
+            e[3][0].record()
             env.get_state(out=obs[g])
-            e[4].record()
+            e[3][1].record()
     sync_all()
-    k_ms = {n: sum(x[i].elapsed_time(x[i + 1]) for x in ev) for i, n in enumerate(names)}
+    k_ms = {n: sum(x[i][0].elapsed_time(x[i][1]) for x in ev) for i, n in enumerate(names)}
     rd1 = totals()
     r_decisions, r_ticks = rd1[0] - rd0[0], rd1[1] - rd0[1]
     n_l = R * G
@@ -498,9 +501,9 @@ def run_b200(a):
     # algorithmic bytes per SURVEY §8(d): 82 N + T per environment and simulated second, 16 T + 88 per decision in the
     # step kernel, 4 S^2 float32 per decision in the observation kernel, S^2 float32 + 24 per decision in the decoder
     alg = dict(step=(r_ticks * (82 * N + T) + r_decisions * (16 * T + 88)) / n_l, observe=r_decisions * (4 * S * S * 4) / n_l,
-               decode=r_decisions * (S * S * 4 + 24) / n_l if a.actions == "controller" else 0.0, reset=0.0)
+               decode=r_decisions * (4 * S * S * 4 + 24) / n_l if a.actions == "controller" else 0.0, reset=0.0)   # (decode: the four channels it reads)
     pass_ms = sum(k_ms.values())
-    kern_name = dict(step="k_env<MODE_STEP>", observe="k_observe<float>", decode="k_decode_map<float> (+ the controller's 3 elementwise torch kernels)",
+    kern_name = dict(step="k_env<MODE_STEP>", observe="k_observe<float>", decode="k_decode_map<float,4> + k_decode_locate",
                      reset="k_env<MODE_RESTORE_RESET>")
     kernels = {}
     for n in names:
@@ -510,7 +513,7 @@ def run_b200(a):
     dom = max(names, key=lambda n: k_ms[n])
     ach = kernels[kern_name[dom]]["gbs"]
     # in situ: the whole timed region's algorithmic bytes over its duration (all kernels, concurrent groups)
-    insitu_bytes = ticks_all * (82 * N + T) + decisions_all * (16 * T + 88 + 4 * S * S * 4 + (S * S * 4 + 24 if a.actions == "controller" else 0))
+    insitu_bytes = ticks_all * (82 * N + T) + decisions_all * (16 * T + 88 + 4 * S * S * 4 + (4 * S * S * 4 + 24 if a.actions == "controller" else 0))
     insitu_gbs = insitu_bytes / world / (elapsed_ms * 1e-3) / 1e9
     traffic, issue = None, None
     try:                                                 # numbers of the committed ncu capture of this launch shape (profiles/)
