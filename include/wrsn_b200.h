@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define WRSN_ABI_VERSION 16
+#define WRSN_ABI_VERSION 17
 #define WRSN_MAX_MC 16          /* chargers per environment */
 #define WRSN_RING 10            /* Node.operate keeps the last 10 per-second consumptions (Node.py:70-77) */
 
@@ -161,6 +161,9 @@ typedef struct wrsn_dims {
                              charges a node, one per other event); a step that needs more returns agent_id = -4 ("in
                              flight") and continues at the next wrsn_step / wrsn_rollout_step call, so that a launch over many
                              environments lasts as long as the budget, not as long as its slowest environment */
+    float obs_sigma_cells;  /* set by the caller (0 = unknown): the largest bandwidth of a node / charger source of get_state in map
+                               cells over the batch's scenarios, charging_range / min(frame width, height) * S.  Narrow sources
+                               (<= 2.9 cells: the shipped 1 km fields give 2.8) let wrsn_observe use its windowed float32 raster. */
     int32_t step_rounds;  /* with step_budget > 0.  0: one launch of the whole engine per wrsn_step / wrsn_rollout_step.
                              R > 0: a step is cut by KIND of work as well — R rounds of two launches, the events kernel (charger
                              events, fitness, deaths, cheap batches: everything but ...) and the batch kernel (... the

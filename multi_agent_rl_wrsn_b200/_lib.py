@@ -20,7 +20,7 @@ class Dims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "B", "N", "T", "M", "S", "Emax", "TEmax", "n_scen", "threads",
         "Npad", "W", "Tw", "n_slot", "state_bytes", "state_resident_bytes", "scen_bytes", "smem_bytes", "obs_pitch",
-        "step_budget", "step_rounds")]
+        "step_budget")] + [("obs_sigma_cells", C.c_float), ("step_rounds", C.c_int32)]
 
 
 class Request(C.Structure):

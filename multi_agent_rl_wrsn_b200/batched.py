@@ -81,6 +81,9 @@ class BatchedWRSN:
         d.n_scen, d.threads = n_scen, int(threads)
         self._call(self.L.wrsn_dims_finalize, C.byref(d))
         d.step_budget, d.step_rounds = int(step_budget), int(step_rounds)
+        # widest node / charger source of get_state in map cells: narrow sources take the windowed float32 raster
+        d.obs_sigma_cells = max(float(self.mc_type["charging_range"]) / min(st["frame"][1] - st["frame"][0], st["frame"][3] - st["frame"][2])
+                                for st in statics) * self.S
         self.dims = d
         self._foff = (C.c_int64 * self.E["WRSN_F_COUNT"])()
         self._soff = (C.c_int64 * self.E["WRSN_S_COUNT"])()

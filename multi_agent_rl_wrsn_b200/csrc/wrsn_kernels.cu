@@ -327,6 +327,170 @@ __global__ void __launch_bounds__(THREADS, sizeof(AccT) == 4 ? OBS_MINB32 : 1) k
 }
 
 
+/* ------------------------------------------------------------------ the float32 raster, windowed
+ * Same sum as k_observe<float> (WRSN.get_state, rl_env/WRSN.py:130-186), restructured around two facts: (1) the sources of
+ * channels 1, 3 and 4 (nodes, other chargers) are Gaussians of bandwidth charging_range / extent — 2.7 cells on the
+ * 1 km fields of the shipped scenarios — so outside a window of OBW cells around its centre a source contributes less
+ * than 3e-9 of its peak (the float32 observation is held to 1e-5 of the channel maximum; the float64 parity raster is
+ * untouched); (2) the time of the chunked kernel goes to its staging rounds (setup -> barrier -> expand -> barrier, seven
+ * times per map), not to its FFMAs.  Here ALL sources of a map are staged once — one warp per source: its scalars, then
+ * its window of the scenario's table scaled by its weight (the own-position source of channel 2, half the field wide, is
+ * staged full width) — one barrier, then every thread accumulates its 4 x 20 tile over the sources whose window meets the
+ * tile, in source order.  Shared memory per source: OBW row entries and OBW column entries between two 16-entry zero
+ * margins (a partly covered tile reads zeros instead of branching): 448 bytes at OBW = 40. */
+#define OBM 16                       /* zero margin on either side of the column window (a tile is 20 columns wide) */
+#define OBW_THREADS 128
+struct WinSrc { int sx, sy; };       /* first row / column of the window; sx < -1000: source unused */
+template <int OBW>                   /* window in cells (multiple of 4): >= 12.2 sigma + 6, chosen by the launcher */
+__global__ void __launch_bounds__(OBW_THREADS, OBW <= 40 ? 4 : (OBW <= 56 ? 3 : 2)) k_observe_win(const KParams P, const int32_t *agent_id, float *obs) {
+    extern __shared__ uint4 smem_u4[];
+    const int S = P.d.S, N = P.d.N, M = P.d.M, TP = P.d.obs_pitch;
+    const int NS = N + 2 * M;                                   /* nodes | chargers as channel-3 sources | as channel-4 sources */
+    float *gxw = reinterpret_cast<float *>(smem_u4);            /* [NS][OBW] */
+    float *gyw = gxw + (size_t)NS * OBW;                        /* [NS][OBM + OBW + OBM] */
+    float *own = gyw + (size_t)NS * (OBW + 2 * OBM);            /* [2][TP]: the observer's own position, full width */
+    WinSrc *win = reinterpret_cast<WinSrc *>(own + 2 * TP);     /* [NS] */
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const int ag = agent_id[b];
+    if (ag < 0) return;
+    const char *row = P.state + (size_t)b * P.L.total;
+    const char *scen_row = P.scen + (size_t)P.scen_id[b] * P.L.scen_total;
+    const double *par = (const double *)(scen_row + P.L.soff[WRSN_S_PAR]);
+    const double *nx = (const double *)(scen_row + P.L.soff[WRSN_S_NX]);
+    const double *ny = (const double *)(scen_row + P.L.soff[WRSN_S_NY]);
+    const double *energy = (const double *)(row + P.L.off[WRSN_F_ENERGY]);
+    const double *cs = (const double *)(row + P.L.off[WRSN_F_CS]);
+    const uint8_t *status = (const uint8_t *)(row + P.L.off[WRSN_F_STATUS]);
+    const double *mc = (const double *)(row + P.L.off[WRSN_F_MC]);
+    const float *tab_gx = (const float *)(scen_row + P.L.soff[WRSN_S_OBS_GX]), *tab_gy = (const float *)(scen_row + P.L.soff[WRSN_S_OBS_GY]);
+    const double f0 = par[WRSN_P_F0], f1 = par[WRSN_P_F1], f2 = par[WRSN_P_F2], f3 = par[WRSN_P_F3];
+    const double Wd = f1 - f0, Hd = f3 - f2;
+    const double unit = 1.0 / (double)S, start = unit / 2.0, delta = (start + unit) - start;   /* np.arange(unit/2, 1.0, unit) */
+    const double R = par[WRSN_P_MC_R], mtm = par[WRSN_P_MTM];
+    const double *me = mc + (size_t)ag * WRSN_MC_LEN;
+    /* ---- stage every source: one warp per source */
+    for (int q = wrp; q < NS + 1; q += OBW_THREADS / 32) {
+        if (q == NS) {                                          /* channel 2: own position, bandwidth 0.5 min(W, H) / extent */
+            const double tmp = fmin(Hd, Wd);
+            const double x0 = (me[WRSN_MC_X] - f0) / Wd, y0 = (me[WRSN_MC_Y] - f2) / Hd;
+            const double hx = 0.5 * tmp / Wd, hy = 0.5 * tmp / Hd, w = me[WRSN_MC_ENERGY] / par[WRSN_P_MC_CAP];
+            const double dnx = -2.0 * (hx * hx), dny = -2.0 * (hy * hy);
+            for (int i = lane; i < TP; i += 32) {
+                const double cc = start + (double)i * delta, ux = cc - x0, uy = cc - y0;
+                const double ax = ux * ux / dnx, ay = uy * uy / dny;
+                own[i] = (float)((i < S && ax > -745.2) ? w * exp(ax) : 0.0);
+                own[TP + i] = (float)((i < S && ay > -745.2) ? exp(ay) : 0.0);
+            }
+            continue;
+        }
+        bool used = false;
+        double x0 = 0.0, y0 = 0.0, w = 0.0;
+        int node = -1;
+        if (q < N) {                                            /* channel 1: alive nodes with traffic */
+            if (status[q] != 0) {
+                w = (cs[q] / par[WRSN_P_MC_AB2]) / ((energy[q] - par[WRSN_P_THR]) / par[WRSN_P_CAPMTHR]);
+                used = w != 0.0; node = q;
+                x0 = (nx[q] - f0) / Wd; y0 = (ny[q] - f2) / Hd;
+            }
+        } else {                                                /* channels 3 / 4: the other chargers at their destinations */
+            const int a = (q - N) % M, ch = q < N + M ? 2 : 3;
+            const double *an = mc + (size_t)a * WRSN_MC_LEN;
+            const bool charging = an[WRSN_MC_TYPE] != 0.0;
+            if (a != ag && (ch == 2 ? charging : !charging)) {
+                used = true;
+                x0 = (an[WRSN_MC_CPA0] - f0) / Wd; y0 = (an[WRSN_MC_CPA1] - f2) / Hd;
+                if (ch == 2) w = an[WRSN_MC_CPA2] / par[WRSN_P_CTM];
+                else {                                          /* the observer's destination y; / moving_time_max folded in */
+                    const double dx = an[WRSN_MC_X] - an[WRSN_MC_CPA0], dy = an[WRSN_MC_Y] - me[WRSN_MC_CPA1];
+                    w = sqrt(dx * dx + dy * dy) / par[WRSN_P_MC_V] / mtm;
+                }
+            }
+        }
+        int sx = -100000, sy = -100000;
+        if (used) {
+            sx = (((int)floor(x0 * (double)S) - OBW / 2) >> 2) << 2; sy = (((int)floor(y0 * (double)S) - OBW / 2) >> 2) << 2;
+            sx = sx < 0 ? 0 : (sx > S - OBW ? S - OBW : sx); sy = sy < 0 ? 0 : (sy > S - OBW ? S - OBW : sy);
+            float *gx = gxw + (size_t)q * OBW, *gy = gyw + (size_t)q * (OBW + 2 * OBM);
+            if (node >= 0) {                                    /* scaled copy of the scenario's table rows */
+                const float wq = (float)w;
+                const float *rx = tab_gx + (size_t)node * TP, *ry = tab_gy + (size_t)node * TP;
+                for (int i = lane; i < OBW; i += 32) gx[i] = rx[sx + i] * wq;
+                for (int i = lane; i < OBW + 2 * OBM; i += 32) {
+                    const int k = i - OBM;
+                    gy[i] = (k >= 0 && k < OBW) ? ry[sy + k] : 0.f;
+                }
+            } else {
+                const double hx = R / Wd, hy = R / Hd, dnx = -2.0 * (hx * hx), dny = -2.0 * (hy * hy);
+                for (int i = lane; i < OBW; i += 32) {
+                    const double ux = (start + (double)(sx + i) * delta) - x0, ax = ux * ux / dnx;
+                    gx[i] = (float)(ax > -745.2 ? w * exp(ax) : 0.0);
+                }
+                for (int i = lane; i < OBW + 2 * OBM; i += 32) {
+                    const int k = i - OBM;
+                    float v = 0.f;
+                    if (k >= 0 && k < OBW) { const double uy = (start + (double)(sy + k) * delta) - y0, ay = uy * uy / dny; v = (float)(ay > -745.2 ? exp(ay) : 0.0); }
+                    gy[i] = v;
+                }
+            }
+        }
+        if (lane == 0) { win[q].sx = sx; win[q].sy = sy; }
+    }
+    __syncthreads();
+    /* ---- accumulate: 4 x 20 tile per thread */
+    const int tiles_j = S / OBS_TJ32, n_tiles = (S / OBS_TI) * tiles_j;
+    if (tid >= n_tiles) return;
+    const int ti = tid / tiles_j, tj = tid - ti * tiles_j, i0 = ti * OBS_TI, j0 = tj * OBS_TJ32;
+    const int SS = S * S;
+    float *out = obs + (size_t)b * 4 * SS;
+    for (int ch = 0; ch < 4; ch++) {
+        float acc[OBS_TI][OBS_TJ32];
+#pragma unroll
+        for (int r = 0; r < OBS_TI; r++)
+#pragma unroll
+            for (int x = 0; x < OBS_TJ32; x++) acc[r][x] = 0.f;
+        if (ch == 1) {
+            const float4 a4 = *reinterpret_cast<const float4 *>(own + i0);
+            const float a[OBS_TI] = {a4.x, a4.y, a4.z, a4.w};
+            const float4 *v4 = reinterpret_cast<const float4 *>(own + TP + j0);
+#pragma unroll
+            for (int x = 0; x < OBS_TJ32; x += 4) {
+                const float4 t4 = v4[x >> 2];
+                const float v[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+                for (int r = 0; r < OBS_TI; r++)
+#pragma unroll
+                    for (int y = 0; y < 4; y++) acc[r][x + y] = fmaf(a[r], v[y], acc[r][x + y]);
+            }
+        } else {
+            const int q0 = ch == 0 ? 0 : (ch == 2 ? N : N + M), q1 = ch == 0 ? N : q0 + M;
+#pragma unroll 1
+            for (int q = q0; q < q1; q++) {
+                const WinSrc ws = win[q];
+                const int ri = i0 - ws.sx, rj = j0 - ws.sy;      /* multiples of 4 */
+                if (ri < 0 || ri > OBW - OBS_TI || rj <= -OBS_TJ32 || rj >= OBW) continue;   /* (an unused source has sx = -100000) */
+                const float4 a4 = *reinterpret_cast<const float4 *>(gxw + (size_t)q * OBW + ri);
+                const float a[OBS_TI] = {a4.x, a4.y, a4.z, a4.w};
+                const float4 *v4 = reinterpret_cast<const float4 *>(gyw + (size_t)q * (OBW + 2 * OBM) + OBM + rj);
+#pragma unroll
+                for (int x = 0; x < OBS_TJ32; x += 4) {
+                    const float4 t4 = v4[x >> 2];
+                    const float v[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+                    for (int r = 0; r < OBS_TI; r++)
+#pragma unroll
+                        for (int y = 0; y < 4; y++) acc[r][x + y] = fmaf(a[r], v[y], acc[r][x + y]);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < OBS_TI; r++) {
+            float4 *o4 = reinterpret_cast<float4 *>(out + (size_t)ch * SS + (size_t)(i0 + r) * S + j0);
+#pragma unroll
+            for (int x = 0; x < OBS_TJ32; x += 4) o4[x >> 2] = make_float4(acc[r][x], acc[r][x + 1], acc[r][x + 2], acc[r][x + 3]);
+        }
+    }
+}
+
 /* ------------------------------------------------------------------ WRSN.density_map_to_action (rl_env/WRSN.py:229-287)
  * and the map normalisation of WRSN.step (:293-296): an S x S density map -> (x-frac, y-frac, charge-time frac).
  * One CTA per environment, ONE streaming pass over the map in HBM (the only traffic that matters: S*S values in, 24
@@ -907,6 +1071,30 @@ int wrsn_observe(const wrsn_dims *d, const void *scen, const int32_t *scen_id, c
         if (smem > 48 * 1024) WRSN_CUDA(cudaFuncSetAttribute(k_observe<double, OBS_TJ64, OBS_THREADS64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         k_observe<double, OBS_TJ64, OBS_THREADS64><<<d->B, OBS_THREADS64, smem, (cudaStream_t)stream>>>(P, agent_id, (double *)obs);
     } else {
+        /* the windowed raster: map sizes it is laid out for, sources narrow enough for its window (the host layer says so in
+           dims.obs_sigma_cells: the largest charging_range / extent * S over the scenarios; 0 = unknown), shared memory */
+        const float sg = d->obs_sigma_cells;
+        /* (measured: the 40-cell window — 4 CTAs per SM — beats the chunked raster; 56 / 72 cells leave 3 / 2 CTAs per SM and
+           lose to it, 0.79 ms against 0.52 ms per 4096 maps at 72: wider sources stay with the chunked kernel) */
+        const int obw = (sg > 0.0f && sg <= 2.9f) ? 40 : 0;
+        const size_t wsmem = sizeof(float) * ((size_t)(d->N + 2 * d->M) * (obw + obw + 2 * OBM) + 2 * (size_t)d->obs_pitch) + sizeof(WinSrc) * (size_t)(d->N + 2 * d->M);
+        if (obw > 0 && OBS_TJ32 == 20 && d->S % 20 == 0 && d->S >= obw && (d->S / OBS_TI) * (d->S / OBS_TJ32) <= OBW_THREADS && wsmem <= 100 * 1024) {
+            static bool wattr[WRSN_MAX_DEVICES];
+            int dev = 0;
+            WRSN_CUDA(cudaGetDevice(&dev));
+            if (dev < 0 || dev >= WRSN_MAX_DEVICES) WRSN_FAIL("device ordinal %d not supported", dev);
+            if (!wattr[dev]) {
+                WRSN_CUDA(cudaFuncSetAttribute(k_observe_win<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                WRSN_CUDA(cudaFuncSetAttribute(k_observe_win<56>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                WRSN_CUDA(cudaFuncSetAttribute(k_observe_win<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                wattr[dev] = true;
+            }
+            if (obw == 40) k_observe_win<40><<<d->B, OBW_THREADS, wsmem, (cudaStream_t)stream>>>(P, agent_id, (float *)obs);
+            else if (obw == 56) k_observe_win<56><<<d->B, OBW_THREADS, wsmem, (cudaStream_t)stream>>>(P, agent_id, (float *)obs);
+            else k_observe_win<72><<<d->B, OBW_THREADS, wsmem, (cudaStream_t)stream>>>(P, agent_id, (float *)obs);
+            WRSN_CUDA(cudaGetLastError());
+            return 0;
+        }
         size_t smem = sizeof(float) * 2 * OBS_CH32 * (size_t)d->obs_pitch;
         if (smem > 200 * 1024) WRSN_FAIL("map_size too large");
         static bool attr[WRSN_MAX_DEVICES];            /* per device, see launch_env */

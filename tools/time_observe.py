@@ -9,7 +9,12 @@ B = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 if k != "base":
     _lib._lib = _lib._bind(ctypes.CDLL(os.path.join(REPO, "multi_agent_rl_wrsn_b200", "csrc", "libwrsn_b200_obs%s.so" % k)))
 dev = torch.device("cuda:0")
-scs = [synthetic(num_nodes=100, num_targets=100, seed=1000 + s) for s in range(64)]
+if os.environ.get("WRSN_SCENARIO"):                  # a shipped scenario of the reference, from its committed fixture
+    from tests import parity_cases as pc
+    from tests.helpers import golden
+    scs = [pc.sc_from_golden(golden(os.environ["WRSN_SCENARIO"]))]
+else:
+    scs = [synthetic(num_nodes=100, num_targets=100, seed=1000 + s) for s in range(64)]
 env = BatchedWRSN(scs, num_agent=3, num_envs=B, device=dev)
 env.reset()
 g = torch.Generator(device=dev); g.manual_seed(0)
