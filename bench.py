@@ -335,67 +335,110 @@ def run_b200(a):
     inflight = float(sum((env.req.agent_id == -4).sum().item() for env in groups)) / B
 
     # ---- end to end through the reference's contract with HOST buffers (rl_env/WRSN.py:289-330: the request's `state` is a host
-    # array, the controller runs on the host and hands `step` a density map).  Per step and group: the request record and the
-    # observations are copied to pinned host memory, the RandomController map is formed ON THE HOST from that copy (torch CPU
-    # ops), copied back, decoded, stepped and rasterised on the device.  The groups pipeline: while the host forms one group's
-    # map the other groups' kernels and copies run.  For uniform actions: actions from pinned host memory, request record back.
-    host_obs = [torch.zeros((Bg, 4, S, S), dtype=torch.float32).pin_memory() for _ in range(G)]
-    host_map = [torch.zeros((Bg, S, S), dtype=torch.float32).pin_memory() for _ in range(G)]
-    dev_map = [torch.zeros((Bg, S, S), dtype=torch.float32, device=dev) for _ in range(G)]
+    # array, the controller runs on the host and hands `step` a density map).  Per step and group: the request record goes to
+    # pinned host memory; the observations of the rows that CARRY a request (a row whose step is still in flight has no request
+    # and no `state` to hand out) are packed on the device and copied to pinned host memory; the RandomController map of those rows
+    # is formed ON THE HOST from that copy (torch CPU ops), copied back, scattered to its rows, decoded, stepped and rasterised on
+    # the device.  The groups pipeline: while the host forms one group's maps the other groups' kernels and copies run.  The byte
+    # counts are those of the tensors actually copied.  For uniform actions: actions from pinned host memory, request record back.
+    ctl = a.actions == "controller"
+    host_obs = [torch.zeros((Bg, 4, S, S), dtype=torch.float32).pin_memory() for _ in range(G)] if ctl else None
+    host_map = [torch.zeros((Bg, S, S), dtype=torch.float32).pin_memory() for _ in range(G)] if ctl else None
+    dev_map = [torch.zeros((Bg, S, S), dtype=torch.float32, device=dev) for _ in range(G)] if ctl else None
+    dev_map_c = [torch.zeros((Bg, S, S), dtype=torch.float32, device=dev) for _ in range(G)] if ctl else None
+    obs_c = [torch.zeros((Bg, 4, S, S), dtype=torch.float32, device=dev) for _ in range(G)] if ctl else None
+    order = [torch.zeros(Bg, dtype=torch.int64, device=dev) for _ in range(G)]
     host_act = [(torch.rand((a.steps, Bg, 3), dtype=torch.float64) * scale.cpu()).pin_memory() for _ in range(G)]
     host_req = [dict(agent_id=torch.zeros(Bg, dtype=torch.int32).pin_memory(), reward=torch.zeros(Bg, dtype=torch.float64).pin_memory(),
                      terminal=torch.zeros(Bg, dtype=torch.uint8).pin_memory(), now=torch.zeros(Bg, dtype=torch.float64).pin_memory())
                 for _ in range(G)]
-    done_ev = [torch.cuda.Event() for _ in range(G)]
+    rec_ev = [torch.cuda.Event() for _ in range(G)]
+    obs_ev = [torch.cuda.Event() for _ in range(G)]
     req_bytes = sum(v.numel() * v.element_size() for v in host_req[0].values())
-    if a.actions == "controller":
-        h2d, d2h = G * host_map[0].numel() * 4, G * (req_bytes + host_obs[0].numel() * 4)
-    else:
-        h2d, d2h = G * host_act[0][0].numel() * 8, G * req_bytes
+    row_obs, row_map = 4 * S * S * 4, S * S * 4
+    h2d = d2h = 0
 
-    def read_back(g):
+    def read_record(g):
+        """request record to the host; the rows with a request first in `order`, their observations packed behind that order"""
         for name, v in host_req[g].items():
             v.copy_(getattr(groups[g].req, name), non_blocking=True)
-        if a.actions == "controller":
-            host_obs[g].copy_(obs[g], non_blocking=True)
-        done_ev[g].record(streams[g])
+        if ctl:
+            has = groups[g].req.agent_id >= 0
+            order[g].copy_(torch.argsort(has.to(torch.uint8), descending=True, stable=True))
+            torch.index_select(obs[g], 0, order[g], out=obs_c[g])
+        rec_ev[g].record(streams[g])
 
     sync_all()
     for g in range(G):
         with torch.cuda.stream(streams[g]):
-            read_back(g)
-    e2e_dec = 0
+            read_record(g)
+    # one host thread per group (the groups are independent callers: each waits for ITS request records, asks for ITS states,
+    # runs ITS controller and issues ITS next step; torch's CPU kernels, the CUDA synchronisations and the C-ABI calls release
+    # the GIL), so that one group's host arithmetic overlaps the other groups' copies and kernels
+    import threading
+    counts = [[0, 0, 0] for _ in range(G)]                  # per group: decisions, h2d bytes, d2h bytes
+    errors = []
+    cpu_threads = torch.get_num_threads()
+    torch.set_num_threads(max(1, cpu_threads // G))
+
+    def caller(g):
+        try:
+            torch.cuda.set_device(dev)
+            cnt = counts[g]
+            for k in range(a.steps + 1):
+                rec_ev[g].synchronize()                    # the caller holds the request records of this group's last step
+                n = int((host_req[g]["agent_id"] >= 0).sum())
+                if k > 0:
+                    cnt[0] += n
+                    cnt[2] += req_bytes
+                if k == a.steps:
+                    break
+                if ctl:
+                    with torch.cuda.stream(streams[g]):    # ... and asks for the `state` of every request
+                        host_obs[g][:n].copy_(obs_c[g][:n], non_blocking=True)
+                        obs_ev[g].record(streams[g])
+                    cnt[2] += n * row_obs
+                    obs_ev[g].synchronize()
+                    o = host_obs[g][:n]
+                    torch.add(o[:, 0], o[:, 1], out=host_map[g][:n])   # RandomController.make_action on the host
+                    host_map[g][:n].add_(o[:, 2], alpha=-10.0).add_(o[:, 3])
+                with torch.cuda.stream(streams[g]):
+                    if ctl:
+                        dev_map_c[g][:n].copy_(host_map[g][:n], non_blocking=True)
+                        dev_map[g].index_copy_(0, order[g][:n], dev_map_c[g][:n])
+                        groups[g].density_map_to_action(dev_map[g], out=act[g])
+                        cnt[1] += n * row_map
+                    else:
+                        act[g].copy_(host_act[g][k], non_blocking=True)
+                        cnt[1] += host_act[g][k].numel() * 8
+                    groups[g].rollout_step(act[g], obs[g])
+                    read_record(g)
+        except Exception as ex:                              # noqa: BLE001 - re-raised on the main thread
+            errors.append(ex)
+
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     cur = torch.cuda.current_stream(dev)
     sync_all()
     f0.record(cur)
     for st in streams:
         st.wait_stream(cur)
-    for k in range(a.steps + 1):
-        for g in range(G):
-            done_ev[g].synchronize()                       # the caller holds the request (and state) of this group's last step
-            if k > 0:
-                e2e_dec += int((host_req[g]["agent_id"] >= 0).sum())
-            if k == a.steps:
-                continue
-            if a.actions == "controller":
-                o = host_obs[g]
-                torch.add(o[:, 0], o[:, 1], out=host_map[g])   # RandomController.make_action on the host
-                host_map[g].add_(o[:, 2], alpha=-10.0).add_(o[:, 3])
-            with torch.cuda.stream(streams[g]):
-                if a.actions == "controller":
-                    dev_map[g].copy_(host_map[g], non_blocking=True)
-                    groups[g].density_map_to_action(dev_map[g], out=act[g])
-                else:
-                    act[g].copy_(host_act[g][k], non_blocking=True)
-                groups[g].rollout_step(act[g], obs[g])
-                read_back(g)
+    workers = [threading.Thread(target=caller, args=(g,)) for g in range(G)]
+    for w in workers:
+        w.start()
+    for w in workers:
+        w.join()
     for st in streams:
         cur.wait_stream(st)
     f1.record(cur)
     sync_all()
+    torch.set_num_threads(cpu_threads)
+    if errors:
+        raise errors[0]
     e2e_ms = f0.elapsed_time(f1)
-    del host_obs, host_map, dev_map
+    e2e_dec = sum(c[0] for c in counts)
+    h2d, d2h = sum(c[1] for c in counts), sum(c[2] for c in counts)
+    h2d, d2h = h2d // a.steps, d2h // a.steps              # per step, averaged over the timed steps
+    del host_obs, host_map, dev_map, dev_map_c, obs_c
 
     # ---- roofline pass: the same hot path issued serially on ONE stream through the separate entry points, a pair of CUDA
     # events around every launch (concurrent groups time-share the SMs and blur per-launch durations).  The row masks are
@@ -550,9 +593,10 @@ def run_b200(a):
         clocks=clocks,
         e2e=dict(value=e2e_dec_all / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                  ms_per_step=e2e_ms / a.steps,
-                 note=("the reference's contract with host buffers: per step the request record AND the observations (the request's "
-                       "`state`) go to pinned host memory, the RandomController map is formed on the host from them, copied to the "
-                       "device, decoded, stepped, rasterised; groups pipelined (PCIe- and host-bound)") if a.actions == "controller" else
+                 note=("the reference's contract with host buffers: per step the request record AND the observations of the rows that "
+                       "carry a request (the request's `state`; a row whose step is still in flight has none) go to pinned host memory, "
+                       "the RandomController map is formed on the host from them, copied to the device, decoded, stepped, rasterised; "
+                       "one host thread per group (PCIe- and host-bound); bytes = per-step mean of the tensors actually copied") if a.actions == "controller" else
                       "per step: actions from pinned host memory, rollout_step, request record read back on the host"),
         gpu_launches=n_launch,
         roofline=dict(bound="hbm", kernel=kern_name[dom], achieved=ach, peak=peak, unit="GB/s", frac=ach / peak,

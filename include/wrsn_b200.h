@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define WRSN_ABI_VERSION 17
+#define WRSN_ABI_VERSION 18
 #define WRSN_MAX_MC 16          /* chargers per environment */
 #define WRSN_RING 10            /* Node.operate keeps the last 10 per-second consumptions (Node.py:70-77) */
 
@@ -169,7 +169,12 @@ typedef struct wrsn_dims {
                              events, fitness, deaths, cheap batches: everything but ...) and the batch kernel (... the
                              second-by-second loop of the seconds in which update_reward is active, at most step_budget of them
                              per launch).  Same results; the hot loop runs in launches of its own, where nothing else
-                             competes for the instruction caches. */
+                             competes for the instruction caches.
+                             R < 0 (one warp per environment only; needs wrsn_request.queue; a measured experiment, slower than R = 0):
+                             ONE persistent launch, one CTA of sixteen warps per SM, every warp one environment at a time from a
+                             queue; the warps of an SM do the same KIND of work at the same time (event phase / batch phase, flipping
+                             when enough warps wait for the other one).  step_budget (0 = none) bounds the work per environment and
+                             launch as above.  Same results. */
 } wrsn_dims;
 
 /* request record written by reset / step, device pointers, one row per environment */
@@ -184,6 +189,8 @@ typedef struct wrsn_request {
     int32_t *flags;                     /* [B]  bit0 = every charger dead (the reference would never return, Q1), bit1 = engine error */
     double *stats;                      /* [B][3] running totals, never cleared by the library (may be NULL): requests handed out
                                            with a deciding charger; simulated seconds advanced by step; resets (episodes begun) */
+    int32_t *queue;                     /* [2]  work queue of the persistent step kernel (wrsn_dims.step_rounds < 0): zeroed once by the caller,
+                                           left zeroed by every launch; may be NULL otherwise.  One per request record (= per stream). */
 } wrsn_request;
 
 const char *wrsn_last_error(void);

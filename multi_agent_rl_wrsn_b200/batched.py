@@ -39,9 +39,10 @@ class Requests:
         self.detail = torch.zeros((B, 2), dtype=torch.float64, device=device)
         self.flags = torch.zeros((B,), dtype=torch.int32, device=device)
         self.stats = torch.zeros((B, 3), dtype=torch.float64, device=device)   # running totals: decisions, simulated seconds, resets
+        self.queue = torch.zeros((2,), dtype=torch.int32, device=device)       # work queue of the persistent step kernel (step_rounds < 0)
         self.c = _lib.Request(self.agent_id.data_ptr(), self.terminal.data_ptr(), self.reward.data_ptr(),
                               self.now.data_ptr(), self.action.data_ptr(), self.detail.data_ptr(), self.flags.data_ptr(),
-                              self.stats.data_ptr())
+                              self.stats.data_ptr(), self.queue.data_ptr())
 
 
 class BatchedWRSN:

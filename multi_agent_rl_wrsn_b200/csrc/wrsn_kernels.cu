@@ -35,6 +35,7 @@ struct KParams {
     double *fitness, *fit_min;
     int with_reward;
     int resume_only;                                 /* later rounds of a split step: only rows whose step is in flight (agent_id == -4) */
+    int sync_slice, sync_th, sync_quantum;           /* k_env_sync: bytes of shared memory per warp, parked sixteenths that flip the phase, seconds per batch quantum */
 };
 
 __device__ __forceinline__ void copy16(char *dst, const char *src, int64_t bytes, int tid, int G) {
@@ -869,7 +870,9 @@ static int launch_env(KParams &P, void *stream) {
 /* WRSN.step: one launch of the whole engine, or — wrsn_dims.step_rounds > 0 with a step budget — rounds of two launches, the
  * events kernel and the batch kernel (see include/wrsn_b200.h).  In the later launches a row is selected by its own state
  * (request record -4 + hdr[INFLIGHT]); rows that finished their step stay out. */
+static int launch_step_sync(KParams &P, void *stream);
 static int launch_step(KParams &P, void *stream) {
+    if (P.d.step_rounds < 0 && P.d.threads == 32) return launch_step_sync(P, stream);
     if (!(P.d.step_budget > 0 && P.d.step_rounds > 0)) return launch_env<MODE_STEP>(P, stream);
     if (!P.req.agent_id) WRSN_FAIL("split steps need req->agent_id");
     for (int r = 0; r < P.d.step_rounds; r++) {
@@ -879,6 +882,38 @@ static int launch_step(KParams &P, void *stream) {
         if (launch_env<MODE_STEP_BATCH>(Q, stream)) return -1;
         P.resume_only = 1;                           /* later rounds: only rows still in flight (the others hold a fresh request) */
     }
+    return 0;
+}
+
+/* wrsn_dims.step_rounds < 0: the persistent, phase-synchronous step kernel (wrsn_env_kernel.cuh: k_env_sync), one CTA of sixteen
+ * warps per SM, environments handed out through req->queue. */
+static int launch_step_sync(KParams &P, void *stream) {
+    if (check_dims(&P.d)) return -1;
+    wrsn_make_layout(&P.d, &P.L);
+    if (!P.scen || !P.scen_id || !P.state) WRSN_FAIL("scen / scen_id / state must not be NULL");
+    if (!P.req.queue) WRSN_FAIL("step_rounds < 0 needs req->queue (two zeroed int32 on the device)");
+    int dev = 0;
+    WRSN_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= WRSN_MAX_DEVICES) WRSN_FAIL("device ordinal %d not supported", dev);
+    static int sms[WRSN_MAX_DEVICES];
+    static int64_t attr_cache[WRSN_MAX_DEVICES];
+    static int th = -1, quantum = -1;
+    if (th < 0) {                                    /* TUNING KNOBS (measured flat: 0.80 - 0.87 M decisions/s over th 4..16, quantum 16..64) */
+        const char *e = getenv("WRSN_SYNC_TH"); th = e ? atoi(e) : 8; if (th < 1 || th > 16) th = 8;
+        e = getenv("WRSN_SYNC_Q"); quantum = e ? atoi(e) : 32; if (quantum < 1) quantum = 32;
+    }
+    if (!sms[dev]) WRSN_CUDA(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
+    P.sync_slice = (int)wrsn_a16(P.L.smem_total); P.sync_th = th; P.sync_quantum = quantum;
+    const int64_t smem = (int64_t)P.sync_slice * WRSN_SYNC_WARPS;
+    if (smem > 227 * 1024 - 256) WRSN_FAIL("step_rounds < 0: %d environments of %lld bytes do not fit one SM's shared memory", WRSN_SYNC_WARPS, (long long)P.L.smem_total);
+    if (smem > attr_cache[dev]) {
+        WRSN_CUDA(cudaFuncSetAttribute(g32::k_env_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_cache[dev] = smem;
+    }
+    int grid = (P.d.B + WRSN_SYNC_WARPS - 1) / WRSN_SYNC_WARPS;
+    if (grid > sms[dev]) grid = sms[dev];
+    g32::k_env_sync<<<grid, 32 * WRSN_SYNC_WARPS, (size_t)smem, (cudaStream_t)stream>>>(P);
+    WRSN_CUDA(cudaGetLastError());
     return 0;
 }
 

@@ -114,7 +114,7 @@ def check_episode(name, device, check_obs=False, replicas=1):
 
 
 def check_vs_oracle(scenarios, device, num_envs, steps, seed, num_agent=3, mc=None, check_obs=False, scale2=0.05,
-                    map_size=100, scenario_index=None, controller=False, obs32=False, threads=0):
+                    map_size=100, scenario_index=None, controller=False, obs32=False, threads=0, rounds=0):
     """B environments with DIFFERENT action streams (and possibly different scenarios) vs B oracle runs (ladder L6).
     ``controller``: the actions are those of the reference's RandomController — the density map s0 + s1 - 10 s2 + s3 of the
     float32 observation, decoded ON THE DEVICE (wrsn_decode_density_map) — and the oracle is fed the decoded 3-vectors, so
@@ -123,7 +123,7 @@ def check_vs_oracle(scenarios, device, num_envs, steps, seed, num_agent=3, mc=No
     if isinstance(scenarios, Scenario):
         scenarios = [scenarios]
     env = BatchedWRSN(scenarios, num_agent=num_agent, mc_type=mc, num_envs=num_envs, device=device, map_size=map_size,
-                      scenario_index=scenario_index, threads=threads)
+                      scenario_index=scenario_index, threads=threads, step_rounds=rounds)
     sid = _np(env.scen_id)
     B = num_envs
     rng = np.random.default_rng(seed)
