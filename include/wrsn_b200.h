@@ -189,6 +189,8 @@ typedef struct wrsn_request {
     int32_t *flags;                     /* [B]  bit0 = every charger dead (the reference would never return, Q1), bit1 = engine error */
     double *stats;                      /* [B][3] running totals, never cleared by the library (may be NULL): requests handed out
                                            with a deciding charger; simulated seconds advanced by step; resets (episodes begun) */
+    int32_t *sticky;                    /* [B]  OR of every `flags` value ever written for the row, never cleared by the library (may be NULL): a
+                                           rollout that resets finished rows inside wrsn_rollout_step checks it once per window, not per step */
     int32_t *queue;                     /* [2]  work queue of the persistent step kernel (wrsn_dims.step_rounds < 0): zeroed once by the caller,
                                            left zeroed by every launch; may be NULL otherwise.  One per request record (= per stream). */
 } wrsn_request;

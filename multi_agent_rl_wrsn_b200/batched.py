@@ -39,10 +39,11 @@ class Requests:
         self.detail = torch.zeros((B, 2), dtype=torch.float64, device=device)
         self.flags = torch.zeros((B,), dtype=torch.int32, device=device)
         self.stats = torch.zeros((B, 3), dtype=torch.float64, device=device)   # running totals: decisions, simulated seconds, resets
+        self.sticky = torch.zeros((B,), dtype=torch.int32, device=device)      # OR of every `flags` value written so far (see raise_on_error)
         self.queue = torch.zeros((2,), dtype=torch.int32, device=device)       # work queue of the persistent step kernel (step_rounds < 0)
         self.c = _lib.Request(self.agent_id.data_ptr(), self.terminal.data_ptr(), self.reward.data_ptr(),
                               self.now.data_ptr(), self.action.data_ptr(), self.detail.data_ptr(), self.flags.data_ptr(),
-                              self.stats.data_ptr(), self.queue.data_ptr())
+                              self.stats.data_ptr(), self.sticky.data_ptr(), self.queue.data_ptr())
 
 
 class BatchedWRSN:
@@ -376,6 +377,18 @@ class BatchedWRSN:
         w = self.view("tact_words").to(torch.int64) & 0xFFFFFFFF
         bits = (w.unsqueeze(-1) >> torch.arange(32, device=self.device)) & 1
         return bits.reshape(w.shape[0], -1)[:, :self.T].to(torch.uint8)
+
+    def raise_on_error(self):
+        """One host synchronisation: raise if any environment has EVER reported an engine error (``flags`` bit 1: e.g. the
+        process slots overflowed) — also one that ``rollout_step`` has reset since; returns the number of environments that have
+        seen every charger dead (bit 0; the reference never returns from such a step, here the episode is reset).  The batched
+        rollouts call it once per window (``controllers.rollout``, ``IPPORollout.collect`` through ``BatchedIPPO.roll_out``)."""
+        s = self.req.sticky
+        both = torch.stack([(s & 2).ne(0).sum(), (s & 1).ne(0).sum()]).tolist()
+        if both[0]:
+            bad = torch.nonzero(s & 2).flatten()[:8].tolist()
+            raise RuntimeError("wrsn_b200: engine error (flags bit 1) in %d environment(s), e.g. rows %s" % (both[0], bad))
+        return int(both[1])
 
     def counters(self):
         """Device counters summed over environments: simulated seconds, events, serial (death) ticks, BFS runs, decisions."""

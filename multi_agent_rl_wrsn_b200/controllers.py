@@ -58,8 +58,9 @@ def rollout(env, controller, steps, obs=None, group=None):
     if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size(group) > 1:
         torch.distributed.all_reduce(local, group=group)
     dec1, sim1 = reduce_stats(env, group)
+    all_dead = env.raise_on_error()                                       # engine errors of any step of the window, reset or not
     return obs, dict(decisions=dec1 - dec0, simulated_seconds=sim1 - sim0, episodes=float(local[0].item()),
-                     reward_sum=float(local[1].item()))
+                     reward_sum=float(local[1].item()), environments_that_saw_every_charger_dead=all_dead)
 
 
 class IPPORollout:

@@ -2539,7 +2539,8 @@ WRSN_D void entry_step(Ctx &c, int agent_id, const double *input_action, ReqOut 
                 if (po[WRSN_PRI_PROCESSED] != 0) po[WRSN_PRI_USED] = 0;
             }
             m[WRSN_MC_SLOT] = new_slot_h(c, agent_id, phy0, phy1, phy2);
-            m[WRSN_MC_PREVFIT] = h[WRSN_H_FIT_MIN];   /* the network has not moved since the last request */
+            m[WRSN_MC_PREVFIT] = h[WRSN_H_FIT_MIN];   /* the network has not moved since the last request (refreshed at every request
+                                                         that leaves the environment steppable: a decider's, an implicit None's) */
             m[WRSN_MC_EXCL] = 0.0;
         } else if (agent_id >= c.M) h[WRSN_H_ERR] = 4.0;
         /* general_process = net_process | p_0 | p_1 ... over chargers with status != 0 (:307-310) */
@@ -2565,7 +2566,9 @@ WRSN_D void entry_step(Ctx &c, int agent_id, const double *input_action, ReqOut 
     int id = -1;
     if (!(watched == 0 || c.hdr[WRSN_H_ALIVE] == 0.0)) { id = scan_decider(c); if (id < 0) id = -2; }   /* all threads */
     double fit = 0.0;
-    if (id >= 0) fit = do_fitness(c, (double *)0);   /* get_reward :222-227 */
+    if (id >= 0 || id == -2) fit = do_fitness(c, (double *)0);   /* get_reward :222-227; after an implicit None (time has moved, no
+                                                                   decider) only the cached minimum is refreshed: the next step(agent,
+                                                                   action) reads get_network_fitness() as of now (:303) */
     if (c.tid == 0) {
         c.hdr[WRSN_H_INFLIGHT] = 0.0;
         r->now = c.hdr[WRSN_H_NOW];
@@ -2582,6 +2585,7 @@ WRSN_D void entry_step(Ctx &c, int agent_id, const double *input_action, ReqOut 
             for (int k = 0; k < 3; k++) r->act[k] = m[WRSN_MC_ACT0 + k];
             c.hdr[WRSN_H_NDECISIONS] += 1.0;
         } else {
+            if (id == -2) c.hdr[WRSN_H_FIT_MIN] = fit;
             r->reward = NAN; r->detail[0] = r->detail[1] = NAN;
             for (int k = 0; k < 3; k++) r->act[k] = NAN;
         }

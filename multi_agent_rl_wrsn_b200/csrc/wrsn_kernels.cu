@@ -53,6 +53,7 @@ __device__ __forceinline__ void write_request(const wrsn_request &q, int b, cons
     if (q.action) for (int k = 0; k < 3; k++) q.action[3 * b + k] = r.act[k];
     if (q.detail) { q.detail[2 * b] = r.detail[0]; q.detail[2 * b + 1] = r.detail[1]; }
     if (q.flags) q.flags[b] = r.flags;
+    if (q.sticky && r.flags) q.sticky[b] |= r.flags;
 }
 
 /* 2^(j/64), j = 0..63, correctly rounded: the table of wrsn_exp_b (wrsn_engine.cuh; reward path only) */

@@ -106,11 +106,12 @@ class BatchedIPPO:
                              ("rewards", bt["rewards"]), ("advantages", advantages), ("returns", returns), ("values", values)):
                     acc[i][k].append(v)
         delta = (self.env.req.stats.sum(0) - st0).clone()
+        all_dead = self.env.raise_on_error()                               # engine errors of any step of these windows, reset or not
         dist = torch.distributed
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             dist.all_reduce(delta, group=self.group)                      # job-wide statistics for log.csv
         self.last_rollout = dict(decisions=float(delta[0]), simulated_seconds=float(delta[1]), episodes=float(delta[2]),
-                                 transitions=list(counts))
+                                 transitions=list(counts), environments_that_saw_every_charger_dead=all_dead)
         if self.shared:                                                  # one pooled batch, agents in id order (PPO.py:164-175)
             acc = [{k: [x for i in range(self.num_agent) for x in acc[i][k]] for k in acc[0]}]
         out = []

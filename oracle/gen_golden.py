@@ -32,7 +32,7 @@ REPO = os.path.dirname(HERE)
 sys.path.insert(0, HERE)
 from ref_runner import load_reference  # noqa: E402
 
-OUT = os.path.join(REPO, "tests", "golden")
+OUT = os.environ.get("WRSN_GOLDEN_OUT") or os.path.join(REPO, "tests", "golden")
 MAX_EVENTS_PER_STEP = 3_000_000      # the reference never returns if every charger is dead (Q1)
 
 

@@ -80,6 +80,7 @@ static int run_mode(int mode, const Args &A) {
             if (q.action) for (int k = 0; k < 3; k++) q.action[3 * b + k] = r.act[k];
             if (q.detail) { q.detail[2 * b] = r.detail[0]; q.detail[2 * b + 1] = r.detail[1]; }
             if (q.flags) q.flags[b] = r.flags;
+            if (q.sticky && r.flags) q.sticky[b] |= r.flags;
             if (q.stats) { if (r.agent >= 0) q.stats[3 * b] += 1.0; if (mode == MODE_STEP || mode == MODE_STEP_BATCH) q.stats[3 * b + 1] += r.now - now_before;
                            if (mode == MODE_RESTORE_RESET || mode == MODE_RESET_FINISH) q.stats[3 * b + 2] += 1.0; }
         }

@@ -214,3 +214,53 @@ def test_linear_controller_decode_equals_materialised_map(cuda_library):
     w = (0.5, -2.0, 3.0, 0.25)                           # any weights: torch multiplies, then adds, left to right
     dm = w[0] * obs[:, 0] + w[1] * obs[:, 1] + w[2] * obs[:, 2] + w[3] * obs[:, 3]
     assert same(env.density_map_to_action(dm.contiguous(), agent_id=agents), env.linear_controller_action(obs, w, agent_id=agents))
+
+
+@pytest.mark.gpu
+def test_random_controller_rollout_stays_on_the_host_decode_trajectory(cuda_library):
+    """How often does a RandomController rollout whose maps are decoded ON THE DEVICE leave the trajectory the reference's own
+    decode (numpy + scipy's L-BFGS-B, oracle/decode_oracle.py) would have driven?  48 environments x 25 rollout steps on the
+    bench's scenarios; at every decision the device's action is compared with the host decode of the same map on the same state.
+    Charge fraction: 1e-6 (float32 maps).  Location: the same point within 1e-3 m in at least 90 % of the decisions (where scipy
+    stops at the box centre — the common case — the device is at that centre exactly); the rest are cusps of a discontinuous
+    objective where the two optimisers stop at different kinks.  The counts are printed."""
+    B, steps = 48, 25
+    scs = [synthetic(num_nodes=100, num_targets=100, seed=1000 + k) for k in range(4)]
+    env = BatchedWRSN(scs, num_agent=3, num_envs=B, device=DEV)
+    env.reset()
+    obs = env.get_state(dtype=torch.float32)
+    n_dec = n_centre = n_close = n_far = n_nan = 0
+    far = []
+    for k in range(steps):
+        dm = (obs[:, 0] + obs[:, 1] - 10.0 * obs[:, 2] + obs[:, 3]).contiguous()
+        aid = env.req.agent_id.clone()
+        act = env.density_map_to_action(dm, agent_id=aid)
+        got = act.cpu().numpy()
+        maps = dm.cpu().numpy().astype(np.float64)
+        for b in range(B):
+            if int(aid[b]) < 0:
+                continue
+            with np.errstate(all="ignore"):
+                ref, res, x0, objective = _oracle_decode(env, scs, b, maps[b])
+            n_dec += 1
+            if not np.isfinite(ref[2]):               # a map that overflows exp(): NaN charge fraction on both paths
+                assert not np.isfinite(got[b, 2])
+                n_nan += 1
+                continue
+            np.testing.assert_allclose(got[b, 2], ref[2], rtol=1e-6)
+            par = env.statics[int(env.scen_id[b])]["par"]
+            loc = np.array([got[b, 0] * (par["F1"] - par["F0"]) + par["F0"], got[b, 1] * (par["F3"] - par["F2"]) + par["F2"]])
+            d = float(np.hypot(*(loc - res.x)))
+            if np.array_equal(res.x, x0) and d <= 1e-9:
+                n_centre += 1
+            elif d <= 1e-3:
+                n_close += 1
+            else:
+                n_far += 1
+                far.append(d)
+        env.rollout_step(torch.nan_to_num(act), obs)
+    print("RandomController rollout, device decode against the host decode: %d decisions, %d at scipy's box centre exactly, %d within "
+          "1e-3 m, %d elsewhere (median distance %.2f m), %d overflowing maps"
+          % (n_dec, n_centre, n_close, n_far, float(np.median(far)) if far else 0.0, n_nan))
+    assert n_dec >= B * steps // 3
+    assert n_centre + n_close >= 0.9 * (n_dec - n_nan), (n_dec, n_centre, n_close, n_far, n_nan)

@@ -161,3 +161,32 @@ def test_scheduling_contract(simpy):
     assert env.run(until=done) is None and env.now == 2      # already processed: returns at once
     env.run(until=p)
     assert trace == [2, 3]
+
+
+def _genuine_simpy():
+    """A real SimPy distribution (not oracle/shims)?"""
+    import importlib.util as iu
+    spec = iu.find_spec("simpy")
+    if spec is None or not spec.origin:
+        return False
+    return not os.path.abspath(spec.origin).startswith(os.path.join(REPO, "oracle", "shims"))
+
+
+@pytest.mark.skipif(not _genuine_simpy(), reason="no genuine simpy distribution in this image (requirements.txt:52 pins simpy==4.0.1)")
+@pytest.mark.skipif(not os.path.isfile("/root/reference/rl_env/WRSN.py"), reason="reference sources absent")
+def test_goldens_under_genuine_simpy(tmp_path):
+    """Pins the one layer the fixtures inherit from the shim: regenerate one pure-network trace and one episode with the
+    UNMODIFIED reference under the GENUINE simpy package and demand the committed fixtures byte for byte.  Skipped where no
+    simpy wheel exists (this image): until it has run, the SimPy layer of every parity claim is 'unpinned against a wheel'."""
+    import subprocess
+    env = dict(os.environ, WRSN_REAL_SIMPY="1", WRSN_GOLDEN_OUT=str(tmp_path))
+    subprocess.run([sys.executable, os.path.join(REPO, "oracle", "gen_golden.py"), "net:hanoi1000n50", "ep:edge_n50"], check=True, env=env,
+                   cwd=REPO, timeout=1800)
+    for name in ("net_hanoi1000n50", "ep_edge_n50"):
+        new = np.load(os.path.join(str(tmp_path), name + ".npz"), allow_pickle=False)
+        old = np.load(os.path.join(REPO, "tests", "golden", name + ".npz"), allow_pickle=False)
+        assert sorted(new.files) == sorted(old.files)
+        for k in old.files:
+            if k.startswith("meta_") or k in ("wall_seconds",):
+                continue
+            assert np.array_equal(new[k], old[k], equal_nan=True) if old[k].dtype.kind == "f" else np.array_equal(new[k], old[k]), (name, k)
