@@ -330,7 +330,8 @@ def run_b200(a):
         time.sleep(0.3)
     elapsed_ms, (decisions, ticks, episodes), t_wall0, t_wall1 = timed(a.actions, a.steps)
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
-    launches_per_step = (4 if a.actions == "controller" else 3) * G
+    # per group and step: [k_decode_map, k_decode_locate,] [k_step_order (launches of >= 2048 rows),] k_env<STEP>, k_env<RESTORE_RESET>, k_observe
+    launches_per_step = ((6 if a.actions == "controller" else 4) - (0 if 2048 <= Bg <= 16384 else 1)) * G
     n_launch = launches_per_step * a.steps
     inflight = float(sum((env.req.agent_id == -4).sum().item() for env in groups)) / B
 
@@ -353,7 +354,10 @@ def run_b200(a):
                      terminal=torch.zeros(Bg, dtype=torch.uint8).pin_memory(), now=torch.zeros(Bg, dtype=torch.float64).pin_memory())
                 for _ in range(G)]
     rec_ev = [torch.cuda.Event() for _ in range(G)]
-    obs_ev = [torch.cuda.Event() for _ in range(G)]
+    CH = 4                                                   # chunks per group and step of the state copy
+    obs_ev = [[torch.cuda.Event() for _ in range(CH)] for _ in range(G)]
+    map_ev = [torch.cuda.Event() for _ in range(G)]
+    copy_streams = [torch.cuda.Stream(device=dev) for _ in range(G)]
     req_bytes = sum(v.numel() * v.element_size() for v in host_req[0].values())
     row_obs, row_map = 4 * S * S * 4, S * S * 4
     h2d = d2h = 0
@@ -377,16 +381,23 @@ def run_b200(a):
     # the GIL), so that one group's host arithmetic overlaps the other groups' copies and kernels
     import threading
     counts = [[0, 0, 0] for _ in range(G)]                  # per group: decisions, h2d bytes, d2h bytes
+    diag = [[0.0, 0.0, 0.0] for _ in range(G)]              # per group: seconds waiting for the records / for the states / in the controller
     errors = []
     cpu_threads = torch.get_num_threads()
-    torch.set_num_threads(max(1, cpu_threads // G))
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+    e2e_threads = int(os.environ.get("WRSN_E2E_THREADS", "0")) or max(1, (os.cpu_count() or cpu_threads) // (G * max(1, local_world)))
+    torch.set_num_threads(e2e_threads)
+    host_w = torch.tensor(CONTROLLER_WEIGHTS, dtype=torch.float32).view(1, 1, 4)
 
     def caller(g):
         try:
             torch.cuda.set_device(dev)
             cnt = counts[g]
+            tm = diag[g]
             for k in range(a.steps + 1):
+                t_a = time.perf_counter()
                 rec_ev[g].synchronize()                    # the caller holds the request records of this group's last step
+                tm[0] += time.perf_counter() - t_a
                 n = int((host_req[g]["agent_id"] >= 0).sum())
                 if k > 0:
                     cnt[0] += n
@@ -394,17 +405,29 @@ def run_b200(a):
                 if k == a.steps:
                     break
                 if ctl:
-                    with torch.cuda.stream(streams[g]):    # ... and asks for the `state` of every request
-                        host_obs[g][:n].copy_(obs_c[g][:n], non_blocking=True)
-                        obs_ev[g].record(streams[g])
+                    # ... and asks for the `state` of every request: copied in CHUNKS, so that the controller works on one chunk
+                    # while the next one crosses PCIe, and its maps go back chunk by chunk
+                    edges = [n * c // CH for c in range(CH + 1)]
+                    with torch.cuda.stream(streams[g]):
+                        for c in range(CH):
+                            host_obs[g][edges[c]:edges[c + 1]].copy_(obs_c[g][edges[c]:edges[c + 1]], non_blocking=True)
+                            obs_ev[g][c].record(streams[g])
                     cnt[2] += n * row_obs
-                    obs_ev[g].synchronize()
-                    o = host_obs[g][:n]
-                    torch.add(o[:, 0], o[:, 1], out=host_map[g][:n])   # RandomController.make_action on the host
-                    host_map[g][:n].add_(o[:, 2], alpha=-10.0).add_(o[:, 3])
+                    for c in range(CH):
+                        lo, hi = edges[c], edges[c + 1]
+                        t_a = time.perf_counter()
+                        obs_ev[g][c].synchronize()
+                        t_b = time.perf_counter()
+                        # RandomController.make_action on the host: the channel combination as ONE pass over the states (a [1 x 4]
+                        # by [4 x S^2] product per request; elementwise adds on channel slices are strided and 20 x slower)
+                        torch.matmul(host_w, host_obs[g][lo:hi].view(hi - lo, 4, S * S), out=host_map[g][lo:hi].view(hi - lo, 1, S * S))
+                        tm[1] += t_b - t_a; tm[2] += time.perf_counter() - t_b
+                        with torch.cuda.stream(copy_streams[g]):       # (the maps go back on a second stream: the state copies of
+                            dev_map_c[g][lo:hi].copy_(host_map[g][lo:hi], non_blocking=True)   # the later chunks are still queued on the first)
+                    map_ev[g].record(copy_streams[g])
                 with torch.cuda.stream(streams[g]):
                     if ctl:
-                        dev_map_c[g][:n].copy_(host_map[g][:n], non_blocking=True)
+                        streams[g].wait_event(map_ev[g])
                         dev_map[g].index_copy_(0, order[g][:n], dev_map_c[g][:n])
                         groups[g].density_map_to_action(dev_map[g], out=act[g])
                         cnt[1] += n * row_map
@@ -435,6 +458,9 @@ def run_b200(a):
     if errors:
         raise errors[0]
     e2e_ms = f0.elapsed_time(f1)
+    if os.environ.get("WRSN_E2E_DIAG") == "1" and rank == 0:
+        print("e2e host threads, ms per step [wait records, wait states, controller]: " +
+              ", ".join("[%.2f %.2f %.2f]" % tuple(1e3 * x / a.steps for x in d) for d in diag), file=sys.stderr)
     e2e_dec = sum(c[0] for c in counts)
     h2d, d2h = sum(c[1] for c in counts), sum(c[2] for c in counts)
     h2d, d2h = h2d // a.steps, d2h // a.steps              # per step, averaged over the timed steps

@@ -191,6 +191,9 @@ typedef struct wrsn_request {
                                            with a deciding charger; simulated seconds advanced by step; resets (episodes begun) */
     int32_t *sticky;                    /* [B]  OR of every `flags` value ever written for the row, never cleared by the library (may be NULL): a
                                            rollout that resets finished rows inside wrsn_rollout_step checks it once per window, not per step */
+    int32_t *order;                     /* [B]  scratch of wrsn_step / wrsn_rollout_step (may be NULL): the order in which the step kernel's CTAs take the
+                                           rows — longest predicted step first (time to the earliest charger's next decision, read from the
+                                           process slots and the new actions), so that the launch does not end on a late, long environment */
     int32_t *queue;                     /* [2]  work queue of the persistent step kernel (wrsn_dims.step_rounds < 0): zeroed once by the caller,
                                            left zeroed by every launch; may be NULL otherwise.  One per request record (= per stream). */
 } wrsn_request;

@@ -40,10 +40,11 @@ class Requests:
         self.flags = torch.zeros((B,), dtype=torch.int32, device=device)
         self.stats = torch.zeros((B, 3), dtype=torch.float64, device=device)   # running totals: decisions, simulated seconds, resets
         self.sticky = torch.zeros((B,), dtype=torch.int32, device=device)      # OR of every `flags` value written so far (see raise_on_error)
+        self.order = torch.zeros((B,), dtype=torch.int32, device=device)       # scratch: launch order of the step kernel's CTAs (longest step first)
         self.queue = torch.zeros((2,), dtype=torch.int32, device=device)       # work queue of the persistent step kernel (step_rounds < 0)
         self.c = _lib.Request(self.agent_id.data_ptr(), self.terminal.data_ptr(), self.reward.data_ptr(),
                               self.now.data_ptr(), self.action.data_ptr(), self.detail.data_ptr(), self.flags.data_ptr(),
-                              self.stats.data_ptr(), self.sticky.data_ptr(), self.queue.data_ptr())
+                              self.stats.data_ptr(), self.sticky.data_ptr(), self.order.data_ptr(), self.queue.data_ptr())
 
 
 class BatchedWRSN:

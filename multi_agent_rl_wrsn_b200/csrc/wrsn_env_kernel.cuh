@@ -3,7 +3,7 @@
 template <int MODE>
 __global__ void __launch_bounds__(WRSN_GFIX ? WRSN_GFIX : 256, WRSN_GFIX ? 16 : 1) k_env(const KParams P) {
     char *smem = reinterpret_cast<char *>(wrsn_smem_u4);
-    const int b = blockIdx.x, tid = threadIdx.x, G = blockDim.x;
+    const int b = (MODE == MODE_STEP && P.order) ? P.order[blockIdx.x] : (int)blockIdx.x, tid = threadIdx.x, G = blockDim.x;
     if (P.mask && !P.mask[b]) return;
     if (P.mask_mode == 1 && P.req.agent_id[b] < 0 && P.req.agent_id[b] != -4) return;     /* (-4: a step in flight continues) */
     if (P.mask_mode == 2 && (P.req.agent_id[b] >= 0 || P.req.agent_id[b] == -4)) return;
