@@ -769,6 +769,9 @@ static int check_dims(const wrsn_dims *d) {
     if (d->N <= 0 || d->N > 32000 || d->T < 0 || d->T > 65000 || d->M < 0 || d->M > WRSN_MAX_MC || d->B <= 0 || d->S <= 0)
         WRSN_FAIL("bad dims N=%d T=%d M=%d B=%d S=%d", d->N, d->T, d->M, d->B, d->S);
     if (d->Npad < d->N || (d->Npad & 15) || d->state_bytes <= 0) WRSN_FAIL("dims not finalized (call wrsn_dims_finalize)");
+    /* the register-resident per-node loops hold at most 4 (one warp) / 9 (several warps) nodes per thread */
+    if (d->threads < 32 || d->threads % 32 || d->threads > 256 || (int64_t)d->N > (int64_t)d->threads * (d->threads == 32 ? 4 : 9))
+        WRSN_FAIL("threads = %d cannot hold N = %d nodes (at most %d per thread)", d->threads, d->N, d->threads == 32 ? 4 : 9);
     return 0;
 }
 
@@ -796,10 +799,15 @@ int wrsn_dims_finalize(wrsn_dims *d) {
                                                         RandomController workload: 1.08 M decisions/s against 0.88 M on two
                                                         warps — no block-wide barriers, no shared-memory reductions, and the
                                                         per-second loops keep four independent chains per lane in flight) */
-        int t = 32; while (t < per && t < 256) t *= 2;
+        int t = 32; while (t < per && t < 128) t *= 2;    /* above 128 nodes: at most four warps, then up to nine nodes per thread
+                                                        (measured, RandomController law, 2 CTAs per SM: 1000 nodes 0.079 M decisions/s on
+                                                        128 threads against 0.074 M on 256; 500 nodes 0.340 M on 128 against 0.287 M on 64) */
+        if (d->N > 9 * t) t = 256;
         d->threads = t;
     }
     if (d->threads % 32 || d->threads > 256) WRSN_FAIL("threads must be a multiple of 32, at most 256");
+    if ((int64_t)d->N > (int64_t)d->threads * (d->threads == 32 ? 4 : 9))
+        WRSN_FAIL("threads = %d cannot hold N = %d nodes (at most %d per thread)", d->threads, d->N, d->threads == 32 ? 4 : 9);
     {
         const int ti = (d->S + OBS_TI - 1) / OBS_TI;
         const int tj = (d->S + OBS_TJ64 - 1) / OBS_TJ64, tk = (d->S + OBS_TJ32 - 1) / OBS_TJ32;
