@@ -4,8 +4,12 @@
 #define WRSN_GANY_MINB 2                            /* CTAs per SM the multi-warp build is compiled for: 128 registers (a few hundred bytes of spills)
                                                        instead of 238 — 1000 nodes / 10 chargers 0.046 -> 0.074 M decisions/s, 500 / 5 0.269 -> 0.340 M */
 #endif
+#ifndef WRSN_G32_MINB
+#define WRSN_G32_MINB 16                            /* CTAs per SM the one-warp build is compiled for (128 registers; measured: 18 CTAs at 96 registers
+                                                       and 0.7 KB of spills is 3 % slower, shared memory allows no more than 18) */
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(WRSN_GFIX ? WRSN_GFIX : 256, WRSN_GFIX ? 16 : WRSN_GANY_MINB) k_env(const KParams P) {
+__global__ void __launch_bounds__(WRSN_GFIX ? WRSN_GFIX : 256, WRSN_GFIX ? WRSN_G32_MINB : WRSN_GANY_MINB) k_env(const KParams P) {
     char *smem = reinterpret_cast<char *>(wrsn_smem_u4);
     const int b = (MODE == MODE_STEP && P.order) ? P.order[blockIdx.x] : (int)blockIdx.x, tid = threadIdx.x, G = blockDim.x;
     if (P.mask && !P.mask[b]) return;
