@@ -152,3 +152,26 @@ def test_sharded_equals_unsharded_records():
     pc.check_sharded_equals_unsharded(scs, "cpu", num_envs=7, steps=40, seed=2, world=2, num_agent=2)
     pc.check_sharded_equals_unsharded(scs, "cpu", num_envs=7, steps=40, seed=2, world=3, num_agent=2, budget=10)
     pc.check_sharded_equals_unsharded(scs, "cpu", num_envs=7, steps=40, seed=2, world=2, num_agent=2, budget=20, rounds=2)
+
+
+def test_sticky_flags_survive_a_reset():
+    """wrsn_request.sticky: the fixture whose 700 J chargers all die ends on an implicit None; one more `step` starts with no alive
+    charger (the reference would never return, Q1): `flags` bit 0.  A reset overwrites the row's `flags` — `sticky` keeps the bit,
+    `BatchedWRSN.raise_on_error()` counts those environments and raises on an engine error (bit 1), also one that was reset since."""
+    import torch
+    from multi_agent_rl_wrsn_b200 import BatchedWRSN
+    from tests.helpers import golden, mc_dict_of
+    g = golden("ep_deadmc_n50")
+    R = 2
+    env = BatchedWRSN(pc.sc_from_golden(g), num_agent=int(g["num_agent"]), mc_type=mc_dict_of(g), num_envs=R, device="cpu")
+    env.reset()
+    for i in range(1, int(g["n"])):
+        env.step(np.full(R, int(g["fed_agent"][i]), np.int32), np.tile(g["fed_action"][i], (R, 1)))
+    assert int(env.req.agent_id[0]) == -2 and env.raise_on_error() == 0
+    env.step(np.full(R, -1, np.int32), np.zeros((R, 3)))
+    assert int((env.req.flags & 1).sum()) == R
+    env.reset()
+    assert int((env.req.flags & 1).sum()) == 0 and env.raise_on_error() == R
+    env.req.sticky[1] |= 2
+    with pytest.raises(RuntimeError, match="engine error"):
+        env.raise_on_error()
