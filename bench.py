@@ -184,7 +184,7 @@ def run_reference(a):
     ms = 1e3 * float(np.mean([c["wall_s"] for c in vals]))
     line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=a.gpus, steps=a.steps, warmup=a.warmup, ms_per_step=ms,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
-                config=config_common(a, note="each step = a %.0f s sample on every host core" % per_step),
+                config=config_common(a), run=dict(note="each step = a %.0f s sample on every host core" % per_step),
                 impl="reference",
                 cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind="port", sample=vals[-1]["sample"]),
                 e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
@@ -192,10 +192,13 @@ def run_reference(a):
 
 
 def config_common(a, **extra):
-    """The keys both arms print (the driver compares them)."""
+    """`config` of the JSON line: the workload, described identically by both arms (the driver compares the two dicts).  What is specific
+    to an arm or measured in a run (groups, budget, simulated seconds per decision ...) goes into the line's `run` object instead."""
     T = a.nodes if a.targets is None else a.targets
     c = dict(workload=workload_name(a), nodes=a.nodes, targets=T, chargers=a.chargers, envs_per_gpu=a.envs, map_size=100,
-             actions=a.actions)
+             actions=a.actions, topologies_per_gpu=a.topologies, observation="float32 [B,4,100,100]",
+             l2="per GPU the environment records (22 KB each at 100 nodes) and the observations (160 KB per environment) are several times "
+                "the 126 MB L2; no explicit flush")
     c.update(extra)
     return c
 
@@ -604,12 +607,11 @@ def run_b200(a):
         metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=a.warmup,
         ms_per_step=elapsed_ms / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
         data="synthetic",
-        config=config_common(
-            a, groups="%d asynchronous groups of %d environments, one CUDA stream each" % (G, Bg),
-            step_budget=a.budget, step_rounds=a.rounds, topologies_per_gpu=a.topologies, threads_per_env=int(groups[0].dims.threads),
-            observation="float32 [B,4,100,100]",
-            l2="working set (state %.0f MB + observations %.0f MB per GPU) exceeds the 126 MB L2; no explicit flush"
-               % (B * groups[0].dims.state_bytes / 1e6, B * 4 * S * S * 4 / 1e6),
+        config=config_common(a),
+        run=dict(
+            groups="%d asynchronous groups of %d environments, one CUDA stream each" % (G, Bg),
+            step_budget=a.budget, step_rounds=a.rounds, threads_per_env=int(groups[0].dims.threads),
+            working_set="state %.0f MB + observations %.0f MB per GPU" % (B * groups[0].dims.state_bytes / 1e6, B * 4 * S * S * 4 / 1e6),
             sim_seconds_per_decision=ticks_all / max(decisions_all, 1.0),
             decisions_per_env_step=decisions_all / (a.steps * B * world),
             steps_in_flight_at_end=inflight,
@@ -634,7 +636,7 @@ def run_b200(a):
                       issue=issue, kernels=kernels))
     if "other_law" in extras:
         other, o_ms, o_dec, o_sim, K2 = extras["other_law"]
-        line["config"]["other_action_law"] = dict(actions=other, value=o_dec / (o_ms * 1e-3), unit=UNIT, steps=K2,
+        line["run"]["other_action_law"] = dict(actions=other, value=o_dec / (o_ms * 1e-3), unit=UNIT, steps=K2,
                                                   sim_seconds_per_decision=o_sim / max(o_dec, 1.0),
                                                   note="same environments, device-resident, not the headline workload")
     if "decode_alone" in extras:
