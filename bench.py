@@ -356,9 +356,11 @@ def run_b200(a):
     host_req = [dict(agent_id=torch.zeros(Bg, dtype=torch.int32).pin_memory(), reward=torch.zeros(Bg, dtype=torch.float64).pin_memory(),
                      terminal=torch.zeros(Bg, dtype=torch.uint8).pin_memory(), now=torch.zeros(Bg, dtype=torch.float64).pin_memory())
                 for _ in range(G)]
-    rec_ev = [torch.cuda.Event() for _ in range(G)]
+    # many callers on few cores (several ranks per host): a waiting thread yields its core instead of spinning
+    ev_blocking = G * int(os.environ.get("LOCAL_WORLD_SIZE", world)) * 2 > (os.cpu_count() or 1)
+    rec_ev = [torch.cuda.Event(blocking=ev_blocking) for _ in range(G)]
     CH = 4                                                   # chunks per group and step of the state copy
-    obs_ev = [[torch.cuda.Event() for _ in range(CH)] for _ in range(G)]
+    obs_ev = [[torch.cuda.Event(blocking=ev_blocking) for _ in range(CH)] for _ in range(G)]
     map_ev = [torch.cuda.Event() for _ in range(G)]
     copy_streams = [torch.cuda.Stream(device=dev) for _ in range(G)]
     req_bytes = sum(v.numel() * v.element_size() for v in host_req[0].values())
