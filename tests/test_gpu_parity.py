@@ -277,3 +277,25 @@ def test_simulator_on_a_device_that_is_not_current():
             obs = env.get_state()
             outs.append((env.state.cpu(), obs.cpu()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+def test_launch_order_changes_no_result():
+    """k_step_order (launches of >= 2048 rows are taken longest predicted step first): 2304 environments — 768 replicas of three
+    scenarios, every replica of a scenario fed the same actions — against 3 environments stepped in index order (no ordering below
+    2048 rows): every replica's requests and record equal, byte for byte, those of its scenario's single environment."""
+    scs = [synthetic(num_nodes=100, num_targets=100, seed=s) for s in BENCH_SCENARIOS[:3]]
+    R, steps = 768, 40
+    big = BatchedWRSN(scs, num_agent=3, num_envs=3 * R, device=DEV, scenario_index=np.arange(3 * R) % 3, step_budget=60)
+    small = BatchedWRSN(scs, num_agent=3, num_envs=3, device=DEV, step_budget=60)
+    rng = np.random.default_rng(11)
+    acts = rng.uniform(0.0, 1.0, size=(steps, 3, 3)); acts[..., 2] *= 0.1
+    end = int(big._foff[big.E["WRSN_F_SCRATCH"]])
+    big.reset(); small.reset()
+    for k in range(steps):
+        small.rollout_step(torch.as_tensor(acts[k], device=DEV))
+        big.rollout_step(torch.as_tensor(np.tile(acts[k], (R, 1)), device=DEV))
+        for f in ("agent_id", "terminal", "now", "reward", "flags"):
+            x, y = getattr(big.req, f).view(R, 3), getattr(small.req, f).view(1, 3)
+            assert bool(((x == y) | ((x != x) & (y != y))).all()), (k, f)
+        assert torch.equal(big.state[:, :end].view(R, 3, end), small.state[:, :end].view(1, 3, end).expand(R, 3, end)), k
+    assert int((big.req.order.sort().values != torch.arange(3 * R, device=DEV, dtype=torch.int32)).sum()) == 0   # a permutation
