@@ -16,7 +16,7 @@ NODES = int(sys.argv[4]) if len(sys.argv) > 4 else 100
 CHARGERS = int(sys.argv[5]) if len(sys.argv) > 5 else 3
 scs = [synthetic(num_nodes=NODES, num_targets=NODES, seed=1000 + k, num_gateways=max(3, NODES // 40)) if NODES > 100 else
        synthetic(num_nodes=NODES, num_targets=NODES, seed=1000 + k) for k in range(64 if NODES <= 100 else 8)]
-env = BatchedWRSN(scs, num_agent=CHARGERS, num_envs=B, device="cuda:0")
+env = BatchedWRSN(scs, num_agent=CHARGERS, num_envs=B, device="cuda:0", step_budget=int(os.environ.get("WRSN_BUDGET", "0")))
 env.reset()
 g = torch.Generator(device="cuda:0"); g.manual_seed(0)
 names = ["total", "serial", "batch", "bfs", "fitness"] if VARIANT == 1 else (
